@@ -1,0 +1,226 @@
+/* bft_arena.h — the flattened Bloom Filter Trie ("arena") and the walk over it.
+ *
+ * The reference keeps a BFT as a pointer-linked burst trie (Node -> CC[] + UC, CC -> UC buckets + child Nodes;
+ * reference include/Node.h:55-58, include/CC.h:34-67, include/UC.h:13-20). The serializer (bft_flatten.c)
+ * turns one .bft file into the structure-of-arrays arena declared here; the same arrays are uploaded verbatim
+ * into HBM. Everything in the arena is derived exactly from the reference's own bytes — no result changes:
+ *
+ *   nodes[]    one descriptor per trie Node.
+ *   firstcc[]  per Node with CCs: 16384 bytes, entry idx14 -> index of the FIRST CC of the node whose Bloom filter
+ *              fires for the 14-bit hash index idx14 (0xff: none fires). The reference probes the CC chain in order
+ *              and lets the first hit decide (src/presenceNode.c:1354-1550); the probe depends only on idx14
+ *              (src/presenceNode.c:1341-1343), so this table is that chain, precomputed (the reference builds the
+ *              same table for its root in get_bf_presence_per_cc, src/presenceNode.c:1213-1270).
+ *   ccs[]      one descriptor per CC.
+ *   csr[]      per CC: 2^p + 1 uint16, csr[pu] = number of stored prefixes whose p_u is < pu. Replaces the
+ *              filter2 bit test + rank (SkipFilter2) + select in the cluster-start bits (SkipFilter3 /
+ *              extra_filter3 / in-band flags) of findCluster (src/presenceNode.c:1578-1821).
+ *   filter3[]  the p_v values, as stored (bytes for s=8, nibbles for s=4; src/presenceNode.c:1478-1479).
+ *   pref[]     per stored prefix: where its suffixes live (inline line range, child Node, or leaf colour class).
+ *              Replaces children_type prefix sums (count_children / count_nodes, include/CC.h:471-550).
+ *   keys[]     every suffix line (CC inline suffixes and Node-UC k-mer remainders) as W little-endian 64-bit
+ *              words holding the suffix as an integer (nucleotide i at bits 2i), sorted ascending inside each
+ *              block so the search is an integer compare (replaces memcmp in binary_search_UC, src/UC.c:81-124).
+ *   linecls[]  per line: colour-class id (index of the line's distinct annotation byte string).
+ *   rootdir[]  262144 entries: the complete answer of the root Node probe for every possible 9-nt prefix, indexed
+ *              by the low 18 bits of the packed k-mer. Every query passes through the root, so its probe is
+ *              collapsed into one 8-byte load.
+ *   colour classes: distinct annotation byte strings (cls_off/cls_bytes) + the comp_set_colors pools; decoded on
+ *              the device once per arena into class rows (bft_kernels.cu: k_decode_classes).
+ *
+ * The walk functions below are plain C, compiled for the device by nvcc (the product path) and for the host by
+ * the flattener (to fill rootdir) and by tests/tools (to debug the arena without a GPU). The shipped library
+ * exposes no host query path.
+ */
+#ifndef BFT_ARENA_H
+#define BFT_ARENA_H
+
+#include <stdint.h>
+#include <stddef.h>
+
+#ifdef __CUDACC__
+#define BFT_HD __host__ __device__ __forceinline__
+#else
+#define BFT_HD static inline
+#endif
+
+#define BFT_NB_CHAR_SUF_PREF 9         /* reference include/default_param.h:12 */
+#define BFT_PREFIX_BITS 18
+#define BFT_N_IDX14 16384
+#define BFT_ROOTDIR_SIZE (1u << BFT_PREFIX_BITS)
+#define BFT_FIRSTCC_NONE 0xffu
+#define BFT_MAX_WORDS 2                /* k <= 63 (126 bits) */
+
+/* kinds of a prefix-probe answer */
+#define BFT_KIND_ABSENT 0u /* a CC's Bloom filter fired but the prefix is not stored there: k-mer absent */
+#define BFT_KIND_UC 1u     /* no CC fired: search the Node's own UC lines [a, a+n) for the whole remainder */
+#define BFT_KIND_INLINE 2u /* prefix stored, suffixes inline: search lines [a, a+n) for the shifted remainder */
+#define BFT_KIND_NODE 3u   /* prefix stored, suffixes in child Node a */
+#define BFT_KIND_LEAF 4u   /* leaf level (9 nt left): prefix stored, a = colour class */
+#define BFT_KIND_SHIFT 28
+#define BFT_CNT_MASK ((1u << BFT_KIND_SHIFT) - 1u)
+
+#define BFT_CLS_NONE 0xffffffffu
+
+typedef struct {
+    uint32_t a; /* line index / node id / class id */
+    uint32_t b; /* kind << 28 | count */
+} bft_entry_t;
+
+typedef struct {
+    uint32_t cc_begin; /* first CC descriptor */
+    uint32_t n_cc;
+    uint32_t fc_off;   /* byte offset of this node's firstcc table (valid when n_cc > 0) */
+    uint32_t uc_begin; /* first line of the Node's own UC */
+    uint32_t uc_n;     /* number of lines in the Node's own UC */
+    uint32_t pad[3];
+} bft_node_t;
+
+typedef struct {
+    uint32_t csr_off;  /* offset into csr[] (uint16 units) */
+    uint32_t f3_off;   /* byte offset into filter3[] */
+    uint32_t pref_off; /* offset into pref[] */
+    uint16_t nb_elem;
+    uint8_t s;         /* bits of p_v: 8 or 4 (reference CC.type bits 1-5) */
+    uint8_t pad;
+} bft_cc_t;
+
+/* Read-only view of an arena; pointers are host pointers on the host and device pointers in kernels. */
+typedef struct {
+    const bft_entry_t* rootdir;
+    const bft_node_t* nodes;
+    const bft_cc_t* ccs;
+    const uint8_t* firstcc;
+    const uint16_t* csr;
+    const uint8_t* filter3;
+    const bft_entry_t* pref;
+    const uint64_t* keys;     /* n_lines * W words */
+    const uint32_t* linecls;  /* n_lines */
+    int k;
+    int W; /* 64-bit words per key: 1 for k <= 27, 2 for k <= 63 */
+} bft_view_t;
+
+/* ---- prefix bit manipulation --------------------------------------------------------------------------------
+ * low18 = the 9 leading nucleotides as stored in the packed k-mer (nuc i at bits 2i).
+ * The reference works on the same 9 nucleotides MSB-first (reverse_word_8, src/presenceNode.c:1327-1329), hashes
+ * nuc1..nuc7 (14 bits, :1341-1343) and stores the prefix rotated as nuc1..nuc8,nuc0 (:1367-1371). */
+BFT_HD uint32_t bft_msb_first18(uint32_t low18) {
+    uint32_t r = 0;
+    for (int i = 0; i < 9; i++) r |= ((low18 >> (2 * i)) & 3u) << (2 * (8 - i));
+    return r;
+}
+BFT_HD uint32_t bft_idx14(uint32_t r18) { return (r18 >> 2) & 0x3fffu; }
+BFT_HD uint32_t bft_rot18(uint32_t r18) { return ((r18 << 2) & 0x3ffffu) | (r18 >> 16); }
+
+BFT_HD bft_entry_t bft_mk_entry(uint32_t kind, uint32_t a, uint32_t n) {
+    bft_entry_t e;
+    e.a = a;
+    e.b = (kind << BFT_KIND_SHIFT) | (n & BFT_CNT_MASK);
+    return e;
+}
+
+/* One Node probe: the reference's presenceKmer (src/presenceNode.c:1284-1576) on the flattened layout. */
+BFT_HD bft_entry_t bft_node_probe(const bft_view_t* v, uint32_t node_id, uint32_t low18, int size_kmer) {
+    const bft_node_t nd = v->nodes[node_id];
+    const uint32_t r18 = bft_msb_first18(low18);
+    if (nd.n_cc) {
+        const uint32_t c = v->firstcc[nd.fc_off + bft_idx14(r18)];
+        if (c != BFT_FIRSTCC_NONE) {
+            const bft_cc_t cc = v->ccs[nd.cc_begin + c];
+            const uint32_t rot = bft_rot18(r18);
+            const uint32_t pu = rot >> cc.s;
+            const uint32_t pv = rot & ((1u << cc.s) - 1u);
+            uint32_t lo = v->csr[cc.csr_off + pu];
+            uint32_t hi = v->csr[cc.csr_off + pu + 1];
+            if (lo >= hi) return bft_mk_entry(BFT_KIND_ABSENT, 0, 0);
+            /* lower_bound of pv in the cluster [lo, hi) of filter3 (src/presenceNode.c:1396-1410 / 1475-1488) */
+            const uint8_t* f3 = v->filter3 + cc.f3_off;
+            uint32_t end = hi;
+            if (cc.s == 8) {
+                while (lo < hi) {
+                    uint32_t mid = (lo + hi) >> 1;
+                    if (f3[mid] < pv) lo = mid + 1; else hi = mid;
+                }
+                if (lo >= end || f3[lo] != pv) return bft_mk_entry(BFT_KIND_ABSENT, 0, 0);
+            } else {
+                while (lo < hi) {
+                    uint32_t mid = (lo + hi) >> 1;
+                    uint32_t t = (mid & 1u) ? (uint32_t)(f3[mid >> 1] >> 4) : (uint32_t)(f3[mid >> 1] & 0xf);
+                    if (t < pv) lo = mid + 1; else hi = mid;
+                }
+                if (lo >= end) return bft_mk_entry(BFT_KIND_ABSENT, 0, 0);
+                uint32_t t = (lo & 1u) ? (uint32_t)(f3[lo >> 1] >> 4) : (uint32_t)(f3[lo >> 1] & 0xf);
+                if (t != pv) return bft_mk_entry(BFT_KIND_ABSENT, 0, 0);
+            }
+            (void)size_kmer;
+            return v->pref[cc.pref_off + lo];
+        }
+    }
+    return bft_mk_entry(BFT_KIND_UC, nd.uc_begin, nd.uc_n);
+}
+
+/* key compare helpers: keys are W words, word W-1 most significant */
+BFT_HD int bft_key_less(const uint64_t* a, const uint64_t* b, int W) {
+    for (int w = W - 1; w >= 0; w--) {
+        if (a[w] < b[w]) return 1;
+        if (a[w] > b[w]) return 0;
+    }
+    return 0;
+}
+BFT_HD int bft_key_eq(const uint64_t* a, const uint64_t* b, int W) {
+    for (int w = 0; w < W; w++)
+        if (a[w] != b[w]) return 0;
+    return 1;
+}
+
+/* Search lines [begin, begin+n) for `key`; returns the line index or 0xffffffff
+ * (binary_search_UC + equality test, src/UC.c:81-124, src/presenceNode.c:1876-1914, 1554-1570). */
+BFT_HD uint32_t bft_search_lines(const bft_view_t* v, uint32_t begin, uint32_t n, const uint64_t* key) {
+    const int W = v->W;
+    uint32_t lo = begin, hi = begin + n;
+    while (lo < hi) {
+        uint32_t mid = lo + ((hi - lo) >> 1);
+        if (bft_key_less(v->keys + (size_t)mid * W, key, W)) lo = mid + 1; else hi = mid;
+    }
+    if (lo < begin + n && bft_key_eq(v->keys + (size_t)lo * W, key, W)) return lo;
+    return 0xffffffffu;
+}
+
+BFT_HD void bft_shift18(uint64_t* cur, int W) {
+    for (int w = 0; w < W; w++) {
+        uint64_t x = cur[w] >> BFT_PREFIX_BITS;
+        if (w + 1 < W) x |= cur[w + 1] << (64 - BFT_PREFIX_BITS);
+        cur[w] = x;
+    }
+}
+
+/* Full lookup: the reference's isKmerPresent (src/presenceNode.c:1823-1921).
+ * kmer: W words (bits above 2k must be zero). Returns the colour class of the k-mer, or BFT_CLS_NONE if absent. */
+BFT_HD uint32_t bft_lookup(const bft_view_t* v, const uint64_t* kmer) {
+    uint64_t cur[BFT_MAX_WORDS];
+    const int W = v->W;
+    for (int w = 0; w < W; w++) cur[w] = kmer[w];
+    int sz = v->k;
+    bft_entry_t e = v->rootdir[(uint32_t)cur[0] & (BFT_ROOTDIR_SIZE - 1u)];
+    for (;;) {
+        const uint32_t kind = e.b >> BFT_KIND_SHIFT;
+        const uint32_t n = e.b & BFT_CNT_MASK;
+        if (kind == BFT_KIND_ABSENT) return BFT_CLS_NONE;
+        if (kind == BFT_KIND_LEAF) return e.a;
+        if (kind == BFT_KIND_UC) {
+            if (n == 0) return BFT_CLS_NONE;
+            uint32_t ln = bft_search_lines(v, e.a, n, cur);
+            return ln == 0xffffffffu ? BFT_CLS_NONE : v->linecls[ln];
+        }
+        bft_shift18(cur, W);
+        sz -= BFT_NB_CHAR_SUF_PREF;
+        if (kind == BFT_KIND_INLINE) {
+            uint32_t ln = bft_search_lines(v, e.a, n, cur);
+            return ln == 0xffffffffu ? BFT_CLS_NONE : v->linecls[ln];
+        }
+        /* BFT_KIND_NODE */
+        e = bft_node_probe(v, e.a, (uint32_t)cur[0] & (BFT_ROOTDIR_SIZE - 1u), sz);
+    }
+}
+
+#endif /* BFT_ARENA_H */

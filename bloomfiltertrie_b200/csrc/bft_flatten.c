@@ -1,0 +1,603 @@
+/* bft_flatten.c — serializer: .bft file -> flattened arena (layout in bft_arena.h).
+ *
+ * File format = what the reference writes in write_BFT_Root / write_Node / write_UC / write_CC
+ * (reference src/write_to_disk.c:21-258) and reads back in read_BFT_Root_offset / read_Node / read_UC / read_CC
+ * (:264-776). Bloom-filter bits, SkipFilter2 and SkipFilter3 are not in the file; the reference rebuilds them on
+ * load (:578-581, 649-772). This serializer rebuilds the Bloom filters the same way (same hash, same prefixes) and
+ * folds them into the per-Node first-CC table; rank/select helpers are replaced by exact prefix sums.
+ * Only root->compressed == 0 files are accepted (the only kind the reference CLI produces, src/main.c:180,185).
+ */
+#define _GNU_SOURCE
+#include "bft_flatten.h"
+#include "bft_xxh64.h"
+
+#include <stdarg.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <setjmp.h>
+
+#define CEILDIV(a, b) (((a) + (b) - 1) / (b))
+
+typedef struct {
+    int nb_bits_skip2, nb_bits_skip3, nb_ucs_skp, nb_kmers_uc, level_min, modulo_hash, tresh_suf_pref;
+} lvl_info_t;
+
+typedef struct { uint64_t k[BFT_MAX_WORDS]; uint32_t cls; } line_tmp_t;
+
+typedef struct {
+    const uint8_t* buf;
+    size_t len, pos;
+    bft_arena_t* a;
+    lvl_info_t lvl[16];
+    uint16_t* h1; /* per idx14: hash1 % modulo, per level modulo may differ -> recomputed per level lazily */
+    uint16_t* h2;
+    uint64_t* hv1; /* raw XXH64 per idx14 */
+    uint64_t* hv2;
+    /* capacities */
+    size_t cap_nodes, cap_ccs, cap_firstcc, cap_csr, cap_filter3, cap_pref, cap_lines, cap_cls_off, cap_cls_bytes;
+    /* class hash map */
+    uint32_t* map; size_t map_cap, map_used;
+    /* scratch */
+    line_tmp_t* tmp; size_t cap_tmp;
+    uint8_t* scratch; size_t cap_scratch;   /* one annotation + extended byte */
+    int16_t* extbuf; size_t cap_extbuf;     /* per line of the UC being read: extended byte or -1 */
+    int depth;
+    char* err; size_t errlen;
+    jmp_buf jb;
+} ctx_t;
+
+static void fail(ctx_t* c, const char* fmt, ...) {
+    if (c->err && c->errlen) {
+        va_list ap;
+        va_start(ap, fmt);
+        vsnprintf(c->err, c->errlen, fmt, ap);
+        va_end(ap);
+    }
+    longjmp(c->jb, 1);
+}
+
+static void* xrealloc(ctx_t* c, void* p, size_t n) {
+    void* q = realloc(p, n ? n : 1);
+    if (!q) fail(c, "bft_flatten: out of memory (%zu bytes)", n);
+    return q;
+}
+
+#define GROW(c, arr, cap, need, type)                                   \
+    do {                                                                \
+        if ((need) > (cap)) {                                           \
+            size_t ncap_ = (cap) ? (cap) : 1024;                        \
+            while (ncap_ < (need)) ncap_ += ncap_ / 2 + 1024;           \
+            (arr) = (type*)xrealloc((c), (arr), ncap_ * sizeof(type));  \
+            (cap) = ncap_;                                              \
+        }                                                               \
+    } while (0)
+
+static const uint8_t* rd(ctx_t* c, size_t n) {
+    if (n > c->len - c->pos) fail(c, "bft_flatten: truncated file (need %zu bytes at offset %zu of %zu)", n, c->pos, c->len);
+    const uint8_t* p = c->buf + c->pos;
+    c->pos += n;
+    return p;
+}
+static uint16_t rd_u16(ctx_t* c) { uint16_t v; memcpy(&v, rd(c, 2), 2); return v; }
+static uint32_t rd_u32(ctx_t* c) { uint32_t v; memcpy(&v, rd(c, 4), 4); return v; }
+static int32_t rd_i32(ctx_t* c) { int32_t v; memcpy(&v, rd(c, 4), 4); return v; }
+static int64_t rd_i64(ctx_t* c) { int64_t v; memcpy(&v, rd(c, 8), 8); return v; }
+
+/* per-level geometry, reference create_info_per_level (src/CC.c:1883-1993) */
+static int size_kmer_in_bytes(int sz) { return CEILDIV(sz * 2, 8); }
+static int size_kmer_in_bytes_minus_1(int sz) { return sz > 9 ? CEILDIV((sz - 9) * 2, 8) : 0; }
+static int exact_byte_level(int sz) { return sz == 45 || sz == 81 || sz == 117; }
+
+/* ---- colour classes ------------------------------------------------------------------------------------ */
+static uint32_t class_of(ctx_t* c, const uint8_t* s, size_t n) {
+    bft_arena_t* a = c->a;
+    if ((c->map_used + 1) * 2 > c->map_cap) {
+        size_t ncap = c->map_cap ? c->map_cap * 2 : (1u << 16);
+        uint32_t* nm = (uint32_t*)xrealloc(c, NULL, ncap * sizeof(uint32_t));
+        memset(nm, 0xff, ncap * sizeof(uint32_t));
+        for (size_t i = 0; i < c->map_cap; i++) {
+            uint32_t id = c->map[i];
+            if (id == 0xffffffffu) continue;
+            uint64_t h = bft_xxh64(a->cls_bytes + a->cls_off[id], a->cls_off[id + 1] - a->cls_off[id], 0x5bd1e995);
+            size_t j = (size_t)h & (ncap - 1);
+            while (nm[j] != 0xffffffffu) j = (j + 1) & (ncap - 1);
+            nm[j] = id;
+        }
+        free(c->map);
+        c->map = nm;
+        c->map_cap = ncap;
+    }
+    uint64_t h = bft_xxh64(s, n, 0x5bd1e995);
+    size_t j = (size_t)h & (c->map_cap - 1);
+    for (;;) {
+        uint32_t id = c->map[j];
+        if (id == 0xffffffffu) break;
+        size_t ln = a->cls_off[id + 1] - a->cls_off[id];
+        if (ln == n && memcmp(a->cls_bytes + a->cls_off[id], s, n) == 0) return id;
+        j = (j + 1) & (c->map_cap - 1);
+    }
+    if (a->n_classes >= 0xfffffff0u) fail(c, "bft_flatten: too many colour classes");
+    uint32_t id = (uint32_t)a->n_classes;
+    GROW(c, a->cls_off, c->cap_cls_off, a->n_classes + 2, uint32_t);
+    GROW(c, a->cls_bytes, c->cap_cls_bytes, a->cls_bytes_len + n + 1, uint8_t);
+    if (a->cls_bytes_len + n > 0xfffffff0u) fail(c, "bft_flatten: colour class bytes exceed 4 GiB");
+    memcpy(a->cls_bytes + a->cls_bytes_len, s, n);
+    a->cls_bytes_len += n;
+    a->n_classes++;
+    a->cls_off[a->n_classes] = (uint32_t)a->cls_bytes_len;
+    if (n > a->max_cls_len) a->max_cls_len = n;
+    c->map[j] = id;
+    c->map_used++;
+    return id;
+}
+
+/* A UC body as stored in the file (reference write_UC, src/write_to_disk.c:119-207, uncompressed branch). */
+typedef struct {
+    const uint8_t* lines; /* n * (size_sub + size_annot) */
+    const uint8_t* ext;   /* nb_ext * 3: (2-byte big-endian delta position, 1 byte) */
+    int n, size_sub, size_annot, nb_ext;
+    int16_t* ext_of_line; /* per line: extended byte or -1 (ctx scratch) */
+} uc_body_t;
+
+static void read_uc_body(ctx_t* c, uc_body_t* u, int size_sub, int n) {
+    memset(u, 0, sizeof(*u));
+    u->n = n;
+    u->size_sub = size_sub;
+    if (n == 0) return;
+    u->nb_ext = rd_u16(c);
+    u->size_annot = rd_i32(c);
+    if (u->nb_ext == 0xffff) fail(c, "bft_flatten: compressed UC encountered (root->compressed files are not supported)");
+    if (u->size_annot < 0 || u->size_annot > (1 << 24)) fail(c, "bft_flatten: implausible annotation size %d", u->size_annot);
+    u->lines = rd(c, (size_t)n * (size_t)(size_sub + u->size_annot));
+    u->ext = rd(c, (size_t)u->nb_ext * 3);
+    GROW(c, c->extbuf, c->cap_extbuf, (size_t)n, int16_t);
+    GROW(c, c->scratch, c->cap_scratch, (size_t)u->size_annot + 16, uint8_t);
+    u->ext_of_line = c->extbuf; /* valid until the next read_uc_body: every UC is consumed before the next is read */
+    for (int i = 0; i < n; i++) u->ext_of_line[i] = -1;
+    /* get_extend_annot (src/UC.c:501-521): cumulative big-endian deltas, first entry reaching a position wins */
+    int pos = 0;
+    for (int i = 0; i < u->nb_ext; i++) {
+        pos += (u->ext[i * 3] << 8) | u->ext[i * 3 + 1];
+        if (pos < n && u->ext_of_line[pos] < 0) u->ext_of_line[pos] = u->ext[i * 3 + 2];
+    }
+}
+
+/* class of line i: get_annot (src/UC.c:171-239) -> bytes handed to get_id_genomes_from_annot (src/bft.c:622-641) */
+static uint32_t uc_line_class(ctx_t* c, const uc_body_t* u, int i) {
+    uint8_t* scratch = c->scratch;
+    if (u->size_annot == 0 || u->n == 0) return 0; /* class 0 = empty annotation */
+    const uint8_t* annot = u->lines + (size_t)i * (size_t)(u->size_sub + u->size_annot) + u->size_sub;
+    if (u->ext_of_line[i] >= 0) {
+        memcpy(scratch, annot, (size_t)u->size_annot);
+        scratch[u->size_annot] = (uint8_t)u->ext_of_line[i];
+        return class_of(c, scratch, (size_t)u->size_annot + 1);
+    }
+    int n = u->size_annot; /* size_annot_sub: strip trailing zero bytes (include/annotation.h:183-191) */
+    while (n > 0 && annot[n - 1] == 0) n--;
+    return class_of(c, annot, (size_t)n);
+}
+
+static void line_key(ctx_t* c, const uc_body_t* u, int i, int key_bits, int strip_bit7, uint64_t* out) {
+    uint8_t b[8 * BFT_MAX_WORDS];
+    memset(b, 0, sizeof(b));
+    if (u->size_sub > (int)sizeof(b)) fail(c, "bft_flatten: suffix of %d bytes exceeds the supported key width", u->size_sub);
+    memcpy(b, u->lines + (size_t)i * (size_t)(u->size_sub + u->size_annot), (size_t)u->size_sub);
+    if (strip_bit7 && u->size_sub > 0) b[u->size_sub - 1] &= 0x7f; /* in-band cluster flag, src/presenceNode.c:1901-1904 */
+    for (int w = 0; w < BFT_MAX_WORDS; w++) memcpy(&out[w], b + 8 * w, 8);
+    /* bits above key_bits must be zero: the reference compares whole bytes (memcmp) */
+    for (int w = 0; w < BFT_MAX_WORDS; w++) {
+        int lo = 64 * w;
+        uint64_t allowed = key_bits >= lo + 64 ? ~0ULL : (key_bits <= lo ? 0ULL : ((1ULL << (key_bits - lo)) - 1));
+        if (out[w] & ~allowed) fail(c, "bft_flatten: stray bits above %d in a stored suffix", key_bits);
+    }
+}
+
+static int cmp_line_tmp(const void* pa, const void* pb) {
+    const line_tmp_t* a = (const line_tmp_t*)pa;
+    const line_tmp_t* b = (const line_tmp_t*)pb;
+    for (int w = BFT_MAX_WORDS - 1; w >= 0; w--) {
+        if (a->k[w] < b->k[w]) return -1;
+        if (a->k[w] > b->k[w]) return 1;
+    }
+    return 0;
+}
+
+/* append lines [first, first+cnt) of a UC body as one sorted block; returns the global index of its first line */
+static uint32_t append_block(ctx_t* c, const uc_body_t* u, int first, int cnt, int key_bits, int strip_bit7) {
+    bft_arena_t* a = c->a;
+    const int W = a->W;
+    GROW(c, c->tmp, c->cap_tmp, (size_t)cnt, line_tmp_t);
+    for (int i = 0; i < cnt; i++) {
+        line_key(c, u, first + i, key_bits, strip_bit7, c->tmp[i].k);
+        c->tmp[i].cls = uc_line_class(c, u, first + i);
+    }
+    if (cnt > 1) qsort(c->tmp, (size_t)cnt, sizeof(line_tmp_t), cmp_line_tmp);
+    if (a->n_lines + (size_t)cnt >= 0xfffffff0u) fail(c, "bft_flatten: more than 2^32 suffix lines");
+    size_t need = a->n_lines + (size_t)cnt;
+    if (need > c->cap_lines) {
+        size_t ncap = c->cap_lines ? c->cap_lines : 4096;
+        while (ncap < need) ncap += ncap / 2 + 4096;
+        a->keys = (uint64_t*)xrealloc(c, a->keys, ncap * (size_t)W * sizeof(uint64_t));
+        a->linecls = (uint32_t*)xrealloc(c, a->linecls, ncap * sizeof(uint32_t));
+        c->cap_lines = ncap;
+    }
+    uint32_t start = (uint32_t)a->n_lines;
+    for (int i = 0; i < cnt; i++) {
+        for (int w = 0; w < W; w++) a->keys[(a->n_lines + (size_t)i) * W + w] = c->tmp[i].k[w];
+        for (int w = W; w < BFT_MAX_WORDS; w++)
+            if (c->tmp[i].k[w]) fail(c, "bft_flatten: key wider than W words");
+        a->linecls[a->n_lines + (size_t)i] = c->tmp[i].cls;
+    }
+    a->n_lines += (size_t)cnt;
+    a->n_kmers += (size_t)cnt;
+    return start;
+}
+
+static uint32_t parse_node(ctx_t* c, int sz, int* cluster_flag);
+
+static int get_nb_elts(const uint8_t* ct, int pos, int type8) { /* include/CC.h:358-366 */
+    if (type8) return ct[pos];
+    return (pos & 1) ? (ct[pos / 2] >> 4) : (ct[pos / 2] & 0xf);
+}
+
+/* parse one CC into descriptor slot cc_id; bf = this CC's regenerated Bloom filter (modulo_hash bits) */
+static void parse_cc(ctx_t* c, int sz, uint32_t cc_id, uint8_t* bf) {
+    bft_arena_t* a = c->a;
+    const int lvl = sz / 9 - 1;
+    const lvl_info_t* li = &c->lvl[lvl];
+    const uint16_t type = rd_u16(c);
+    const int nb_elem = rd_u16(c);
+    const int nb_node_children = rd_u16(c);
+    const int s = (type >> 1) & 0x1f;
+    const int type8 = (type >> 6) & 1;
+    if (s != 8 && s != 4) fail(c, "bft_flatten: CC with s=%d (expected 8 or 4)", s);
+    const int p = BFT_PREFIX_BITS - s;
+    const int n_pu = 1 << p;
+    const int nb_skp = CEILDIV(nb_elem, li->nb_ucs_skp);
+
+    const uint8_t* f2 = rd(c, (size_t)n_pu / 8);
+    const size_t f3_bytes = s == 8 ? (size_t)nb_elem : (size_t)CEILDIV(nb_elem, 2);
+    const uint8_t* f3 = rd(c, f3_bytes);
+    const uint8_t* ef3 = li->level_min == 1 ? rd(c, (size_t)CEILDIV(nb_elem, 8)) : NULL;
+
+    GROW(c, a->filter3, c->cap_filter3, a->filter3_bytes + f3_bytes + 8, uint8_t);
+    if (a->filter3_bytes + f3_bytes > 0xfffffff0u) fail(c, "bft_flatten: filter3 arena exceeds 4 GiB");
+    const uint32_t f3_off = (uint32_t)a->filter3_bytes;
+    memcpy(a->filter3 + f3_off, f3, f3_bytes);
+    a->filter3_bytes += f3_bytes;
+
+    if (a->n_pref + (size_t)nb_elem > 0xfffffff0u) fail(c, "bft_flatten: more than 2^32 stored prefixes");
+    const uint32_t pref_off = (uint32_t)a->n_pref;
+    GROW(c, a->pref, c->cap_pref, a->n_pref + (size_t)nb_elem, bft_entry_t);
+    a->n_pref += (size_t)nb_elem;
+
+    uint8_t* flags = (uint8_t*)xrealloc(c, NULL, (size_t)nb_elem + 1);
+    memset(flags, 0, (size_t)nb_elem + 1);
+    if (ef3)
+        for (int j = 0; j < nb_elem; j++) flags[j] = (ef3[j / 8] >> (j % 8)) & 1;
+
+    int n_node_prefixes = 0;
+    if (lvl > 0) {
+        const uint8_t* ct = rd(c, type8 ? (size_t)nb_elem : (size_t)CEILDIV(nb_elem, 2));
+        const int size_sub = size_kmer_in_bytes_minus_1(sz);
+        const int key_bits = 2 * (sz - 9);
+        const int strip = !exact_byte_level(sz);
+        for (int b = 0; b < nb_skp; b++) {
+            const int nlines = rd_u16(c);
+            uc_body_t u;
+            read_uc_body(c, &u, size_sub, nlines);
+            const int j0 = b * li->nb_ucs_skp;
+            const int j1 = j0 + li->nb_ucs_skp < nb_elem ? j0 + li->nb_ucs_skp : nb_elem;
+            int off = 0;
+            for (int j = j0; j < j1; j++) {
+                const int ne = get_nb_elts(ct, j, type8);
+                if (ne == 0) {
+                    a->pref[pref_off + j] = bft_mk_entry(BFT_KIND_NODE, 0, 0);
+                    n_node_prefixes++;
+                    continue;
+                }
+                if (off + ne > nlines) fail(c, "bft_flatten: children_type overruns its UC bucket");
+                if (li->level_min == 0) /* in-band cluster flag: bit 7 of the last suffix byte of the first line */
+                    flags[j] = u.lines[(size_t)off * (size_t)(size_sub + u.size_annot) + size_sub - 1] >> 7;
+                uint32_t start = append_block(c, &u, off, ne, key_bits, strip);
+                a->pref[pref_off + j] = bft_mk_entry(BFT_KIND_INLINE, start, (uint32_t)ne);
+                off += ne;
+            }
+            if (off != nlines) fail(c, "bft_flatten: UC bucket holds %d lines but children_type accounts for %d", nlines, off);
+        }
+        /* child Nodes follow, in prefix order (write_CC, src/write_to_disk.c:254-255) */
+        if (n_node_prefixes != nb_node_children)
+            fail(c, "bft_flatten: CC declares %d child nodes but children_type has %d", nb_node_children, n_node_prefixes);
+        for (int j = 0; j < nb_elem; j++) {
+            if ((a->pref[pref_off + j].b >> BFT_KIND_SHIFT) != BFT_KIND_NODE) continue;
+            int flag = 0;
+            uint32_t child = parse_node(c, sz - 9, &flag);
+            a->pref[pref_off + j].a = child;
+            if (li->level_min == 0) flags[j] = (uint8_t)flag; /* UC_array.nb_children & 1, src/presenceNode.c:1732 */
+        }
+    } else {
+        /* leaf level: zero-length suffixes, one annotation per prefix (src/presenceNode.c:1453-1463) */
+        if (nb_node_children) fail(c, "bft_flatten: leaf CC with child nodes");
+        for (int b = 0; b < nb_skp; b++) {
+            const int j0 = b * li->nb_ucs_skp;
+            const int j1 = j0 + li->nb_ucs_skp < nb_elem ? j0 + li->nb_ucs_skp : nb_elem;
+            uc_body_t u;
+            read_uc_body(c, &u, 0, j1 - j0);
+            for (int j = j0; j < j1; j++)
+                a->pref[pref_off + j] = bft_mk_entry(BFT_KIND_LEAF, uc_line_class(c, &u, j - j0), 1);
+        }
+        a->n_kmers += (size_t)nb_elem;
+        a->n_leaf_prefixes += (size_t)nb_elem;
+    }
+
+    /* cluster directory: rank over filter2 + select over the cluster-start flags (findCluster,
+     * src/presenceNode.c:1578-1821) folded into exclusive prefix sums */
+    int* starts = (int*)xrealloc(c, NULL, ((size_t)nb_elem + 2) * sizeof(int));
+    int n_starts = 0;
+    for (int j = 0; j < nb_elem; j++)
+        if (flags[j]) starts[n_starts++] = j;
+    starts[n_starts] = nb_elem;
+    GROW(c, a->csr, c->cap_csr, a->n_csr + (size_t)n_pu + 1, uint16_t);
+    if (a->n_csr + (size_t)n_pu + 1 > 0xfffffff0u) fail(c, "bft_flatten: cluster directory exceeds 2^32 entries");
+    const uint32_t csr_off = (uint32_t)a->n_csr;
+    uint16_t* csr = a->csr + csr_off;
+    int rank = 0;
+    for (int pu = 0; pu < n_pu; pu++) {
+        csr[pu] = (uint16_t)(rank < n_starts ? starts[rank] : nb_elem); /* a p_u without flag: pos == nb_elem (:1394) */
+        if ((f2[pu / 8] >> (pu % 8)) & 1) rank++;
+    }
+    csr[n_pu] = (uint16_t)(rank < n_starts ? starts[rank] : nb_elem);
+    if (rank != n_starts) fail(c, "bft_flatten: filter2 has %d p_u but %d cluster starts", rank, n_starts);
+    if (nb_elem && starts[0] != 0) fail(c, "bft_flatten: first stored prefix does not start a cluster");
+    a->n_csr += (size_t)n_pu + 1;
+
+    /* regenerate this CC's Bloom filter from its stored prefixes (read_CC, src/write_to_disk.c:656-683, 696-772) */
+    const int nbf = CEILDIV(li->modulo_hash, 8);
+    memset(bf, 0, (size_t)nbf);
+    for (int pu = 0; pu < n_pu; pu++) {
+        for (int j = csr[pu]; j < csr[pu + 1]; j++) {
+            uint32_t pv = s == 8 ? f3[j] : ((j & 1) ? (uint32_t)(f3[j / 2] >> 4) : (uint32_t)(f3[j / 2] & 0xf));
+            uint32_t rot = ((uint32_t)pu << s) | pv;
+            uint32_t idx = (rot >> 4) & 0x3fffu;
+            uint32_t h1 = (uint32_t)(c->hv1[idx] % (uint64_t)li->modulo_hash);
+            uint32_t h2 = (uint32_t)(c->hv2[idx] % (uint64_t)li->modulo_hash);
+            bf[h1 / 8] |= (uint8_t)(1u << (h1 % 8));
+            bf[h2 / 8] |= (uint8_t)(1u << (h2 % 8));
+        }
+    }
+
+    bft_cc_t* cc = &a->ccs[cc_id];
+    cc->csr_off = csr_off;
+    cc->f3_off = f3_off;
+    cc->pref_off = pref_off;
+    cc->nb_elem = (uint16_t)nb_elem;
+    cc->s = (uint8_t)s;
+    cc->pad = 0;
+    free(starts);
+    free(flags);
+}
+
+static uint32_t parse_node(ctx_t* c, int sz, int* cluster_flag) {
+    bft_arena_t* a = c->a;
+    if (sz < 9) fail(c, "bft_flatten: trie deeper than k/9 levels");
+    const int lvl = sz / 9 - 1;
+    const lvl_info_t* li = &c->lvl[lvl];
+    c->depth++;
+    if (c->depth > a->max_depth) a->max_depth = c->depth;
+
+    if (a->n_nodes >= 0xfffffff0u) fail(c, "bft_flatten: more than 2^32 nodes");
+    const uint32_t id = (uint32_t)a->n_nodes;
+    GROW(c, a->nodes, c->cap_nodes, a->n_nodes + 1, bft_node_t);
+    a->n_nodes++;
+    memset(&a->nodes[id], 0, sizeof(bft_node_t));
+
+    /* the Node's own UC (write_Node, src/write_to_disk.c:102-103): nb_children = count << 1 | cluster flag */
+    const uint16_t raw = rd_u16(c);
+    if (cluster_flag) *cluster_flag = raw & 1;
+    const int n_uc = raw >> 1;
+    uc_body_t u;
+    read_uc_body(c, &u, size_kmer_in_bytes(sz), n_uc);
+    uint32_t uc_begin = 0;
+    if (n_uc) {
+        uc_begin = append_block(c, &u, 0, n_uc, 2 * sz, 0);
+    }
+    const uint32_t n_cc = rd_u32(c);
+    if (n_cc >= BFT_FIRSTCC_NONE) fail(c, "bft_flatten: node with %u CCs (first-CC table holds at most 254)", n_cc);
+    if (a->n_ccs + n_cc > 0xfffffff0u) fail(c, "bft_flatten: more than 2^32 CCs");
+    const uint32_t cc_begin = (uint32_t)a->n_ccs;
+    GROW(c, a->ccs, c->cap_ccs, a->n_ccs + n_cc, bft_cc_t);
+    a->n_ccs += n_cc;
+    if ((int)n_cc > a->max_cc_per_node) a->max_cc_per_node = (int)n_cc;
+
+    uint32_t fc_off = 0;
+    if (n_cc) {
+        const int nbf = CEILDIV(li->modulo_hash, 8);
+        uint8_t* bfs = (uint8_t*)xrealloc(c, NULL, (size_t)n_cc * (size_t)nbf);
+        for (uint32_t i = 0; i < n_cc; i++) parse_cc(c, sz, cc_begin + i, bfs + (size_t)i * nbf);
+        /* first CC whose Bloom filter fires, per 14-bit hash index (src/presenceNode.c:1354-1362) */
+        if (a->firstcc_bytes + BFT_N_IDX14 > 0xfffffff0u) fail(c, "bft_flatten: first-CC tables exceed 4 GiB");
+        GROW(c, a->firstcc, c->cap_firstcc, a->firstcc_bytes + BFT_N_IDX14, uint8_t);
+        fc_off = (uint32_t)a->firstcc_bytes;
+        uint8_t* fc = a->firstcc + fc_off;
+        for (uint32_t idx = 0; idx < BFT_N_IDX14; idx++) {
+            uint32_t h1 = (uint32_t)(c->hv1[idx] % (uint64_t)li->modulo_hash);
+            uint32_t h2 = (uint32_t)(c->hv2[idx] % (uint64_t)li->modulo_hash);
+            uint8_t hit = BFT_FIRSTCC_NONE;
+            for (uint32_t i = 0; i < n_cc; i++) {
+                const uint8_t* bf = bfs + (size_t)i * nbf;
+                if ((bf[h1 / 8] >> (h1 % 8)) & (bf[h2 / 8] >> (h2 % 8)) & 1) { hit = (uint8_t)i; break; }
+            }
+            fc[idx] = hit;
+        }
+        a->firstcc_bytes += BFT_N_IDX14;
+        free(bfs);
+    }
+    bft_node_t* nd = &a->nodes[id];
+    nd->cc_begin = cc_begin;
+    nd->n_cc = n_cc;
+    nd->fc_off = fc_off;
+    nd->uc_begin = uc_begin;
+    nd->uc_n = (uint32_t)n_uc;
+    c->depth--;
+    return id;
+}
+
+void bft_arena_view(const bft_arena_t* a, bft_view_t* v) {
+    v->rootdir = a->rootdir;
+    v->nodes = a->nodes;
+    v->ccs = a->ccs;
+    v->firstcc = a->firstcc;
+    v->csr = a->csr;
+    v->filter3 = a->filter3;
+    v->pref = a->pref;
+    v->keys = a->keys;
+    v->linecls = a->linecls;
+    v->k = a->k;
+    v->W = a->W;
+}
+
+void bft_arena_free(bft_arena_t* a) {
+    if (!a) return;
+    if (a->filenames) {
+        for (int i = 0; i < a->n_genomes; i++) free(a->filenames[i]);
+        free(a->filenames);
+    }
+    free(a->rootdir); free(a->nodes); free(a->ccs); free(a->firstcc); free(a->csr); free(a->filter3);
+    free(a->pref); free(a->keys); free(a->linecls); free(a->cls_off); free(a->cls_bytes);
+    free(a->pool_last_index); free(a->pool_size_annot); free(a->pool_off); free(a->pool_bytes);
+    free(a);
+}
+
+size_t bft_arena_bytes(const bft_arena_t* a) {
+    return BFT_ROOTDIR_SIZE * sizeof(bft_entry_t) + a->n_nodes * sizeof(bft_node_t) + a->n_ccs * sizeof(bft_cc_t) +
+           a->firstcc_bytes + a->n_csr * 2 + a->filter3_bytes + a->n_pref * sizeof(bft_entry_t) +
+           a->n_lines * ((size_t)a->W * 8 + 4) + (a->n_classes + 1) * 4 + a->cls_bytes_len + a->pool_bytes_len;
+}
+
+bft_arena_t* bft_arena_from_memory(const uint8_t* buf, size_t len, char* err, size_t errlen) {
+    ctx_t* c = (ctx_t*)calloc(1, sizeof(ctx_t));
+    bft_arena_t* a = (bft_arena_t*)calloc(1, sizeof(bft_arena_t));
+    if (!c || !a) { free(c); free(a); if (err) snprintf(err, errlen, "bft_flatten: out of memory"); return NULL; }
+    c->buf = buf; c->len = len; c->a = a; c->err = err; c->errlen = errlen;
+    if (err && errlen) err[0] = 0;
+    if (setjmp(c->jb)) {
+        free(c->map); free(c->tmp); free(c->hv1); free(c->hv2); free(c->scratch); free(c->extbuf);
+        free(c);
+        bft_arena_free(a);
+        return NULL;
+    }
+    /* header: comp_set_colors pools (write_BFT_Root, src/write_to_disk.c:34-61) */
+    a->n_pools = rd_i32(c);
+    if (a->n_pools < 0 || a->n_pools > (1 << 20)) fail(c, "bft_flatten: not a .bft file (pool count %d)", a->n_pools);
+    a->pool_last_index = (int64_t*)xrealloc(c, NULL, (size_t)(a->n_pools + 1) * sizeof(int64_t));
+    a->pool_size_annot = (int32_t*)xrealloc(c, NULL, (size_t)(a->n_pools + 1) * sizeof(int32_t));
+    a->pool_off = (uint64_t*)xrealloc(c, NULL, (size_t)(a->n_pools + 1) * sizeof(uint64_t));
+    size_t cap_pool = 0;
+    for (int i = 0; i < a->n_pools; i++) {
+        a->pool_last_index[i] = rd_i64(c);
+        a->pool_size_annot[i] = rd_i32(c);
+        int64_t cnt = i ? a->pool_last_index[i] - a->pool_last_index[i - 1] : a->pool_last_index[i] + 1;
+        if (cnt < 0 || a->pool_size_annot[i] < 0) fail(c, "bft_flatten: corrupt colour pool %d", i);
+        size_t nbytes = (size_t)cnt * (size_t)a->pool_size_annot[i];
+        a->pool_off[i] = a->pool_bytes_len;
+        GROW(c, a->pool_bytes, cap_pool, a->pool_bytes_len + nbytes + 1, uint8_t);
+        memcpy(a->pool_bytes + a->pool_bytes_len, rd(c, nbytes), nbytes);
+        a->pool_bytes_len += nbytes;
+    }
+    a->r1 = rd_i32(c);
+    a->r2 = rd_i32(c);
+    a->treshold_compression = rd_i32(c);
+    a->n_genomes = rd_i32(c);
+    a->k = rd_i32(c);
+    a->compressed = *rd(c, 1);
+    if (a->k <= 0 || a->k % 9 != 0 || a->k > 126) fail(c, "bft_flatten: not a .bft file (k=%d)", a->k);
+    if (a->k > 63) fail(c, "bft_flatten: k=%d is not supported by this build (k <= 63)", a->k);
+    if (a->compressed) fail(c, "bft_flatten: root->compressed=%d files are not supported", a->compressed);
+    if (a->n_genomes < 0 || a->n_genomes > 100000000) fail(c, "bft_flatten: implausible genome count %d", a->n_genomes);
+    a->W = a->k <= 27 ? 1 : 2;
+    a->n_levels = a->k / 9;
+    a->filenames = (char**)xrealloc(c, NULL, (size_t)(a->n_genomes + 1) * sizeof(char*));
+    memset(a->filenames, 0, (size_t)(a->n_genomes + 1) * sizeof(char*));
+    for (int i = 0; i < a->n_genomes; i++) {
+        uint16_t sl = rd_u16(c);
+        const uint8_t* s = rd(c, sl);
+        a->filenames[i] = (char*)xrealloc(c, NULL, (size_t)sl + 1);
+        memcpy(a->filenames[i], s, sl);
+        a->filenames[i][sl] = 0;
+    }
+    for (int i = 0; i < a->n_levels; i++) { /* src/write_to_disk.c:78-86 */
+        c->lvl[i].nb_bits_skip2 = rd_i32(c);
+        c->lvl[i].nb_bits_skip3 = rd_i32(c);
+        c->lvl[i].nb_ucs_skp = rd_i32(c);
+        c->lvl[i].nb_kmers_uc = rd_i32(c);
+        c->lvl[i].level_min = rd_i32(c);
+        c->lvl[i].modulo_hash = rd_i32(c);
+        c->lvl[i].tresh_suf_pref = rd_i32(c);
+        if (c->lvl[i].nb_ucs_skp <= 0 || c->lvl[i].modulo_hash <= 0 || c->lvl[i].modulo_hash > 65536)
+            fail(c, "bft_flatten: corrupt level table");
+    }
+    /* hash_v restricted to the 16384 reachable entries (create_hash_v_array, include/Node.h:158-185;
+     * use at src/presenceNode.c:1341-1343): bytes of i MSB-first over 18 bits */
+    c->hv1 = (uint64_t*)xrealloc(c, NULL, BFT_N_IDX14 * sizeof(uint64_t));
+    c->hv2 = (uint64_t*)xrealloc(c, NULL, BFT_N_IDX14 * sizeof(uint64_t));
+    for (uint32_t i = 0; i < BFT_N_IDX14; i++) {
+        uint8_t g[3] = {(uint8_t)((i >> 10) & 0xff), (uint8_t)((i >> 2) & 0xff), (uint8_t)((i << 6) & 0xff)};
+        c->hv1[i] = bft_xxh64(g, 3, (uint64_t)(int64_t)a->r1);
+        c->hv2[i] = bft_xxh64(g, 3, (uint64_t)(int64_t)a->r2);
+    }
+    /* class 0 = empty annotation */
+    GROW(c, a->cls_off, c->cap_cls_off, 2, uint32_t);
+    a->cls_off[0] = 0;
+    uint8_t dummy = 0;
+    class_of(c, &dummy, 0);
+
+    if (c->pos < c->len) {
+        parse_node(c, a->k, NULL);
+    } else { /* write_root_only file: empty trie */
+        GROW(c, a->nodes, c->cap_nodes, 1, bft_node_t);
+        memset(&a->nodes[0], 0, sizeof(bft_node_t));
+        a->n_nodes = 1;
+    }
+    if (c->pos != c->len) fail(c, "bft_flatten: %zu trailing bytes after the root node", c->len - c->pos);
+
+    /* pad arrays the device reads with vector loads */
+    GROW(c, a->filter3, c->cap_filter3, a->filter3_bytes + 16, uint8_t);
+    memset(a->filter3 + a->filter3_bytes, 0, 16);
+    GROW(c, a->csr, c->cap_csr, a->n_csr + 8, uint16_t);
+    GROW(c, a->pref, c->cap_pref, a->n_pref + 1, bft_entry_t);
+    GROW(c, a->ccs, c->cap_ccs, a->n_ccs + 1, bft_cc_t);
+    GROW(c, a->firstcc, c->cap_firstcc, a->firstcc_bytes + 1, uint8_t);
+    if (!a->keys) {
+        a->keys = (uint64_t*)xrealloc(c, NULL, 8 * BFT_MAX_WORDS);
+        a->linecls = (uint32_t*)xrealloc(c, NULL, 8);
+    }
+
+    /* root directory: the root probe for every 9-nt prefix */
+    a->rootdir = (bft_entry_t*)xrealloc(c, NULL, BFT_ROOTDIR_SIZE * sizeof(bft_entry_t));
+    bft_view_t v;
+    bft_arena_view(a, &v);
+    for (uint32_t low18 = 0; low18 < BFT_ROOTDIR_SIZE; low18++) a->rootdir[low18] = bft_node_probe(&v, 0, low18, a->k);
+
+    free(c->map); free(c->tmp); free(c->hv1); free(c->hv2); free(c->scratch); free(c->extbuf);
+    free(c);
+    return a;
+}
+
+bft_arena_t* bft_arena_from_file(const char* path, char* err, size_t errlen) {
+    FILE* f = fopen(path, "rb");
+    if (!f) { if (err) snprintf(err, errlen, "bft_flatten: cannot open %s", path); return NULL; }
+    fseek(f, 0, SEEK_END);
+    long n = ftell(f);
+    fseek(f, 0, SEEK_SET);
+    uint8_t* buf = (uint8_t*)malloc(n > 0 ? (size_t)n : 1);
+    if (!buf || (n > 0 && fread(buf, 1, (size_t)n, f) != (size_t)n)) {
+        if (err) snprintf(err, errlen, "bft_flatten: cannot read %s", path);
+        free(buf); fclose(f);
+        return NULL;
+    }
+    fclose(f);
+    bft_arena_t* a = bft_arena_from_memory(buf, (size_t)n, err, errlen);
+    free(buf);
+    return a;
+}
