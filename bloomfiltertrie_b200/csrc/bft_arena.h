@@ -44,6 +44,19 @@
 #define BFT_HD static inline
 #endif
 
+/* read-only loads: non-coherent path on the device, plain loads on the host */
+#ifdef __CUDA_ARCH__
+#define BFT_LD8(p) __ldg((const unsigned char*)(p))
+#define BFT_LD16(p) __ldg((const unsigned short*)(p))
+#define BFT_LD32(p) __ldg((const unsigned int*)(p))
+#define BFT_LD64(p) __ldg((const unsigned long long*)(p))
+#else
+#define BFT_LD8(p) (*(const uint8_t*)(p))
+#define BFT_LD16(p) (*(const uint16_t*)(p))
+#define BFT_LD32(p) (*(const uint32_t*)(p))
+#define BFT_LD64(p) (*(const uint64_t*)(p))
+#endif
+
 #define BFT_NB_CHAR_SUF_PREF 9         /* reference include/default_param.h:12 */
 #define BFT_PREFIX_BITS 18
 #define BFT_N_IDX14 16384
@@ -112,6 +125,18 @@ BFT_HD uint32_t bft_msb_first18(uint32_t low18) {
 BFT_HD uint32_t bft_idx14(uint32_t r18) { return (r18 >> 2) & 0x3fffu; }
 BFT_HD uint32_t bft_rot18(uint32_t r18) { return ((r18 << 2) & 0x3ffffu) | (r18 >> 16); }
 
+BFT_HD bft_entry_t bft_ld_entry(const bft_entry_t* p) {
+    bft_entry_t e;
+#ifdef __CUDA_ARCH__
+    const uint2 t = __ldg((const uint2*)p);
+    e.a = t.x;
+    e.b = t.y;
+#else
+    e = *p;
+#endif
+    return e;
+}
+
 BFT_HD bft_entry_t bft_mk_entry(uint32_t kind, uint32_t a, uint32_t n) {
     bft_entry_t e;
     e.a = a;
@@ -119,19 +144,42 @@ BFT_HD bft_entry_t bft_mk_entry(uint32_t kind, uint32_t a, uint32_t n) {
     return e;
 }
 
-/* One Node probe: the reference's presenceKmer (src/presenceNode.c:1284-1576) on the flattened layout. */
-BFT_HD bft_entry_t bft_node_probe(const bft_view_t* v, uint32_t node_id, uint32_t low18, int size_kmer) {
-    const bft_node_t nd = v->nodes[node_id];
-    const uint32_t r18 = bft_msb_first18(low18);
+/* One Node probe: the reference's presenceKmer (src/presenceNode.c:1284-1576) on the flattened layout.
+ * succ_leaf_quirk != 0 reproduces presenceNeighborsRight at the leaf level (size_kmer == 9,
+ * src/presenceNode.c:719-723): the reference clears nucleotide 7 of the prefix (`& 0xfc` on the second byte) before
+ * hashing and before forming p_u/p_v, so the CC path answers for the prefix with nuc 7 = A; the Node-UC path
+ * (:1164-1208) compares the unmodified k-mer. Only the successor lookups of the branching queries pass it. */
+BFT_HD bft_entry_t bft_node_probe(const bft_view_t* v, uint32_t node_id, uint32_t low18, int succ_leaf_quirk) {
+    bft_node_t nd;
+#ifdef __CUDA_ARCH__
+    {
+        const uint4 t = __ldg((const uint4*)(v->nodes + node_id));
+        nd.cc_begin = t.x; nd.n_cc = t.y; nd.fc_off = t.z; nd.uc_begin = t.w;
+        nd.uc_n = BFT_LD32(&v->nodes[node_id].uc_n);
+    }
+#else
+    nd = v->nodes[node_id];
+#endif
+    uint32_t r18 = bft_msb_first18(low18);
+    if (succ_leaf_quirk) r18 &= ~0xcu; /* nuc 7 sits at bits 2-3 of the MSB-first prefix */
     if (nd.n_cc) {
-        const uint32_t c = v->firstcc[nd.fc_off + bft_idx14(r18)];
+        const uint32_t c = BFT_LD8(v->firstcc + nd.fc_off + bft_idx14(r18));
         if (c != BFT_FIRSTCC_NONE) {
-            const bft_cc_t cc = v->ccs[nd.cc_begin + c];
+            bft_cc_t cc;
+#ifdef __CUDA_ARCH__
+            {
+                const uint4 t = __ldg((const uint4*)(v->ccs + nd.cc_begin + c));
+                cc.csr_off = t.x; cc.f3_off = t.y; cc.pref_off = t.z;
+                cc.nb_elem = (uint16_t)(t.w & 0xffffu); cc.s = (uint8_t)((t.w >> 16) & 0xffu); cc.pad = 0;
+            }
+#else
+            cc = v->ccs[nd.cc_begin + c];
+#endif
             const uint32_t rot = bft_rot18(r18);
             const uint32_t pu = rot >> cc.s;
             const uint32_t pv = rot & ((1u << cc.s) - 1u);
-            uint32_t lo = v->csr[cc.csr_off + pu];
-            uint32_t hi = v->csr[cc.csr_off + pu + 1];
+            uint32_t lo = BFT_LD16(v->csr + cc.csr_off + pu);
+            uint32_t hi = BFT_LD16(v->csr + cc.csr_off + pu + 1);
             if (lo >= hi) return bft_mk_entry(BFT_KIND_ABSENT, 0, 0);
             /* lower_bound of pv in the cluster [lo, hi) of filter3 (src/presenceNode.c:1396-1410 / 1475-1488) */
             const uint8_t* f3 = v->filter3 + cc.f3_off;
@@ -139,50 +187,45 @@ BFT_HD bft_entry_t bft_node_probe(const bft_view_t* v, uint32_t node_id, uint32_
             if (cc.s == 8) {
                 while (lo < hi) {
                     uint32_t mid = (lo + hi) >> 1;
-                    if (f3[mid] < pv) lo = mid + 1; else hi = mid;
+                    if (BFT_LD8(f3 + mid) < pv) lo = mid + 1; else hi = mid;
                 }
-                if (lo >= end || f3[lo] != pv) return bft_mk_entry(BFT_KIND_ABSENT, 0, 0);
+                if (lo >= end || BFT_LD8(f3 + lo) != pv) return bft_mk_entry(BFT_KIND_ABSENT, 0, 0);
             } else {
                 while (lo < hi) {
                     uint32_t mid = (lo + hi) >> 1;
-                    uint32_t t = (mid & 1u) ? (uint32_t)(f3[mid >> 1] >> 4) : (uint32_t)(f3[mid >> 1] & 0xf);
+                    uint32_t t = (mid & 1u) ? (uint32_t)(BFT_LD8(f3 + (mid >> 1)) >> 4) : (uint32_t)(BFT_LD8(f3 + (mid >> 1)) & 0xf);
                     if (t < pv) lo = mid + 1; else hi = mid;
                 }
                 if (lo >= end) return bft_mk_entry(BFT_KIND_ABSENT, 0, 0);
-                uint32_t t = (lo & 1u) ? (uint32_t)(f3[lo >> 1] >> 4) : (uint32_t)(f3[lo >> 1] & 0xf);
+                uint32_t t = (lo & 1u) ? (uint32_t)(BFT_LD8(f3 + (lo >> 1)) >> 4) : (uint32_t)(BFT_LD8(f3 + (lo >> 1)) & 0xf);
                 if (t != pv) return bft_mk_entry(BFT_KIND_ABSENT, 0, 0);
             }
-            (void)size_kmer;
-            return v->pref[cc.pref_off + lo];
+            return bft_ld_entry(v->pref + cc.pref_off + lo);
         }
     }
     return bft_mk_entry(BFT_KIND_UC, nd.uc_begin, nd.uc_n);
 }
 
-/* key compare helpers: keys are W words, word W-1 most significant */
-BFT_HD int bft_key_less(const uint64_t* a, const uint64_t* b, int W) {
-    for (int w = W - 1; w >= 0; w--) {
-        if (a[w] < b[w]) return 1;
-        if (a[w] > b[w]) return 0;
-    }
-    return 0;
-}
-BFT_HD int bft_key_eq(const uint64_t* a, const uint64_t* b, int W) {
-    for (int w = 0; w < W; w++)
-        if (a[w] != b[w]) return 0;
-    return 1;
-}
-
-/* Search lines [begin, begin+n) for `key`; returns the line index or 0xffffffff
- * (binary_search_UC + equality test, src/UC.c:81-124, src/presenceNode.c:1876-1914, 1554-1570). */
-BFT_HD uint32_t bft_search_lines(const bft_view_t* v, uint32_t begin, uint32_t n, const uint64_t* key) {
-    const int W = v->W;
+/* Search the sorted lines [begin, begin+n) for `key` (W words, word W-1 most significant); returns the line index
+ * or 0xffffffff (binary_search_UC + equality test, src/UC.c:81-124, src/presenceNode.c:1876-1914, 1554-1570). */
+BFT_HD uint32_t bft_search_lines(const bft_view_t* v, uint32_t begin, uint32_t n, const uint64_t* key, const int W) {
     uint32_t lo = begin, hi = begin + n;
     while (lo < hi) {
-        uint32_t mid = lo + ((hi - lo) >> 1);
-        if (bft_key_less(v->keys + (size_t)mid * W, key, W)) lo = mid + 1; else hi = mid;
+        const uint32_t mid = lo + ((hi - lo) >> 1);
+        const uint64_t* p = v->keys + (size_t)mid * W;
+        int less = 0;
+        for (int w = W - 1; w >= 0; w--) {
+            const uint64_t x = BFT_LD64(p + w);
+            if (x != key[w]) { less = x < key[w]; break; }
+        }
+        if (less) lo = mid + 1; else hi = mid;
     }
-    if (lo < begin + n && bft_key_eq(v->keys + (size_t)lo * W, key, W)) return lo;
+    if (lo < begin + n) {
+        const uint64_t* p = v->keys + (size_t)lo * W;
+        int eq = 1;
+        for (int w = 0; w < W; w++) eq &= (BFT_LD64(p + w) == key[w]);
+        if (eq) return lo;
+    }
     return 0xffffffffu;
 }
 
@@ -195,13 +238,13 @@ BFT_HD void bft_shift18(uint64_t* cur, int W) {
 }
 
 /* Full lookup: the reference's isKmerPresent (src/presenceNode.c:1823-1921).
- * kmer: W words (bits above 2k must be zero). Returns the colour class of the k-mer, or BFT_CLS_NONE if absent. */
-BFT_HD uint32_t bft_lookup(const bft_view_t* v, const uint64_t* kmer) {
+ * kmer: W words (bits above 2k must be zero). Returns the colour class of the k-mer, or BFT_CLS_NONE if absent.
+ * W is passed explicitly so device callers can make it a compile-time constant. */
+BFT_HD uint32_t bft_lookup_ex(const bft_view_t* v, const uint64_t* kmer, const int W, const int succ_leaf_quirk) {
     uint64_t cur[BFT_MAX_WORDS];
-    const int W = v->W;
-    for (int w = 0; w < W; w++) cur[w] = kmer[w];
+    for (int w = 0; w < BFT_MAX_WORDS; w++) cur[w] = w < W ? kmer[w] : 0;
     int sz = v->k;
-    bft_entry_t e = v->rootdir[(uint32_t)cur[0] & (BFT_ROOTDIR_SIZE - 1u)];
+    bft_entry_t e = bft_ld_entry(v->rootdir + ((uint32_t)cur[0] & (BFT_ROOTDIR_SIZE - 1u)));
     for (;;) {
         const uint32_t kind = e.b >> BFT_KIND_SHIFT;
         const uint32_t n = e.b & BFT_CNT_MASK;
@@ -209,18 +252,22 @@ BFT_HD uint32_t bft_lookup(const bft_view_t* v, const uint64_t* kmer) {
         if (kind == BFT_KIND_LEAF) return e.a;
         if (kind == BFT_KIND_UC) {
             if (n == 0) return BFT_CLS_NONE;
-            uint32_t ln = bft_search_lines(v, e.a, n, cur);
-            return ln == 0xffffffffu ? BFT_CLS_NONE : v->linecls[ln];
+            const uint32_t ln = bft_search_lines(v, e.a, n, cur, W);
+            return ln == 0xffffffffu ? BFT_CLS_NONE : BFT_LD32(v->linecls + ln);
         }
         bft_shift18(cur, W);
         sz -= BFT_NB_CHAR_SUF_PREF;
         if (kind == BFT_KIND_INLINE) {
-            uint32_t ln = bft_search_lines(v, e.a, n, cur);
-            return ln == 0xffffffffu ? BFT_CLS_NONE : v->linecls[ln];
+            const uint32_t ln = bft_search_lines(v, e.a, n, cur, W);
+            return ln == 0xffffffffu ? BFT_CLS_NONE : BFT_LD32(v->linecls + ln);
         }
         /* BFT_KIND_NODE */
-        e = bft_node_probe(v, e.a, (uint32_t)cur[0] & (BFT_ROOTDIR_SIZE - 1u), sz);
+        e = bft_node_probe(v, e.a, (uint32_t)cur[0] & (BFT_ROOTDIR_SIZE - 1u), succ_leaf_quirk && sz == BFT_NB_CHAR_SUF_PREF);
     }
 }
+
+BFT_HD uint32_t bft_lookup_w(const bft_view_t* v, const uint64_t* kmer, const int W) { return bft_lookup_ex(v, kmer, W, 0); }
+
+BFT_HD uint32_t bft_lookup(const bft_view_t* v, const uint64_t* kmer) { return bft_lookup_w(v, kmer, v->W); }
 
 #endif /* BFT_ARENA_H */

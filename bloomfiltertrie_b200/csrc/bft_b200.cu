@@ -1,0 +1,616 @@
+/* bft_b200.cu — the C-ABI (include/bft_b200.h) over the sm_100a kernels (bft_kernels.cuh).
+ * Host logic only: context life cycle, arena upload, launch configuration, chunked host<->device pipelines.
+ * There is deliberately no CPU query path here: every query entry point launches kernels or fails. */
+#include "../../include/bft_b200.h"
+
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <time.h>
+
+#include "bft_flatten.h"
+#include "bft_io.h"
+#include "bft_kernels.cuh"
+
+static __thread char g_err[512];
+
+static int set_err(int code, const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof g_err, fmt, ap);
+    va_end(ap);
+    return code;
+}
+
+#define CK(call)                                                                                             \
+    do {                                                                                                     \
+        cudaError_t e_ = (call);                                                                             \
+        if (e_ != cudaSuccess)                                                                               \
+            return set_err(BFT_B200_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
+    } while (0)
+
+static double now_s(void) {
+    struct timespec ts;
+    clock_gettime(CLOCK_MONOTONIC, &ts);
+    return ts.tv_sec + ts.tv_nsec * 1e-9;
+}
+
+#define BFT_CHUNK_KMERS ((size_t)1 << 22)
+#define BFT_CHUNK_SEQ_CHARS ((size_t)1 << 28)
+#define BFT_CHUNK_SEQS ((size_t)1 << 21)
+
+typedef struct {
+    void* d_in;        size_t cap_in;
+    uint64_t* d_offs;  size_t cap_offs;
+    uint64_t* d_kmers; size_t cap_kmers; /* packed k-mers when the input was ASCII */
+    uint8_t* d_u8a;    size_t cap_u8a;
+    uint8_t* d_u8b;    size_t cap_u8b;
+    uint32_t* d_cls;   size_t cap_cls;
+    uint32_t* d_rows;  size_t cap_rows;
+} slot_t;
+
+struct bft_b200_ctx {
+    int device, sm_count;
+    cudaStream_t streams[2];
+    int k, W, G, rw;
+    char** names;
+    bft_b200_stats stats;
+    /* device arena */
+    void* d_arena[9];
+    bft_view_t dview;
+    bft_pools_t dpools;
+    void* d_pool[4];
+    uint32_t* d_class_rows;
+    uint32_t* d_class_counts;
+    uint32_t* h_class_rows;
+    uint32_t* h_class_counts;
+    size_t n_classes;
+    unsigned long long* d_counter;
+    slot_t slot[2];
+    uint64_t launches;
+    size_t seq_smem;
+    int ref_quirks;
+    uint32_t* d_nbr; size_t cap_nbr;
+};
+
+extern "C" const char* bft_b200_last_error(void) { return g_err; }
+
+static int ensure(void** p, size_t* cap, size_t need) {
+    if (need <= *cap && *p) return 0;
+    if (*p) cudaFree(*p);
+    *p = NULL;
+    *cap = 0;
+    size_t n = need + need / 4 + 256;
+    cudaError_t e = cudaMalloc(p, n);
+    if (e != cudaSuccess) return set_err(BFT_B200_ERR_NOMEM, "cudaMalloc(%zu) failed: %s", n, cudaGetErrorString(e));
+    *cap = n;
+    return 0;
+}
+#define ENSURE(ptr, cap, need)                                         \
+    do {                                                               \
+        int r_ = ensure((void**)&(ptr), &(cap), (need));               \
+        if (r_) return r_;                                             \
+    } while (0)
+
+static int upload(void** dst, const void* src, size_t bytes) {
+    size_t n = bytes ? bytes : 16;
+    cudaError_t e = cudaMalloc(dst, n + 32); /* slack for vector loads at the tail */
+    if (e != cudaSuccess) return set_err(BFT_B200_ERR_NOMEM, "cudaMalloc(%zu) failed: %s", n, cudaGetErrorString(e));
+    e = cudaMemset(*dst, 0, n + 32);
+    if (e == cudaSuccess && bytes) e = cudaMemcpy(*dst, src, bytes, cudaMemcpyHostToDevice);
+    if (e != cudaSuccess) return set_err(BFT_B200_ERR_CUDA, "arena upload failed: %s", cudaGetErrorString(e));
+    return 0;
+}
+
+static int grid_for(const bft_b200_ctx* c, size_t items, int per_block) {
+    size_t blocks = (items + (size_t)per_block - 1) / (size_t)per_block;
+    size_t cap = (size_t)c->sm_count * 8; /* persistent, grid-stride: whole multiples of the SM count */
+    if (blocks > cap) blocks = cap;
+    if (blocks < 1) blocks = 1;
+    return (int)blocks;
+}
+
+extern "C" void bft_b200_close(bft_b200_ctx* c) {
+    if (!c) return;
+    cudaSetDevice(c->device);
+    cudaDeviceSynchronize();
+    for (int i = 0; i < 9; i++) if (c->d_arena[i]) cudaFree(c->d_arena[i]);
+    for (int i = 0; i < 4; i++) if (c->d_pool[i]) cudaFree(c->d_pool[i]);
+    if (c->d_class_rows) cudaFree(c->d_class_rows);
+    if (c->d_class_counts) cudaFree(c->d_class_counts);
+    if (c->d_counter) cudaFree(c->d_counter);
+    if (c->d_nbr) cudaFree(c->d_nbr);
+    for (int s = 0; s < 2; s++) {
+        slot_t* sl = &c->slot[s];
+        if (sl->d_in) cudaFree(sl->d_in);
+        if (sl->d_offs) cudaFree(sl->d_offs);
+        if (sl->d_kmers) cudaFree(sl->d_kmers);
+        if (sl->d_u8a) cudaFree(sl->d_u8a);
+        if (sl->d_u8b) cudaFree(sl->d_u8b);
+        if (sl->d_cls) cudaFree(sl->d_cls);
+        if (sl->d_rows) cudaFree(sl->d_rows);
+        if (c->streams[s]) cudaStreamDestroy(c->streams[s]);
+    }
+    if (c->names) {
+        for (int i = 0; i < c->G; i++) free(c->names[i]);
+        free(c->names);
+    }
+    free(c->h_class_rows);
+    free(c->h_class_counts);
+    free(c);
+}
+
+extern "C" int bft_b200_open(const char* path, int device, bft_b200_ctx** out) {
+    if (!path || !out) return set_err(BFT_B200_ERR_ARG, "bft_b200_open: NULL argument");
+    *out = NULL;
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0)
+        return set_err(BFT_B200_ERR_CUDA, "bft_b200_open: no CUDA device (%s); this engine has no CPU fallback",
+                       e != cudaSuccess ? cudaGetErrorString(e) : "device count 0");
+    if (device < 0 || device >= ndev) return set_err(BFT_B200_ERR_ARG, "bft_b200_open: device %d out of range (0..%d)", device, ndev - 1);
+    CK(cudaSetDevice(device));
+
+    char ferr[256];
+    double t0 = now_s();
+    bft_arena_t* a = bft_arena_from_file(path, ferr, sizeof ferr);
+    if (!a) return set_err(BFT_B200_ERR_FILE, "%s", ferr);
+    double t1 = now_s();
+
+    bft_b200_ctx* c = (bft_b200_ctx*)calloc(1, sizeof(bft_b200_ctx));
+    if (!c) { bft_arena_free(a); return set_err(BFT_B200_ERR_NOMEM, "out of host memory"); }
+    c->device = device;
+    c->ref_quirks = 1;
+    cudaDeviceProp prop;
+    e = cudaGetDeviceProperties(&prop, device);
+    if (e != cudaSuccess) { free(c); bft_arena_free(a); return set_err(BFT_B200_ERR_CUDA, "cudaGetDeviceProperties: %s", cudaGetErrorString(e)); }
+    c->sm_count = prop.multiProcessorCount;
+    c->k = a->k; c->W = a->W; c->G = a->n_genomes; c->rw = (a->n_genomes + 31) / 32;
+    if (c->rw < 1) c->rw = 1;
+    c->names = a->filenames;
+    a->filenames = NULL; /* ownership moved */
+    c->n_classes = a->n_classes;
+
+    int rc = 0;
+#define UP(i, field, bytes) if (!rc) rc = upload(&c->d_arena[i], a->field, (bytes))
+    UP(0, rootdir, BFT_ROOTDIR_SIZE * sizeof(bft_entry_t));
+    UP(1, nodes, a->n_nodes * sizeof(bft_node_t));
+    UP(2, ccs, a->n_ccs * sizeof(bft_cc_t));
+    UP(3, firstcc, a->firstcc_bytes);
+    UP(4, csr, a->n_csr * sizeof(uint16_t));
+    UP(5, filter3, a->filter3_bytes);
+    UP(6, pref, a->n_pref * sizeof(bft_entry_t));
+    UP(7, keys, a->n_lines * (size_t)a->W * sizeof(uint64_t));
+    UP(8, linecls, a->n_lines * sizeof(uint32_t));
+#undef UP
+    void* d_cls_off = NULL; void* d_cls_bytes = NULL;
+    if (!rc) rc = upload(&d_cls_off, a->cls_off, (a->n_classes + 1) * sizeof(uint32_t));
+    if (!rc) rc = upload(&d_cls_bytes, a->cls_bytes, a->cls_bytes_len);
+    if (!rc) rc = upload(&c->d_pool[0], a->pool_last_index, (size_t)a->n_pools * sizeof(int64_t));
+    if (!rc) rc = upload(&c->d_pool[1], a->pool_size_annot, (size_t)a->n_pools * sizeof(int32_t));
+    if (!rc) rc = upload(&c->d_pool[2], a->pool_off, (size_t)a->n_pools * sizeof(uint64_t));
+    if (!rc) rc = upload(&c->d_pool[3], a->pool_bytes, a->pool_bytes_len);
+    double t2 = now_s();
+    if (!rc) {
+        c->dview.rootdir = (const bft_entry_t*)c->d_arena[0];
+        c->dview.nodes = (const bft_node_t*)c->d_arena[1];
+        c->dview.ccs = (const bft_cc_t*)c->d_arena[2];
+        c->dview.firstcc = (const uint8_t*)c->d_arena[3];
+        c->dview.csr = (const uint16_t*)c->d_arena[4];
+        c->dview.filter3 = (const uint8_t*)c->d_arena[5];
+        c->dview.pref = (const bft_entry_t*)c->d_arena[6];
+        c->dview.keys = (const uint64_t*)c->d_arena[7];
+        c->dview.linecls = (const uint32_t*)c->d_arena[8];
+        c->dview.k = a->k;
+        c->dview.W = a->W;
+        c->dpools.n_pools = a->n_pools;
+        c->dpools.last_index = (const int64_t*)c->d_pool[0];
+        c->dpools.size_annot = (const int32_t*)c->d_pool[1];
+        c->dpools.off = (const uint64_t*)c->d_pool[2];
+        c->dpools.bytes = (const uint8_t*)c->d_pool[3];
+    }
+    /* decode every distinct annotation on the device */
+    int* d_bad = NULL;
+    int h_bad = 0;
+    const size_t row_bytes = (a->n_classes + 1) * (size_t)c->rw * sizeof(uint32_t);
+    if (!rc && cudaMalloc((void**)&c->d_class_rows, row_bytes) != cudaSuccess) rc = set_err(BFT_B200_ERR_NOMEM, "cudaMalloc(class rows, %zu) failed", row_bytes);
+    if (!rc && cudaMalloc((void**)&c->d_class_counts, (a->n_classes + 1) * sizeof(uint32_t)) != cudaSuccess) rc = set_err(BFT_B200_ERR_NOMEM, "cudaMalloc(class counts) failed");
+    if (!rc && cudaMalloc((void**)&d_bad, sizeof(int)) != cudaSuccess) rc = set_err(BFT_B200_ERR_NOMEM, "cudaMalloc failed");
+    if (!rc && cudaMalloc((void**)&c->d_counter, sizeof(unsigned long long)) != cudaSuccess) rc = set_err(BFT_B200_ERR_NOMEM, "cudaMalloc failed");
+    for (int s = 0; s < 2 && !rc; s++)
+        if (cudaStreamCreateWithFlags(&c->streams[s], cudaStreamNonBlocking) != cudaSuccess) rc = set_err(BFT_B200_ERR_CUDA, "cudaStreamCreate failed");
+    if (!rc) {
+        cudaMemsetAsync(d_bad, 0, sizeof(int), c->streams[0]);
+        k_decode_classes<<<grid_for(c, a->n_classes, BFT_TPB), BFT_TPB, 0, c->streams[0]>>>(
+            (const uint32_t*)d_cls_off, (const uint8_t*)d_cls_bytes, a->n_classes, c->dpools, c->d_class_rows, c->d_class_counts, c->rw, d_bad);
+        c->launches++;
+        cudaMemcpyAsync(&h_bad, d_bad, sizeof(int), cudaMemcpyDeviceToHost, c->streams[0]);
+        e = cudaStreamSynchronize(c->streams[0]);
+        if (e != cudaSuccess) rc = set_err(BFT_B200_ERR_CUDA, "k_decode_classes failed: %s", cudaGetErrorString(e));
+        else if (h_bad) rc = set_err(BFT_B200_ERR_FILE, "%d colour annotations are malformed (mode 3 pointing outside the colour pools)", h_bad);
+    }
+    double t3 = now_s();
+    if (d_bad) cudaFree(d_bad);
+    if (d_cls_off) cudaFree(d_cls_off);
+    if (d_cls_bytes) cudaFree(d_cls_bytes);
+
+    c->stats.n_kmers = a->n_kmers; c->stats.n_nodes = a->n_nodes; c->stats.n_ccs = a->n_ccs; c->stats.n_lines = a->n_lines;
+    c->stats.n_prefixes = a->n_pref; c->stats.n_classes = a->n_classes; c->stats.arena_bytes = bft_arena_bytes(a);
+    c->stats.class_row_bytes = row_bytes; c->stats.max_cc_per_node = a->max_cc_per_node; c->stats.max_depth = a->max_depth;
+    c->stats.n_pools = a->n_pools;
+    c->stats.flatten_seconds = t1 - t0; c->stats.upload_seconds = t2 - t1; c->stats.decode_seconds = t3 - t2;
+    bft_arena_free(a);
+
+    /* shared memory for the sequence kernel */
+    c->seq_smem = bft_seq_smem_per_warp(c->G) * BFT_SEQ_WARPS;
+    if (!rc && c->seq_smem > 48 * 1024) {
+        if (c->seq_smem > (size_t)prop.sharedMemPerBlockOptin)
+            c->seq_smem = 0; /* too many genomes for the shared-memory counters: sequence queries will refuse */
+        else {
+            cudaFuncSetAttribute(k_query_sequences<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->seq_smem);
+            cudaFuncSetAttribute(k_query_sequences<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->seq_smem);
+        }
+    }
+    if (rc) { bft_b200_close(c); return rc; }
+    *out = c;
+    return BFT_B200_OK;
+}
+
+extern "C" int bft_b200_k(const bft_b200_ctx* c) { return c ? c->k : 0; }
+extern "C" int bft_b200_n_genomes(const bft_b200_ctx* c) { return c ? c->G : 0; }
+extern "C" const char* bft_b200_genome_name(const bft_b200_ctx* c, int i) { return (c && i >= 0 && i < c->G) ? c->names[i] : NULL; }
+extern "C" int bft_b200_kmer_words(const bft_b200_ctx* c) { return c ? c->W : 0; }
+extern "C" int bft_b200_row_words(const bft_b200_ctx* c) { return c ? c->rw : 0; }
+extern "C" int bft_b200_device(const bft_b200_ctx* c) { return c ? c->device : -1; }
+extern "C" void* bft_b200_stream(const bft_b200_ctx* c) { return c ? (void*)c->streams[0] : NULL; }
+extern "C" uint64_t bft_b200_launch_count(const bft_b200_ctx* c) { return c ? c->launches : 0; }
+extern "C" int bft_b200_get_stats(const bft_b200_ctx* c, bft_b200_stats* out) {
+    if (!c || !out) return set_err(BFT_B200_ERR_ARG, "bft_b200_get_stats: NULL argument");
+    *out = c->stats;
+    return 0;
+}
+
+extern "C" void* bft_b200_host_alloc(size_t bytes) {
+    void* p = NULL;
+    if (cudaMallocHost(&p, bytes ? bytes : 1) != cudaSuccess) { set_err(BFT_B200_ERR_NOMEM, "cudaMallocHost(%zu) failed", bytes); return NULL; }
+    return p;
+}
+extern "C" void bft_b200_host_free(void* p) { if (p) cudaFreeHost(p); }
+
+extern "C" int bft_b200_sync(bft_b200_ctx* c) {
+    if (!c) return set_err(BFT_B200_ERR_ARG, "bft_b200_sync: NULL context");
+    CK(cudaSetDevice(c->device));
+    CK(cudaStreamSynchronize(c->streams[0]));
+    CK(cudaStreamSynchronize(c->streams[1]));
+    return 0;
+}
+
+/* ---- enqueue helpers (device pointers, one stream) ---------------------------------------------------------- */
+static int enqueue_kmers(bft_b200_ctx* c, cudaStream_t st, const uint64_t* d_kmers, size_t n, uint8_t* d_present, uint32_t* d_rows,
+                         uint32_t* d_cls) {
+    if (n == 0) return 0;
+    const int grid = grid_for(c, n, BFT_TPB);
+    if (c->W == 1) k_query_kmers<1><<<grid, BFT_TPB, 0, st>>>(c->dview, d_kmers, n, d_present, d_cls);
+    else k_query_kmers<2><<<grid, BFT_TPB, 0, st>>>(c->dview, d_kmers, n, d_present, d_cls);
+    c->launches++;
+    if (d_rows) {
+        k_expand_rows<<<grid_for(c, n * (size_t)c->rw, BFT_TPB), BFT_TPB, 0, st>>>(d_cls, n, c->d_class_rows, c->rw, d_rows);
+        c->launches++;
+    }
+    CK(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int bft_b200_query_kmers_device(bft_b200_ctx* c, const uint64_t* d_kmers, size_t n, uint8_t* d_present, uint32_t* d_rows,
+                                           uint32_t* d_cls) {
+    if (!c || (!d_kmers && n)) return set_err(BFT_B200_ERR_ARG, "bft_b200_query_kmers_device: NULL argument");
+    CK(cudaSetDevice(c->device));
+    if (d_rows && !d_cls) { /* rows need the class ids as an intermediate */
+        slot_t* sl = &c->slot[0];
+        ENSURE(sl->d_cls, sl->cap_cls, n * sizeof(uint32_t));
+        d_cls = sl->d_cls;
+    }
+    return enqueue_kmers(c, c->streams[0], d_kmers, n, d_present, d_rows, d_cls);
+}
+
+static int query_kmers_host(bft_b200_ctx* c, const uint64_t* kmers, const char* ascii, size_t n, uint8_t* valid, uint8_t* present,
+                            uint32_t* rows, uint32_t* class_ids) {
+    CK(cudaSetDevice(c->device));
+    const size_t rw = (size_t)c->rw, W = (size_t)c->W, k = (size_t)c->k;
+    size_t done = 0;
+    int it = 0;
+    while (done < n) {
+        const size_t m = n - done < BFT_CHUNK_KMERS ? n - done : BFT_CHUNK_KMERS;
+        const int s = it & 1;
+        slot_t* sl = &c->slot[s];
+        cudaStream_t st = c->streams[s];
+        CK(cudaStreamSynchronize(st)); /* slot buffers free again */
+        const uint64_t* d_k;
+        if (ascii) {
+            ENSURE(sl->d_in, sl->cap_in, m * k);
+            ENSURE(sl->d_kmers, sl->cap_kmers, m * W * 8);
+            ENSURE(sl->d_u8b, sl->cap_u8b, m);
+            CK(cudaMemcpyAsync(sl->d_in, ascii + done * k, m * k, cudaMemcpyHostToDevice, st));
+            if (c->W == 1) k_encode_ascii<1><<<grid_for(c, m, BFT_TPB), BFT_TPB, 0, st>>>((const char*)sl->d_in, m, c->k, sl->d_kmers, sl->d_u8b);
+            else k_encode_ascii<2><<<grid_for(c, m, BFT_TPB), BFT_TPB, 0, st>>>((const char*)sl->d_in, m, c->k, sl->d_kmers, sl->d_u8b);
+            c->launches++;
+            d_k = sl->d_kmers;
+        } else {
+            ENSURE(sl->d_in, sl->cap_in, m * W * 8);
+            CK(cudaMemcpyAsync(sl->d_in, kmers + done * W, m * W * 8, cudaMemcpyHostToDevice, st));
+            d_k = (const uint64_t*)sl->d_in;
+        }
+        ENSURE(sl->d_u8a, sl->cap_u8a, m);
+        ENSURE(sl->d_cls, sl->cap_cls, m * sizeof(uint32_t));
+        if (rows) ENSURE(sl->d_rows, sl->cap_rows, m * rw * sizeof(uint32_t));
+        int rc = enqueue_kmers(c, st, d_k, m, sl->d_u8a, rows ? sl->d_rows : NULL, sl->d_cls);
+        if (rc) return rc;
+        if (present) CK(cudaMemcpyAsync(present + done, sl->d_u8a, m, cudaMemcpyDeviceToHost, st));
+        if (valid) CK(cudaMemcpyAsync(valid + done, sl->d_u8b, m, cudaMemcpyDeviceToHost, st));
+        if (class_ids) CK(cudaMemcpyAsync(class_ids + done, sl->d_cls, m * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+        if (rows) CK(cudaMemcpyAsync(rows + done * rw, sl->d_rows, m * rw * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+        done += m;
+        it++;
+    }
+    CK(cudaStreamSynchronize(c->streams[0]));
+    CK(cudaStreamSynchronize(c->streams[1]));
+    return 0;
+}
+
+extern "C" int bft_b200_query_kmers(bft_b200_ctx* c, const uint64_t* kmers, size_t n, uint8_t* present, uint32_t* rows, uint32_t* class_ids) {
+    if (!c || (!kmers && n)) return set_err(BFT_B200_ERR_ARG, "bft_b200_query_kmers: NULL argument");
+    return query_kmers_host(c, kmers, NULL, n, NULL, present, rows, class_ids);
+}
+
+extern "C" int bft_b200_query_kmers_ascii(bft_b200_ctx* c, const char* ascii, size_t n, uint8_t* valid, uint8_t* present, uint32_t* rows,
+                                          uint32_t* class_ids) {
+    if (!c || (!ascii && n)) return set_err(BFT_B200_ERR_ARG, "bft_b200_query_kmers_ascii: NULL argument");
+    return query_kmers_host(c, NULL, ascii, n, valid, present, rows, class_ids);
+}
+
+extern "C" int bft_b200_class_rows(bft_b200_ctx* c, const uint32_t** rows, uint64_t* n_classes) {
+    if (!c || !rows) return set_err(BFT_B200_ERR_ARG, "bft_b200_class_rows: NULL argument");
+    CK(cudaSetDevice(c->device));
+    if (!c->h_class_rows) {
+        const size_t bytes = (c->n_classes + 1) * (size_t)c->rw * sizeof(uint32_t);
+        c->h_class_rows = (uint32_t*)malloc(bytes);
+        if (!c->h_class_rows) return set_err(BFT_B200_ERR_NOMEM, "out of host memory");
+        CK(cudaMemcpy(c->h_class_rows, c->d_class_rows, bytes, cudaMemcpyDeviceToHost));
+    }
+    *rows = c->h_class_rows;
+    if (n_classes) *n_classes = c->n_classes;
+    return 0;
+}
+
+extern "C" int bft_b200_class_counts(bft_b200_ctx* c, const uint32_t** counts, uint64_t* n_classes) {
+    if (!c || !counts) return set_err(BFT_B200_ERR_ARG, "bft_b200_class_counts: NULL argument");
+    CK(cudaSetDevice(c->device));
+    if (!c->h_class_counts) {
+        const size_t bytes = (c->n_classes + 1) * sizeof(uint32_t);
+        c->h_class_counts = (uint32_t*)malloc(bytes);
+        if (!c->h_class_counts) return set_err(BFT_B200_ERR_NOMEM, "out of host memory");
+        CK(cudaMemcpy(c->h_class_counts, c->d_class_counts, bytes, cudaMemcpyDeviceToHost));
+    }
+    *counts = c->h_class_counts;
+    if (n_classes) *n_classes = c->n_classes;
+    return 0;
+}
+
+/* ---- sequences ---------------------------------------------------------------------------------------------- */
+static int enqueue_sequences(bft_b200_ctx* c, cudaStream_t st, const char* d_chars, const uint64_t* d_offs, size_t n_seq, double thr,
+                             int canonical, uint32_t* d_rows, uint8_t* d_status) {
+    if (n_seq == 0) return 0;
+    if (!c->seq_smem) return set_err(BFT_B200_ERR_ARG, "sequence queries: %d genomes exceed the shared-memory counter budget", c->G);
+    size_t blocks = (n_seq + BFT_SEQ_WARPS - 1) / BFT_SEQ_WARPS;
+    const size_t cap = (size_t)c->sm_count * 16;
+    if (blocks > cap) blocks = cap;
+    if (c->W == 1)
+        k_query_sequences<1><<<(int)blocks, 32 * BFT_SEQ_WARPS, c->seq_smem, st>>>(c->dview, d_chars, d_offs, n_seq, thr, canonical,
+                                                                                c->d_class_rows, c->rw, c->G, d_rows, d_status);
+    else
+        k_query_sequences<2><<<(int)blocks, 32 * BFT_SEQ_WARPS, c->seq_smem, st>>>(c->dview, d_chars, d_offs, n_seq, thr, canonical,
+                                                                                c->d_class_rows, c->rw, c->G, d_rows, d_status);
+    c->launches++;
+    CK(cudaGetLastError());
+    return 0;
+}
+
+static int check_threshold(double thr) {
+    if (!(thr > 0)) return set_err(BFT_B200_ERR_ARG, "query_sequence(): the threshold must be superior to 0.");
+    if (thr > 1) return set_err(BFT_B200_ERR_ARG, "query_sequence(): the threshold must be inferior or equal to 1.");
+    return 0;
+}
+
+extern "C" int bft_b200_query_sequences_device(bft_b200_ctx* c, const char* d_chars, const uint64_t* d_offs, size_t n_seq, double thr,
+                                               int canonical, uint32_t* d_rows, uint8_t* d_status) {
+    if (!c || !d_offs || !d_rows) return set_err(BFT_B200_ERR_ARG, "bft_b200_query_sequences_device: NULL argument");
+    int rc = check_threshold(thr);
+    if (rc) return rc;
+    CK(cudaSetDevice(c->device));
+    return enqueue_sequences(c, c->streams[0], d_chars, d_offs, n_seq, thr, canonical, d_rows, d_status);
+}
+
+extern "C" int bft_b200_query_sequences(bft_b200_ctx* c, const char* chars, const uint64_t* offs, size_t n_seq, double thr, int canonical,
+                                        uint32_t* rows, uint8_t* status) {
+    if (!c || !offs || !rows) return set_err(BFT_B200_ERR_ARG, "bft_b200_query_sequences: NULL argument");
+    int rc = check_threshold(thr);
+    if (rc) return rc;
+    CK(cudaSetDevice(c->device));
+    const size_t rw = (size_t)c->rw;
+    size_t done = 0;
+    int it = 0;
+    while (done < n_seq) {
+        size_t m = 0;
+        while (done + m < n_seq && m < BFT_CHUNK_SEQS && (m == 0 || offs[done + m + 1] - offs[done] <= BFT_CHUNK_SEQ_CHARS)) m++;
+        const uint64_t c0 = offs[done], c1 = offs[done + m];
+        const int s = it & 1;
+        slot_t* sl = &c->slot[s];
+        cudaStream_t st = c->streams[s];
+        CK(cudaStreamSynchronize(st));
+        ENSURE(sl->d_in, sl->cap_in, (size_t)(c1 - c0) + 64);
+        ENSURE(sl->d_offs, sl->cap_offs, (m + 1) * sizeof(uint64_t));
+        ENSURE(sl->d_rows, sl->cap_rows, m * rw * sizeof(uint32_t));
+        ENSURE(sl->d_u8a, sl->cap_u8a, m);
+        if (c1 > c0) CK(cudaMemcpyAsync(sl->d_in, chars + c0, (size_t)(c1 - c0), cudaMemcpyHostToDevice, st));
+        CK(cudaMemcpyAsync(sl->d_offs, offs + done, (m + 1) * sizeof(uint64_t), cudaMemcpyHostToDevice, st));
+        /* offsets stay absolute: hand the kernel a base pointer shifted back by the chunk's first offset */
+        rc = enqueue_sequences(c, st, (const char*)sl->d_in - c0, sl->d_offs, m, thr, canonical, sl->d_rows, sl->d_u8a);
+        if (rc) return rc;
+        CK(cudaMemcpyAsync(rows + done * rw, sl->d_rows, m * rw * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+        if (status) CK(cudaMemcpyAsync(status + done, sl->d_u8a, m, cudaMemcpyDeviceToHost, st));
+        done += m;
+        it++;
+    }
+    CK(cudaStreamSynchronize(c->streams[0]));
+    CK(cudaStreamSynchronize(c->streams[1]));
+    return 0;
+}
+
+/* ---- branching ---------------------------------------------------------------------------------------------- */
+static int enqueue_branching(bft_b200_ctx* c, cudaStream_t st, const uint64_t* d_kmers, size_t n, uint8_t* d_succ, uint8_t* d_pred,
+                             unsigned long long* d_count, uint32_t* d_nbr) {
+    if (n == 0) return 0;
+    const int grid = grid_for(c, n * 8, BFT_TPB);
+    if (c->W == 1) k_query_branching<1><<<grid, BFT_TPB, 0, st>>>(c->dview, d_kmers, n, d_succ, d_pred, d_count, d_nbr, c->ref_quirks);
+    else k_query_branching<2><<<grid, BFT_TPB, 0, st>>>(c->dview, d_kmers, n, d_succ, d_pred, d_count, d_nbr, c->ref_quirks);
+    c->launches++;
+    CK(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int bft_b200_query_branching_device(bft_b200_ctx* c, const uint64_t* d_kmers, size_t n, uint8_t* d_succ, uint8_t* d_pred,
+                                               uint64_t* d_n_branching) {
+    if (!c || (!d_kmers && n)) return set_err(BFT_B200_ERR_ARG, "bft_b200_query_branching_device: NULL argument");
+    CK(cudaSetDevice(c->device));
+    if (d_n_branching) CK(cudaMemsetAsync(d_n_branching, 0, sizeof(uint64_t), c->streams[0]));
+    return enqueue_branching(c, c->streams[0], d_kmers, n, d_succ, d_pred, (unsigned long long*)d_n_branching, NULL);
+}
+
+extern "C" int bft_b200_query_branching(bft_b200_ctx* c, const uint64_t* kmers, size_t n, uint8_t* succ, uint8_t* pred, uint64_t* n_branching) {
+    if (!c || (!kmers && n)) return set_err(BFT_B200_ERR_ARG, "bft_b200_query_branching: NULL argument");
+    CK(cudaSetDevice(c->device));
+    const size_t W = (size_t)c->W;
+    CK(cudaStreamSynchronize(c->streams[0]));
+    CK(cudaStreamSynchronize(c->streams[1]));
+    CK(cudaMemsetAsync(c->d_counter, 0, sizeof(unsigned long long), c->streams[0]));
+    CK(cudaStreamSynchronize(c->streams[0]));
+    size_t done = 0;
+    int it = 0;
+    while (done < n) {
+        const size_t m = n - done < BFT_CHUNK_KMERS ? n - done : BFT_CHUNK_KMERS;
+        const int s = it & 1;
+        slot_t* sl = &c->slot[s];
+        cudaStream_t st = c->streams[s];
+        CK(cudaStreamSynchronize(st));
+        ENSURE(sl->d_in, sl->cap_in, m * W * 8);
+        ENSURE(sl->d_u8a, sl->cap_u8a, m);
+        ENSURE(sl->d_u8b, sl->cap_u8b, m);
+        CK(cudaMemcpyAsync(sl->d_in, kmers + done * W, m * W * 8, cudaMemcpyHostToDevice, st));
+        int rc = enqueue_branching(c, st, (const uint64_t*)sl->d_in, m, sl->d_u8a, sl->d_u8b, c->d_counter, NULL);
+        if (rc) return rc;
+        if (succ) CK(cudaMemcpyAsync(succ + done, sl->d_u8a, m, cudaMemcpyDeviceToHost, st));
+        if (pred) CK(cudaMemcpyAsync(pred + done, sl->d_u8b, m, cudaMemcpyDeviceToHost, st));
+        done += m;
+        it++;
+    }
+    CK(cudaStreamSynchronize(c->streams[0]));
+    CK(cudaStreamSynchronize(c->streams[1]));
+    if (n_branching) {
+        unsigned long long h = 0;
+        CK(cudaMemcpy(&h, c->d_counter, sizeof h, cudaMemcpyDeviceToHost));
+        *n_branching = h;
+    }
+    return 0;
+}
+
+extern "C" int bft_b200_set_reference_exact_branching(bft_b200_ctx* c, int exact) {
+    if (!c) return set_err(BFT_B200_ERR_ARG, "bft_b200_set_reference_exact_branching: NULL context");
+    c->ref_quirks = exact != 0;
+    return 0;
+}
+
+extern "C" int bft_b200_query_neighbors(bft_b200_ctx* c, const uint64_t* kmers, size_t n, uint32_t* nbr) {
+    if (!c || !nbr || (!kmers && n)) return set_err(BFT_B200_ERR_ARG, "bft_b200_query_neighbors: NULL argument");
+    CK(cudaSetDevice(c->device));
+    const size_t W = (size_t)c->W;
+    CK(cudaStreamSynchronize(c->streams[0]));
+    size_t done = 0;
+    while (done < n) {
+        const size_t m = n - done < BFT_CHUNK_KMERS ? n - done : BFT_CHUNK_KMERS;
+        slot_t* sl = &c->slot[0];
+        cudaStream_t st = c->streams[0];
+        ENSURE(sl->d_in, sl->cap_in, m * W * 8);
+        ENSURE(c->d_nbr, c->cap_nbr, m * 8 * sizeof(uint32_t));
+        CK(cudaMemcpyAsync(sl->d_in, kmers + done * W, m * W * 8, cudaMemcpyHostToDevice, st));
+        int rc = enqueue_branching(c, st, (const uint64_t*)sl->d_in, m, NULL, NULL, NULL, c->d_nbr);
+        if (rc) return rc;
+        CK(cudaMemcpyAsync(nbr + done * 8, c->d_nbr, m * 8 * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
+        done += m;
+    }
+    return 0;
+}
+
+/* ---- file-level drivers ------------------------------------------------------------------------------------- */
+extern "C" int bft_b200_query_kmers_file(bft_b200_ctx* c, const char* query_path, int binary_file, const char* csv_path, uint64_t* n_present) {
+    if (!c || !query_path || !csv_path) return set_err(BFT_B200_ERR_ARG, "bft_b200_query_kmers_file: NULL argument");
+    uint64_t* q = NULL;
+    size_t n = 0;
+    if (bft_read_kmer_file(query_path, binary_file, c->k, c->W, &q, &n)) return set_err(BFT_B200_ERR_FILE, "cannot read k-mer file %s", query_path);
+    uint8_t* present = (uint8_t*)malloc(n + 1);
+    uint32_t* rows = (uint32_t*)malloc((n + 1) * (size_t)c->rw * sizeof(uint32_t));
+    int rc = (!present || !rows) ? set_err(BFT_B200_ERR_NOMEM, "out of host memory") : bft_b200_query_kmers(c, q, n, present, rows, NULL);
+    if (!rc) {
+        FILE* f = fopen(csv_path, "w");
+        if (!f) rc = set_err(BFT_B200_ERR_FILE, "cannot write %s", csv_path);
+        else {
+            if (bft_csv_write_header(f, c->names, c->G) || bft_csv_write_rows(f, rows, n, c->G, c->rw) || bft_csv_finish(f))
+                rc = set_err(BFT_B200_ERR_FILE, "could not write output to CSV file %s", csv_path);
+            fclose(f);
+        }
+        uint64_t np = 0;
+        for (size_t i = 0; i < n; i++) np += present[i];
+        if (n_present) *n_present = np;
+    }
+    free(q); free(present); free(rows);
+    return rc;
+}
+
+extern "C" int bft_b200_query_branching_file(bft_b200_ctx* c, const char* query_path, int binary_file, uint64_t* n_branching) {
+    if (!c || !query_path) return set_err(BFT_B200_ERR_ARG, "bft_b200_query_branching_file: NULL argument");
+    uint64_t* q = NULL;
+    size_t n = 0;
+    if (bft_read_kmer_file(query_path, binary_file, c->k, c->W, &q, &n)) return set_err(BFT_B200_ERR_FILE, "cannot read k-mer file %s", query_path);
+    int rc = bft_b200_query_branching(c, q, n, NULL, NULL, n_branching);
+    free(q);
+    return rc;
+}
+
+extern "C" int bft_b200_query_sequences_file(bft_b200_ctx* c, const char* query_path, const char* csv_path, double thr, int canonical) {
+    if (!c || !query_path || !csv_path) return set_err(BFT_B200_ERR_ARG, "bft_b200_query_sequences_file: NULL argument");
+    char* chars = NULL;
+    uint64_t* offs = NULL;
+    size_t n = 0;
+    if (bft_read_sequence_file(query_path, &chars, &offs, &n)) return set_err(BFT_B200_ERR_FILE, "cannot read sequence file %s", query_path);
+    uint32_t* rows = (uint32_t*)malloc((n + 1) * (size_t)c->rw * sizeof(uint32_t));
+    uint8_t* status = (uint8_t*)malloc(n + 1);
+    int rc = (!rows || !status) ? set_err(BFT_B200_ERR_NOMEM, "out of host memory") : bft_b200_query_sequences(c, chars, offs, n, thr, canonical, rows, status);
+    if (!rc) {
+        for (size_t i = 0; i < n && !rc; i++)
+            if (status[i] == BFT_B200_SEQ_BAD_CHAR) rc = set_err(BFT_B200_ERR_ARG, "get_kmer(): Unexpected character encountered in k-mer (sequence %zu).", i);
+    }
+    if (!rc) {
+        FILE* f = fopen(csv_path, "w");
+        if (!f) rc = set_err(BFT_B200_ERR_FILE, "cannot write %s", csv_path);
+        else {
+            if (bft_csv_write_header(f, c->names, c->G) || bft_csv_write_rows(f, rows, n, c->G, c->rw) || bft_csv_finish(f))
+                rc = set_err(BFT_B200_ERR_FILE, "could not write output to CSV file %s", csv_path);
+            fclose(f);
+        }
+    }
+    free(chars); free(offs); free(rows); free(status);
+    return rc;
+}

@@ -1,0 +1,274 @@
+/* bft_compat.c — reference-named entry points over the GPU engine (see include/bft_compat.h). */
+#define _GNU_SOURCE
+#include "bft_compat.h"
+#include "bft_b200.h"
+
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#define DIE(...) do { fprintf(stderr, __VA_ARGS__); exit(EXIT_FAILURE); } while (0)
+#define ENGINE_OK(call, who) do { if ((call) != BFT_B200_OK) DIE("%s: %s\n", who, bft_b200_last_error()); } while (0)
+#define NOT_NULL(p, who) do { if ((p) == NULL) DIE("%s: NULL pointer\n", who); } while (0)
+
+static int nb_bytes(int k) { return (2 * k + 7) / 8; }
+
+/* parseKmerCount (src/fasta.c:3-53) */
+static int parse_kmer_bytes(const char* s, int k, uint8_t* out) {
+    for (int i = 0; i < k; i++) {
+        uint8_t code;
+        switch (s[i]) {
+            case 'a': case 'A': code = 0; break;
+            case 'c': case 'C': code = 1; break;
+            case 'g': case 'G': code = 2; break;
+            case 't': case 'T': case 'u': case 'U': code = 3; break;
+            default: return 0;
+        }
+        out[i / 4] |= (uint8_t)(code << (2 * (i % 4)));
+    }
+    return 1;
+}
+
+BFT* load_BFT(char* filename) {
+    NOT_NULL(filename, "load_BFT()");
+    BFT* bft = (BFT*)calloc(1, sizeof(BFT));
+    NOT_NULL(bft, "load_BFT()");
+    ENGINE_OK(bft_b200_open(filename, 0, &bft->engine), "load_BFT()");
+    bft->k = bft_b200_k(bft->engine);
+    bft->nb_genomes = bft_b200_n_genomes(bft->engine);
+    bft->filenames = (char**)calloc((size_t)bft->nb_genomes + 1, sizeof(char*));
+    for (int i = 0; i < bft->nb_genomes; i++) bft->filenames[i] = strdup(bft_b200_genome_name(bft->engine, i));
+    return bft;
+}
+
+void free_cdbg(BFT* bft) {
+    NOT_NULL(bft, "free_cdbg()");
+    for (int i = 0; i < bft->nb_genomes; i++) free(bft->filenames[i]);
+    free(bft->filenames);
+    bft_b200_close(bft->engine);
+    free(bft);
+}
+
+BFT_kmer* create_empty_kmer(void) {
+    BFT_kmer* km = (BFT_kmer*)calloc(1, sizeof(BFT_kmer));
+    NOT_NULL(km, "create_empty_kmer()");
+    return km;
+}
+
+BFT_kmer* create_kmer(const char* kmer, int k) { /* src/bft.c:122-150 */
+    NOT_NULL(kmer, "create_kmer()");
+    BFT_kmer* km = create_empty_kmer();
+    km->kmer = (char*)malloc((size_t)k + 1);
+    km->kmer_comp = (uint8_t*)calloc((size_t)nb_bytes(k), 1);
+    memcpy(km->kmer, kmer, (size_t)k);
+    km->kmer[k] = '\0';
+    if (!parse_kmer_bytes(km->kmer, k, km->kmer_comp)) DIE("create_kmer(): Unexpected character encountered in k-mer.\n");
+    km->res = (resultPresence*)calloc(1, sizeof(resultPresence));
+    km->res->class_id = 0xffffffffu;
+    return km;
+}
+
+void free_BFT_kmer_content(BFT_kmer* km, int n) {
+    NOT_NULL(km, "free_BFT_kmer_content()");
+    for (int i = 0; i < n; i++) {
+        free(km[i].kmer);
+        free(km[i].kmer_comp);
+        free(km[i].res);
+    }
+}
+
+void free_BFT_kmer(BFT_kmer* km, int n) {
+    free_BFT_kmer_content(km, n);
+    free(km);
+}
+
+static void lookup_into(BFT* bft, BFT_kmer* kms, int n) {
+    const int W = bft_b200_kmer_words(bft->engine), nb = nb_bytes(bft->k);
+    uint64_t words[8 * 2];
+    uint8_t present[8];
+    uint32_t cls[8];
+    memset(words, 0, sizeof words);
+    for (int i = 0; i < n; i++) memcpy(&words[i * W], kms[i].kmer_comp, (size_t)nb);
+    ENGINE_OK(bft_b200_query_kmers(bft->engine, words, (size_t)n, present, NULL, cls), "get_kmer()");
+    for (int i = 0; i < n; i++) {
+        kms[i].res = (resultPresence*)calloc(1, sizeof(resultPresence));
+        kms[i].res->present = present[i];
+        kms[i].res->class_id = cls[i];
+        kms[i].res->bft = bft;
+    }
+}
+
+BFT_kmer* get_kmer(const char* kmer, BFT* bft) { /* src/bft.c:216-240 */
+    NOT_NULL(kmer, "get_kmer()");
+    NOT_NULL(bft, "get_kmer()");
+    BFT_kmer* km = (BFT_kmer*)calloc(1, sizeof(BFT_kmer));
+    km->kmer = (char*)malloc((size_t)bft->k + 1);
+    km->kmer_comp = (uint8_t*)calloc((size_t)nb_bytes(bft->k), 1);
+    memcpy(km->kmer, kmer, (size_t)bft->k);
+    km->kmer[bft->k] = '\0';
+    if (!parse_kmer_bytes(km->kmer, bft->k, km->kmer_comp)) DIE("get_kmer(): Unexpected character encountered in k-mer.\n");
+    lookup_into(bft, km, 1);
+    return km;
+}
+
+bool is_kmer_in_cdbg(BFT_kmer* km) { return km->res != NULL && km->res->present != 0; }
+
+BFT_annotation* create_BFT_annotation(void) {
+    BFT_annotation* a = (BFT_annotation*)calloc(1, sizeof(BFT_annotation));
+    NOT_NULL(a, "create_BFT_annotation()");
+    a->class_id = 0xffffffffu;
+    return a;
+}
+
+void free_BFT_annotation(BFT_annotation* a) {
+    NOT_NULL(a, "free_BFT_annotation()");
+    free(a);
+}
+
+BFT_annotation* get_annotation(BFT_kmer* km) { /* src/bft.c:363-387 */
+    NOT_NULL(km, "get_annotation()");
+    if (!is_kmer_in_cdbg(km)) DIE("get_annotation(): k-mer is not present in the graph.\n");
+    BFT_annotation* a = create_BFT_annotation();
+    a->class_id = km->res->class_id;
+    a->from_BFT = 1;
+    return a;
+}
+
+static const uint32_t* class_row(BFT* bft, uint32_t cls, int* rw) {
+    const uint32_t* rows;
+    uint64_t n;
+    ENGINE_OK(bft_b200_class_rows(bft->engine, &rows, &n), "get_list_id_genomes()");
+    *rw = bft_b200_row_words(bft->engine);
+    if (cls >= n) DIE("get_list_id_genomes(): annotation does not belong to this BFT\n");
+    return rows + (size_t)cls * (size_t)*rw;
+}
+
+uint32_t* get_list_id_genomes(BFT_annotation* a, BFT* bft) { /* src/bft.c:622-641: [count, ids ascending] */
+    NOT_NULL(a, "get_list_id_genomes()");
+    NOT_NULL(bft, "get_list_id_genomes()");
+    int rw;
+    const uint32_t* row = class_row(bft, a->class_id, &rw);
+    uint32_t cnt = 0;
+    for (int w = 0; w < rw; w++) cnt += (uint32_t)__builtin_popcount(row[w]);
+    uint32_t* ids = (uint32_t*)malloc(((size_t)cnt + 1) * sizeof(uint32_t));
+    NOT_NULL(ids, "get_list_id_genomes()");
+    ids[0] = cnt;
+    uint32_t j = 1;
+    for (int g = 0; g < bft->nb_genomes; g++)
+        if ((row[g >> 5] >> (g & 31)) & 1u) ids[j++] = (uint32_t)g;
+    return ids;
+}
+
+uint32_t get_count_id_genomes(BFT_annotation* a, BFT* bft) { /* src/bft.c:648 */
+    NOT_NULL(a, "get_count_id_genomes()");
+    NOT_NULL(bft, "get_count_id_genomes()");
+    const uint32_t* counts;
+    uint64_t n;
+    ENGINE_OK(bft_b200_class_counts(bft->engine, &counts, &n), "get_count_id_genomes()");
+    if (a->class_id >= n) DIE("get_count_id_genomes(): annotation does not belong to this BFT\n");
+    return counts[a->class_id];
+}
+
+bool presence_genome(uint32_t id_genome, BFT_annotation* a, BFT* bft) { /* src/bft.c:395-413 */
+    NOT_NULL(a, "is_genome_present()");
+    NOT_NULL(bft, "is_genome_present()");
+    if (id_genome >= (uint32_t)bft->nb_genomes) return false;
+    int rw;
+    const uint32_t* row = class_row(bft, a->class_id, &rw);
+    return (row[id_genome >> 5] >> (id_genome & 31)) & 1u;
+}
+
+uint32_t* query_sequence(BFT* bft, char* sequence, double threshold, bool canonical_search) { /* src/bft.c:1241-1351 */
+    NOT_NULL(bft, "query_sequence()");
+    NOT_NULL(sequence, "query_sequence()");
+    if (threshold <= 0) DIE("query_sequence(): the threshold must be superior to 0.\n");
+    if (threshold > 1) DIE("query_sequence(): the threshold must be inferior or equal to 1.\n");
+    const int rw = bft_b200_row_words(bft->engine);
+    uint64_t offs[2] = {0, strlen(sequence)};
+    uint32_t* row = (uint32_t*)calloc((size_t)rw, sizeof(uint32_t));
+    uint8_t status = 0;
+    if ((long long)offs[1] - bft->k + 1 < 0)
+        printf("query_sequence(): query %s is too small and must be at least of length k.\n", sequence);
+    ENGINE_OK(bft_b200_query_sequences(bft->engine, sequence, offs, 1, threshold, canonical_search, row, &status), "query_sequence()");
+    if (status == BFT_B200_SEQ_BAD_CHAR) DIE("get_kmer(): Unexpected character encountered in k-mer.\n");
+    uint32_t cnt = 0;
+    for (int w = 0; w < rw; w++) cnt += (uint32_t)__builtin_popcount(row[w]);
+    uint32_t* ids = (uint32_t*)malloc(((size_t)cnt + 1) * sizeof(uint32_t));
+    ids[0] = cnt;
+    uint32_t j = 1;
+    for (int g = 0; g < bft->nb_genomes; g++)
+        if ((row[g >> 5] >> (g & 31)) & 1u) ids[j++] = (uint32_t)g;
+    free(row);
+    return ids;
+}
+
+/* The reference builds a node-rank directory here (build_skip_nodes, src/CC.c:2297-2331); the flattened arena
+ * already carries exact prefix sums, so locking is a no-op. */
+void set_neighbors_traversal(BFT* bft) { NOT_NULL(bft, "set_neighbors_traversal()"); }
+void unset_neighbors_traversal(BFT* bft) { NOT_NULL(bft, "unset_neighbors_traversal()"); }
+
+static BFT_kmer* neighbours(BFT_kmer* km, BFT* bft, int first, int count, const char* who) { /* src/bft.c:804-1003 */
+    NOT_NULL(km, who);
+    NOT_NULL(bft, who);
+    if (!is_kmer_in_cdbg(km)) DIE("%s: k-mer is not present in the graph.\n", who);
+    static const char nuc[4] = {'A', 'C', 'G', 'T'};
+    const int k = bft->k;
+    BFT_kmer* out = (BFT_kmer*)calloc((size_t)count, sizeof(BFT_kmer));
+    for (int i = 0; i < count; i++) {
+        const int slot = first + i; /* 0-3 predecessors, 4-7 successors */
+        out[i].kmer = (char*)malloc((size_t)k + 1);
+        out[i].kmer_comp = (uint8_t*)calloc((size_t)nb_bytes(k), 1);
+        if (slot < 4) {
+            out[i].kmer[0] = nuc[slot];
+            memcpy(out[i].kmer + 1, km->kmer, (size_t)k - 1);
+        } else {
+            memcpy(out[i].kmer, km->kmer + 1, (size_t)k - 1);
+            out[i].kmer[k - 1] = nuc[slot - 4];
+        }
+        out[i].kmer[k] = '\0';
+        parse_kmer_bytes(out[i].kmer, k, out[i].kmer_comp);
+    }
+    /* presence + class of the 8 neighbours in the reference's own order (and with its leaf-level successor rule) */
+    uint64_t words[2] = {0, 0};
+    uint32_t cls[8];
+    memcpy(words, km->kmer_comp, (size_t)nb_bytes(k));
+    ENGINE_OK(bft_b200_query_neighbors(bft->engine, words, 1, cls), who);
+    for (int i = 0; i < count; i++) {
+        out[i].res = (resultPresence*)calloc(1, sizeof(resultPresence));
+        out[i].res->present = cls[first + i] != 0xffffffffu;
+        out[i].res->class_id = cls[first + i];
+        out[i].res->bft = bft;
+    }
+    return out;
+}
+BFT_kmer* get_neighbors(BFT_kmer* km, BFT* bft) { return neighbours(km, bft, 0, 8, "get_neighbors()"); }
+BFT_kmer* get_predecessors(BFT_kmer* km, BFT* bft) { return neighbours(km, bft, 0, 4, "get_predecessors()"); }
+BFT_kmer* get_successors(BFT_kmer* km, BFT* bft) { return neighbours(km, bft, 4, 4, "get_successors()"); }
+
+int queryBFT_kmerPresences_from_KmerFiles(BFT_Root* root, char* query_filename, int binary_file, char* output_filename) {
+    NOT_NULL(root, "queryBFT_kmerPresences_from_KmerFiles()");
+    NOT_NULL(query_filename, "queryBFT_kmerPresences_from_KmerFiles()");
+    uint64_t n = 0;
+    printf("\nQuerying BFT for k-mers in %s\n\n", query_filename);
+    ENGINE_OK(bft_b200_query_kmers_file(root->engine, query_filename, binary_file, output_filename, &n), "queryBFT_kmerPresences_from_KmerFiles()");
+    return (int)n;
+}
+
+int queryBFT_kmerBranching_from_KmerFiles(BFT_Root* root, char* query_filename, int binary_file) {
+    NOT_NULL(root, "queryBFT_kmerBranching_from_KmerFiles()");
+    NOT_NULL(query_filename, "queryBFT_kmerBranching_from_KmerFiles()");
+    uint64_t n = 0;
+    printf("\nQuerying BFT for branching k-mers in %s\n\n", query_filename);
+    ENGINE_OK(bft_b200_query_branching_file(root->engine, query_filename, binary_file, &n), "queryBFT_kmerBranching_from_KmerFiles()");
+    return (int)n;
+}
+
+void query_sequences_outputCSV(BFT_Root* root, char* query_filename, char* output_filename, double threshold, bool canonical_search) {
+    NOT_NULL(root, "query_sequences_outputCSV()");
+    NOT_NULL(query_filename, "query_sequences_outputCSV()");
+    NOT_NULL(output_filename, "query_sequences_outputCSV()");
+    if (threshold <= 0) DIE("query_sequences_outputCSV(): the threshold must be superior to 0.\n");
+    if (threshold > 1) DIE("query_sequences_outputCSV(): the threshold must be inferior or equal to 1.\n");
+    ENGINE_OK(bft_b200_query_sequences_file(root->engine, query_filename, output_filename, threshold, canonical_search), "query_sequences_outputCSV()");
+    printf("\nFile %s has been processed.\n", query_filename);
+}

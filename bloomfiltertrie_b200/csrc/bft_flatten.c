@@ -577,7 +577,7 @@ bft_arena_t* bft_arena_from_memory(const uint8_t* buf, size_t len, char* err, si
     a->rootdir = (bft_entry_t*)xrealloc(c, NULL, BFT_ROOTDIR_SIZE * sizeof(bft_entry_t));
     bft_view_t v;
     bft_arena_view(a, &v);
-    for (uint32_t low18 = 0; low18 < BFT_ROOTDIR_SIZE; low18++) a->rootdir[low18] = bft_node_probe(&v, 0, low18, a->k);
+    for (uint32_t low18 = 0; low18 < BFT_ROOTDIR_SIZE; low18++) a->rootdir[low18] = bft_node_probe(&v, 0, low18, 0);
 
     free(c->map); free(c->tmp); free(c->hv1); free(c->hv2); free(c->scratch); free(c->extbuf);
     free(c);

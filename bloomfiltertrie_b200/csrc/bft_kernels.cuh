@@ -1,0 +1,395 @@
+/* bft_kernels.cuh — sm_100a kernels of the BFT query engine.
+ *
+ * Nothing on this path is a dense contraction, so tensor cores / TMEM are not used; the kernels are bound by the
+ * random-access rate of the memory system (one dependent 32-byte sector per step of a lookup). The design levers
+ * are therefore: (1) as few dependent loads per lookup as possible (root directory, prefix-sum directories — see
+ * bft_arena.h), (2) as many independent lookups in flight as the SMs hold (one lookup per thread, 2048 threads/SM),
+ * (3) coalesced streaming of the query and result arrays, (4) small hot tables (root directory 2 MB, class rows)
+ * resident in the 126 MB L2.
+ */
+#ifndef BFT_KERNELS_CUH
+#define BFT_KERNELS_CUH
+
+#include <cuda_runtime.h>
+#include "bft_arena.h"
+#include "bft_colour.h"
+
+#define BFT_TPB 256
+
+/* ---- a4/a5/a7/a8: k-mer lookup ---------------------------------------------------------------------------- */
+template <int W>
+__global__ void __launch_bounds__(BFT_TPB) k_query_kmers(const bft_view_t v, const uint64_t* __restrict__ kmers, size_t n,
+                                                         uint8_t* __restrict__ present, uint32_t* __restrict__ cls_out) {
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        uint64_t km[W];
+        if (W == 1) {
+            km[0] = __ldcs((const unsigned long long*)kmers + i);
+        } else {
+            const ulonglong2 t = __ldcs((const ulonglong2*)kmers + i);
+            km[0] = t.x;
+            km[W - 1] = t.y;
+        }
+        const uint32_t cls = bft_lookup_w(&v, km, W);
+        if (present) present[i] = cls != BFT_CLS_NONE;
+        if (cls_out) cls_out[i] = cls;
+    }
+}
+
+/* a10 (read side of get_list_id_genomes): class id -> colour row, one thread per output word */
+__global__ void __launch_bounds__(BFT_TPB) k_expand_rows(const uint32_t* __restrict__ cls, size_t n, const uint32_t* __restrict__ class_rows,
+                                                         int rw, uint32_t* __restrict__ rows) {
+    const size_t total = n * (size_t)rw;
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += stride) {
+        const size_t i = t / (size_t)rw;
+        const int w = (int)(t - i * (size_t)rw);
+        const uint32_t c = cls[i];
+        rows[t] = c == BFT_CLS_NONE ? 0u : __ldg(class_rows + (size_t)c * rw + w);
+    }
+}
+
+/* a9/a10: decode every distinct annotation once (get_id_genomes_from_annot, src/annotation.c:2086-2250) */
+__global__ void __launch_bounds__(BFT_TPB) k_decode_classes(const uint32_t* __restrict__ cls_off, const uint8_t* __restrict__ cls_bytes,
+                                                            size_t n_classes, const bft_pools_t pools, uint32_t* __restrict__ rows,
+                                                            uint32_t* __restrict__ counts, int rw, int* __restrict__ n_bad) {
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (size_t c = (size_t)blockIdx.x * blockDim.x + threadIdx.x; c < n_classes; c += stride) {
+        uint32_t* row = rows + c * (size_t)rw;
+        for (int w = 0; w < rw; w++) row[w] = 0;
+        const uint32_t o = cls_off[c];
+        if (bft_decode_annotation(cls_bytes + o, (int)(cls_off[c + 1] - o), &pools, row, rw)) atomicAdd(n_bad, 1);
+        uint32_t cnt = 0;
+        for (int w = 0; w < rw; w++) cnt += __popc(row[w]);
+        counts[c] = cnt;
+    }
+}
+
+/* a1: ASCII -> packed k-mers (parseKmerCount, src/fasta.c:3-53). One thread per k-mer. */
+template <int W>
+__global__ void __launch_bounds__(BFT_TPB) k_encode_ascii(const char* __restrict__ ascii, size_t n, int k, uint64_t* __restrict__ kmers,
+                                                          uint8_t* __restrict__ valid) {
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        const char* s = ascii + i * (size_t)k;
+        uint64_t km[W];
+#pragma unroll
+        for (int w = 0; w < W; w++) km[w] = 0;
+        int ok = 1;
+        for (int j = 0; j < k; j++) {
+            uint64_t code = 0;
+            switch (s[j]) {
+                case 'A': case 'a': code = 0; break;
+                case 'C': case 'c': code = 1; break;
+                case 'G': case 'g': code = 2; break;
+                case 'T': case 't': case 'U': case 'u': code = 3; break;
+                default: ok = 0; break;
+            }
+            km[j >> 5] |= code << (2 * (j & 31));
+        }
+        if (!ok) {
+#pragma unroll
+            for (int w = 0; w < W; w++) km[w] = 0;
+        }
+#pragma unroll
+        for (int w = 0; w < W; w++) kmers[i * W + w] = km[w];
+        valid[i] = (uint8_t)ok;
+    }
+}
+
+/* ---- a13/a14: branching ------------------------------------------------------------------------------------
+ * 8 lanes per query: lanes 0-3 look up the four successors (drop nuc 0, append c), lanes 4-7 the four
+ * predecessors (prepend c, drop the last nuc) — isBranchingRight / isBranchingLeft (src/branchingNode.c:16-110,
+ * 240-413) count exactly the neighbours present in the graph. */
+template <int W>
+__global__ void __launch_bounds__(BFT_TPB) k_query_branching(const bft_view_t v, const uint64_t* __restrict__ kmers, size_t n,
+                                                             uint8_t* __restrict__ succ, uint8_t* __restrict__ pred,
+                                                             unsigned long long* __restrict__ n_branching,
+                                                             uint32_t* __restrict__ nbr_cls, int ref_quirks) {
+    const int k = v.k;
+    const size_t stride = ((size_t)gridDim.x * blockDim.x) >> 3;
+    const int sub = threadIdx.x & 7;
+    const uint32_t c = sub & 3;
+    unsigned long long local = 0;
+    /* all 32 lanes of a warp iterate the same number of times so the shuffles below are full-warp */
+    const size_t n_rounds = (n + stride - 1) / stride;
+    size_t q = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 3;
+    for (size_t r = 0; r < n_rounds; r++, q += stride) {
+        uint32_t hit = 0;
+        if (q < n) {
+            uint64_t x[W], y[W];
+#pragma unroll
+            for (int w = 0; w < W; w++) x[w] = kmers[q * W + w];
+            if (sub < 4) { /* successor: (x >> 2) | c << 2(k-1) */
+#pragma unroll
+                for (int w = 0; w < W; w++) {
+                    y[w] = x[w] >> 2;
+                    if (w + 1 < W) y[w] |= x[w + 1] << 62;
+                }
+                const int top = 2 * (k - 1); /* W == 2 means k >= 36, i.e. top >= 70: always the upper word */
+                y[W - 1] |= (uint64_t)c << (top - 64 * (W - 1));
+            } else { /* predecessor: (x << 2 | c) masked to 2k bits */
+#pragma unroll
+                for (int w = W - 1; w >= 0; w--) {
+                    y[w] = x[w] << 2;
+                    if (w > 0) y[w] |= x[w - 1] >> 62;
+                }
+                y[0] |= c;
+                const int bits_last = 2 * k - 64 * (W - 1);
+                if (bits_last < 64) y[W - 1] &= (1ULL << bits_last) - 1ULL;
+            }
+            /* the reference's successor search deviates from set membership at the leaf level; see bft_node_probe */
+            const uint32_t cls = bft_lookup_ex(&v, y, W, ref_quirks && sub < 4);
+            hit = cls != BFT_CLS_NONE;
+            if (nbr_cls) nbr_cls[q * 8 + (sub < 4 ? 4 + sub : sub - 4)] = cls; /* get_neighbors order: 0-3 pred, 4-7 succ */
+        }
+        const uint32_t ball = __ballot_sync(0xffffffffu, hit);
+        const uint32_t grp = (ball >> ((threadIdx.x & 31) & ~7)) & 0xffu;
+        const int ns = __popc(grp & 0x0fu), np = __popc(grp >> 4);
+        if (sub == 0 && q < n) {
+            if (succ) succ[q] = (uint8_t)ns;
+            if (pred) pred[q] = (uint8_t)np;
+            local += (ns > 1) || (np > 1); /* isBranchingRight > 1, else isBranchingLeft > 1 (src/file_io.c:971-976) */
+        }
+    }
+    if (n_branching) {
+        for (int o = 16; o > 0; o >>= 1) local += __shfl_down_sync(0xffffffffu, local, o);
+        if ((threadIdx.x & 31) == 0 && local) atomicAdd(n_branching, local);
+    }
+}
+
+/* ---- a1/a2/a12: sequences ----------------------------------------------------------------------------------
+ * One warp per sequence. The warp streams the sequence in tiles: 32 characters per step are classified and
+ * 2-bit-encoded by the 32 lanes and packed with warp ballots into shared-memory bit planes (codes + character-class
+ * masks). Every k-mer window is then a funnel shift out of the packed plane; the reverse complement is a
+ * 2-bit-group reversal of the complemented word (reverse_complement, src/fasta.c:387-440) and the canonical pick
+ * compares the nucleotide-lexicographic keys (strcmp rule, src/bft.c:1287-1293). Windows sharing a colour class are
+ * merged with __match_any_sync before the per-genome counters in shared memory are bumped. */
+#define BFT_SEQ_TILE 512                       /* window start positions per tile */
+#define BFT_SEQ_SPAN (BFT_SEQ_TILE + 64)       /* characters held per tile (k <= 63 overlap, rounded to 64) */
+#define BFT_SEQ_WARPS 4
+
+/* shared memory one warp of k_query_sequences needs (codes + 4 masks + characters + per-genome counters) */
+__host__ __device__ inline size_t bft_seq_smem_per_warp(int n_genomes) {
+    const size_t n_code_words = BFT_SEQ_SPAN / 32 + 2, n_mask_words = BFT_SEQ_SPAN / 64 + 2;
+    const size_t b = n_code_words * 8 + 4 * n_mask_words * 8 + BFT_SEQ_SPAN + (size_t)((n_genomes + 31) & ~31) * 4;
+    return (b + 15) & ~(size_t)15;
+}
+
+/* character classes (see bft_b200.h, bft_b200_query_sequences) */
+#define BFT_CH_ACGT 0   /* A C G T U, either case */
+#define BFT_CH_IUPAC 1  /* IUPAC letter accepted by reverse_complement and matched by is_substring_IUPAC */
+#define BFT_CH_DOTDASH 2 /* '.' '-' : matched by is_substring_IUPAC (src/fasta.c:361) but rejected by reverse_complement */
+#define BFT_CH_OTHER 3  /* anything else */
+
+__device__ __forceinline__ void bft_classify_char(unsigned char ch, uint32_t& code, uint32_t& cls, uint32_t& nonplain) {
+    code = 0; cls = BFT_CH_OTHER; nonplain = 0;
+    const unsigned char up = ch & 0xdf;
+    const bool letter = (up >= 'A' && up <= 'Z') && (ch & 0x40);
+    if (letter) {
+        const bool lower = (ch & 0x20) != 0;
+        switch (up) {
+            case 'A': code = 0; cls = BFT_CH_ACGT; nonplain = lower; break;
+            case 'C': code = 1; cls = BFT_CH_ACGT; nonplain = lower; break;
+            case 'G': code = 2; cls = BFT_CH_ACGT; nonplain = lower; break;
+            case 'T': code = 3; cls = BFT_CH_ACGT; nonplain = lower; break;
+            case 'U': code = 3; cls = BFT_CH_ACGT; nonplain = 1; break;
+            case 'R': case 'Y': case 'S': case 'W': case 'K': case 'M': case 'B': case 'D': case 'H': case 'V': case 'N':
+                cls = BFT_CH_IUPAC; break;
+            default: break;
+        }
+    } else if (ch == '.' || ch == '-') {
+        cls = BFT_CH_DOTDASH;
+    }
+}
+
+__device__ __forceinline__ uint64_t bft_spread32(uint32_t x) { /* bit i -> bit 2i */
+    uint64_t v = x;
+    v = (v | (v << 16)) & 0x0000ffff0000ffffULL;
+    v = (v | (v << 8)) & 0x00ff00ff00ff00ffULL;
+    v = (v | (v << 4)) & 0x0f0f0f0f0f0f0f0fULL;
+    v = (v | (v << 2)) & 0x3333333333333333ULL;
+    v = (v | (v << 1)) & 0x5555555555555555ULL;
+    return v;
+}
+
+__device__ __forceinline__ uint64_t bft_rev2_64(uint64_t x) { /* reverse the 32 2-bit groups of a word */
+    x = __brevll(x);
+    return ((x & 0xaaaaaaaaaaaaaaaaULL) >> 1) | ((x & 0x5555555555555555ULL) << 1);
+}
+
+/* bits [pos, pos+len) of a little-endian bit plane of uint64 words (len <= 64) */
+__device__ __forceinline__ uint64_t bft_extract_bits(const uint64_t* plane, int pos, int len) {
+    const int w = pos >> 6, sh = pos & 63;
+    uint64_t x = plane[w] >> sh;
+    if (sh && sh + len > 64) x |= plane[w + 1] << (64 - sh);
+    return len < 64 ? x & ((1ULL << len) - 1ULL) : x;
+}
+
+__device__ __forceinline__ char bft_rc_char(char c) { /* reverse_complement on ACGTU (src/fasta.c:396-405) */
+    switch (c) {
+        case 'a': return 't'; case 'A': return 'T';
+        case 'c': return 'g'; case 'C': return 'G';
+        case 'g': return 'c'; case 'G': return 'C';
+        case 't': case 'u': return 'a';
+        default: return 'A'; /* 'T', 'U' */
+    }
+}
+
+template <int W>
+__global__ void __launch_bounds__(32 * BFT_SEQ_WARPS) k_query_sequences(const bft_view_t v, const char* __restrict__ chars,
+                                                                        const uint64_t* __restrict__ offs, size_t n_seq, double threshold,
+                                                                        int canonical, const uint32_t* __restrict__ class_rows, int rw,
+                                                                        int n_genomes, uint32_t* __restrict__ rows,
+                                                                        uint8_t* __restrict__ status) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int k = v.k;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    /* per-warp shared layout */
+    const int n_code_words = BFT_SEQ_SPAN / 32 + 2; /* 2 bits per base, +slack for the funnel */
+    const int n_mask_words = BFT_SEQ_SPAN / 64 + 2;
+    unsigned char* base = smem_raw + (size_t)warp * bft_seq_smem_per_warp(n_genomes);
+    uint64_t* codes = (uint64_t*)base;
+    uint64_t* m_iupac = codes + n_code_words;   /* class IUPAC or DOTDASH */
+    uint64_t* m_rcbad = m_iupac + n_mask_words; /* class DOTDASH or OTHER */
+    uint64_t* m_other = m_rcbad + n_mask_words; /* class OTHER */
+    uint64_t* m_nonpl = m_other + n_mask_words; /* lowercase acgt / U / u */
+    char* tile_chars = (char*)(m_nonpl + n_mask_words);
+    uint32_t* counts = (uint32_t*)(tile_chars + BFT_SEQ_SPAN);
+    const int n_counts = (n_genomes + 31) & ~31;
+
+    const size_t warp_stride = (size_t)gridDim.x * BFT_SEQ_WARPS;
+    for (size_t s = (size_t)blockIdx.x * BFT_SEQ_WARPS + warp; s < n_seq; s += warp_stride) {
+        const uint64_t o0 = offs[s], o1 = offs[s + 1];
+        const long long len = (long long)(o1 - o0);
+        const long long n_win = len - k + 1;
+        for (int g = lane; g < n_counts; g += 32) counts[g] = 0;
+        int bad = 0;
+        __syncwarp();
+        for (long long t0 = 0; t0 < n_win; t0 += BFT_SEQ_TILE) {
+            const int n_here = (int)(n_win - t0 < BFT_SEQ_TILE ? n_win - t0 : BFT_SEQ_TILE); /* windows in this tile */
+            const int n_chars = n_here + k - 1;
+            /* stage + encode: 32 characters per step */
+            for (int c0 = 0; c0 < BFT_SEQ_SPAN + 64; c0 += 32) {
+                const int ci = c0 + lane;
+                uint32_t code = 0, cls = BFT_CH_ACGT, nonplain = 0;
+                if (ci < n_chars) {
+                    const char ch = chars[o0 + (uint64_t)t0 + (uint64_t)ci];
+                    tile_chars[ci] = ch;
+                    bft_classify_char((unsigned char)ch, code, cls, nonplain);
+                }
+                const uint32_t b0 = __ballot_sync(0xffffffffu, code & 1u);
+                const uint32_t b1 = __ballot_sync(0xffffffffu, code >> 1);
+                const uint32_t bi = __ballot_sync(0xffffffffu, cls == BFT_CH_IUPAC || cls == BFT_CH_DOTDASH);
+                const uint32_t br = __ballot_sync(0xffffffffu, cls == BFT_CH_DOTDASH || cls == BFT_CH_OTHER);
+                const uint32_t bo = __ballot_sync(0xffffffffu, cls == BFT_CH_OTHER);
+                const uint32_t bn = __ballot_sync(0xffffffffu, nonplain);
+                if (lane == 0 && (c0 >> 5) < n_code_words) codes[c0 >> 5] = bft_spread32(b0) | (bft_spread32(b1) << 1);
+                if (lane == 1 && (c0 >> 6) < n_mask_words) {
+                    uint32_t* p;
+                    p = (uint32_t*)m_iupac; p[c0 >> 5] = bi;
+                    p = (uint32_t*)m_rcbad; p[c0 >> 5] = br;
+                    p = (uint32_t*)m_other; p[c0 >> 5] = bo;
+                    p = (uint32_t*)m_nonpl; p[c0 >> 5] = bn;
+                }
+            }
+            __syncwarp();
+            /* windows: lane handles j = lane, lane+32, ... (whole warp iterates together for the collectives) */
+            for (int j0 = 0; j0 < n_here; j0 += 32) {
+                const int j = j0 + lane;
+                uint32_t cls = BFT_CLS_NONE;
+                if (j < n_here) {
+                    const uint64_t wi = bft_extract_bits(m_iupac, j, k);
+                    const uint64_t wr = bft_extract_bits(m_rcbad, j, k);
+                    const uint64_t wo = bft_extract_bits(m_other, j, k);
+                    int skip = 0;
+                    if (canonical) {
+                        if (wr) bad = 1;
+                        if (wr || wi) skip = 1;
+                    } else {
+                        if (wi) skip = 1;
+                        else if (wo) { bad = 1; skip = 1; }
+                    }
+                    if (!skip) {
+                        uint64_t x[W];
+                        if (W == 1) {
+                            x[0] = bft_extract_bits(codes, 2 * j, 2 * k);
+                        } else {
+                            x[0] = bft_extract_bits(codes, 2 * j, 64);
+                            x[W - 1] = bft_extract_bits(codes, 2 * j + 64, 2 * k - 64);
+                        }
+                        if (canonical) {
+                            /* key(fwd) = R(x), key(rc) = ~x (masked); rc = ~R(x) (masked). strcmp(fwd, rc) >= 0 -> rc */
+                            uint64_t rx[W], nx[W];
+                            int use_rc;
+                            if (W == 1) {
+                                const uint64_t mask = (1ULL << (2 * k)) - 1ULL;
+                                rx[0] = bft_rev2_64(x[0]) >> (64 - 2 * k);
+                                nx[0] = ~x[0] & mask;
+                                use_rc = rx[0] >= nx[0];
+                                if (bft_extract_bits(m_nonpl, j, k)) { /* mixed case / U: ASCII order decides */
+                                    use_rc = 1;
+                                    for (int i = 0; i < k; i++) {
+                                        const char a = tile_chars[j + i], b = bft_rc_char(tile_chars[j + k - 1 - i]);
+                                        if (a != b) { use_rc = (unsigned char)a > (unsigned char)b; break; }
+                                    }
+                                }
+                                if (use_rc) x[0] = ~rx[0] & mask;
+                            } else {
+                                const int sh = 128 - 2 * k; /* 2..56 for 36 <= k <= 63 */
+                                const uint64_t hi = bft_rev2_64(x[0]), lo = bft_rev2_64(x[W - 1]); /* 128-bit reversal */
+                                rx[0] = (lo >> sh) | (hi << (64 - sh));
+                                rx[W - 1] = hi >> sh;
+                                const uint64_t mask_hi = (1ULL << (2 * k - 64)) - 1ULL;
+                                nx[0] = ~x[0];
+                                nx[W - 1] = ~x[W - 1] & mask_hi;
+                                use_rc = rx[W - 1] > nx[W - 1] || (rx[W - 1] == nx[W - 1] && rx[0] >= nx[0]);
+                                if (bft_extract_bits(m_nonpl, j, k)) {
+                                    use_rc = 1;
+                                    for (int i = 0; i < k; i++) {
+                                        const char a = tile_chars[j + i], b = bft_rc_char(tile_chars[j + k - 1 - i]);
+                                        if (a != b) { use_rc = (unsigned char)a > (unsigned char)b; break; }
+                                    }
+                                }
+                                if (use_rc) { x[0] = ~rx[0]; x[W - 1] = ~rx[W - 1] & mask_hi; }
+                            }
+                        }
+                        cls = bft_lookup_w(&v, x, W);
+                    }
+                }
+                /* merge windows with the same colour class, then bump the per-genome counters warp-wide */
+                const uint32_t active = __ballot_sync(0xffffffffu, cls != BFT_CLS_NONE);
+                if (active) {
+                    uint32_t grp = 0;
+                    if (cls != BFT_CLS_NONE) grp = __match_any_sync(active, cls);
+                    uint32_t leaders = __ballot_sync(0xffffffffu, cls != BFT_CLS_NONE && (__ffs(grp) - 1) == lane);
+                    while (leaders) {
+                        const int src = __ffs(leaders) - 1;
+                        leaders &= leaders - 1;
+                        const uint32_t c = __shfl_sync(0xffffffffu, cls, src);
+                        const uint32_t add = __popc(__shfl_sync(0xffffffffu, grp, src));
+                        const uint32_t* row = class_rows + (size_t)c * rw;
+                        for (int w = 0; w < rw; w++) {
+                            const uint32_t bits = __ldg(row + w);
+                            if ((bits >> lane) & 1u) counts[w * 32 + lane] += add;
+                        }
+                    }
+                }
+            }
+            __syncwarp();
+        }
+        /* threshold: count >= ceil(n_win * threshold) (src/bft.c:1279, 1327-1339) */
+        bad = __any_sync(0xffffffffu, bad);
+        long long need = 0;
+        if (n_win > 0) need = (long long)ceil((double)n_win * threshold);
+        for (int w = 0; w < rw; w++) {
+            const uint32_t cnt = counts[w * 32 + lane];
+            const uint32_t bits = __ballot_sync(0xffffffffu, n_win > 0 && cnt > 0 && (long long)cnt >= need);
+            if (lane == 0) rows[s * (size_t)rw + w] = bits;
+        }
+        if (lane == 0 && status) status[s] = bad ? 2 : (n_win <= 0 ? 1 : 0);
+        __syncwarp();
+    }
+}
+
+#endif /* BFT_KERNELS_CUH */

@@ -1,0 +1,143 @@
+/* bft_b200.h — C-ABI of the B200 batched query engine for Bloom Filter Tries.
+ *
+ * Plain C linkage, plain pointers and sizes; no torch or C++ types. One context = one .bft file flattened into
+ * device-resident arenas on one GPU. Every entry point cites the reference interface it stands in for
+ * (paths relative to the GuillaumeHolley/BloomFilterTrie tree). All query results are bit-exact with the
+ * reference's own query path on the same .bft and inputs.
+ *
+ * Conventions
+ *   - packed k-mers: W = bft_b200_kmer_words() little-endian uint64 per k-mer, nucleotide i at bits 2i
+ *     (A=0 C=1 G=2 T=3), i.e. the reference's byte layout (include/fasta.h:15, src/fasta.c:13-23) zero-padded to W
+ *     words; bits above 2k must be zero.
+ *   - colour rows: RW = bft_b200_row_words() uint32 per item, genome g = bit (g & 31) of word g >> 5. A row is the
+ *     reference's ascending id list (src/bft.c:622-641) as a bitmap; an absent k-mer has an all-zero row.
+ *   - every function returns BFT_B200_OK (0) or a negative status; bft_b200_last_error() gives the message of the
+ *     last failure on the calling thread. Where the reference would fprintf+exit(1) (include/useful_macros.h:33-43)
+ *     the batched calls return a status / per-item flag instead; the drop-in wrappers in bft_compat.h keep exit(1).
+ *   - "host" entry points take ordinary host pointers (pinned memory from bft_b200_host_alloc avoids a staging
+ *     copy) and include the host<->device transfers; "_device" entry points take pointers into this context's GPU
+ *     and only enqueue work on bft_b200_stream().
+ *   - there is no CPU fallback: without a usable CUDA device every call fails with BFT_B200_ERR_CUDA.
+ */
+#ifndef BFT_B200_H
+#define BFT_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define BFT_B200_OK 0
+#define BFT_B200_ERR_ARG (-1)    /* invalid argument */
+#define BFT_B200_ERR_FILE (-2)   /* cannot read / not a supported .bft file */
+#define BFT_B200_ERR_CUDA (-3)   /* CUDA runtime failure or no device */
+#define BFT_B200_ERR_NOMEM (-4)
+
+/* per-sequence status written by bft_b200_query_sequences */
+#define BFT_B200_SEQ_OK 0
+#define BFT_B200_SEQ_TOO_SHORT 1 /* shorter than k: all-zero row, as the reference (src/bft.c:1276-1277) */
+#define BFT_B200_SEQ_BAD_CHAR 2  /* a character the reference would exit(1) on (src/bft.c:239, src/fasta.c:431-434) */
+
+typedef struct bft_b200_ctx bft_b200_ctx;
+
+const char* bft_b200_last_error(void);
+
+/* load_BFT (include/bft.h:176, src/bft.c:1222 -> read_BFT_Root, src/write_to_disk.c:264-357) + the serializer:
+ * reads the .bft file, flattens the trie into SoA arenas, uploads them to `device`, and decodes every distinct
+ * colour annotation on the GPU (get_id_genomes_from_annot, src/annotation.c:2086-2250). */
+int bft_b200_open(const char* bft_path, int device, bft_b200_ctx** out);
+/* free_cdbg (include/bft.h:63) */
+void bft_b200_close(bft_b200_ctx* ctx);
+
+/* BFT_Root fields (include/Node.h:96-122): k, nb_genomes, filenames */
+int bft_b200_k(const bft_b200_ctx* ctx);
+int bft_b200_n_genomes(const bft_b200_ctx* ctx);
+const char* bft_b200_genome_name(const bft_b200_ctx* ctx, int i);
+int bft_b200_kmer_words(const bft_b200_ctx* ctx); /* W */
+int bft_b200_row_words(const bft_b200_ctx* ctx);  /* RW = ceil(nb_genomes / 32) */
+int bft_b200_device(const bft_b200_ctx* ctx);
+void* bft_b200_stream(const bft_b200_ctx* ctx);   /* cudaStream_t the _device calls enqueue on */
+
+/* arena statistics (what printMemoryUsedFromNode reports for the pointer structure, src/printMemory.c:68-254) */
+typedef struct {
+    uint64_t n_kmers, n_nodes, n_ccs, n_lines, n_prefixes, n_classes, arena_bytes, class_row_bytes;
+    int max_cc_per_node, max_depth, n_pools;
+    double flatten_seconds, upload_seconds, decode_seconds;
+} bft_b200_stats;
+int bft_b200_get_stats(const bft_b200_ctx* ctx, bft_b200_stats* out);
+
+/* pinned host memory for the host entry points */
+void* bft_b200_host_alloc(size_t bytes);
+void bft_b200_host_free(void* p);
+
+/* ---- k-mer membership + colours -------------------------------------------------------------------------------
+ * Batch form of get_kmer + is_kmer_in_cdbg + get_annotation + get_list_id_genomes (include/bft.h:125,126,97,115;
+ * src/bft.c:216-248, 363-387, 622-641), i.e. the per-k-mer body of queryBFT_kmerPresences_from_KmerFiles
+ * (src/file_io.c:732-752, 810-834). present[i] = 1/0; rows (n*RW) and class_ids (n) may be NULL.
+ * class_ids[i] = index of the k-mer's distinct annotation (0xffffffff if absent); see bft_b200_class_rows. */
+int bft_b200_query_kmers(bft_b200_ctx* ctx, const uint64_t* kmers, size_t n, uint8_t* present, uint32_t* rows,
+                         uint32_t* class_ids);
+int bft_b200_query_kmers_device(bft_b200_ctx* ctx, const uint64_t* d_kmers, size_t n, uint8_t* d_present,
+                                uint32_t* d_rows, uint32_t* d_class_ids);
+/* ASCII input, n k-mers of exactly k characters each, back to back: parseKmerCount (src/fasta.c:3-53) on the GPU.
+ * valid[i] = 0 for a k-mer with a non-ACGTU character (the reference drops such lines, src/file_io.c:786-862);
+ * its present/rows are zero. */
+int bft_b200_query_kmers_ascii(bft_b200_ctx* ctx, const char* ascii, size_t n, uint8_t* valid, uint8_t* present,
+                               uint32_t* rows, uint32_t* class_ids);
+/* the decoded class table: n_classes * RW words, row c = colour set of class c (host copy owned by ctx) */
+int bft_b200_class_rows(bft_b200_ctx* ctx, const uint32_t** rows, uint64_t* n_classes);
+/* get_count_id_genomes (include/bft.h:116): number of genomes per class (host copy owned by ctx) */
+int bft_b200_class_counts(bft_b200_ctx* ctx, const uint32_t** counts, uint64_t* n_classes);
+
+/* ---- sequences ------------------------------------------------------------------------------------------------
+ * Batch form of query_sequence (include/bft.h:127, src/bft.c:1241-1351) / query_sequences_outputCSV
+ * (src/file_io.c:1464-1574): sequence i = chars[offs[i] .. offs[i+1]). For every window: optional canonical pick
+ * (reverse_complement + strcmp, src/bft.c:1287-1293), IUPAC windows skipped (src/fasta.c:357-363), lookup, colour
+ * decode, per-genome hit count; genome g is reported iff count >= ceil(n_windows * threshold) (double arithmetic,
+ * src/bft.c:1279). rows: n_seq*RW. status (may be NULL): BFT_B200_SEQ_*. 0 < threshold <= 1 (src/bft.c:1246-1247). */
+int bft_b200_query_sequences(bft_b200_ctx* ctx, const char* chars, const uint64_t* offs, size_t n_seq,
+                             double threshold, int canonical, uint32_t* rows, uint8_t* status);
+int bft_b200_query_sequences_device(bft_b200_ctx* ctx, const char* d_chars, const uint64_t* d_offs, size_t n_seq,
+                                    double threshold, int canonical, uint32_t* d_rows, uint8_t* d_status);
+
+/* ---- branching ------------------------------------------------------------------------------------------------
+ * Batch form of isBranchingRight / isBranchingLeft (src/branchingNode.c:16-110, 240-413) as driven by
+ * queryBFT_kmerBranching_from_KmerFiles (src/file_io.c:897-1020): succ[i] / pred[i] = number of successors /
+ * predecessors of k-mer i present in the graph (0..4); *n_branching = #{i : succ[i] > 1 or pred[i] > 1}.
+ * succ, pred and n_branching may each be NULL. */
+int bft_b200_query_branching(bft_b200_ctx* ctx, const uint64_t* kmers, size_t n, uint8_t* succ, uint8_t* pred,
+                             uint64_t* n_branching);
+int bft_b200_query_branching_device(bft_b200_ctx* ctx, const uint64_t* d_kmers, size_t n, uint8_t* d_succ,
+                                    uint8_t* d_pred, uint64_t* d_n_branching);
+/* Batch form of get_neighbors (include/bft.h:156, src/bft.c:804-886): neighbour_classes[8*i + j] = colour class of
+ * neighbour j of k-mer i, or 0xffffffff if that neighbour is not in the graph; j = 0..3 predecessors (A,C,G,T
+ * prepended), 4..7 successors (A,C,G,T appended) — the reference's order. Host pointers. */
+int bft_b200_query_neighbors(bft_b200_ctx* ctx, const uint64_t* kmers, size_t n, uint32_t* neighbour_classes);
+/* Successor lookups follow the reference bit for bit by default, including its behaviour at the leaf level of deep
+ * tries (presenceNeighborsRight clears nucleotide 7 of the last 9-nt prefix before probing the CCs,
+ * src/presenceNode.c:719-723, so there it reports the successors of a neighbouring k-mer). exact != 0 keeps that;
+ * exact == 0 switches to plain set membership of the four successors. */
+int bft_b200_set_reference_exact_branching(bft_b200_ctx* ctx, int exact);
+
+/* ---- file-level drivers (the CLI-visible bytes) ---------------------------------------------------------------
+ * queryBFT_kmerPresences_from_KmerFiles (src/file_io.c:651-895): CSV of colour rows; returns #present via out.
+ * queryBFT_kmerBranching_from_KmerFiles (src/file_io.c:897-1020): count of branching k-mers.
+ * query_sequences_outputCSV (src/file_io.c:1464-1574). */
+int bft_b200_query_kmers_file(bft_b200_ctx* ctx, const char* query_path, int binary_file, const char* csv_path,
+                              uint64_t* n_present);
+int bft_b200_query_branching_file(bft_b200_ctx* ctx, const char* query_path, int binary_file, uint64_t* n_branching);
+int bft_b200_query_sequences_file(bft_b200_ctx* ctx, const char* query_path, const char* csv_path, double threshold,
+                                  int canonical);
+
+/* wait for everything enqueued on the context's streams */
+int bft_b200_sync(bft_b200_ctx* ctx);
+
+/* number of kernels this context has launched (bench.py's gpu_launches) */
+uint64_t bft_b200_launch_count(const bft_b200_ctx* ctx);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* BFT_B200_H */

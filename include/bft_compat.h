@@ -1,0 +1,94 @@
+/* bft_compat.h — source-level drop-in for the QUERY subset of the reference's public API (include/bft.h).
+ *
+ * Same names, argument meaning, ownership and error behaviour as the reference (fprintf(stderr)+exit(1) on the
+ * conditions where the reference calls ERROR(), include/useful_macros.h:33-43), implemented as batch-of-one /
+ * batch-of-eight calls into the GPU engine (include/bft_b200.h). Graph construction and mutation
+ * (create_cdbg, insert_*, marking, iteration, set algebra, write_BFT) stay on the reference host library and
+ * are not declared here. Do not include the reference's bft.h in the same translation unit.
+ *
+ * Reference declarations replaced (include/bft.h): load_BFT :176, free_cdbg :63, get_kmer :125,
+ * is_kmer_in_cdbg :126, query_sequence :127, get_annotation :97, presence_genome :98, get_list_id_genomes :115,
+ * get_count_id_genomes :116, free_BFT_annotation :96, create_kmer/free_BFT_kmer/free_BFT_kmer_content :78-82,
+ * set/unset_neighbors_traversal :154-155, get_neighbors/get_predecessors/get_successors :156-158; and the
+ * file-level drivers of include/file_io.h (queryBFT_kmerPresences_from_KmerFiles, queryBFT_kmerBranching_from_KmerFiles,
+ * query_sequences_outputCSV).
+ */
+#ifndef BFT_COMPAT_H
+#define BFT_COMPAT_H
+
+#include <stdbool.h>
+#include <stdint.h>
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+struct bft_b200_ctx;
+
+/* BFT_Root (include/Node.h:96-122): the documented public fields, then the engine handle. */
+typedef struct {
+    char** filenames; /* inserted genome file names */
+    int k;            /* size of k-mers */
+    int nb_genomes;   /* number of genomes inserted */
+    struct bft_b200_ctx* engine;
+} BFT_Root;
+typedef BFT_Root BFT;
+
+/* resultPresence (include/Node.h:61-89) holds raw pointers into the host trie in the reference; here it is the
+ * device-side locator of the k-mer: presence + colour class. Treat as opaque, as reference users do. */
+typedef struct {
+    uint32_t present;
+    uint32_t class_id;
+    BFT* bft;
+} resultPresence;
+
+typedef struct {
+    char* kmer;          /* ASCII null-terminated k-mer */
+    uint8_t* kmer_comp;  /* 2 bits encoded form */
+    resultPresence* res;
+} BFT_kmer;
+
+typedef struct {
+    uint8_t* annot;      /* not materialised on the host (the colour class below identifies the set) */
+    uint8_t* annot_ext;
+    uint8_t* annot_cplx;
+    int size_annot;
+    int size_annot_cplx;
+    uint8_t from_BFT;
+    uint32_t class_id;
+} BFT_annotation;
+
+BFT* load_BFT(char* filename);
+void free_cdbg(BFT* bft);
+
+BFT_kmer* create_kmer(const char* kmer, int k);
+BFT_kmer* create_empty_kmer(void);
+void free_BFT_kmer(BFT_kmer* bft_kmer, int nb_bft_kmer);
+void free_BFT_kmer_content(BFT_kmer* bft_kmer, int nb_bft_kmer);
+
+BFT_kmer* get_kmer(const char* kmer, BFT* bft);
+bool is_kmer_in_cdbg(BFT_kmer* bft_kmer);
+uint32_t* query_sequence(BFT* bft, char* sequence, double threshold, bool canonical_search);
+
+BFT_annotation* create_BFT_annotation(void);
+void free_BFT_annotation(BFT_annotation* bft_annot);
+BFT_annotation* get_annotation(BFT_kmer* bft_kmer);
+bool presence_genome(uint32_t id_genome, BFT_annotation* bft_annot, BFT* bft);
+uint32_t* get_list_id_genomes(BFT_annotation* bft_annot, BFT* bft);
+uint32_t get_count_id_genomes(BFT_annotation* bft_annot, BFT* bft);
+
+void set_neighbors_traversal(BFT* bft);
+void unset_neighbors_traversal(BFT* bft);
+BFT_kmer* get_neighbors(BFT_kmer* bft_kmer, BFT* bft);
+BFT_kmer* get_predecessors(BFT_kmer* bft_kmer, BFT* bft);
+BFT_kmer* get_successors(BFT_kmer* bft_kmer, BFT* bft);
+
+int queryBFT_kmerPresences_from_KmerFiles(BFT_Root* root, char* query_filename, int binary_file, char* output_filename);
+int queryBFT_kmerBranching_from_KmerFiles(BFT_Root* root, char* query_filename, int binary_file);
+void query_sequences_outputCSV(BFT_Root* root, char* query_filename, char* output_filename, double threshold, bool canonical_search);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,152 @@
+"""Parity of the CUDA path (through the C-ABI) against the reference's own query path (oracle/_ref), bit-exact:
+presence bits, colour rows, branching answers and threshold calls on the same .bft and the same inputs."""
+import os
+
+import numpy as np
+import pytest
+
+from bloomfiltertrie_b200 import synth
+import cases
+import refutil
+
+pytestmark = pytest.mark.gpu
+
+THRESHOLDS = [0.8, 0.5, 1.0, 0.3, 1e-6]
+
+
+@pytest.fixture(scope="module")
+def engine_mod():
+    from bloomfiltertrie_b200 import engine
+    return engine
+
+
+@pytest.fixture(scope="module", params=list(cases.CASES))
+def built(request, workdir, engine_mod):
+    if not refutil.have_ref():
+        pytest.skip("oracle/_ref (compiled reference) not present; golden-fixture tests cover parity")
+    c = cases.make_case(request.param)
+    path = refutil.build_bft(workdir, c["name"], c["genome_words"], c["k"])
+    eng = engine_mod.BFTEngine(path)
+    yield c, path, eng
+    eng.close()
+
+
+def test_kmer_presence_and_colours(built):
+    c, path, eng = built
+    q = c["queries"]
+    ref_present, ref_rows = refutil.ref_kmers(path, q, c["k"], c["n_genomes"])
+    present, rows, cls = eng.query_kmers(q, want_rows=True, want_classes=True)
+    assert ref_present.sum() > 0 and (ref_present == 0).sum() > 0
+    np.testing.assert_array_equal(present, ref_present)
+    np.testing.assert_array_equal(rows, ref_rows)
+    # class ids are consistent with rows and counts
+    table = eng.class_rows()
+    counts = eng.class_counts()
+    hit = present.astype(bool)
+    assert (cls[~hit] == 0xFFFFFFFF).all()
+    np.testing.assert_array_equal(table[cls[hit]], rows[hit])
+    pop = np.unpackbits(rows[hit].view(np.uint8), axis=1).sum(axis=1)
+    np.testing.assert_array_equal(counts[cls[hit]], pop)
+
+
+def test_kmer_ascii_input(built):
+    c, path, eng = built
+    q = c["queries"][:2000]
+    asc = synth.words_to_ascii(q, c["k"]).copy()
+    asc[5, 3] = ord("N")        # invalid k-mer: dropped by the reference, flagged here
+    asc[7] = np.char.lower(asc[7].view("S1")).view(np.uint8)
+    valid, present, rows = eng.query_kmers_ascii(asc.tobytes())
+    p2, r2, _ = eng.query_kmers(q)
+    assert valid[5] == 0 and present[5] == 0 and not rows[5].any()
+    ok = np.ones(len(q), bool)
+    ok[5] = False
+    assert valid[ok].all()
+    np.testing.assert_array_equal(present[ok], p2[ok])
+    np.testing.assert_array_equal(rows[ok], r2[ok])
+
+
+def test_branching(built):
+    c, path, eng = built
+    if c["k"] == 9:
+        pytest.skip("the reference itself segfaults on -query_branching at k=9 (root level == leaf level)")
+    q = c["queries"][:4000]
+    ref_succ, ref_pred = refutil.ref_branching(path, q, c["k"])
+    succ, pred, count = eng.query_branching(q)
+    np.testing.assert_array_equal(succ, ref_succ)
+    np.testing.assert_array_equal(pred, ref_pred)
+    assert count == int(((ref_succ > 1) | (ref_pred > 1)).sum())
+    # get_neighbors order: 0-3 predecessors, 4-7 successors; counts must agree with the per-neighbour classes
+    nb = eng.query_neighbors(q[:500])
+    np.testing.assert_array_equal((nb[:, :4] != 0xFFFFFFFF).sum(axis=1), ref_pred[:500])
+    np.testing.assert_array_equal((nb[:, 4:] != 0xFFFFFFFF).sum(axis=1), ref_succ[:500])
+
+
+def test_branching_set_semantics_mode(built):
+    """exact=False: successors/predecessors by plain membership of the 8 neighbour k-mers (what the reference
+    computes everywhere except at the leaf level of deep tries)."""
+    c, path, eng = built
+    k = c["k"]
+    q = c["queries"][:1500]
+    allw = np.unique(np.concatenate(c["genome_words"]), axis=0)
+    two = q.shape[1] > 1
+    members = set((int(r[0]) | (int(r[1]) << 64 if two else 0)) for r in allw)
+    mask = (1 << (2 * k)) - 1
+    ints = [int(r[0]) | (int(r[1]) << 64 if two else 0) for r in q]
+
+    def has(x):
+        return x in members
+
+    exp_succ = np.array([sum(has((x >> 2) | (cc << (2 * (k - 1)))) for cc in range(4)) for x in ints], dtype=np.uint8)
+    exp_pred = np.array([sum(has(((x << 2) & mask) | cc) for cc in range(4)) for x in ints], dtype=np.uint8)
+    eng.set_reference_exact_branching(False)
+    try:
+        succ, pred, _ = eng.query_branching(q)
+    finally:
+        eng.set_reference_exact_branching(True)
+    np.testing.assert_array_equal(succ, exp_succ)
+    np.testing.assert_array_equal(pred, exp_pred)
+
+
+@pytest.mark.parametrize("canonical", [False, True])
+def test_sequences_threshold(built, canonical):
+    c, path, eng = built
+    seqs = c["seqs"]
+    for thr in THRESHOLDS:
+        ref_rows = refutil.ref_sequences(path, seqs, thr, canonical, c["n_genomes"])
+        rows, status = eng.query_sequence_list(seqs, thr, canonical)
+        assert (status != 2).all()
+        short = np.array([len(s) < c["k"] for s in seqs])
+        np.testing.assert_array_equal(status == 1, short)
+        np.testing.assert_array_equal(rows, ref_rows, err_msg=f"thr={thr} canonical={canonical}")
+
+
+def test_file_drivers_match_reference_cli(built, workdir):
+    c, path, eng = built
+    d = os.path.join(workdir, c["name"], "cli")
+    os.makedirs(d, exist_ok=True)
+    k = c["k"]
+    qk = os.path.join(d, "queries.kc")
+    synth.write_kmers_comp(qk, c["queries"][:3000], k)
+    qt = os.path.join(d, "queries_txt.txt")
+    synth.write_kmers_text(qt, c["queries"][:1000], k)
+    qs = os.path.join(d, "reads.txt")
+    with open(qs, "wb") as f:
+        f.write(b"\n".join(c["seqs"]) + b"\n")
+    for name, p in (("lk", qk), ("lt", qt), ("ls", qs)):
+        with open(os.path.join(d, name), "w") as f:
+            f.write(p + "\n")
+    out = refutil.ref_cli(path, ["-query_kmers", "kmers_comp", os.path.join(d, "lk"),
+                                 "-query_kmers", "kmers", os.path.join(d, "lt"),
+                                 "-query_sequences", "0.8", "canonical" if c["canonical"] else "non_canonical", os.path.join(d, "ls")]
+                          + (["-query_branching", "kmers_comp", os.path.join(d, "lk")] if k > 9 else []), cwd=d)
+    n_present = eng.query_kmers_file(qk, True, os.path.join(d, "mine_k.csv"))
+    eng.query_kmers_file(qt, False, os.path.join(d, "mine_t.csv"))
+    eng.query_sequences_file(qs, os.path.join(d, "mine_s.csv"), 0.8, c["canonical"])
+    n_branching = eng.query_branching_file(qk, True)
+    assert open(os.path.join(d, "mine_k.csv"), "rb").read() == open(os.path.join(d, "queries.csv"), "rb").read()
+    assert open(os.path.join(d, "mine_t.csv"), "rb").read() == open(os.path.join(d, "queries_txt.csv"), "rb").read()
+    assert open(os.path.join(d, "mine_s.csv"), "rb").read() == open(os.path.join(d, "reads.csv"), "rb").read()
+    counts = [int(x) for x in __import__("re").findall(r"Nb k-mers present = (\d+)", out)]
+    assert counts[0] == n_present
+    if k > 9:
+        assert refutil.parse_count(out, "Nb branching k-mers") == n_branching
