@@ -1,0 +1,358 @@
+#!/usr/bin/env python
+"""bench.py — k-mers queried/sec on the 100-genome synthetic pan-genome BFT (BASELINE.json metric, config[2];
+k=27 stands in for "k=31": the reference only accepts k divisible by 9).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W]          engine arm (one process per GPU; torchrun for N>1)
+  python bench.py --impl reference [...]                       reference arm: the unmodified reference's CPU query
+                                                               path (oracle/_ref) on the box's host cores
+A step = one pass of the hot path (k-mer membership + colour rows) over one batch of synthetic queries per GPU.
+`value` is measured with the batch already resident in HBM; `e2e` goes through the host C-ABI call with pinned host
+buffers, host<->device copies inside the timed region. Prints ONE JSON line on rank 0.
+"""
+import argparse
+import json
+import os
+import re
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "kmers_queried_per_sec"
+UNIT = "k-mers/s"
+K = 27
+DEFAULT_LEN = 5_000_000
+FALLBACK_LEN = 200_000  # built on the fly with the reference when no prebuilt BFT travelled with the repo
+MIX = (0.5, 0.25, 0.25)
+
+
+def log(*a):
+    print("[bench]", *a, file=sys.stderr, flush=True)
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md clocks line)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index=0):
+        self.index = index
+        self.rows = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                                          "-i", str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._pump, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.rows.append((time.time(), line.strip()))
+
+    def stop(self, t0, t1):
+        if not self.proc:
+            return None
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for t, line in self.rows:
+            if t < t0 or t > t1 + 0.2:
+                continue
+            f = [x.strip() for x in line.split(",")]
+            try:
+                sm.append(float(f[1]))
+                mx.append(float(f[2]))
+            except Exception:
+                continue
+            for nme, v in zip(names, f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(nme)
+        if not sm:
+            for t, line in self.rows[-3:]:
+                f = [x.strip() for x in line.split(",")]
+                try:
+                    sm.append(float(f[1]))
+                    mx.append(float(f[2]))
+                except Exception:
+                    pass
+        if not sm:
+            return None
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": max(mx), "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def pick_workload(args):
+    from bloomfiltertrie_b200 import workloads as wl
+    cfg = wl.C3
+    if args.genome_len:
+        L = args.genome_len
+    else:
+        have = wl.available_lengths(cfg, K)
+        L = DEFAULT_LEN if DEFAULT_LEN in have else (max(have) if have else FALLBACK_LEN)
+    return cfg, L
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def ncu_traffic():
+    """dram bytes per launch of the dominant kernel from the committed ncu --set full capture, if any."""
+    p = os.path.join(ROOT, "profiles", "ncu_k_query_kmers.json")
+    if os.path.exists(p):
+        try:
+            return json.load(open(p)).get("dram_bytes_per_kmer")
+        except Exception:
+            return None
+    return None
+
+
+def write_query_file(path, q_np, k):
+    from bloomfiltertrie_b200 import synth
+    import numpy as np
+    synth.write_kmers_comp(path, q_np.view(np.uint64), k)
+
+
+def run_reference_harness(bft, qfile, threads, passes):
+    from bloomfiltertrie_b200 import workloads as wl
+    out = qfile + ".out"
+    p = subprocess.run([wl.REF_HARNESS, "kmers", bft, qfile, out, str(threads), str(passes)], stdout=subprocess.PIPE,
+                       stderr=subprocess.STDOUT, text=True)
+    if os.path.exists(out):
+        os.remove(out)
+    if p.returncode != 0:
+        raise RuntimeError("ref_harness failed: " + p.stdout[-1000:])
+    return [float(x) for x in re.findall(r"REF_PASS \d+ seconds=([0-9.]+)", p.stdout)]
+
+
+def reference_arm(args):
+    """The reference's own CPU implementation of the path (isKmerPresent + get_annotation + get_list_id_genomes under
+    OpenMP, one copy_BFT_Root per thread) on all host cores, each step a bounded sample of the workload."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import torch
+    from bloomfiltertrie_b200 import workloads as wl
+    cfg, L = pick_workload(args)
+    genomes = wl.pangenome(cfg, L)
+    bft = wl.ensure_bft(cfg, K, L, genomes)
+    cores = os.cpu_count() or 1
+    n = args.ref_sample
+    cat, starts, lens = wl.genomes_to_torch(genomes, torch.device("cpu"))
+    q = wl.gen_kmer_queries(cat, starts, lens, K, n, seed=777, mix=MIX).numpy()
+    qfile = os.path.join("/tmp", f"bft_bench_ref_{os.getpid()}.kc")
+    write_query_file(qfile, q, K)
+    secs = run_reference_harness(bft, qfile, cores, args.warmup + args.steps)
+    os.remove(qfile)
+    timed = secs[args.warmup:]
+    ms = 1e3 * sum(timed) / len(timed)
+    value = n / (ms / 1e3)
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "u64", "data": "synthetic",
+            "config": {"workload": f"{cfg['name']}_k{K}: -query_kmers on a {cfg['n_genomes']}-genome synthetic pan-genome BFT",
+                       "k": K, "n_genomes": cfg["n_genomes"], "genome_len": L, "query_mix_present_mismatch_random": MIX},
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "reference",
+                             "sample": f"{n} k-mers per step (same generator and mix as the GPU batch), all {cores} host threads"},
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+def engine_arm(args):
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    from bloomfiltertrie_b200 import engine as E
+    from bloomfiltertrie_b200 import workloads as wl
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the engine has no CPU fallback (use --impl reference for the CPU reference)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    cfg, L = pick_workload(args)
+    t0 = time.time()
+    genomes = wl.pangenome(cfg, L)
+    if rank == 0:
+        bft = wl.ensure_bft(cfg, K, L, genomes)
+    if world > 1:
+        dist.barrier()
+    bft = wl.bft_path(cfg, K, L)
+    eng = E.BFTEngine(bft, device=local)
+    st = eng.stats()
+    if rank == 0:
+        log(f"arena: {st['n_kmers']} k-mers, {st['n_nodes']} nodes, {st['n_ccs']} CCs, {st['n_classes']} colour classes, "
+            f"{st['arena_bytes'] / 1e6:.0f} MB (+{st['class_row_bytes'] / 1e6:.0f} MB class rows); flatten {st['flatten_seconds']:.1f}s "
+            f"upload {st['upload_seconds']:.1f}s decode {st['decode_seconds']:.3f}s; setup {time.time() - t0:.1f}s")
+    n = args.queries_per_gpu
+    cat, starts, lens = wl.genomes_to_torch(genomes, dev)
+    q = wl.gen_kmer_queries(cat, starts, lens, K, n, seed=1000 + rank, mix=MIX)
+    del cat
+    torch.cuda.empty_cache()
+    RW, W = eng.RW, eng.W
+    d_present = torch.empty(n, dtype=torch.uint8, device=dev)
+    d_rows = torch.empty((n, RW), dtype=torch.int32, device=dev)
+    d_cls = torch.empty(n, dtype=torch.int32, device=dev)
+    es = torch.cuda.ExternalStream(eng.stream, device=dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def step():
+        eng.query_kmers_device(q, n, d_present, d_rows, d_cls)
+        if world > 1:  # the only exchange the path has: a summary of each rank's results (no data-path collective)
+            with torch.cuda.stream(es):
+                s = d_present.sum(dtype=torch.int64).reshape(1)
+                dist.all_reduce(s)
+
+    # ---- timed region: K steps, inputs resident in HBM (batch of n*8*W bytes >> 126 MB L2, so no L2 flush needed)
+    for _ in range(args.warmup):
+        step()
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+        time.sleep(0.3)
+    launches0 = eng.launch_count()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    tw0 = time.time()
+    ev0.record(es)
+    for _ in range(args.steps):
+        step()
+    ev1.record(es)
+    barrier()
+    tw1 = time.time()
+    ms_total = ev0.elapsed_time(ev1)
+    launches = eng.launch_count() - launches0
+    clocks = sampler.stop(tw0, tw1) if rank == 0 else None
+    t = torch.tensor([ms_total], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_step = float(t.item()) / args.steps
+    value = n * world / (ms_step / 1e3)
+    n_present = int(d_present.sum().item())
+
+    # ---- dominant kernel alone (k_query_kmers: walk -> presence + class id), CUDA events on its own stream
+    kms = []
+    for i in range(args.warmup + args.steps):
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record(es)
+        eng.query_kmers_device(q, n, d_present, None, d_cls)
+        b.record(es)
+        b.synchronize()
+        if i >= args.warmup:
+            kms.append(a.elapsed_time(b))
+    k_ms = sum(kms) / len(kms)
+    ws = eng.kmer_walk_stats_device(q, n)
+    nodes_pk, depth_pk, found_pk = ws["nodes"] / n, ws["search_depth"] / n, ws["found"] / n
+    # A_min per k-mer: key words in + (presence byte + class id) out + 32-byte sectors the walk must
+    # touch: 6 per Node probed, ceil(log2(lines+1)) per suffix search, 1 for the annotation of a found k-mer
+    a_min = 8 * W + (1 + 4) + 32.0 * (6 * nodes_pk + depth_pk + found_pk)
+    achieved = a_min * n / (k_ms / 1e3) / 1e9
+    peak, peak_src = peaks()
+    traffic = ncu_traffic()
+    roofline = {"bound": "hbm", "kernel": "k_query_kmers", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                "traffic": (traffic * n if traffic else None), "peak_source": peak_src, "kernel_ms": k_ms,
+                "kmers_per_sec_kernel": n / (k_ms / 1e3), "a_min_bytes_per_kmer": a_min,
+                "nodes_per_kmer": nodes_pk, "search_depth_per_kmer": depth_pk, "found_frac": found_pk}
+
+    # ---- e2e: host C-ABI call with pinned host buffers, copies inside the timed region
+    e2e = None
+    if not args.no_e2e:
+        hq = E.PinnedBuffer((n, W), np.uint64)
+        hp = E.PinnedBuffer((n,), np.uint8)
+        hr = E.PinnedBuffer((n, RW), np.uint32)
+        hq.array[:] = q.cpu().numpy().view(np.uint64)
+        for _ in range(max(1, args.warmup - 1)):
+            eng.query_kmers(hq.array, out_present=hp.array, out_rows=hr.array)
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            eng.query_kmers(hq.array, out_present=hp.array, out_rows=hr.array)
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        tt = torch.tensor([dt], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        e2e_ms = float(tt.item()) / args.steps * 1e3
+        assert int(hp.array.sum()) == n_present, "e2e and device-resident paths disagree"
+        e2e = {"value": n * world / (e2e_ms / 1e3), "unit": UNIT, "h2d_bytes_per_step": n * W * 8 * world,
+               "d2h_bytes_per_step": n * (1 + 4 * RW) * world, "ms_per_step": e2e_ms,
+               "api": "bft_b200_query_kmers (host pointers, pinned)"}
+        hq.free(); hp.free(); hr.free()
+
+    # ---- CPU baseline beside it: the unmodified reference on a bounded sample (rank 0, N=1 only)
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline and os.access(wl.REF_HARNESS, os.X_OK):
+        cores = os.cpu_count() or 1
+        ns = min(args.ref_sample, n)
+        qfile = os.path.join("/tmp", f"bft_bench_cpu_{os.getpid()}.kc")
+        write_query_file(qfile, q[:ns].cpu().numpy(), K)
+        secs = run_reference_harness(bft, qfile, cores, 2)
+        os.remove(qfile)
+        cpu = {"value": ns / min(secs), "unit": UNIT, "cores": cores, "kind": "reference",
+               "sample": f"first {ns} k-mers of the GPU batch; isKmerPresent+get_annotation+get_list_id_genomes, OpenMP over "
+                         f"{cores} threads with one copy_BFT_Root each; best of 2 passes"}
+
+    if rank == 0:
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+                "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u64",
+                "data": "synthetic",
+                "config": {"workload": f"{cfg['name']}_k{K}: -query_kmers (presence + colour rows) on a {cfg['n_genomes']}-genome "
+                                       f"synthetic pan-genome BFT built by the reference",
+                           "k": K, "k_note": "reference accepts only k % 9 == 0; 27 stands in for 31", "n_genomes": cfg["n_genomes"],
+                           "genome_len": L, "kmers_in_bft": st["n_kmers"], "colour_classes": st["n_classes"],
+                           "arena_mb": round(st["arena_bytes"] / 1e6, 1), "queries_per_gpu": n,
+                           "query_mix_present_mismatch_random": MIX, "present_frac": n_present / n,
+                           "l2": "inputs larger than L2 (no flush needed)", "sharding": f"arena replicated, queries sharded x{world}"},
+                "clocks": clocks, "e2e": e2e, "gpu_launches": launches * world, "roofline": roofline, "cpu_baseline": cpu}
+        print(json.dumps(line), flush=True)
+    eng.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="engine", choices=["engine", "reference"])
+    ap.add_argument("--genome-len", type=int, default=0, help="override the genome length of the 100-genome pan-genome")
+    ap.add_argument("--queries-per-gpu", type=int, default=125_000_000)
+    ap.add_argument("--ref-sample", type=int, default=1 << 24, help="k-mers per step of the CPU reference legs")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.warmup < 3:
+        args.warmup = 3
+    if args.impl == "reference":
+        reference_arm(args)
+    else:
+        engine_arm(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -240,33 +240,50 @@ BFT_HD void bft_shift18(uint64_t* cur, int W) {
 /* Full lookup: the reference's isKmerPresent (src/presenceNode.c:1823-1921).
  * kmer: W words (bits above 2k must be zero). Returns the colour class of the k-mer, or BFT_CLS_NONE if absent.
  * W is passed explicitly so device callers can make it a compile-time constant. */
-BFT_HD uint32_t bft_lookup_ex(const bft_view_t* v, const uint64_t* kmer, const int W, const int succ_leaf_quirk) {
+/* st (optional, NULL on the product path): walk statistics for the roofline accounting of SURVEY.md §8(d) —
+ * st[0] += Nodes probed, st[1] += sum of ceil(log2(lines+1)) over the line searches, st[2] += 1 if found. */
+BFT_HD uint32_t bft_ceil_log2p1(uint32_t n) { /* ceil(log2(n + 1)) */
+    uint32_t b = 0;
+    while ((1u << b) < n + 1u) b++;
+    return b;
+}
+
+BFT_HD uint32_t bft_lookup_ex(const bft_view_t* v, const uint64_t* kmer, const int W, const int succ_leaf_quirk, uint32_t* st) {
     uint64_t cur[BFT_MAX_WORDS];
     for (int w = 0; w < BFT_MAX_WORDS; w++) cur[w] = w < W ? kmer[w] : 0;
     int sz = v->k;
     bft_entry_t e = bft_ld_entry(v->rootdir + ((uint32_t)cur[0] & (BFT_ROOTDIR_SIZE - 1u)));
+    if (st) st[0]++;
     for (;;) {
         const uint32_t kind = e.b >> BFT_KIND_SHIFT;
         const uint32_t n = e.b & BFT_CNT_MASK;
         if (kind == BFT_KIND_ABSENT) return BFT_CLS_NONE;
-        if (kind == BFT_KIND_LEAF) return e.a;
+        if (kind == BFT_KIND_LEAF) {
+            if (st) st[2]++;
+            return e.a;
+        }
         if (kind == BFT_KIND_UC) {
             if (n == 0) return BFT_CLS_NONE;
+            if (st) st[1] += bft_ceil_log2p1(n);
             const uint32_t ln = bft_search_lines(v, e.a, n, cur, W);
+            if (st && ln != 0xffffffffu) st[2]++;
             return ln == 0xffffffffu ? BFT_CLS_NONE : BFT_LD32(v->linecls + ln);
         }
         bft_shift18(cur, W);
         sz -= BFT_NB_CHAR_SUF_PREF;
         if (kind == BFT_KIND_INLINE) {
+            if (st) st[1] += bft_ceil_log2p1(n);
             const uint32_t ln = bft_search_lines(v, e.a, n, cur, W);
+            if (st && ln != 0xffffffffu) st[2]++;
             return ln == 0xffffffffu ? BFT_CLS_NONE : BFT_LD32(v->linecls + ln);
         }
         /* BFT_KIND_NODE */
+        if (st) st[0]++;
         e = bft_node_probe(v, e.a, (uint32_t)cur[0] & (BFT_ROOTDIR_SIZE - 1u), succ_leaf_quirk && sz == BFT_NB_CHAR_SUF_PREF);
     }
 }
 
-BFT_HD uint32_t bft_lookup_w(const bft_view_t* v, const uint64_t* kmer, const int W) { return bft_lookup_ex(v, kmer, W, 0); }
+BFT_HD uint32_t bft_lookup_w(const bft_view_t* v, const uint64_t* kmer, const int W) { return bft_lookup_ex(v, kmer, W, 0, (uint32_t*)0); }
 
 BFT_HD uint32_t bft_lookup(const bft_view_t* v, const uint64_t* kmer) { return bft_lookup_w(v, kmer, v->W); }
 

@@ -554,6 +554,27 @@ extern "C" int bft_b200_query_neighbors(bft_b200_ctx* c, const uint64_t* kmers, 
     return 0;
 }
 
+extern "C" int bft_b200_kmer_walk_stats_device(bft_b200_ctx* c, const uint64_t* d_kmers, size_t n, uint64_t out[3]) {
+    if (!c || !out || (!d_kmers && n)) return set_err(BFT_B200_ERR_ARG, "bft_b200_kmer_walk_stats_device: NULL argument");
+    CK(cudaSetDevice(c->device));
+    unsigned long long* d_acc = NULL;
+    CK(cudaMalloc((void**)&d_acc, 3 * sizeof(unsigned long long)));
+    cudaMemsetAsync(d_acc, 0, 3 * sizeof(unsigned long long), c->streams[0]);
+    if (n) {
+        const int grid = grid_for(c, n, BFT_TPB);
+        if (c->W == 1) k_kmer_walk_stats<1><<<grid, BFT_TPB, 0, c->streams[0]>>>(c->dview, d_kmers, n, d_acc);
+        else k_kmer_walk_stats<2><<<grid, BFT_TPB, 0, c->streams[0]>>>(c->dview, d_kmers, n, d_acc);
+        c->launches++;
+    }
+    unsigned long long h[3] = {0, 0, 0};
+    cudaError_t e = cudaMemcpyAsync(h, d_acc, sizeof h, cudaMemcpyDeviceToHost, c->streams[0]);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(c->streams[0]);
+    cudaFree(d_acc);
+    if (e != cudaSuccess) return set_err(BFT_B200_ERR_CUDA, "k_kmer_walk_stats failed: %s", cudaGetErrorString(e));
+    out[0] = h[0]; out[1] = h[1]; out[2] = h[2];
+    return 0;
+}
+
 /* ---- file-level drivers ------------------------------------------------------------------------------------- */
 extern "C" int bft_b200_query_kmers_file(bft_b200_ctx* c, const char* query_path, int binary_file, const char* csv_path, uint64_t* n_present) {
     if (!c || !query_path || !csv_path) return set_err(BFT_B200_ERR_ARG, "bft_b200_query_kmers_file: NULL argument");

@@ -36,6 +36,33 @@ __global__ void __launch_bounds__(BFT_TPB) k_query_kmers(const bft_view_t v, con
     }
 }
 
+/* Instrumented walk for the roofline accounting: sums over the batch of Nodes probed, binary-search
+ * depths ceil(log2(lines+1)) and hits. Not on the product path; bench.py runs it once on the timed batch. */
+template <int W>
+__global__ void __launch_bounds__(BFT_TPB) k_kmer_walk_stats(const bft_view_t v, const uint64_t* __restrict__ kmers, size_t n,
+                                                             unsigned long long* __restrict__ acc) {
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    unsigned long long a0 = 0, a1 = 0, a2 = 0;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        uint64_t km[W];
+#pragma unroll
+        for (int w = 0; w < W; w++) km[w] = kmers[i * W + w];
+        uint32_t st[3] = {0, 0, 0};
+        bft_lookup_ex(&v, km, W, 0, st);
+        a0 += st[0]; a1 += st[1]; a2 += st[2];
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+        a0 += __shfl_down_sync(0xffffffffu, a0, o);
+        a1 += __shfl_down_sync(0xffffffffu, a1, o);
+        a2 += __shfl_down_sync(0xffffffffu, a2, o);
+    }
+    if ((threadIdx.x & 31) == 0) {
+        atomicAdd(acc + 0, a0);
+        atomicAdd(acc + 1, a1);
+        atomicAdd(acc + 2, a2);
+    }
+}
+
 /* a10 (read side of get_list_id_genomes): class id -> colour row, one thread per output word */
 __global__ void __launch_bounds__(BFT_TPB) k_expand_rows(const uint32_t* __restrict__ cls, size_t n, const uint32_t* __restrict__ class_rows,
                                                          int rw, uint32_t* __restrict__ rows) {
@@ -139,7 +166,7 @@ __global__ void __launch_bounds__(BFT_TPB) k_query_branching(const bft_view_t v,
                 if (bits_last < 64) y[W - 1] &= (1ULL << bits_last) - 1ULL;
             }
             /* the reference's successor search deviates from set membership at the leaf level; see bft_node_probe */
-            const uint32_t cls = bft_lookup_ex(&v, y, W, ref_quirks && sub < 4);
+            const uint32_t cls = bft_lookup_ex(&v, y, W, ref_quirks && sub < 4, (uint32_t*)0);
             hit = cls != BFT_CLS_NONE;
             if (nbr_cls) nbr_cls[q * 8 + (sub < 4 ? 4 + sub : sub - 4)] = cls; /* get_neighbors order: 0-3 pred, 4-7 succ */
         }

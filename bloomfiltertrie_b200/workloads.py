@@ -1,0 +1,128 @@
+"""Benchmark workloads (BASELINE.json configs): synthetic pan-genome BFTs and query batches.
+
+The BFT itself is always built by the UNMODIFIED reference (`oracle/_ref/bft build`, graph construction stays on the
+reference host path); this module only generates the seeded inputs, caches the resulting .bft under data/ and
+generates query batches with torch (on the GPU for the engine, on the CPU for the bounded reference sample).
+"""
+from __future__ import annotations
+
+import os
+import subprocess
+import sys
+import time
+from typing import List, Tuple
+
+import numpy as np
+
+from . import synth
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+DATA = os.path.join(ROOT, "data")
+REF_BFT = os.path.join(ROOT, "oracle", "_ref", "bft")
+REF_HARNESS = os.path.join(ROOT, "oracle", "_ref", "ref_harness")
+
+# config[2] of BASELINE.json: 100-genome synthetic bacterial pan-genome, tree-structured SNP/indel strains
+C3 = dict(name="c3_g100", n_genomes=100, snp=0.002, indel=0.0002, seed=12345, tree=True)
+
+
+def log(*a):
+    print("[workloads]", *a, file=sys.stderr, flush=True)
+
+
+def pangenome(cfg: dict, genome_len: int) -> List[np.ndarray]:
+    return synth.make_pangenome(cfg["n_genomes"], genome_len, cfg["snp"], cfg["indel"], seed=cfg["seed"], tree=cfg["tree"])
+
+
+def bft_path(cfg: dict, k: int, genome_len: int) -> str:
+    return os.path.join(DATA, f"{cfg['name']}_k{k}_L{genome_len}.bft")
+
+
+def available_lengths(cfg: dict, k: int) -> List[int]:
+    out = []
+    if os.path.isdir(DATA):
+        pre = f"{cfg['name']}_k{k}_L"
+        for f in os.listdir(DATA):
+            if f.startswith(pre) and f.endswith(".bft"):
+                try:
+                    out.append(int(f[len(pre):-4]))
+                except ValueError:
+                    pass
+    return sorted(out)
+
+
+def ensure_bft(cfg: dict, k: int, genome_len: int, genomes=None) -> str:
+    """Path of the cached .bft for (cfg, k, genome_len); builds it with the reference binary when absent."""
+    path = bft_path(cfg, k, genome_len)
+    if os.path.exists(path):
+        return path
+    if not os.access(REF_BFT, os.X_OK):
+        raise RuntimeError(f"{path} is absent and the reference binary {REF_BFT} is not built: cannot construct the BFT "
+                           "(graph construction is the reference's job)")
+    os.makedirs(DATA, exist_ok=True)
+    tmp = os.path.join(os.environ.get("TMPDIR", "/tmp"), f"bft_build_{cfg['name']}_k{k}_L{genome_len}_{os.getpid()}")
+    os.makedirs(tmp, exist_ok=True)
+    t0 = time.time()
+    if genomes is None:
+        genomes = pangenome(cfg, genome_len)
+    lst = synth.write_genome_kmer_files(tmp, genomes, k)
+    log(f"building {os.path.basename(path)} with the reference ({cfg['n_genomes']} genomes x {genome_len} bp)...")
+    out = os.path.join(tmp, "out.bft")
+    p = subprocess.run([REF_BFT, "build", str(k), "kmers_comp", lst, out], cwd=tmp, stdout=subprocess.PIPE, stderr=subprocess.STDOUT)
+    if p.returncode != 0:
+        raise RuntimeError("reference build failed:\n" + p.stdout.decode(errors="replace")[-2000:])
+    os.replace(out, path)
+    for f in os.listdir(tmp):
+        os.remove(os.path.join(tmp, f))
+    os.rmdir(tmp)
+    log(f"built in {time.time() - t0:.1f}s, {os.path.getsize(path) / 1e6:.1f} MB")
+    return path
+
+
+def genomes_to_torch(genomes: List[np.ndarray], device):
+    import torch
+    cat = torch.from_numpy(np.concatenate(genomes)).to(device)
+    lens = torch.tensor([len(g) for g in genomes], dtype=torch.int64, device=device)
+    starts = torch.cumsum(lens, 0) - lens
+    return cat, starts, lens
+
+
+def gen_kmer_queries(cat, starts, lens, k: int, n: int, seed: int, mix: Tuple[float, float, float] = (0.5, 0.25, 0.25)):
+    """Query batch on cat.device: mix = (windows present in some genome, windows with one substituted nucleotide,
+    uniform random k-mers), shuffled. Returns int64 [n, W] (bit pattern = packed k-mer words)."""
+    import torch
+    dev = cat.device
+    g = torch.Generator(device=dev)
+    g.manual_seed(seed)
+    W = (2 * k + 63) // 64
+    n_p = int(n * mix[0])
+    n_m = int(n * mix[1])
+    n_r = n - n_p - n_m
+    m = n_p + n_m
+    gi = torch.randint(0, len(lens), (m,), generator=g, device=dev)
+    span = (lens[gi] - k + 1).to(torch.float64)
+    pos = (torch.rand(m, generator=g, device=dev, dtype=torch.float64) * span).to(torch.int64) + starts[gi]
+    q = torch.zeros((m, W), dtype=torch.int64, device=dev)
+    for j in range(k):
+        q[:, j // 32] |= cat[pos + j].to(torch.int64) << (2 * (j % 32))
+    if n_m:
+        sub = q[n_p:]
+        p = torch.randint(0, k, (n_m,), generator=g, device=dev)
+        d = torch.randint(1, 4, (n_m,), generator=g, device=dev)
+        for w in range(W):
+            in_w = (p // 32) == w
+            sh = 2 * (p % 32)
+            cur = (sub[:, w] >> sh) & 3
+            new = (cur + d) & 3
+            sub[:, w] = torch.where(in_w, (sub[:, w] & ~(torch.full_like(sh, 3) << sh)) | (new << sh), sub[:, w])
+    parts = [q]
+    if n_r:
+        r = torch.empty((n_r, W), dtype=torch.int64, device=dev)
+        for w in range(W):
+            bits = min(64, 2 * k - 64 * w)
+            lo = torch.randint(0, 1 << 32, (n_r,), generator=g, device=dev)
+            hi = torch.randint(0, 1 << max(1, min(32, bits - 32)), (n_r,), generator=g, device=dev) if bits > 32 else torch.zeros_like(lo)
+            r[:, w] = lo | (hi << 32)
+        parts.append(r)
+    out = torch.cat(parts)
+    perm = torch.randperm(n, generator=g, device=dev)
+    return out[perm].contiguous()

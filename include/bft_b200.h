@@ -131,6 +131,10 @@ int bft_b200_query_branching_file(bft_b200_ctx* ctx, const char* query_path, int
 int bft_b200_query_sequences_file(bft_b200_ctx* ctx, const char* query_path, const char* csv_path, double threshold,
                                   int canonical);
 
+/* Roofline accounting helper: over a device-resident batch, sums of Nodes probed, binary-search
+ * depths ceil(log2(lines+1)) and found k-mers: out[0..2]. Diagnostic; synchronous. */
+int bft_b200_kmer_walk_stats_device(bft_b200_ctx* ctx, const uint64_t* d_kmers, size_t n, uint64_t out[3]);
+
 /* wait for everything enqueued on the context's streams */
 int bft_b200_sync(bft_b200_ctx* ctx);
 

@@ -12,7 +12,8 @@
  *       per query: isBranchingRight, isBranchingLeft (src/file_io.c:943-946); out.bin: succ u8[n], pred u8[n]
  *   ref_harness sequences file.bft seqs.txt threshold {canonical|non_canonical} out.bin [threads] [repeat]
  *       per line: query_sequence (src/bft.c:1241); out.bin: rows u32[n][RW]
- * Prints one line: "REF mode=... n=... threads=... seconds=... per_sec=..." (best of `repeat` passes).
+ * Prints "REF_PASS i seconds=..." per pass and one line "REF mode=... n=... threads=... seconds=... per_sec=..."
+ * (best of `repeat` passes).
  */
 #define _GNU_SOURCE
 #include <omp.h>
@@ -94,6 +95,7 @@ int main(int argc, char** argv) {
                     free(km.res);
                 }
                 double dt = now_s() - t0;
+                printf("REF_PASS %d seconds=%.6f\n", rep, dt);
                 if (dt < best) best = dt;
             }
             fwrite(present, 1, n, fo);
@@ -110,6 +112,7 @@ int main(int argc, char** argv) {
                     pred[i] = (uint8_t)isBranchingLeft(&(b->node), b, lvl_root, &q[i * (size_t)nb], k);
                 }
                 double dt = now_s() - t0;
+                printf("REF_PASS %d seconds=%.6f\n", rep, dt);
                 if (dt < best) best = dt;
             }
             fwrite(succ, 1, n, fo);
@@ -145,6 +148,7 @@ int main(int argc, char** argv) {
                 free(ids);
             }
             double dt = now_s() - t0;
+            printf("REF_PASS %d seconds=%.6f\n", rep, dt);
             if (dt < best) best = dt;
         }
         fwrite(rows, 4, n * (size_t)rw, fo);

@@ -116,3 +116,57 @@ def rows_from_sets(sets: Sequence[set], n_genomes: int) -> np.ndarray:
         for g in s:
             rows[i, g >> 5] |= np.uint32(1 << (g & 31))
     return rows
+
+
+# ---- the plain-C restatement (oracle/bft_oracle.c), same conventions as the reference harness -------------------
+ORACLE_CLI = os.path.join(ROOT, "oracle", "oracle_cli")
+
+
+def ensure_oracle() -> str:
+    if not os.access(ORACLE_CLI, os.X_OK):
+        env = {k: v for k, v in os.environ.items() if k not in ("CC", "CXX")}
+        subprocess.run(["make", "-C", os.path.join(ROOT, "oracle"), "oracle"], check=True, env=env,
+                       stdout=subprocess.PIPE, stderr=subprocess.STDOUT)
+    return ORACLE_CLI
+
+
+def oracle_kmers(bft_path: str, words: np.ndarray, k: int, n_genomes: int, workdir: str):
+    q = _write_queries(workdir, words, k, "ok")
+    out = q + ".out"
+    _run([ensure_oracle(), "kmers", bft_path, q, out], cwd=workdir)
+    rw = max(1, (n_genomes + 31) // 32)
+    n = len(words)
+    raw = np.fromfile(out, dtype=np.uint8)
+    os.remove(q)
+    os.remove(out)
+    return raw[:n].copy(), raw[n:n + 4 * n * rw].view(np.uint32).reshape(n, rw).copy()
+
+
+def oracle_branching(bft_path: str, words: np.ndarray, k: int, workdir: str):
+    q = _write_queries(workdir, words, k, "ob")
+    out = q + ".out"
+    _run([ensure_oracle(), "branching", bft_path, q, out], cwd=workdir)
+    n = len(words)
+    raw = np.fromfile(out, dtype=np.uint8)
+    os.remove(q)
+    os.remove(out)
+    return raw[:n].copy(), raw[n:2 * n].copy()
+
+
+def oracle_sequences(bft_path: str, seqs: Sequence[bytes], threshold: float, canonical: bool, n_genomes: int, workdir: str):
+    q = os.path.join(workdir, f"os_{os.getpid()}.txt")
+    with open(q, "wb") as f:
+        f.write(b"\n".join(seqs) + b"\n")
+    out = q + ".out"
+    _run([ensure_oracle(), "sequences", bft_path, q, repr(float(threshold)), "canonical" if canonical else "non_canonical", out],
+         cwd=workdir)
+    rw = max(1, (n_genomes + 31) // 32)
+    rows = np.fromfile(out, dtype=np.uint32).reshape(len(seqs), rw).copy()
+    os.remove(q)
+    os.remove(out)
+    return rows
+
+
+def split_seqs(chars: np.ndarray, offs: np.ndarray) -> List[bytes]:
+    b = chars.tobytes()
+    return [b[int(offs[i]):int(offs[i + 1])] for i in range(len(offs) - 1)]

@@ -1,0 +1,209 @@
+"""CPU suite, part 2: host logic — codecs, the serializer + arena walk (run on the host by tests/tools), the C-ABI
+library's exports, and the multi-process sharding/gather logic under gloo (world_size 2)."""
+import ctypes
+import glob
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+import refutil
+from bloomfiltertrie_b200 import shard, synth
+
+ROOT = refutil.ROOT
+CSRC = os.path.join(ROOT, "bloomfiltertrie_b200", "csrc")
+NAMES = sorted(os.path.basename(p)[:-4] for p in glob.glob(os.path.join(refutil.GOLDEN, "*.npz")))
+
+
+def _gcc(args, **kw):
+    env = {k: v for k, v in os.environ.items() if k not in ("CC", "CXX")}
+    return subprocess.run(["gcc"] + args, env=env, check=True, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, **kw)
+
+
+# ---- codecs ---------------------------------------------------------------------------------------------------
+def test_readme_encoding_kat():
+    # reference README.md:172: ACTTGTCTG -> 11110100 11011110 00000010
+    b = synth.words_to_bytes(synth.pack_windows(synth.ascii_to_codes(b"ACTTGTCTG"), 9), 9)[0]
+    assert [format(x, "08b") for x in b] == ["11110100", "11011110", "00000010"]
+
+
+@pytest.mark.parametrize("k", [9, 27, 36, 63])
+def test_revcomp_and_canonical_match_string_semantics(k):
+    rng = np.random.default_rng(k)
+    codes = rng.integers(0, 4, size=(300, k), dtype=np.uint8)
+    codes[0] = 0                      # poly-A
+    codes[1, : k // 2] = 0            # low half
+    comp = {65: 84, 67: 71, 71: 67, 84: 65}
+    words = np.concatenate([synth.pack_windows(c, k) for c in codes])
+    rc = synth.revcomp_words(words, k)
+    canon = synth.canonical_words(words, k)
+    asc = synth.words_to_ascii(words, k)
+    for i in range(len(codes)):
+        s = bytes(asc[i])
+        r = bytes(comp[c] for c in reversed(s))
+        assert bytes(synth.words_to_ascii(rc[i:i + 1], k)[0]) == r
+        want = r if s >= r else s      # strcmp(fwd, rc) >= 0 -> rc (reference src/bft.c:1291)
+        assert bytes(synth.words_to_ascii(canon[i:i + 1], k)[0]) == want
+    np.testing.assert_array_equal(synth.bytes_to_words(synth.words_to_bytes(words, k), k), words)
+
+
+def test_xxh64_known_answers_and_reference(tmp_path):
+    src = tmp_path / "x.c"
+    src.write_text('#include <stdio.h>\n#include <stdlib.h>\n#include "bft_xxh64.h"\n'
+                   'int main(int c, char** v){ unsigned long long seed = strtoull(v[2], 0, 10);'
+                   ' printf("%016llx\\n", (unsigned long long)bft_xxh64(v[1], strlen(v[1]), seed)); return 0; }\n')
+    exe = str(tmp_path / "x")
+    _gcc(["-O2", "-I", CSRC, str(src), "-o", exe])
+
+    def mine(s, seed=0):
+        return int(subprocess.run([exe, s, str(seed)], stdout=subprocess.PIPE, check=True).stdout, 16)
+
+    assert mine("") == 0xEF46DB3751D8E999      # published xxHash64 test vectors
+    assert mine("abc") == 0x44BC2CF5AD770999
+    lib_path = os.path.join(refutil.REF_DIR, "libbft_ref.so")
+    if os.path.exists(lib_path):               # the reference's vendored XXH64 (src/xxhash.c), all length classes
+        ref = ctypes.CDLL(lib_path).BFT_HASH_XXH64
+        ref.restype = ctypes.c_uint64
+        ref.argtypes = [ctypes.c_char_p, ctypes.c_size_t, ctypes.c_uint64]
+        for s, seed in [("a", 1), ("abc", 1804289383), ("0123456789abcdef", 7), ("x" * 31, 3), ("y" * 32, 5), ("z" * 77, 846930886)]:
+            assert mine(s, seed) == ref(s.encode(), len(s), seed)
+
+
+# ---- serializer + walk + colour decoder on the host --------------------------------------------------------------
+@pytest.fixture(scope="module")
+def host_tool(tmp_path_factory):
+    exe = str(tmp_path_factory.mktemp("tool") / "arena_host_query")
+    _gcc(["-O2", "-std=c11", "-I", CSRC, os.path.join(ROOT, "tests", "tools", "arena_host_query.c"),
+          os.path.join(CSRC, "bft_flatten.c"), os.path.join(CSRC, "bft_io.c"), "-o", exe])
+    return exe
+
+
+def _csv_bytes(names, rows, n_genomes):
+    out = [",".join(names).encode() + b"\n"]
+    bits = np.unpackbits(rows.view(np.uint8), axis=1, bitorder="little")[:, :n_genomes]
+    for r in bits:
+        out.append(b",".join(b"1" if x else b"0" for x in r) + b"\n")
+    data = b"".join(out)
+    return data[:-1] + b"\0"           # the reference overwrites the last byte with NUL (src/file_io.c:873-876)
+
+
+@pytest.mark.parametrize("name", NAMES)
+def test_flattened_arena_walk_reproduces_golden(name, host_tool, tmp_path):
+    z = np.load(os.path.join(refutil.GOLDEN, name + ".npz"))
+    k, G = int(z["k"]), int(z["n_genomes"])
+    q = str(tmp_path / "q.kc")
+    synth.write_kmers_comp(q, z["queries"], k)
+    out = str(tmp_path / "out.csv")
+    p = subprocess.run([host_tool, os.path.join(refutil.GOLDEN, name + ".bft"), "kmers_comp", q, out], stdout=subprocess.PIPE,
+                       stderr=subprocess.PIPE, check=True)
+    assert int(p.stdout.split(b"=")[1]) == int(z["present"].sum())
+    names = [f"genome_{i:04d}.kc" for i in range(G)]
+    assert open(out, "rb").read() == _csv_bytes(names, z["rows"], G)
+
+
+def test_flattener_rejects_garbage(host_tool, tmp_path):
+    bad = tmp_path / "bad.bft"
+    bad.write_bytes(b"\x01\x02\x03")
+    p = subprocess.run([host_tool, str(bad), "kmers_comp", "/dev/null", "/dev/null"], stdout=subprocess.PIPE, stderr=subprocess.PIPE)
+    assert p.returncode != 0 and b"bft_flatten" in p.stderr
+    g = os.path.join(refutil.GOLDEN, NAMES[0] + ".bft")
+    trunc = tmp_path / "trunc.bft"
+    trunc.write_bytes(open(g, "rb").read()[:5000])
+    p = subprocess.run([host_tool, str(trunc), "kmers_comp", "/dev/null", "/dev/null"], stdout=subprocess.PIPE, stderr=subprocess.PIPE)
+    assert p.returncode != 0 and b"truncated" in p.stderr
+
+
+# ---- the C-ABI library -----------------------------------------------------------------------------------------
+def test_abi_library_loads_and_exports_every_declared_symbol():
+    from bloomfiltertrie_b200 import engine
+    lib = engine.load_library()
+    header = open(os.path.join(ROOT, "include", "bft_b200.h")).read()
+    import re
+    declared = sorted(set(re.findall(r"\b(bft_b200_[a-z0-9_]+)\s*\(", header)))
+    assert declared and set(declared) == set(engine.ABI_SYMBOLS)
+    for s in declared:
+        assert hasattr(lib, s), s
+    compat = open(os.path.join(ROOT, "include", "bft_compat.h")).read()
+    for s in ["load_BFT", "free_cdbg", "get_kmer", "is_kmer_in_cdbg", "get_annotation", "get_list_id_genomes",
+              "get_count_id_genomes", "presence_genome", "query_sequence", "get_neighbors", "get_predecessors",
+              "get_successors", "queryBFT_kmerPresences_from_KmerFiles", "queryBFT_kmerBranching_from_KmerFiles",
+              "query_sequences_outputCSV", "free_BFT_kmer", "free_BFT_annotation", "create_kmer"]:
+        assert s in compat and hasattr(lib, s), s
+
+
+def test_engine_fails_loudly_without_a_gpu():
+    import torch
+    from bloomfiltertrie_b200 import engine
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    with pytest.raises(engine.BFTError, match="no CPU fallback"):
+        engine.BFTEngine(os.path.join(refutil.GOLDEN, NAMES[0] + ".bft"))
+
+
+# ---- sharding ---------------------------------------------------------------------------------------------------
+def test_shard_ranges_cover_everything_in_order():
+    for n in [0, 1, 7, 8, 1000, 1001]:
+        for world in [1, 2, 3, 8]:
+            r = [shard.shard_range(n, k, world) for k in range(world)]
+            assert r[0][0] == 0 and r[-1][1] == n
+            assert all(r[i][1] == r[i + 1][0] for i in range(world - 1))
+            assert max(e - b for b, e in r) - min(e - b for b, e in r) <= 1
+    offs = np.concatenate([[0], np.cumsum(np.random.default_rng(0).integers(0, 400, size=257))]).astype(np.uint64)
+    for world in [1, 2, 4, 8]:
+        r = [shard.shard_sequences(offs, k, world) for k in range(world)]
+        assert r[0][0] == 0 and r[-1][1] == 257 and all(r[i][1] == r[i + 1][0] for i in range(world - 1))
+
+
+_WORKER = r'''
+import os, sys
+sys.path.insert(0, {root!r}); sys.path.insert(0, os.path.join({root!r}, "tests"))
+import numpy as np, torch, torch.distributed as dist
+import refutil
+from bloomfiltertrie_b200 import shard
+rank, world = int(sys.argv[1]), int(sys.argv[2])
+os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=sys.argv[3], RANK=str(rank), WORLD_SIZE=str(world))
+dist.init_process_group("gloo", rank=rank, world_size=world)
+z = np.load(os.path.join(refutil.GOLDEN, {name!r} + ".npz"))
+bft = os.path.join(refutil.GOLDEN, {name!r} + ".bft")
+k, G = int(z["k"]), int(z["n_genomes"])
+wd = sys.argv[4]
+
+class OracleEngine:          # stands in for BFTEngine on the CPU: same methods, answers from the C restatement
+    device = None
+    def query_kmers(self, q):
+        p, r = refutil.oracle_kmers(bft, q, k, G, wd); return p, r, None
+    def query_sequences(self, chars, offs, thr, canonical):
+        return refutil.oracle_sequences(bft, refutil.split_seqs(chars, offs), thr, canonical, G, wd), None
+    def query_branching(self, q):
+        s, p = refutil.oracle_branching(bft, q, k, wd); return s, p, int(((s > 1) | (p > 1)).sum())
+
+sq = shard.ShardedQuery(OracleEngine())
+q = z["queries"][:601]
+present, rows = sq.query_kmers(q)
+srows = sq.query_sequences(z["seq_chars"], z["seq_offs"], 0.8, False)
+cnt = sq.query_branching_count(q[:301])
+if rank == 0:
+    assert np.array_equal(present, z["present"][:601]) and np.array_equal(rows, z["rows"][:601])
+    assert np.array_equal(srows, z["seqrows_c0_t0.8"])
+    assert cnt == int(((z["succ"][:301] > 1) | (z["pred"][:301] > 1)).sum())
+    print("SHARD_OK")
+dist.destroy_process_group()
+'''
+
+
+def test_sharded_query_gathers_in_order_gloo_world2(tmp_path):
+    refutil.ensure_oracle()
+    script = tmp_path / "worker.py"
+    script.write_text(_WORKER.format(root=ROOT, name="golden_shallow_k27_g4"))
+    port = str(29500 + os.getpid() % 2000)
+    procs = []
+    for r in range(2):
+        wd = tmp_path / f"r{r}"
+        wd.mkdir()
+        procs.append(subprocess.Popen([sys.executable, str(script), str(r), "2", port, str(wd)], stdout=subprocess.PIPE,
+                                      stderr=subprocess.STDOUT))
+    outs = [p.communicate(timeout=600)[0].decode() for p in procs]
+    assert all(p.returncode == 0 for p in procs), outs
+    assert "SHARD_OK" in outs[0]
