@@ -18,13 +18,18 @@
  *   filter3[]  the p_v values, as stored (bytes for s=8, nibbles for s=4; src/presenceNode.c:1478-1479).
  *   pref[]     per stored prefix: where its suffixes live (inline line range, child Node, or leaf colour class).
  *              Replaces children_type prefix sums (count_children / count_nodes, include/CC.h:471-550).
- *   keys[]     every suffix line (CC inline suffixes and Node-UC k-mer remainders) as W little-endian 64-bit
- *              words holding the suffix as an integer (nucleotide i at bits 2i), sorted ascending inside each
- *              block so the search is an integer compare (replaces memcmp in binary_search_UC, src/UC.c:81-124).
- *   linecls[]  per line: colour-class id (index of the line's distinct annotation byte string).
+ *   keys[]     every CC inline suffix line as W little-endian 64-bit words holding the suffix as an integer
+ *              (nucleotide i at bits 2i), sorted ascending inside each prefix's block so the search is an integer
+ *              compare (replaces memcmp in binary_search_UC, src/UC.c:81-124). When the colour-class ids fit
+ *              above the widest suffix (cls_shift != 0) the line's class is stored in the top bits of its most
+ *              significant word, so a hit needs no second load; otherwise linecls[] holds it.
+ *   prefsub[]  per stored prefix: a 32-byte radix index over its block — byte i = number of lines whose top five
+ *              suffix bits are <= i — which narrows the search to ~cnt/32 adjacent lines (one or two sectors)
+ *              before keys[] is touched. rootsub[] is the same, indexed like rootdir[].
+ *   uckeys[] / uccls[]  the Node-UC lines (whole k-mer remainders, src/presenceNode.c:1554-1573) and their classes.
  *   rootdir[]  262144 entries: the complete answer of the root Node probe for every possible 9-nt prefix, indexed
  *              by the low 18 bits of the packed k-mer. Every query passes through the root, so its probe is
- *              collapsed into one 8-byte load.
+ *              collapsed into one 8-byte load (+ one 32-byte rootsub load issued alongside).
  *   colour classes: distinct annotation byte strings (cls_off/cls_bytes) + the comp_set_colors pools; decoded on
  *              the device once per arena into class rows (bft_kernels.cu: k_decode_classes).
  *
@@ -63,6 +68,8 @@
 #define BFT_ROOTDIR_SIZE (1u << BFT_PREFIX_BITS)
 #define BFT_FIRSTCC_NONE 0xffu
 #define BFT_MAX_WORDS 2                /* k <= 63 (126 bits) */
+#define BFT_SUB_BYTES 32               /* radix index of one inline block: 32 cumulative counts */
+#define BFT_SUB_BITS 5
 
 /* kinds of a prefix-probe answer */
 #define BFT_KIND_ABSENT 0u /* a CC's Bloom filter fired but the prefix is not stored there: k-mer absent */
@@ -107,10 +114,15 @@ typedef struct {
     const uint16_t* csr;
     const uint8_t* filter3;
     const bft_entry_t* pref;
-    const uint64_t* keys;     /* n_lines * W words */
-    const uint32_t* linecls;  /* n_lines */
+    const uint8_t* rootsub;   /* BFT_ROOTDIR_SIZE * BFT_SUB_BYTES */
+    const uint8_t* prefsub;   /* n_pref * BFT_SUB_BYTES */
+    const uint64_t* keys;     /* n_lines * W words (inline suffix lines) */
+    const uint32_t* linecls;  /* n_lines, only when cls_shift == 0 */
+    const uint64_t* uckeys;   /* n_uc_lines * W words (Node-UC lines) */
+    const uint32_t* uccls;    /* n_uc_lines */
     int k;
-    int W; /* 64-bit words per key: 1 for k <= 27, 2 for k <= 63 */
+    int W;         /* 64-bit words per key: 1 for k <= 27, 2 for k <= 63 */
+    int cls_shift; /* != 0: class id of an inline line = top word >> cls_shift, suffix = the bits below */
 } bft_view_t;
 
 /* ---- prefix bit manipulation --------------------------------------------------------------------------------
@@ -149,7 +161,7 @@ BFT_HD bft_entry_t bft_mk_entry(uint32_t kind, uint32_t a, uint32_t n) {
  * src/presenceNode.c:719-723): the reference clears nucleotide 7 of the prefix (`& 0xfc` on the second byte) before
  * hashing and before forming p_u/p_v, so the CC path answers for the prefix with nuc 7 = A; the Node-UC path
  * (:1164-1208) compares the unmodified k-mer. Only the successor lookups of the branching queries pass it. */
-BFT_HD bft_entry_t bft_node_probe(const bft_view_t* v, uint32_t node_id, uint32_t low18, int succ_leaf_quirk) {
+BFT_HD bft_entry_t bft_node_probe(const bft_view_t* v, uint32_t node_id, uint32_t low18, int succ_leaf_quirk, uint32_t* pref_idx) {
     bft_node_t nd;
 #ifdef __CUDA_ARCH__
     {
@@ -200,19 +212,20 @@ BFT_HD bft_entry_t bft_node_probe(const bft_view_t* v, uint32_t node_id, uint32_
                 uint32_t t = (lo & 1u) ? (uint32_t)(BFT_LD8(f3 + (lo >> 1)) >> 4) : (uint32_t)(BFT_LD8(f3 + (lo >> 1)) & 0xf);
                 if (t != pv) return bft_mk_entry(BFT_KIND_ABSENT, 0, 0);
             }
+            *pref_idx = cc.pref_off + lo;
             return bft_ld_entry(v->pref + cc.pref_off + lo);
         }
     }
     return bft_mk_entry(BFT_KIND_UC, nd.uc_begin, nd.uc_n);
 }
 
-/* Search the sorted lines [begin, begin+n) for `key` (W words, word W-1 most significant); returns the line index
- * or 0xffffffff (binary_search_UC + equality test, src/UC.c:81-124, src/presenceNode.c:1876-1914, 1554-1570). */
-BFT_HD uint32_t bft_search_lines(const bft_view_t* v, uint32_t begin, uint32_t n, const uint64_t* key, const int W) {
+/* Search the Node-UC lines [begin, begin+n) for `key` (W words, word W-1 most significant); returns the line index
+ * or 0xffffffff (binary_search_UC + equality test, src/UC.c:81-124, src/presenceNode.c:1554-1570). */
+BFT_HD uint32_t bft_search_uc(const bft_view_t* v, uint32_t begin, uint32_t n, const uint64_t* key, const int W) {
     uint32_t lo = begin, hi = begin + n;
     while (lo < hi) {
         const uint32_t mid = lo + ((hi - lo) >> 1);
-        const uint64_t* p = v->keys + (size_t)mid * W;
+        const uint64_t* p = v->uckeys + (size_t)mid * W;
         int less = 0;
         for (int w = W - 1; w >= 0; w--) {
             const uint64_t x = BFT_LD64(p + w);
@@ -221,12 +234,50 @@ BFT_HD uint32_t bft_search_lines(const bft_view_t* v, uint32_t begin, uint32_t n
         if (less) lo = mid + 1; else hi = mid;
     }
     if (lo < begin + n) {
-        const uint64_t* p = v->keys + (size_t)lo * W;
+        const uint64_t* p = v->uckeys + (size_t)lo * W;
         int eq = 1;
         for (int w = 0; w < W; w++) eq &= (BFT_LD64(p + w) == key[w]);
         if (eq) return lo;
     }
     return 0xffffffffu;
+}
+
+/* Search one prefix's inline block [begin, begin+n) for `key` (the suffix left after the 9-nt prefix, key_bits wide)
+ * and return the colour class of the matching line, or BFT_CLS_NONE (binary_search_UC over the block + equality,
+ * src/presenceNode.c:1876-1914). `sub` is the block's radix index: the candidates are the lines whose top five
+ * suffix bits equal the key's — on average n/32 adjacent lines, fetched with independent loads. */
+BFT_HD uint32_t bft_search_block(const bft_view_t* v, uint32_t begin, uint32_t n, const uint8_t* sub, const uint64_t* key,
+                                 const int W, const int key_bits) {
+    /* top five bits of the suffix: in the upper word only when the suffix is wider than 64 bits (W == 2) */
+    const int upper = (W > 1) && (key_bits > 64);
+    const uint64_t topw = upper ? key[W - 1] : key[0];
+    const uint32_t t = (uint32_t)(topw >> (key_bits - (upper ? 64 : 0) - BFT_SUB_BITS)) & (BFT_SUB_BYTES - 1u);
+    const uint32_t c_hi = BFT_LD8(sub + t);
+    const uint32_t c_lo = t ? BFT_LD8(sub + t - 1) : 0u;
+    uint32_t lo = begin + c_lo, hi = begin + c_hi;
+    if (hi > begin + n) hi = begin + n;
+    const int shift = v->cls_shift;
+    const uint64_t top_mask = shift ? ((1ULL << shift) - 1ULL) : ~0ULL;
+    while (hi - lo > 4 && lo < hi) { /* crowded bucket (skewed suffixes): bisect down to a handful */
+        const uint32_t mid = lo + ((hi - lo) >> 1);
+        const uint64_t* p = v->keys + (size_t)mid * W;
+        int less = 0;
+        for (int w = W - 1; w >= 0; w--) {
+            uint64_t x = BFT_LD64(p + w);
+            if (w == W - 1) x &= top_mask;
+            if (x != key[w]) { less = x < key[w]; break; }
+        }
+        if (less) lo = mid + 1; else hi = mid + 1;
+    }
+    uint32_t found = BFT_CLS_NONE;
+    for (uint32_t i = lo; i < hi; i++) { /* <= 4 independent loads, adjacent addresses */
+        const uint64_t* p = v->keys + (size_t)i * W;
+        const uint64_t top = BFT_LD64(p + W - 1);
+        int eq = (top & top_mask) == key[W - 1];
+        for (int w = 0; w < W - 1; w++) eq &= (BFT_LD64(p + w) == key[w]);
+        if (eq) found = shift ? (uint32_t)(top >> shift) : BFT_LD32(v->linecls + i);
+    }
+    return found;
 }
 
 BFT_HD void bft_shift18(uint64_t* cur, int W) {
@@ -252,7 +303,9 @@ BFT_HD uint32_t bft_lookup_ex(const bft_view_t* v, const uint64_t* kmer, const i
     uint64_t cur[BFT_MAX_WORDS];
     for (int w = 0; w < BFT_MAX_WORDS; w++) cur[w] = w < W ? kmer[w] : 0;
     int sz = v->k;
-    bft_entry_t e = bft_ld_entry(v->rootdir + ((uint32_t)cur[0] & (BFT_ROOTDIR_SIZE - 1u)));
+    const uint32_t low18 = (uint32_t)cur[0] & (BFT_ROOTDIR_SIZE - 1u);
+    bft_entry_t e = bft_ld_entry(v->rootdir + low18);
+    const uint8_t* sub = v->rootsub + (size_t)low18 * BFT_SUB_BYTES;
     if (st) st[0]++;
     for (;;) {
         const uint32_t kind = e.b >> BFT_KIND_SHIFT;
@@ -265,21 +318,23 @@ BFT_HD uint32_t bft_lookup_ex(const bft_view_t* v, const uint64_t* kmer, const i
         if (kind == BFT_KIND_UC) {
             if (n == 0) return BFT_CLS_NONE;
             if (st) st[1] += bft_ceil_log2p1(n);
-            const uint32_t ln = bft_search_lines(v, e.a, n, cur, W);
+            const uint32_t ln = bft_search_uc(v, e.a, n, cur, W);
             if (st && ln != 0xffffffffu) st[2]++;
-            return ln == 0xffffffffu ? BFT_CLS_NONE : BFT_LD32(v->linecls + ln);
+            return ln == 0xffffffffu ? BFT_CLS_NONE : BFT_LD32(v->uccls + ln);
         }
         bft_shift18(cur, W);
         sz -= BFT_NB_CHAR_SUF_PREF;
         if (kind == BFT_KIND_INLINE) {
             if (st) st[1] += bft_ceil_log2p1(n);
-            const uint32_t ln = bft_search_lines(v, e.a, n, cur, W);
-            if (st && ln != 0xffffffffu) st[2]++;
-            return ln == 0xffffffffu ? BFT_CLS_NONE : BFT_LD32(v->linecls + ln);
+            const uint32_t cls = bft_search_block(v, e.a, n, sub, cur, W, 2 * sz);
+            if (st && cls != BFT_CLS_NONE) st[2]++;
+            return cls;
         }
         /* BFT_KIND_NODE */
         if (st) st[0]++;
-        e = bft_node_probe(v, e.a, (uint32_t)cur[0] & (BFT_ROOTDIR_SIZE - 1u), succ_leaf_quirk && sz == BFT_NB_CHAR_SUF_PREF);
+        uint32_t pi = 0;
+        e = bft_node_probe(v, e.a, (uint32_t)cur[0] & (BFT_ROOTDIR_SIZE - 1u), succ_leaf_quirk && sz == BFT_NB_CHAR_SUF_PREF, &pi);
+        sub = v->prefsub + (size_t)pi * BFT_SUB_BYTES;
     }
 }
 

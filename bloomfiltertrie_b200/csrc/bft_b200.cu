@@ -59,7 +59,7 @@ struct bft_b200_ctx {
     char** names;
     bft_b200_stats stats;
     /* device arena */
-    void* d_arena[9];
+    void* d_arena[13];
     bft_view_t dview;
     bft_pools_t dpools;
     void* d_pool[4];
@@ -117,7 +117,7 @@ extern "C" void bft_b200_close(bft_b200_ctx* c) {
     if (!c) return;
     cudaSetDevice(c->device);
     cudaDeviceSynchronize();
-    for (int i = 0; i < 9; i++) if (c->d_arena[i]) cudaFree(c->d_arena[i]);
+    for (int i = 0; i < 13; i++) if (c->d_arena[i]) cudaFree(c->d_arena[i]);
     for (int i = 0; i < 4; i++) if (c->d_pool[i]) cudaFree(c->d_pool[i]);
     if (c->d_class_rows) cudaFree(c->d_class_rows);
     if (c->d_class_counts) cudaFree(c->d_class_counts);
@@ -184,7 +184,11 @@ extern "C" int bft_b200_open(const char* path, int device, bft_b200_ctx** out) {
     UP(5, filter3, a->filter3_bytes);
     UP(6, pref, a->n_pref * sizeof(bft_entry_t));
     UP(7, keys, a->n_lines * (size_t)a->W * sizeof(uint64_t));
-    UP(8, linecls, a->n_lines * sizeof(uint32_t));
+    UP(8, linecls, a->linecls ? a->n_lines * sizeof(uint32_t) : 0);
+    UP(9, rootsub, (size_t)BFT_ROOTDIR_SIZE * BFT_SUB_BYTES);
+    UP(10, prefsub, a->n_pref * BFT_SUB_BYTES);
+    UP(11, uckeys, a->n_uc_lines * (size_t)a->W * sizeof(uint64_t));
+    UP(12, uccls, a->n_uc_lines * sizeof(uint32_t));
 #undef UP
     void* d_cls_off = NULL; void* d_cls_bytes = NULL;
     if (!rc) rc = upload(&d_cls_off, a->cls_off, (a->n_classes + 1) * sizeof(uint32_t));
@@ -204,6 +208,11 @@ extern "C" int bft_b200_open(const char* path, int device, bft_b200_ctx** out) {
         c->dview.pref = (const bft_entry_t*)c->d_arena[6];
         c->dview.keys = (const uint64_t*)c->d_arena[7];
         c->dview.linecls = (const uint32_t*)c->d_arena[8];
+        c->dview.rootsub = (const uint8_t*)c->d_arena[9];
+        c->dview.prefsub = (const uint8_t*)c->d_arena[10];
+        c->dview.uckeys = (const uint64_t*)c->d_arena[11];
+        c->dview.uccls = (const uint32_t*)c->d_arena[12];
+        c->dview.cls_shift = a->cls_shift;
         c->dview.k = a->k;
         c->dview.W = a->W;
         c->dpools.n_pools = a->n_pools;
@@ -237,7 +246,7 @@ extern "C" int bft_b200_open(const char* path, int device, bft_b200_ctx** out) {
     if (d_cls_off) cudaFree(d_cls_off);
     if (d_cls_bytes) cudaFree(d_cls_bytes);
 
-    c->stats.n_kmers = a->n_kmers; c->stats.n_nodes = a->n_nodes; c->stats.n_ccs = a->n_ccs; c->stats.n_lines = a->n_lines;
+    c->stats.n_kmers = a->n_kmers; c->stats.n_nodes = a->n_nodes; c->stats.n_ccs = a->n_ccs; c->stats.n_lines = a->n_lines + a->n_uc_lines;
     c->stats.n_prefixes = a->n_pref; c->stats.n_classes = a->n_classes; c->stats.arena_bytes = bft_arena_bytes(a);
     c->stats.class_row_bytes = row_bytes; c->stats.max_cc_per_node = a->max_cc_per_node; c->stats.max_depth = a->max_depth;
     c->stats.n_pools = a->n_pools;
