@@ -153,7 +153,7 @@ def reference_arm(args):
     cores = os.cpu_count() or 1
     n = args.ref_sample
     cat, starts, lens = wl.genomes_to_torch(genomes, torch.device("cpu"))
-    q = wl.gen_kmer_queries(cat, starts, lens, K, n, seed=777, mix=MIX).numpy()
+    q = wl.gen_kmer_queries(cat, starts, lens, K, n, seed=777, mix=MIX)[0].numpy()
     qfile = os.path.join("/tmp", f"bft_bench_ref_{os.getpid()}.kc")
     write_query_file(qfile, q, K)
     secs = run_reference_harness(bft, qfile, cores, args.warmup + args.steps)
@@ -205,13 +205,12 @@ def engine_arm(args):
             f"upload {st['upload_seconds']:.1f}s decode {st['decode_seconds']:.3f}s; setup {time.time() - t0:.1f}s")
     n = args.queries_per_gpu
     cat, starts, lens = wl.genomes_to_torch(genomes, dev)
-    q = wl.gen_kmer_queries(cat, starts, lens, K, n, seed=1000 + rank, mix=MIX)
+    q, q_kind = wl.gen_kmer_queries(cat, starts, lens, K, n, seed=1000 + rank, mix=MIX)
     del cat
     torch.cuda.empty_cache()
     RW, W = eng.RW, eng.W
     d_present = torch.empty(n, dtype=torch.uint8, device=dev)
     d_rows = torch.empty((n, RW), dtype=torch.int32, device=dev)
-    d_cls = torch.empty(n, dtype=torch.int32, device=dev)
     es = torch.cuda.ExternalStream(eng.stream, device=dev)
 
     def barrier():
@@ -220,7 +219,7 @@ def engine_arm(args):
         torch.cuda.synchronize()
 
     def step():
-        eng.query_kmers_device(q, n, d_present, d_rows, d_cls)
+        eng.query_kmers_device(q, n, d_present, d_rows, None)
         if world > 1:  # the only exchange the path has: a summary of each rank's results (no data-path collective)
             with torch.cuda.stream(es):
                 s = d_present.sum(dtype=torch.int64).reshape(1)
@@ -253,13 +252,19 @@ def engine_arm(args):
     ms_step = float(t.item()) / args.steps
     value = n * world / (ms_step / 1e3)
     n_present = int(d_present.sum().item())
+    # size-independent property at full size: every window sampled from an inserted genome must be found, and a
+    # found k-mer must carry at least one colour
+    assert bool(d_present[q_kind == 0].all()), "a k-mer window of an inserted genome was reported absent"
+    assert bool((d_rows[d_present.bool()] != 0).any(dim=1).all()), "a present k-mer came back without colours"
+    assert not bool((d_rows[~d_present.bool()] != 0).any()), "an absent k-mer came back with colours"
 
-    # ---- dominant kernel alone (k_query_kmers: walk -> presence + class id), CUDA events on its own stream
+    # ---- dominant kernel alone: the fused walk + colour-row kernel (k_query_kmers_rows for RW in {1,2,4}; for wider
+    # rows k_query_kmers followed by k_expand_rows), CUDA events on the stream it is launched on
     kms = []
     for i in range(args.warmup + args.steps):
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         a.record(es)
-        eng.query_kmers_device(q, n, d_present, None, d_cls)
+        eng.query_kmers_device(q, n, d_present, d_rows, None)
         b.record(es)
         b.synchronize()
         if i >= args.warmup:
@@ -267,16 +272,24 @@ def engine_arm(args):
     k_ms = sum(kms) / len(kms)
     ws = eng.kmer_walk_stats_device(q, n)
     nodes_pk, depth_pk, found_pk = ws["nodes"] / n, ws["search_depth"] / n, ws["found"] / n
-    # A_min per k-mer: key words in + (presence byte + class id) out + 32-byte sectors the walk must
+    # A_min per k-mer: key words in + (presence byte + colour row) out + 32-byte sectors the walk must
     # touch: 6 per Node probed, ceil(log2(lines+1)) per suffix search, 1 for the annotation of a found k-mer
-    a_min = 8 * W + (1 + 4) + 32.0 * (6 * nodes_pk + depth_pk + found_pk)
+    a_min = 8 * W + (1 + 4 * RW) + 32.0 * (6 * nodes_pk + depth_pk + found_pk)
     achieved = a_min * n / (k_ms / 1e3) / 1e9
     peak, peak_src = peaks()
     traffic = ncu_traffic()
-    roofline = {"bound": "hbm", "kernel": "k_query_kmers", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+    probe = None
+    if not args.no_probe:
+        probe = eng.random_gather_probe(4 << 30, 1 << 28)
+    roofline = {"bound": "hbm", "kernel": "k_query_kmers_rows" if RW in (1, 2, 4) else "k_query_kmers+k_expand_rows",
+                "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "traffic": (traffic * n if traffic else None), "peak_source": peak_src, "kernel_ms": k_ms,
                 "kmers_per_sec_kernel": n / (k_ms / 1e3), "a_min_bytes_per_kmer": a_min,
-                "nodes_per_kmer": nodes_pk, "search_depth_per_kmer": depth_pk, "found_frac": found_pk}
+                "nodes_per_kmer": nodes_pk, "search_depth_per_kmer": depth_pk, "found_frac": found_pk,
+                "dram_bytes_per_kmer_ncu": traffic,
+                "random_gather_probe_loads_per_s": probe,
+                "note": "A_min counts the sectors of the REFERENCE layout's walk; the flattened arena serves the root probe from "
+                        "an L2-resident directory, so achieved can exceed the DRAM peak; dram_bytes_per_kmer_ncu is the physical traffic"}
 
     # ---- e2e: host C-ABI call with pinned host buffers, copies inside the timed region
     e2e = None
@@ -345,6 +358,7 @@ def main():
     ap.add_argument("--ref-sample", type=int, default=1 << 24, help="k-mers per step of the CPU reference legs")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-probe", action="store_true")
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3

@@ -302,6 +302,15 @@ static int enqueue_kmers(bft_b200_ctx* c, cudaStream_t st, const uint64_t* d_kme
                          uint32_t* d_cls) {
     if (n == 0) return 0;
     const int grid = grid_for(c, n, BFT_TPB);
+    if (d_rows && (c->rw == 1 || c->rw == 2 || c->rw == 4) && ((uintptr_t)d_rows & 15) == 0) { /* narrow rows: one fused kernel */
+#define BFT_FUSED(W_, RW_) k_query_kmers_rows<W_, RW_><<<grid, BFT_TPB, 0, st>>>(c->dview, d_kmers, n, d_present, d_cls, c->d_class_rows, d_rows)
+        if (c->W == 1) { if (c->rw == 4) BFT_FUSED(1, 4); else if (c->rw == 2) BFT_FUSED(1, 2); else BFT_FUSED(1, 1); }
+        else { if (c->rw == 4) BFT_FUSED(2, 4); else if (c->rw == 2) BFT_FUSED(2, 2); else BFT_FUSED(2, 1); }
+#undef BFT_FUSED
+        c->launches++;
+        CK(cudaGetLastError());
+        return 0;
+    }
     if (c->W == 1) k_query_kmers<1><<<grid, BFT_TPB, 0, st>>>(c->dview, d_kmers, n, d_present, d_cls);
     else k_query_kmers<2><<<grid, BFT_TPB, 0, st>>>(c->dview, d_kmers, n, d_present, d_cls);
     c->launches++;
@@ -317,7 +326,7 @@ extern "C" int bft_b200_query_kmers_device(bft_b200_ctx* c, const uint64_t* d_km
                                            uint32_t* d_cls) {
     if (!c || (!d_kmers && n)) return set_err(BFT_B200_ERR_ARG, "bft_b200_query_kmers_device: NULL argument");
     CK(cudaSetDevice(c->device));
-    if (d_rows && !d_cls) { /* rows need the class ids as an intermediate */
+    if (d_rows && !d_cls && !((c->rw == 1 || c->rw == 2 || c->rw == 4) && ((uintptr_t)d_rows & 15) == 0)) { /* wide rows need the class ids as an intermediate */
         slot_t* sl = &c->slot[0];
         ENSURE(sl->d_cls, sl->cap_cls, n * sizeof(uint32_t));
         d_cls = sl->d_cls;
@@ -581,6 +590,39 @@ extern "C" int bft_b200_kmer_walk_stats_device(bft_b200_ctx* c, const uint64_t* 
     cudaFree(d_acc);
     if (e != cudaSuccess) return set_err(BFT_B200_ERR_CUDA, "k_kmer_walk_stats failed: %s", cudaGetErrorString(e));
     out[0] = h[0]; out[1] = h[1]; out[2] = h[2];
+    return 0;
+}
+
+extern "C" int bft_b200_random_gather_probe(bft_b200_ctx* c, size_t table_bytes, size_t n_loads, double* loads_per_sec) {
+    if (!c || !loads_per_sec || table_bytes < 4096) return set_err(BFT_B200_ERR_ARG, "bft_b200_random_gather_probe: bad argument");
+    CK(cudaSetDevice(c->device));
+    uint64_t* table = NULL;
+    unsigned long long* sink = NULL;
+    CK(cudaMalloc((void**)&table, table_bytes));
+    if (cudaMalloc((void**)&sink, 8) != cudaSuccess) { cudaFree(table); return set_err(BFT_B200_ERR_NOMEM, "cudaMalloc failed"); }
+    cudaMemsetAsync(table, 1, table_bytes, c->streams[0]);
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0);
+    cudaEventCreate(&e1);
+    const int grid = grid_for(c, n_loads, BFT_TPB);
+    float best = 1e30f;
+    for (int rep = 0; rep < 4; rep++) {
+        cudaEventRecord(e0, c->streams[0]);
+        k_random_gather<<<grid, BFT_TPB, 0, c->streams[0]>>>(table, table_bytes / 8, n_loads, sink);
+        cudaEventRecord(e1, c->streams[0]);
+        cudaEventSynchronize(e1);
+        float ms = 0;
+        cudaEventElapsedTime(&ms, e0, e1);
+        if (rep && ms < best) best = ms;
+        c->launches++;
+    }
+    cudaError_t e = cudaGetLastError();
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    cudaFree(table);
+    cudaFree(sink);
+    if (e != cudaSuccess) return set_err(BFT_B200_ERR_CUDA, "k_random_gather failed: %s", cudaGetErrorString(e));
+    *loads_per_sec = (double)n_loads / (best * 1e-3);
     return 0;
 }
 

@@ -36,6 +36,57 @@ __global__ void __launch_bounds__(BFT_TPB) k_query_kmers(const bft_view_t v, con
     }
 }
 
+/* a4-a10 fused for narrow colour rows (RW = 1, 2 or 4 words, i.e. up to 128 genomes): the thread that finished a
+ * lookup fetches its class row (L2-resident table) and stores it with one vector store — no class-id round trip
+ * through HBM and no second launch. Wider rows go through k_expand_rows. */
+template <int W, int RW>
+__global__ void __launch_bounds__(BFT_TPB) k_query_kmers_rows(const bft_view_t v, const uint64_t* __restrict__ kmers, size_t n,
+                                                              uint8_t* __restrict__ present, uint32_t* __restrict__ cls_out,
+                                                              const uint32_t* __restrict__ class_rows, uint32_t* __restrict__ rows) {
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        uint64_t km[W];
+        if (W == 1) {
+            km[0] = __ldcs((const unsigned long long*)kmers + i);
+        } else {
+            const ulonglong2 t = __ldcs((const ulonglong2*)kmers + i);
+            km[0] = t.x;
+            km[W - 1] = t.y;
+        }
+        const uint32_t cls = bft_lookup_w(&v, km, W);
+        if (present) present[i] = cls != BFT_CLS_NONE;
+        if (cls_out) cls_out[i] = cls;
+        if (RW == 4) {
+            uint4 r = make_uint4(0, 0, 0, 0);
+            if (cls != BFT_CLS_NONE) r = __ldg((const uint4*)class_rows + cls);
+            __stcs((uint4*)rows + i, r);
+        } else if (RW == 2) {
+            uint2 r = make_uint2(0, 0);
+            if (cls != BFT_CLS_NONE) r = __ldg((const uint2*)class_rows + cls);
+            __stcs((uint2*)rows + i, r);
+        } else {
+            uint32_t r = 0;
+            if (cls != BFT_CLS_NONE) r = __ldg(class_rows + cls);
+            __stcs(rows + i, r);
+        }
+    }
+}
+
+/* Random-access roofline probe: n independent 8-byte loads at pseudo-random offsets of a table far
+ * larger than L2, one per thread per iteration — the rate the memory system sustains for dependent-free random
+ * sectors. Not on the product path; bench.py runs it to put the walk's sector rate in context. */
+__global__ void __launch_bounds__(BFT_TPB) k_random_gather(const uint64_t* __restrict__ table, size_t n_words, size_t n_loads,
+                                                           unsigned long long* __restrict__ sink) {
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    unsigned long long acc = 0;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_loads; i += stride) {
+        uint64_t x = (i + 0x9E3779B97F4A7C15ULL) * 0xBF58476D1CE4E5B9ULL; /* splitmix-style scramble */
+        x ^= x >> 31; x *= 0x94D049BB133111EBULL; x ^= x >> 29;
+        acc += __ldg(table + (x % n_words));
+    }
+    if (acc == 0x1234567ULL) *sink = acc; /* keep the loads alive */
+}
+
 /* Instrumented walk for the roofline accounting: sums over the batch of Nodes probed, binary-search
  * depths ceil(log2(lines+1)) and hits. Not on the product path; bench.py runs it once on the timed batch. */
 template <int W>

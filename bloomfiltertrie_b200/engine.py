@@ -27,7 +27,7 @@ ABI_SYMBOLS = [
     "bft_b200_query_sequences", "bft_b200_query_sequences_device", "bft_b200_query_branching",
     "bft_b200_query_branching_device", "bft_b200_query_neighbors", "bft_b200_set_reference_exact_branching",
     "bft_b200_query_kmers_file", "bft_b200_query_branching_file",
-    "bft_b200_query_sequences_file", "bft_b200_sync", "bft_b200_launch_count", "bft_b200_kmer_walk_stats_device",
+    "bft_b200_query_sequences_file", "bft_b200_sync", "bft_b200_launch_count", "bft_b200_kmer_walk_stats_device", "bft_b200_random_gather_probe",
 ]
 
 
@@ -85,6 +85,7 @@ def load_library() -> C.CDLL:
     lib.bft_b200_query_branching_file.argtypes = [vp, C.c_char_p, C.c_int, C.POINTER(C.c_uint64)]
     lib.bft_b200_query_sequences_file.argtypes = [vp, C.c_char_p, C.c_char_p, C.c_double, C.c_int]
     lib.bft_b200_kmer_walk_stats_device.argtypes = [vp, u64p, sz, C.POINTER(C.c_uint64 * 3)]
+    lib.bft_b200_random_gather_probe.argtypes = [vp, sz, sz, C.POINTER(C.c_double)]
     lib.bft_b200_sync.argtypes = [vp]
     lib.bft_b200_launch_count.argtypes = [vp]
     lib.bft_b200_launch_count.restype = C.c_uint64
@@ -223,6 +224,12 @@ class BFTEngine:
         self._ck(self.lib.bft_b200_kmer_walk_stats_device(self.h, _ptr(d_kmers), n, C.byref(out)),
                  "bft_b200_kmer_walk_stats_device")
         return dict(nodes=int(out[0]), search_depth=int(out[1]), found=int(out[2]), n=n)
+
+    def random_gather_probe(self, table_bytes: int, n_loads: int) -> float:
+        out = C.c_double()
+        self._ck(self.lib.bft_b200_random_gather_probe(self.h, table_bytes, n_loads, C.byref(out)),
+                 "bft_b200_random_gather_probe")
+        return float(out.value)
 
     # -- sequences
     def query_sequences(self, chars: np.ndarray, offs: np.ndarray, threshold: float, canonical: bool,

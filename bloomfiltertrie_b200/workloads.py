@@ -88,7 +88,8 @@ def genomes_to_torch(genomes: List[np.ndarray], device):
 
 def gen_kmer_queries(cat, starts, lens, k: int, n: int, seed: int, mix: Tuple[float, float, float] = (0.5, 0.25, 0.25)):
     """Query batch on cat.device: mix = (windows present in some genome, windows with one substituted nucleotide,
-    uniform random k-mers), shuffled. Returns int64 [n, W] (bit pattern = packed k-mer words)."""
+    uniform random k-mers), shuffled. Returns (int64 [n, W] whose bit pattern is the packed k-mer words,
+    uint8 [n] kind: 0 window / 1 mismatch / 2 random)."""
     import torch
     dev = cat.device
     g = torch.Generator(device=dev)
@@ -124,5 +125,7 @@ def gen_kmer_queries(cat, starts, lens, k: int, n: int, seed: int, mix: Tuple[fl
             r[:, w] = lo | (hi << 32)
         parts.append(r)
     out = torch.cat(parts)
+    kind = torch.cat([torch.zeros(n_p, dtype=torch.uint8, device=dev), torch.ones(n_m, dtype=torch.uint8, device=dev),
+                      torch.full((n_r,), 2, dtype=torch.uint8, device=dev)])
     perm = torch.randperm(n, generator=g, device=dev)
-    return out[perm].contiguous()
+    return out[perm].contiguous(), kind[perm].contiguous()

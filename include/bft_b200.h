@@ -135,6 +135,10 @@ int bft_b200_query_sequences_file(bft_b200_ctx* ctx, const char* query_path, con
  * depths ceil(log2(lines+1)) and found k-mers: out[0..2]. Diagnostic; synchronous. */
 int bft_b200_kmer_walk_stats_device(bft_b200_ctx* ctx, const uint64_t* d_kmers, size_t n, uint64_t out[3]);
 
+/* Random-access roofline probe: rate (loads/s) of independent 8-byte loads at random offsets of a table_bytes table
+ * (choose it far larger than the 126 MB L2). Diagnostic; synchronous. */
+int bft_b200_random_gather_probe(bft_b200_ctx* ctx, size_t table_bytes, size_t n_loads, double* loads_per_sec);
+
 /* wait for everything enqueued on the context's streams */
 int bft_b200_sync(bft_b200_ctx* ctx);
 
