@@ -18,18 +18,20 @@
  *   filter3[]  the p_v values, as stored (bytes for s=8, nibbles for s=4; src/presenceNode.c:1478-1479).
  *   pref[]     per stored prefix: where its suffixes live (inline line range, child Node, or leaf colour class).
  *              Replaces children_type prefix sums (count_children / count_nodes, include/CC.h:471-550).
- *   keys[]     every CC inline suffix line as W little-endian 64-bit words holding the suffix as an integer
- *              (nucleotide i at bits 2i), sorted ascending inside each prefix's block so the search is an integer
- *              compare (replaces memcmp in binary_search_UC, src/UC.c:81-124). When the colour-class ids fit
- *              above the widest suffix (cls_shift != 0) the line's class is stored in the top bits of its most
- *              significant word, so a hit needs no second load; otherwise linecls[] holds it.
- *   prefsub[]  per stored prefix: a 32-byte radix index over its block — byte i = number of lines whose top five
- *              suffix bits are <= i — which narrows the search to ~cnt/32 adjacent lines (one or two sectors)
- *              before keys[] is touched. rootsub[] is the same, indexed like rootdir[].
+ *   buckets[]  every CC inline suffix line, as W little-endian 64-bit words holding the suffix as an integer
+ *              (nucleotide i at bits 2i; replaces memcmp in binary_search_UC, src/UC.c:81-124), hashed by its own
+ *              top bits into fixed-size buckets: a prefix with cnt suffixes owns B = 2^lb consecutive buckets
+ *              (B >= cnt/2, lb <= 8) of BFT_BUCKET_KEYS = 4 slots — one 32-byte sector for W = 1, one 64-byte pair
+ *              for W = 2 — and suffix x lives in bucket hash(x) >> (64 - lb). A lookup therefore touches exactly one
+ *              aligned bucket: ONE random DRAM access per k-mer. Buckets that would hold more than 4 suffixes keep
+ *              3 and an overflow descriptor pointing into ovf[] (rare: the load factor is <= 1/2).
+ *              When the colour-class ids fit above the widest suffix (cls_shift != 0) the line's class is stored in
+ *              the spare top bits of its most significant word, so a hit needs no second load; otherwise
+ *              slotcls[]/ovfcls[] hold it. Bit 63 of the top word marks empty slots / overflow descriptors.
  *   uckeys[] / uccls[]  the Node-UC lines (whole k-mer remainders, src/presenceNode.c:1554-1573) and their classes.
  *   rootdir[]  262144 entries: the complete answer of the root Node probe for every possible 9-nt prefix, indexed
  *              by the low 18 bits of the packed k-mer. Every query passes through the root, so its probe is
- *              collapsed into one 8-byte load (+ one 32-byte rootsub load issued alongside).
+ *              collapsed into one 8-byte load.
  *   colour classes: distinct annotation byte strings (cls_off/cls_bytes) + the comp_set_colors pools; decoded on
  *              the device once per arena into class rows (bft_kernels.cu: k_decode_classes).
  *
@@ -68,8 +70,10 @@
 #define BFT_ROOTDIR_SIZE (1u << BFT_PREFIX_BITS)
 #define BFT_FIRSTCC_NONE 0xffu
 #define BFT_MAX_WORDS 2                /* k <= 63 (126 bits) */
-#define BFT_SUB_BYTES 32               /* radix index of one inline block: 32 cumulative counts */
-#define BFT_SUB_BITS 5
+#define BFT_BUCKET_KEYS 4              /* slots per bucket */
+#define BFT_MAX_LB 8                   /* at most 256 buckets per prefix */
+#define BFT_SLOT_EMPTY 0xffffffffffffffffULL
+#define BFT_SLOT_SPECIAL (1ULL << 63)  /* top word: empty slot (all ones) or overflow descriptor (count << 32 | start) */
 
 /* kinds of a prefix-probe answer */
 #define BFT_KIND_ABSENT 0u /* a CC's Bloom filter fired but the prefix is not stored there: k-mer absent */
@@ -78,13 +82,15 @@
 #define BFT_KIND_NODE 3u   /* prefix stored, suffixes in child Node a */
 #define BFT_KIND_LEAF 4u   /* leaf level (9 nt left): prefix stored, a = colour class */
 #define BFT_KIND_SHIFT 28
-#define BFT_CNT_MASK ((1u << BFT_KIND_SHIFT) - 1u)
+#define BFT_LB_SHIFT 24                /* INLINE entries: log2(#buckets) of the prefix's block */
+#define BFT_LB_MASK 0xfu
+#define BFT_CNT_MASK ((1u << BFT_LB_SHIFT) - 1u)
 
 #define BFT_CLS_NONE 0xffffffffu
 
 typedef struct {
-    uint32_t a; /* line index / node id / class id */
-    uint32_t b; /* kind << 28 | count */
+    uint32_t a; /* first bucket (INLINE) / first UC line (UC) / node id (NODE) / class id (LEAF) */
+    uint32_t b; /* kind << 28 | log2(#buckets) << 24 | count */
 } bft_entry_t;
 
 typedef struct {
@@ -114,15 +120,16 @@ typedef struct {
     const uint16_t* csr;
     const uint8_t* filter3;
     const bft_entry_t* pref;
-    const uint8_t* rootsub;   /* BFT_ROOTDIR_SIZE * BFT_SUB_BYTES */
-    const uint8_t* prefsub;   /* n_pref * BFT_SUB_BYTES */
-    const uint64_t* keys;     /* n_lines * W words (inline suffix lines) */
-    const uint32_t* linecls;  /* n_lines, only when cls_shift == 0 */
+    const uint64_t* buckets;  /* n_buckets * BFT_BUCKET_KEYS * W words (inline suffix lines, bucketed) */
+    const uint64_t* ovf;      /* n_ovf * W words (suffixes that did not fit their bucket) */
+    const uint32_t* slotcls;  /* n_buckets * BFT_BUCKET_KEYS, only when cls_shift == 0 */
+    const uint32_t* ovfcls;   /* n_ovf, only when cls_shift == 0 */
     const uint64_t* uckeys;   /* n_uc_lines * W words (Node-UC lines) */
     const uint32_t* uccls;    /* n_uc_lines */
     int k;
-    int W;         /* 64-bit words per key: 1 for k <= 27, 2 for k <= 63 */
-    int cls_shift; /* != 0: class id of an inline line = top word >> cls_shift, suffix = the bits below */
+    int W;             /* 64-bit words per key: 1 for k <= 27, 2 for k <= 63 */
+    int cls_shift;     /* != 0: class id of an inline line = (top word >> cls_shift) & cls_mask, suffix = the bits below */
+    uint32_t cls_mask;
 } bft_view_t;
 
 /* ---- prefix bit manipulation --------------------------------------------------------------------------------
@@ -156,12 +163,27 @@ BFT_HD bft_entry_t bft_mk_entry(uint32_t kind, uint32_t a, uint32_t n) {
     return e;
 }
 
+/* a bucket's 4*W words. On the device each 32-byte half is ONE 256-bit load (LDG.E.256, new on sm_100): measured on
+ * B200 (tools/gather_probe.cu) a random 256-bit load sustains the same 37.9 G accesses/s as a random 8-byte load,
+ * while two 128-bit loads of the same sector reach only 31-35 G/s. The L2::64B qualifier caps the sector promotion
+ * on a miss (128 B of HBM traffic per random access by default, 64 B with it). */
+BFT_HD void bft_ld_bucket(const uint64_t* p, uint64_t* out, const int W) {
+#ifdef __CUDA_ARCH__
+    for (int i = 0; i < W; i++)
+        asm volatile("ld.global.nc.L2::64B.v4.u64 {%0,%1,%2,%3}, [%4];"
+                     : "=l"(out[4 * i]), "=l"(out[4 * i + 1]), "=l"(out[4 * i + 2]), "=l"(out[4 * i + 3])
+                     : "l"(p + 4 * i));
+#else
+    for (int i = 0; i < BFT_BUCKET_KEYS * W; i++) out[i] = p[i];
+#endif
+}
+
 /* One Node probe: the reference's presenceKmer (src/presenceNode.c:1284-1576) on the flattened layout.
  * succ_leaf_quirk != 0 reproduces presenceNeighborsRight at the leaf level (size_kmer == 9,
  * src/presenceNode.c:719-723): the reference clears nucleotide 7 of the prefix (`& 0xfc` on the second byte) before
  * hashing and before forming p_u/p_v, so the CC path answers for the prefix with nuc 7 = A; the Node-UC path
  * (:1164-1208) compares the unmodified k-mer. Only the successor lookups of the branching queries pass it. */
-BFT_HD bft_entry_t bft_node_probe(const bft_view_t* v, uint32_t node_id, uint32_t low18, int succ_leaf_quirk, uint32_t* pref_idx) {
+BFT_HD bft_entry_t bft_node_probe(const bft_view_t* v, uint32_t node_id, uint32_t low18, int succ_leaf_quirk) {
     bft_node_t nd;
 #ifdef __CUDA_ARCH__
     {
@@ -212,7 +234,6 @@ BFT_HD bft_entry_t bft_node_probe(const bft_view_t* v, uint32_t node_id, uint32_
                 uint32_t t = (lo & 1u) ? (uint32_t)(BFT_LD8(f3 + (lo >> 1)) >> 4) : (uint32_t)(BFT_LD8(f3 + (lo >> 1)) & 0xf);
                 if (t != pv) return bft_mk_entry(BFT_KIND_ABSENT, 0, 0);
             }
-            *pref_idx = cc.pref_off + lo;
             return bft_ld_entry(v->pref + cc.pref_off + lo);
         }
     }
@@ -242,40 +263,44 @@ BFT_HD uint32_t bft_search_uc(const bft_view_t* v, uint32_t begin, uint32_t n, c
     return 0xffffffffu;
 }
 
-/* Search one prefix's inline block [begin, begin+n) for `key` (the suffix left after the 9-nt prefix, key_bits wide)
- * and return the colour class of the matching line, or BFT_CLS_NONE (binary_search_UC over the block + equality,
- * src/presenceNode.c:1876-1914). `sub` is the block's radix index: the candidates are the lines whose top five
- * suffix bits equal the key's — on average n/32 adjacent lines, fetched with independent loads. */
-BFT_HD uint32_t bft_search_block(const bft_view_t* v, uint32_t begin, uint32_t n, const uint8_t* sub, const uint64_t* key,
-                                 const int W, const int key_bits) {
-    /* top five bits of the suffix: in the upper word only when the suffix is wider than 64 bits (W == 2) */
-    const int upper = (W > 1) && (key_bits > 64);
-    const uint64_t topw = upper ? key[W - 1] : key[0];
-    const uint32_t t = (uint32_t)(topw >> (key_bits - (upper ? 64 : 0) - BFT_SUB_BITS)) & (BFT_SUB_BYTES - 1u);
-    const uint32_t c_hi = BFT_LD8(sub + t);
-    const uint32_t c_lo = t ? BFT_LD8(sub + t - 1) : 0u;
-    uint32_t lo = begin + c_lo, hi = begin + c_hi;
-    if (hi > begin + n) hi = begin + n;
+/* Search one prefix's inline block for `key` (the suffix left after the 9-nt prefix) and return the colour class of
+ * the matching line, or BFT_CLS_NONE (binary_search_UC over the block + equality, src/presenceNode.c:1876-1914).
+ * The block is 2^lb buckets starting at bucket `base`; a hash of the key names the only bucket that can hold it. */
+BFT_HD uint32_t bft_bucket_of(const uint64_t* key, const int W, const uint32_t lb) {
+    /* multiplicative hash of the whole suffix: the suffixes of one prefix are near-duplicates of each other in a
+     * pan-genome (SNP variants share all but one nucleotide), so raw leading bits would pile them into one bucket */
+    uint64_t x = key[0];
+    if (W > 1) x ^= key[W - 1] * 0xC2B2AE3D27D4EB4FULL;
+    x ^= x >> 29;
+    return lb ? (uint32_t)((x * 0x9E3779B97F4A7C15ULL) >> (64 - lb)) : 0u;
+}
+
+BFT_HD uint32_t bft_search_block(const bft_view_t* v, uint32_t base, uint32_t lb, const uint64_t* key, const int W) {
+    const size_t bucket = (size_t)base + bft_bucket_of(key, W, lb);
+    uint64_t s[BFT_BUCKET_KEYS * BFT_MAX_WORDS];
+    bft_ld_bucket(v->buckets + bucket * (size_t)(BFT_BUCKET_KEYS * W), s, W);
     const int shift = v->cls_shift;
-    const uint64_t top_mask = shift ? ((1ULL << shift) - 1ULL) : ~0ULL;
-    while (hi - lo > 4 && lo < hi) { /* crowded bucket (skewed suffixes): bisect down to a handful */
-        const uint32_t mid = lo + ((hi - lo) >> 1);
-        const uint64_t* p = v->keys + (size_t)mid * W;
-        int less = 0;
-        for (int w = W - 1; w >= 0; w--) {
-            uint64_t x = BFT_LD64(p + w);
-            if (w == W - 1) x &= top_mask;
-            if (x != key[w]) { less = x < key[w]; break; }
-        }
-        if (less) lo = mid + 1; else hi = mid + 1;
-    }
+    const uint64_t top_mask = shift ? ((1ULL << shift) - 1ULL) : ~BFT_SLOT_SPECIAL;
     uint32_t found = BFT_CLS_NONE;
-    for (uint32_t i = lo; i < hi; i++) { /* <= 4 independent loads, adjacent addresses */
-        const uint64_t* p = v->keys + (size_t)i * W;
-        const uint64_t top = BFT_LD64(p + W - 1);
-        int eq = (top & top_mask) == key[W - 1];
-        for (int w = 0; w < W - 1; w++) eq &= (BFT_LD64(p + w) == key[w]);
-        if (eq) found = shift ? (uint32_t)(top >> shift) : BFT_LD32(v->linecls + i);
+#ifdef __CUDA_ARCH__
+#pragma unroll
+#endif
+    for (int j = 0; j < BFT_BUCKET_KEYS; j++) {
+        const uint64_t top = s[j * W + W - 1];
+        int eq = !(top & BFT_SLOT_SPECIAL) && (top & top_mask) == key[W - 1];
+        if (W > 1) eq = eq && s[j * W] == key[0];
+        if (eq) found = shift ? ((uint32_t)(top >> shift) & v->cls_mask) : BFT_LD32(v->slotcls + bucket * BFT_BUCKET_KEYS + j);
+    }
+    const uint64_t last = s[(BFT_BUCKET_KEYS - 1) * W + W - 1];
+    if (found == BFT_CLS_NONE && (last & BFT_SLOT_SPECIAL) && last != BFT_SLOT_EMPTY) { /* overflow run */
+        const uint32_t start = (uint32_t)last, cnt = (uint32_t)(last >> 32) & 0x7fffffffu;
+        for (uint32_t i = 0; i < cnt; i++) {
+            const uint64_t* p = v->ovf + ((size_t)start + i) * W;
+            const uint64_t top = BFT_LD64(p + W - 1);
+            int eq = (top & top_mask) == key[W - 1];
+            if (W > 1) eq = eq && BFT_LD64(p) == key[0];
+            if (eq) found = shift ? ((uint32_t)(top >> shift) & v->cls_mask) : BFT_LD32(v->ovfcls + start + i);
+        }
     }
     return found;
 }
@@ -303,9 +328,7 @@ BFT_HD uint32_t bft_lookup_ex(const bft_view_t* v, const uint64_t* kmer, const i
     uint64_t cur[BFT_MAX_WORDS];
     for (int w = 0; w < BFT_MAX_WORDS; w++) cur[w] = w < W ? kmer[w] : 0;
     int sz = v->k;
-    const uint32_t low18 = (uint32_t)cur[0] & (BFT_ROOTDIR_SIZE - 1u);
-    bft_entry_t e = bft_ld_entry(v->rootdir + low18);
-    const uint8_t* sub = v->rootsub + (size_t)low18 * BFT_SUB_BYTES;
+    bft_entry_t e = bft_ld_entry(v->rootdir + ((uint32_t)cur[0] & (BFT_ROOTDIR_SIZE - 1u)));
     if (st) st[0]++;
     for (;;) {
         const uint32_t kind = e.b >> BFT_KIND_SHIFT;
@@ -326,15 +349,13 @@ BFT_HD uint32_t bft_lookup_ex(const bft_view_t* v, const uint64_t* kmer, const i
         sz -= BFT_NB_CHAR_SUF_PREF;
         if (kind == BFT_KIND_INLINE) {
             if (st) st[1] += bft_ceil_log2p1(n);
-            const uint32_t cls = bft_search_block(v, e.a, n, sub, cur, W, 2 * sz);
+            const uint32_t cls = bft_search_block(v, e.a, (e.b >> BFT_LB_SHIFT) & BFT_LB_MASK, cur, W);
             if (st && cls != BFT_CLS_NONE) st[2]++;
             return cls;
         }
         /* BFT_KIND_NODE */
         if (st) st[0]++;
-        uint32_t pi = 0;
-        e = bft_node_probe(v, e.a, (uint32_t)cur[0] & (BFT_ROOTDIR_SIZE - 1u), succ_leaf_quirk && sz == BFT_NB_CHAR_SUF_PREF, &pi);
-        sub = v->prefsub + (size_t)pi * BFT_SUB_BYTES;
+        e = bft_node_probe(v, e.a, (uint32_t)cur[0] & (BFT_ROOTDIR_SIZE - 1u), succ_leaf_quirk && sz == BFT_NB_CHAR_SUF_PREF);
     }
 }
 

@@ -154,6 +154,13 @@ extern "C" int bft_b200_open(const char* path, int device, bft_b200_ctx** out) {
     if (device < 0 || device >= ndev) return set_err(BFT_B200_ERR_ARG, "bft_b200_open: device %d out of range (0..%d)", device, ndev - 1);
     CK(cudaSetDevice(device));
 
+    /* the walk reads isolated 32-byte sectors; ask L2 not to over-fetch their neighbours from HBM (a hint) */
+    {
+        const char* g = getenv("BFT_B200_L2_FETCH");
+        size_t gran = g ? (size_t)atoi(g) : 32;
+        if (gran == 32 || gran == 64 || gran == 128) cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, gran);
+    }
+
     char ferr[256];
     double t0 = now_s();
     bft_arena_t* a = bft_arena_from_file(path, ferr, sizeof ferr);
@@ -183,10 +190,10 @@ extern "C" int bft_b200_open(const char* path, int device, bft_b200_ctx** out) {
     UP(4, csr, a->n_csr * sizeof(uint16_t));
     UP(5, filter3, a->filter3_bytes);
     UP(6, pref, a->n_pref * sizeof(bft_entry_t));
-    UP(7, keys, a->n_lines * (size_t)a->W * sizeof(uint64_t));
-    UP(8, linecls, a->linecls ? a->n_lines * sizeof(uint32_t) : 0);
-    UP(9, rootsub, (size_t)BFT_ROOTDIR_SIZE * BFT_SUB_BYTES);
-    UP(10, prefsub, a->n_pref * BFT_SUB_BYTES);
+    UP(7, buckets, a->n_buckets * (size_t)(BFT_BUCKET_KEYS * a->W) * sizeof(uint64_t));
+    UP(8, slotcls, a->slotcls ? a->n_buckets * BFT_BUCKET_KEYS * sizeof(uint32_t) : 0);
+    UP(9, ovf, a->n_ovf * (size_t)a->W * sizeof(uint64_t));
+    UP(10, ovfcls, a->ovfcls ? a->n_ovf * sizeof(uint32_t) : 0);
     UP(11, uckeys, a->n_uc_lines * (size_t)a->W * sizeof(uint64_t));
     UP(12, uccls, a->n_uc_lines * sizeof(uint32_t));
 #undef UP
@@ -206,13 +213,14 @@ extern "C" int bft_b200_open(const char* path, int device, bft_b200_ctx** out) {
         c->dview.csr = (const uint16_t*)c->d_arena[4];
         c->dview.filter3 = (const uint8_t*)c->d_arena[5];
         c->dview.pref = (const bft_entry_t*)c->d_arena[6];
-        c->dview.keys = (const uint64_t*)c->d_arena[7];
-        c->dview.linecls = (const uint32_t*)c->d_arena[8];
-        c->dview.rootsub = (const uint8_t*)c->d_arena[9];
-        c->dview.prefsub = (const uint8_t*)c->d_arena[10];
+        c->dview.buckets = (const uint64_t*)c->d_arena[7];
+        c->dview.slotcls = (const uint32_t*)c->d_arena[8];
+        c->dview.ovf = (const uint64_t*)c->d_arena[9];
+        c->dview.ovfcls = (const uint32_t*)c->d_arena[10];
         c->dview.uckeys = (const uint64_t*)c->d_arena[11];
         c->dview.uccls = (const uint32_t*)c->d_arena[12];
         c->dview.cls_shift = a->cls_shift;
+        c->dview.cls_mask = a->cls_mask;
         c->dview.k = a->k;
         c->dview.W = a->W;
         c->dpools.n_pools = a->n_pools;

@@ -33,13 +33,14 @@ typedef struct {
     uint64_t* hv1; /* raw XXH64 per idx14 */
     uint64_t* hv2;
     /* capacities */
-    size_t cap_nodes, cap_ccs, cap_firstcc, cap_csr, cap_filter3, cap_pref, cap_prefsub, cap_lines, cap_uc_lines, cap_cls_off, cap_cls_bytes;
+    size_t cap_nodes, cap_ccs, cap_firstcc, cap_csr, cap_filter3, cap_pref, cap_buckets, cap_ovf, cap_uc_lines, cap_cls_off, cap_cls_bytes;
     /* class hash map */
     uint32_t* map; size_t map_cap, map_used;
     /* scratch */
     line_tmp_t* tmp; size_t cap_tmp;
     uint8_t* scratch; size_t cap_scratch;   /* one annotation + extended byte */
     int16_t* extbuf; size_t cap_extbuf;     /* per line of the UC being read: extended byte or -1 */
+    uint32_t* bkt; size_t cap_bkt;          /* bucketing scratch */
     int depth;
     char* err; size_t errlen;
     jmp_buf jb;
@@ -201,12 +202,9 @@ static int cmp_line_tmp(const void* pa, const void* pb) {
     return 0;
 }
 
-/* append lines [first, first+cnt) of a UC body as one sorted block; returns the index of its first line in the
- * arena it went to. sub == NULL: a Node's own UC (uckeys/uccls). sub != NULL: a prefix's inline block (keys/linecls);
- * its 32-byte radix index over the top five suffix bits is written to sub. */
-static uint32_t append_block(ctx_t* c, const uc_body_t* u, int first, int cnt, int key_bits, int strip_bit7, uint8_t* sub) {
-    bft_arena_t* a = c->a;
-    const int W = a->W;
+/* read lines [first, first+cnt) of a UC body into c->tmp (key + colour class), sorted by key */
+static void load_block(ctx_t* c, const uc_body_t* u, int first, int cnt, int key_bits, int strip_bit7) {
+    const int W = c->a->W;
     GROW(c, c->tmp, c->cap_tmp, (size_t)cnt, line_tmp_t);
     for (int i = 0; i < cnt; i++) {
         line_key(c, u, first + i, key_bits, strip_bit7, c->tmp[i].k);
@@ -215,35 +213,100 @@ static uint32_t append_block(ctx_t* c, const uc_body_t* u, int first, int cnt, i
             if (c->tmp[i].k[w]) fail(c, "bft_flatten: key wider than W words");
     }
     if (cnt > 1) qsort(c->tmp, (size_t)cnt, sizeof(line_tmp_t), cmp_line_tmp);
-    uint64_t** keys = sub ? &a->keys : &a->uckeys;
-    uint32_t** cls = sub ? &a->linecls : &a->uccls;
-    size_t* n = sub ? &a->n_lines : &a->n_uc_lines;
-    size_t* cap = sub ? &c->cap_lines : &c->cap_uc_lines;
-    if (*n + (size_t)cnt >= 0xfffffff0u) fail(c, "bft_flatten: more than 2^32 suffix lines");
-    const size_t need = *n + (size_t)cnt;
-    if (need > *cap) {
-        size_t ncap = *cap ? *cap : 4096;
+}
+
+/* a Node's own UC -> uckeys/uccls (sorted, binary-searched); returns the index of its first line */
+static uint32_t append_uc_lines(ctx_t* c, const uc_body_t* u, int cnt, int key_bits) {
+    bft_arena_t* a = c->a;
+    const int W = a->W;
+    load_block(c, u, 0, cnt, key_bits, 0);
+    if (a->n_uc_lines + (size_t)cnt >= 0xfffffff0u) fail(c, "bft_flatten: more than 2^32 Node-UC lines");
+    const size_t need = a->n_uc_lines + (size_t)cnt;
+    if (need > c->cap_uc_lines) {
+        size_t ncap = c->cap_uc_lines ? c->cap_uc_lines : 4096;
         while (ncap < need) ncap += ncap / 2 + 4096;
-        *keys = (uint64_t*)xrealloc(c, *keys, ncap * (size_t)W * sizeof(uint64_t));
-        *cls = (uint32_t*)xrealloc(c, *cls, ncap * sizeof(uint32_t));
-        *cap = ncap;
+        a->uckeys = (uint64_t*)xrealloc(c, a->uckeys, ncap * (size_t)W * sizeof(uint64_t));
+        a->uccls = (uint32_t*)xrealloc(c, a->uccls, ncap * sizeof(uint32_t));
+        c->cap_uc_lines = ncap;
     }
-    const uint32_t start = (uint32_t)*n;
+    const uint32_t start = (uint32_t)a->n_uc_lines;
     for (int i = 0; i < cnt; i++) {
-        for (int w = 0; w < W; w++) (*keys)[(*n + (size_t)i) * W + w] = c->tmp[i].k[w];
-        (*cls)[*n + (size_t)i] = c->tmp[i].cls;
+        for (int w = 0; w < W; w++) a->uckeys[(a->n_uc_lines + (size_t)i) * W + w] = c->tmp[i].k[w];
+        a->uccls[a->n_uc_lines + (size_t)i] = c->tmp[i].cls;
     }
-    if (sub) {
-        if (cnt > 255) fail(c, "bft_flatten: inline block of %d lines (radix index holds at most 255)", cnt);
-        uint32_t hist[BFT_SUB_BYTES] = {0};
-        const int tw = key_bits > 64 ? 1 : 0;
-        for (int i = 0; i < cnt; i++) hist[(c->tmp[i].k[tw] >> (key_bits - 64 * tw - BFT_SUB_BITS)) & (BFT_SUB_BYTES - 1)]++;
-        uint32_t run = 0;
-        for (int t = 0; t < BFT_SUB_BYTES; t++) { run += hist[t]; sub[t] = (uint8_t)run; }
-    }
-    *n += (size_t)cnt;
+    a->n_uc_lines += (size_t)cnt;
     a->n_kmers += (size_t)cnt;
     return start;
+}
+
+/* a prefix's inline suffixes -> 2^lb buckets of BFT_BUCKET_KEYS slots keyed by the top lb bits of the suffix
+ * (layout in bft_arena.h). Returns the INLINE entry (first bucket, lb, count). */
+static bft_entry_t append_inline_block(ctx_t* c, const uc_body_t* u, int first, int cnt, int key_bits, int strip_bit7) {
+    bft_arena_t* a = c->a;
+    const int W = a->W, S = BFT_BUCKET_KEYS;
+    load_block(c, u, first, cnt, key_bits, strip_bit7);
+    uint32_t lb = 0;
+    while (lb < BFT_MAX_LB && ((size_t)1 << lb) * (S / 2) < (size_t)cnt) lb++;
+    const size_t B = (size_t)1 << lb;
+    if (a->n_buckets + B >= 0xfffffff0u) fail(c, "bft_flatten: more than 2^32 suffix buckets");
+    if (a->n_buckets + B > c->cap_buckets) {
+        size_t ncap = c->cap_buckets ? c->cap_buckets : 4096;
+        while (ncap < a->n_buckets + B) ncap += ncap / 2 + 4096;
+        a->buckets = (uint64_t*)xrealloc(c, a->buckets, ncap * (size_t)(S * W) * sizeof(uint64_t));
+        a->slotcls = (uint32_t*)xrealloc(c, a->slotcls, ncap * (size_t)S * sizeof(uint32_t));
+        c->cap_buckets = ncap;
+    }
+    const uint32_t base = (uint32_t)a->n_buckets;
+    uint64_t* bk = a->buckets + (size_t)base * (S * W);
+    uint32_t* bc = a->slotcls + (size_t)base * S;
+    for (size_t i = 0; i < B * (size_t)(S * W); i++) bk[i] = BFT_SLOT_EMPTY;
+    for (size_t i = 0; i < B * (size_t)S; i++) bc[i] = BFT_CLS_NONE;
+    /* bucket of every line, then a counting sort of the block by bucket */
+    GROW(c, c->bkt, c->cap_bkt, (size_t)cnt * 2 + 2 * ((size_t)1 << BFT_MAX_LB) + 2, uint32_t);
+    uint32_t* bkt = c->bkt;                 /* [cnt] bucket per line */
+    uint32_t* order = c->bkt + cnt;         /* [cnt] lines grouped by bucket */
+    uint32_t* head = c->bkt + 2 * (size_t)cnt; /* [B + 1] */
+    for (size_t t = 0; t <= B; t++) head[t] = 0;
+    for (int i = 0; i < cnt; i++) { bkt[i] = bft_bucket_of(c->tmp[i].k, W, lb); head[bkt[i] + 1]++; }
+    for (size_t t = 0; t < B; t++) head[t + 1] += head[t];
+    uint32_t* fill = head + B + 1;          /* [B] running cursor */
+    for (size_t t = 0; t < B; t++) fill[t] = head[t];
+    for (int i = 0; i < cnt; i++) order[fill[bkt[i]]++] = (uint32_t)i;
+    (void)key_bits;
+    for (size_t t = 0; t < B; t++) {
+        const int m = (int)(head[t + 1] - head[t]);
+        if (!m) continue;
+        const uint32_t* idx = order + head[t];
+        const int in_bucket = m <= S ? m : S - 1;
+        for (int q = 0; q < in_bucket; q++) {
+            for (int w = 0; w < W; w++) bk[(t * S + q) * W + w] = c->tmp[idx[q]].k[w];
+            bc[t * S + q] = c->tmp[idx[q]].cls;
+        }
+        if (m > S) { /* spill the rest; the last slot becomes the overflow descriptor */
+            const int spill = m - (S - 1);
+            if (a->n_ovf + (size_t)spill >= 0xfffffff0u) fail(c, "bft_flatten: overflow area exceeds 2^32 lines");
+            if (a->n_ovf + (size_t)spill > c->cap_ovf) {
+                size_t ncap = c->cap_ovf ? c->cap_ovf : 4096;
+                while (ncap < a->n_ovf + (size_t)spill) ncap += ncap / 2 + 4096;
+                a->ovf = (uint64_t*)xrealloc(c, a->ovf, ncap * (size_t)W * sizeof(uint64_t));
+                a->ovfcls = (uint32_t*)xrealloc(c, a->ovfcls, ncap * sizeof(uint32_t));
+                c->cap_ovf = ncap;
+            }
+            for (int q = 0; q < spill; q++) {
+                for (int w = 0; w < W; w++) a->ovf[(a->n_ovf + (size_t)q) * W + w] = c->tmp[idx[S - 1 + q]].k[w];
+                a->ovfcls[a->n_ovf + (size_t)q] = c->tmp[idx[S - 1 + q]].cls;
+            }
+            for (int w = 0; w < W - 1; w++) bk[(t * S + S - 1) * W + w] = 0;
+            bk[(t * S + S - 1) * W + W - 1] = BFT_SLOT_SPECIAL | ((uint64_t)spill << 32) | (uint64_t)a->n_ovf;
+            a->n_ovf += (size_t)spill;
+        }
+    }
+    a->n_buckets += B;
+    a->n_lines += (size_t)cnt;
+    a->n_kmers += (size_t)cnt;
+    bft_entry_t e = bft_mk_entry(BFT_KIND_INLINE, base, (uint32_t)cnt);
+    e.b |= lb << BFT_LB_SHIFT;
+    return e;
 }
 
 static uint32_t parse_node(ctx_t* c, int sz, int* cluster_flag);
@@ -282,8 +345,6 @@ static void parse_cc(ctx_t* c, int sz, uint32_t cc_id, uint8_t* bf) {
     if (a->n_pref + (size_t)nb_elem > 0xfffffff0u) fail(c, "bft_flatten: more than 2^32 stored prefixes");
     const uint32_t pref_off = (uint32_t)a->n_pref;
     GROW(c, a->pref, c->cap_pref, a->n_pref + (size_t)nb_elem, bft_entry_t);
-    GROW(c, a->prefsub, c->cap_prefsub, (a->n_pref + (size_t)nb_elem) * BFT_SUB_BYTES, uint8_t);
-    memset(a->prefsub + a->n_pref * BFT_SUB_BYTES, 0, (size_t)nb_elem * BFT_SUB_BYTES);
     a->n_pref += (size_t)nb_elem;
 
     uint8_t* flags = (uint8_t*)xrealloc(c, NULL, (size_t)nb_elem + 1);
@@ -314,8 +375,7 @@ static void parse_cc(ctx_t* c, int sz, uint32_t cc_id, uint8_t* bf) {
                 if (off + ne > nlines) fail(c, "bft_flatten: children_type overruns its UC bucket");
                 if (li->level_min == 0) /* in-band cluster flag: bit 7 of the last suffix byte of the first line */
                     flags[j] = u.lines[(size_t)off * (size_t)(size_sub + u.size_annot) + size_sub - 1] >> 7;
-                uint32_t start = append_block(c, &u, off, ne, key_bits, strip, a->prefsub + ((size_t)pref_off + j) * BFT_SUB_BYTES);
-                a->pref[pref_off + j] = bft_mk_entry(BFT_KIND_INLINE, start, (uint32_t)ne);
+                a->pref[pref_off + j] = append_inline_block(c, &u, off, ne, key_bits, strip);
                 off += ne;
             }
             if (off != nlines) fail(c, "bft_flatten: UC bucket holds %d lines but children_type accounts for %d", nlines, off);
@@ -414,7 +474,7 @@ static uint32_t parse_node(ctx_t* c, int sz, int* cluster_flag) {
     read_uc_body(c, &u, size_kmer_in_bytes(sz), n_uc);
     uint32_t uc_begin = 0;
     if (n_uc) {
-        uc_begin = append_block(c, &u, 0, n_uc, 2 * sz, 0, NULL);
+        uc_begin = append_uc_lines(c, &u, n_uc, 2 * sz);
     }
     const uint32_t n_cc = rd_u32(c);
     if (n_cc >= BFT_FIRSTCC_NONE) fail(c, "bft_flatten: node with %u CCs (first-CC table holds at most 254)", n_cc);
@@ -465,13 +525,14 @@ void bft_arena_view(const bft_arena_t* a, bft_view_t* v) {
     v->csr = a->csr;
     v->filter3 = a->filter3;
     v->pref = a->pref;
-    v->rootsub = a->rootsub;
-    v->prefsub = a->prefsub;
-    v->keys = a->keys;
-    v->linecls = a->linecls;
+    v->buckets = a->buckets;
+    v->ovf = a->ovf;
+    v->slotcls = a->slotcls;
+    v->ovfcls = a->ovfcls;
     v->uckeys = a->uckeys;
     v->uccls = a->uccls;
     v->cls_shift = a->cls_shift;
+    v->cls_mask = a->cls_mask;
     v->k = a->k;
     v->W = a->W;
 }
@@ -483,15 +544,15 @@ void bft_arena_free(bft_arena_t* a) {
         free(a->filenames);
     }
     free(a->rootdir); free(a->nodes); free(a->ccs); free(a->firstcc); free(a->csr); free(a->filter3);
-    free(a->pref); free(a->prefsub); free(a->rootsub); free(a->keys); free(a->linecls); free(a->uckeys); free(a->uccls); free(a->cls_off); free(a->cls_bytes);
+    free(a->pref); free(a->buckets); free(a->slotcls); free(a->ovf); free(a->ovfcls); free(a->uckeys); free(a->uccls); free(a->cls_off); free(a->cls_bytes);
     free(a->pool_last_index); free(a->pool_size_annot); free(a->pool_off); free(a->pool_bytes);
     free(a);
 }
 
 size_t bft_arena_bytes(const bft_arena_t* a) {
     return BFT_ROOTDIR_SIZE * sizeof(bft_entry_t) + a->n_nodes * sizeof(bft_node_t) + a->n_ccs * sizeof(bft_cc_t) +
-           a->firstcc_bytes + a->n_csr * 2 + a->filter3_bytes + a->n_pref * (sizeof(bft_entry_t) + BFT_SUB_BYTES) +
-           (size_t)BFT_ROOTDIR_SIZE * BFT_SUB_BYTES + a->n_lines * ((size_t)a->W * 8 + (a->cls_shift ? 0 : 4)) +
+           a->firstcc_bytes + a->n_csr * 2 + a->filter3_bytes + a->n_pref * sizeof(bft_entry_t) +
+           (a->n_buckets * BFT_BUCKET_KEYS + a->n_ovf) * ((size_t)a->W * 8 + (a->cls_shift ? 0 : 4)) +
            a->n_uc_lines * ((size_t)a->W * 8 + 4) + (a->n_classes + 1) * 4 + a->cls_bytes_len + a->pool_bytes_len;
 }
 
@@ -502,7 +563,7 @@ bft_arena_t* bft_arena_from_memory(const uint8_t* buf, size_t len, char* err, si
     c->buf = buf; c->len = len; c->a = a; c->err = err; c->errlen = errlen;
     if (err && errlen) err[0] = 0;
     if (setjmp(c->jb)) {
-        free(c->map); free(c->tmp); free(c->hv1); free(c->hv2); free(c->scratch); free(c->extbuf);
+        free(c->map); free(c->tmp); free(c->hv1); free(c->hv2); free(c->scratch); free(c->extbuf); free(c->bkt);
         free(c);
         bft_arena_free(a);
         return NULL;
@@ -586,20 +647,23 @@ bft_arena_t* bft_arena_from_memory(const uint8_t* buf, size_t len, char* err, si
     memset(a->filter3 + a->filter3_bytes, 0, 16);
     GROW(c, a->csr, c->cap_csr, a->n_csr + 8, uint16_t);
     GROW(c, a->pref, c->cap_pref, a->n_pref + 1, bft_entry_t);
-    GROW(c, a->prefsub, c->cap_prefsub, (a->n_pref + 1) * BFT_SUB_BYTES, uint8_t);
     GROW(c, a->ccs, c->cap_ccs, a->n_ccs + 1, bft_cc_t);
     GROW(c, a->firstcc, c->cap_firstcc, a->firstcc_bytes + 1, uint8_t);
-    if (!a->keys) {
-        a->keys = (uint64_t*)xrealloc(c, NULL, 8 * BFT_MAX_WORDS);
-        a->linecls = (uint32_t*)xrealloc(c, NULL, 8);
+    if (!a->buckets) {
+        a->buckets = (uint64_t*)xrealloc(c, NULL, 8 * BFT_MAX_WORDS * BFT_BUCKET_KEYS);
+        a->slotcls = (uint32_t*)xrealloc(c, NULL, 4 * BFT_BUCKET_KEYS);
+    }
+    if (!a->ovf) {
+        a->ovf = (uint64_t*)xrealloc(c, NULL, 8 * BFT_MAX_WORDS);
+        a->ovfcls = (uint32_t*)xrealloc(c, NULL, 8);
     }
     if (!a->uckeys) {
         a->uckeys = (uint64_t*)xrealloc(c, NULL, 8 * BFT_MAX_WORDS);
         a->uccls = (uint32_t*)xrealloc(c, NULL, 8);
     }
 
-    /* colour class ids into the spare top bits of the inline keys when they fit above the widest suffix:
-     * k <= 27: 36 suffix bits + up to 28 class bits; k <= 63: 44 bits in the upper word + up to 20 class bits */
+    /* colour class ids into the spare top bits of the inline keys when they fit between the widest suffix and the
+     * flag bit 63: k <= 27: 36 suffix bits + up to 27 class bits; k <= 63: 44 bits in the upper word + up to 19 */
     {
         int cls_bits = 1;
         while (((size_t)1 << cls_bits) < a->n_classes) cls_bits++;
@@ -609,30 +673,31 @@ bft_arena_t* bft_arena_from_memory(const uint8_t* buf, size_t len, char* err, si
             if (kb > top_bits) top_bits = kb;
         }
         a->cls_shift = 0;
-        const char* no_embed = getenv("BFT_B200_NO_EMBED"); /* test hook: keep the separate linecls[] path */
-        if (top_bits + cls_bits <= 64 && cls_bits < 32 && !(no_embed && no_embed[0] == '1')) {
-            a->cls_shift = 64 - cls_bits;
-            for (size_t i = 0; i < a->n_lines; i++)
-                a->keys[i * (size_t)a->W + (size_t)a->W - 1] |= (uint64_t)a->linecls[i] << a->cls_shift;
-            free(a->linecls);
-            a->linecls = NULL;
+        a->cls_mask = 0;
+        const char* no_embed = getenv("BFT_B200_NO_EMBED"); /* test hook: keep the separate class arrays */
+        if (top_bits + cls_bits <= 63 && cls_bits < 32 && !(no_embed && no_embed[0] == '1')) {
+            a->cls_shift = 63 - cls_bits;
+            a->cls_mask = (uint32_t)(((uint64_t)1 << cls_bits) - 1);
+            const size_t W = (size_t)a->W;
+            for (size_t i = 0; i < a->n_buckets * BFT_BUCKET_KEYS; i++) {
+                uint64_t* top = &a->buckets[i * W + W - 1];
+                if (!(*top & BFT_SLOT_SPECIAL)) *top |= (uint64_t)a->slotcls[i] << a->cls_shift;
+            }
+            for (size_t i = 0; i < a->n_ovf; i++) a->ovf[i * W + W - 1] |= (uint64_t)a->ovfcls[i] << a->cls_shift;
+            free(a->slotcls);
+            free(a->ovfcls);
+            a->slotcls = NULL;
+            a->ovfcls = NULL;
         }
     }
 
-    /* root directory: the root probe for every 9-nt prefix, and the radix index of the block it lands in */
+    /* root directory: the root probe for every 9-nt prefix */
     a->rootdir = (bft_entry_t*)xrealloc(c, NULL, BFT_ROOTDIR_SIZE * sizeof(bft_entry_t));
-    a->rootsub = (uint8_t*)xrealloc(c, NULL, (size_t)BFT_ROOTDIR_SIZE * BFT_SUB_BYTES);
-    memset(a->rootsub, 0, (size_t)BFT_ROOTDIR_SIZE * BFT_SUB_BYTES);
     bft_view_t v;
     bft_arena_view(a, &v);
-    for (uint32_t low18 = 0; low18 < BFT_ROOTDIR_SIZE; low18++) {
-        uint32_t pi = 0;
-        a->rootdir[low18] = bft_node_probe(&v, 0, low18, 0, &pi);
-        if ((a->rootdir[low18].b >> BFT_KIND_SHIFT) == BFT_KIND_INLINE)
-            memcpy(a->rootsub + (size_t)low18 * BFT_SUB_BYTES, a->prefsub + (size_t)pi * BFT_SUB_BYTES, BFT_SUB_BYTES);
-    }
+    for (uint32_t low18 = 0; low18 < BFT_ROOTDIR_SIZE; low18++) a->rootdir[low18] = bft_node_probe(&v, 0, low18, 0);
 
-    free(c->map); free(c->tmp); free(c->hv1); free(c->hv2); free(c->scratch); free(c->extbuf);
+    free(c->map); free(c->tmp); free(c->hv1); free(c->hv2); free(c->scratch); free(c->extbuf); free(c->bkt);
     free(c);
     return a;
 }

@@ -21,13 +21,15 @@ typedef struct bft_arena {
     uint16_t* csr;       size_t n_csr;
     uint8_t* filter3;    size_t filter3_bytes;
     bft_entry_t* pref;   size_t n_pref;
-    uint8_t* prefsub;    /* n_pref * BFT_SUB_BYTES */
-    uint8_t* rootsub;    /* BFT_ROOTDIR_SIZE * BFT_SUB_BYTES */
-    uint64_t* keys;      /* n_lines * W: CC inline suffix lines */
-    uint32_t* linecls;   size_t n_lines; /* NULL once the classes are embedded in keys (cls_shift != 0) */
+    uint64_t* buckets;   size_t n_buckets; /* n_buckets * BFT_BUCKET_KEYS * W words */
+    uint32_t* slotcls;   /* n_buckets * BFT_BUCKET_KEYS; NULL once the classes are embedded (cls_shift != 0) */
+    uint64_t* ovf;       size_t n_ovf;     /* n_ovf * W words */
+    uint32_t* ovfcls;    /* n_ovf; NULL once embedded */
+    size_t n_lines;      /* inline suffix lines stored (in buckets + ovf) */
     uint64_t* uckeys;    /* n_uc_lines * W: Node-UC lines */
     uint32_t* uccls;     size_t n_uc_lines;
     int cls_shift;
+    uint32_t cls_mask;
 
     /* colour classes: distinct annotation byte strings (annotation ‖ extended byte, reference src/UC.c:171-239) */
     uint32_t* cls_off;   /* n_classes + 1 */

@@ -42,18 +42,35 @@ def available_lengths(cfg: dict, k: int) -> List[int]:
     if os.path.isdir(DATA):
         pre = f"{cfg['name']}_k{k}_L"
         for f in os.listdir(DATA):
-            if f.startswith(pre) and f.endswith(".bft"):
+            if f.startswith(pre) and (f.endswith(".bft") or f.endswith(".bft.xz")):
                 try:
-                    out.append(int(f[len(pre):-4]))
+                    out.append(int(f[len(pre):].split(".")[0]))
                 except ValueError:
                     pass
-    return sorted(out)
+    return sorted(set(out))
 
 
 def ensure_bft(cfg: dict, k: int, genome_len: int, genomes=None) -> str:
     """Path of the cached .bft for (cfg, k, genome_len); builds it with the reference binary when absent."""
     path = bft_path(cfg, k, genome_len)
     if os.path.exists(path):
+        return path
+    if os.path.exists(path + ".xz"):  # shipped compressed (the snapshot sent to the GPU box is size-limited)
+        t0 = time.time()
+        tmp_out = f"{path}.{os.getpid()}.tmp"
+        try:
+            with open(tmp_out, "wb") as f:
+                subprocess.run(["xz", "-d", "-c", "-T0", path + ".xz"], stdout=f, check=True)
+        except (OSError, subprocess.CalledProcessError):
+            import lzma
+            with lzma.open(path + ".xz", "rb") as src, open(tmp_out, "wb") as f:
+                while True:
+                    b = src.read(1 << 24)
+                    if not b:
+                        break
+                    f.write(b)
+        os.replace(tmp_out, path)
+        log(f"decompressed {os.path.basename(path)}.xz in {time.time() - t0:.1f}s")
         return path
     if not os.access(REF_BFT, os.X_OK):
         raise RuntimeError(f"{path} is absent and the reference binary {REF_BFT} is not built: cannot construct the BFT "

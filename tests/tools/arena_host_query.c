@@ -15,8 +15,8 @@ int main(int argc, char** argv) {
     char err[256];
     bft_arena_t* a = bft_arena_from_file(argv[1], err, sizeof err);
     if (!a) { fprintf(stderr, "%s\n", err); return 1; }
-    fprintf(stderr, "k=%d W=%d genomes=%d nodes=%zu ccs=%zu (max/node %d) depth=%d lines=%zu uc_lines=%zu leaf_prefixes=%zu kmers=%zu classes=%zu cls_shift=%d pools=%d arena=%.1f MB\n",
-            a->k, a->W, a->n_genomes, a->n_nodes, a->n_ccs, a->max_cc_per_node, a->max_depth, a->n_lines, a->n_uc_lines, a->n_leaf_prefixes,
+    fprintf(stderr, "k=%d W=%d genomes=%d nodes=%zu ccs=%zu (max/node %d) depth=%d lines=%zu buckets=%zu overflow=%zu uc_lines=%zu leaf_prefixes=%zu kmers=%zu classes=%zu cls_shift=%d pools=%d arena=%.1f MB\n",
+            a->k, a->W, a->n_genomes, a->n_nodes, a->n_ccs, a->max_cc_per_node, a->max_depth, a->n_lines, a->n_buckets, a->n_ovf, a->n_uc_lines, a->n_leaf_prefixes,
             a->n_kmers, a->n_classes, a->cls_shift, a->n_pools, bft_arena_bytes(a) / 1e6);
     bft_view_t v;
     bft_arena_view(a, &v);
