@@ -23,6 +23,8 @@ REF_HARNESS = os.path.join(ROOT, "oracle", "_ref", "ref_harness")
 
 # config[2] of BASELINE.json: 100-genome synthetic bacterial pan-genome, tree-structured SNP/indel strains
 C3 = dict(name="c3_g100", n_genomes=100, snp=0.002, indel=0.0002, seed=12345, tree=True)
+# config[1]: 16-genome pan-genome, canonical k-mers inserted, queried with 150 bp reads (threshold 0.8, canonical)
+C2 = dict(name="c2_g16_canon", n_genomes=16, snp=0.005, indel=0.0005, seed=2345, tree=False, canonical=True)
 
 
 def log(*a):
@@ -81,7 +83,7 @@ def ensure_bft(cfg: dict, k: int, genome_len: int, genomes=None) -> str:
     t0 = time.time()
     if genomes is None:
         genomes = pangenome(cfg, genome_len)
-    lst = synth.write_genome_kmer_files(tmp, genomes, k)
+    lst = synth.write_genome_kmer_files(tmp, genomes, k, canonical=bool(cfg.get("canonical")))
     log(f"building {os.path.basename(path)} with the reference ({cfg['n_genomes']} genomes x {genome_len} bp)...")
     out = os.path.join(tmp, "out.bft")
     p = subprocess.run([REF_BFT, "build", str(k), "kmers_comp", lst, out], cwd=tmp, stdout=subprocess.PIPE, stderr=subprocess.STDOUT)
