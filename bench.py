@@ -347,6 +347,106 @@ def engine_arm(args):
         dist.destroy_process_group()
 
 
+def side_workload(args):
+    """Informational single-GPU lines for the other two query kinds (not the headline metric): BASELINE config[1]
+    (-query_sequences 0.8 canonical, 150 bp reads vs the 16-genome canonical BFT) and config[3] (-query_branching at
+    k=63 on the 100-genome BFT). Same JSON keys; `metric` stays k-mers (windows / k-mers) per second."""
+    import numpy as np
+    import torch
+    from bloomfiltertrie_b200 import engine as E
+    from bloomfiltertrie_b200 import workloads as wl
+    dev = torch.device("cuda", 0)
+    torch.cuda.set_device(0)
+    seq = args.workload == "sequences"
+    cfg, k, L = (wl.C2, 27, args.genome_len or 5_000_000) if seq else (wl.C3, 63, args.genome_len or 1_000_000)
+    genomes = wl.pangenome(cfg, L)
+    bft = wl.ensure_bft(cfg, k, L, genomes)
+    eng = E.BFTEngine(bft, device=0)
+    st = eng.stats()
+    cat, starts, lens = wl.genomes_to_torch(genomes, dev)
+    es = torch.cuda.ExternalStream(eng.stream, device=dev)
+    cores = os.cpu_count() or 1
+    if seq:
+        n, rl = args.reads, 150
+        chars, offs = wl.gen_reads(cat, starts, lens, n, rl, seed=4242)
+        units = n * (rl - k + 1)
+        d_rows = torch.empty((n, eng.RW), dtype=torch.int32, device=dev)
+        d_stat = torch.empty(n, dtype=torch.uint8, device=dev)
+        run = lambda: eng.query_sequences_device(chars, offs, n, 0.8, True, d_rows, d_stat)
+        h_chars = E.PinnedBuffer((n * rl,), np.uint8); h_chars.array[:] = chars.cpu().numpy()
+        h_offs = E.PinnedBuffer((n + 1,), np.uint64); h_offs.array[:] = offs.cpu().numpy().view(np.uint64)
+        h_rows = E.PinnedBuffer((n, eng.RW), np.uint32); h_stat = E.PinnedBuffer((n,), np.uint8)
+        run_e2e = lambda: eng.query_sequences(h_chars.array, h_offs.array, 0.8, True, out_rows=h_rows.array, out_status=h_stat.array)
+        h2d, d2h = n * rl + 8 * (n + 1), n * (4 * eng.RW + 1)
+    else:
+        n = args.queries_per_gpu
+        q, _ = wl.gen_kmer_queries(cat, starts, lens, k, n, seed=99, mix=MIX)
+        units = n
+        d_succ = torch.empty(n, dtype=torch.uint8, device=dev)
+        d_pred = torch.empty(n, dtype=torch.uint8, device=dev)
+        d_cnt = torch.zeros(1, dtype=torch.int64, device=dev)
+        run = lambda: eng.query_branching_device(q, n, d_succ, d_pred, d_cnt)
+        hq = E.PinnedBuffer((n, eng.W), np.uint64); hq.array[:] = q.cpu().numpy().view(np.uint64)
+        run_e2e = lambda: eng.query_branching(hq.array)
+        h2d, d2h = n * 8 * eng.W, 2 * n + 8
+    for _ in range(args.warmup):
+        run()
+    torch.cuda.synchronize()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    l0 = eng.launch_count()
+    a.record(es)
+    for _ in range(args.steps):
+        run()
+    b.record(es)
+    b.synchronize()
+    ms = a.elapsed_time(b) / args.steps
+    launches = eng.launch_count() - l0
+    run_e2e()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        run_e2e()
+    e2e_ms = (time.perf_counter() - t0) / args.steps * 1e3
+    cpu = None
+    if not args.no_cpu_baseline and os.access(wl.REF_HARNESS, os.X_OK):
+        if seq:
+            ns = min(n, 200_000)
+            p = f"/tmp/bft_bench_reads_{os.getpid()}.txt"
+            arr = chars[: ns * 150].cpu().numpy().reshape(ns, 150)
+            with open(p, "wb") as f:
+                f.write(np.concatenate([arr, np.full((ns, 1), 10, np.uint8)], axis=1).tobytes())
+            out = subprocess.run([wl.REF_HARNESS, "sequences", bft, p, "0.8", "canonical", p + ".out", str(cores), "2"],
+                                 stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True).stdout
+            secs = [float(x) for x in re.findall(r"REF_PASS \d+ seconds=([0-9.]+)", out)]
+            ref_rows = np.fromfile(p + ".out", dtype=np.uint32).reshape(ns, eng.RW)
+            assert np.array_equal(ref_rows, d_rows[:ns].cpu().numpy().view(np.uint32)), "GPU and reference disagree on the sample"
+            os.remove(p); os.remove(p + ".out")
+            cpu = {"value": ns * (150 - k + 1) / min(secs), "unit": UNIT, "cores": cores, "kind": "reference",
+                   "sample": f"first {ns} reads; query_sequence under OpenMP, one copy_BFT_Root per thread; rows identical to the GPU's"}
+        else:
+            ns = min(n, 1 << 22)
+            p = f"/tmp/bft_bench_br_{os.getpid()}.kc"
+            write_query_file(p, q[:ns].cpu().numpy(), k)
+            out = subprocess.run([wl.REF_HARNESS, "branching", bft, p, p + ".out", str(cores), "2"], stdout=subprocess.PIPE,
+                                 stderr=subprocess.STDOUT, text=True).stdout
+            secs = [float(x) for x in re.findall(r"REF_PASS \d+ seconds=([0-9.]+)", out)]
+            raw = np.fromfile(p + ".out", dtype=np.uint8)
+            assert np.array_equal(raw[:ns], d_succ[:ns].cpu().numpy()) and np.array_equal(raw[ns:2 * ns], d_pred[:ns].cpu().numpy()), \
+                "GPU and reference disagree on the sample"
+            os.remove(p); os.remove(p + ".out")
+            cpu = {"value": ns / min(secs), "unit": UNIT, "cores": cores, "kind": "reference",
+                   "sample": f"first {ns} k-mers; isBranchingRight + isBranchingLeft under OpenMP; counts identical to the GPU's"}
+    line = {"metric": METRIC, "value": units / (ms / 1e3), "unit": UNIT, "n_gpus": 1, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u64", "data": "synthetic",
+            "config": {"workload": ("c2: -query_sequences 0.8 canonical, 150 bp reads vs 16-genome canonical BFT (value counts k-mer windows)"
+                                    if seq else "c4: -query_branching at k=63 on the 100-genome BFT (value counts query k-mers; 8 neighbour lookups each)"),
+                       "k": k, "n_genomes": cfg["n_genomes"], "genome_len": L, "kmers_in_bft": st["n_kmers"], "items_per_step": n,
+                       "reads_per_sec": (n / (ms / 1e3)) if seq else None},
+            "e2e": {"value": units / (e2e_ms / 1e3), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms},
+            "gpu_launches": launches, "cpu_baseline": cpu}
+    print(json.dumps(line), flush=True)
+    eng.close()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -359,10 +459,17 @@ def main():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-probe", action="store_true")
+    ap.add_argument("--workload", default="kmers", choices=["kmers", "sequences", "branching"],
+                    help="kmers = the headline metric (default); the other two print informational single-GPU lines")
+    ap.add_argument("--reads", type=int, default=1_000_000)
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3
-    if args.impl == "reference":
+    if args.workload != "kmers":
+        if args.queries_per_gpu == 125_000_000:
+            args.queries_per_gpu = 20_000_000
+        side_workload(args)
+    elif args.impl == "reference":
         reference_arm(args)
     else:
         engine_arm(args)

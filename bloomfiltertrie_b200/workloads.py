@@ -148,3 +148,29 @@ def gen_kmer_queries(cat, starts, lens, k: int, n: int, seed: int, mix: Tuple[fl
                       torch.full((n_r,), 2, dtype=torch.uint8, device=dev)])
     perm = torch.randperm(n, generator=g, device=dev)
     return out[perm].contiguous(), kind[perm].contiguous()
+
+
+def gen_reads(cat, starts, lens, n_reads: int, read_len: int, seed: int, err: float = 0.005, frac_random: float = 0.0):
+    """Synthetic reads on cat.device: uniform positions over the genomes, random strand, substitution errors.
+    Returns (uint8 chars [n_reads * read_len], int64 offsets [n_reads + 1])."""
+    import torch
+    dev = cat.device
+    g = torch.Generator(device=dev)
+    g.manual_seed(seed)
+    gi = torch.randint(0, len(lens), (n_reads,), generator=g, device=dev)
+    span = (lens[gi] - read_len + 1).to(torch.float64)
+    pos = (torch.rand(n_reads, generator=g, device=dev, dtype=torch.float64) * span).to(torch.int64) + starts[gi]
+    idx = pos[:, None] + torch.arange(read_len, device=dev)[None, :]
+    codes = cat[idx]
+    if frac_random > 0:
+        rnd = torch.rand(n_reads, generator=g, device=dev) < frac_random
+        codes = torch.where(rnd[:, None], torch.randint(0, 4, codes.shape, generator=g, device=dev, dtype=torch.uint8), codes)
+    if err > 0:
+        e = torch.rand(codes.shape, generator=g, device=dev) < err
+        codes = torch.where(e, (codes + torch.randint(1, 4, codes.shape, generator=g, device=dev, dtype=torch.uint8)) & 3, codes)
+    flip = torch.rand(n_reads, generator=g, device=dev) < 0.5
+    codes = torch.where(flip[:, None], 3 - codes.flip(1), codes)
+    lut = torch.tensor(list(b"ACGT"), dtype=torch.uint8, device=dev)
+    chars = lut[codes.long()].reshape(-1).contiguous()
+    offs = (torch.arange(n_reads + 1, device=dev, dtype=torch.int64) * read_len).contiguous()
+    return chars, offs

@@ -138,6 +138,8 @@ CASES = {
     "lowcomplex_k27_g3": (case_lowcomplexity, dict(k=27, n_genomes=3, length=100_000, seed=405)),
     "lowcomplex_k45_g2": (case_lowcomplexity, dict(k=45, n_genomes=2, length=100_000, seed=406)),
     "pan_k27_g100": (case_pangenome, dict(k=27, n_genomes=100, seed=303)),
+    "pan_k27_g1000": (case_pangenome, dict(k=27, n_genomes=1000, length=2_000, seed=304)),
+    "pan_k63_g130": (case_pangenome, dict(k=63, n_genomes=130, length=6_000, seed=305)),
 }
 
 
