@@ -347,8 +347,10 @@ __global__ void __launch_bounds__(32 * BFT_SEQ_WARPS) k_query_sequences(const bf
         for (long long t0 = 0; t0 < n_win; t0 += BFT_SEQ_TILE) {
             const int n_here = (int)(n_win - t0 < BFT_SEQ_TILE ? n_win - t0 : BFT_SEQ_TILE); /* windows in this tile */
             const int n_chars = n_here + k - 1;
-            /* stage + encode: 32 characters per step */
-            for (int c0 = 0; c0 < BFT_SEQ_SPAN + 64; c0 += 32) {
+            /* stage + encode: 32 characters per step, up to one zeroed 64-base word past the data (the funnel
+             * shifts below may read one word beyond the last window) */
+            const int stage_end = min(BFT_SEQ_SPAN + 64, ((n_chars + 63) & ~63) + 64);
+            for (int c0 = 0; c0 < stage_end; c0 += 32) {
                 const int ci = c0 + lane;
                 uint32_t code = 0, cls = BFT_CH_ACGT, nonplain = 0;
                 if (ci < n_chars) {
