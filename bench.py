@@ -387,7 +387,8 @@ def side_workload(args):
         d_cnt = torch.zeros(1, dtype=torch.int64, device=dev)
         run = lambda: eng.query_branching_device(q, n, d_succ, d_pred, d_cnt)
         hq = E.PinnedBuffer((n, eng.W), np.uint64); hq.array[:] = q.cpu().numpy().view(np.uint64)
-        run_e2e = lambda: eng.query_branching(hq.array)
+        hs = E.PinnedBuffer((n,), np.uint8); hp = E.PinnedBuffer((n,), np.uint8)
+        run_e2e = lambda: eng.query_branching(hq.array, out_succ=hs.array, out_pred=hp.array)
         h2d, d2h = n * 8 * eng.W, 2 * n + 8
     for _ in range(args.warmup):
         run()

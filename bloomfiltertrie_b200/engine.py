@@ -254,11 +254,12 @@ class BFTEngine:
                  "bft_b200_query_sequences_device")
 
     # -- branching
-    def query_branching(self, kmers: np.ndarray) -> Tuple[np.ndarray, np.ndarray, int]:
+    def query_branching(self, kmers: np.ndarray, out_succ: Optional[np.ndarray] = None,
+                        out_pred: Optional[np.ndarray] = None) -> Tuple[np.ndarray, np.ndarray, int]:
         kmers = np.ascontiguousarray(kmers, dtype=np.uint64).reshape(-1, self.W)
         n = kmers.shape[0]
-        succ = np.empty(n, dtype=np.uint8)
-        pred = np.empty(n, dtype=np.uint8)
+        succ = out_succ if out_succ is not None else np.empty(n, dtype=np.uint8)
+        pred = out_pred if out_pred is not None else np.empty(n, dtype=np.uint8)
         cnt = C.c_uint64()
         self._ck(self.lib.bft_b200_query_branching(self.h, _ptr(kmers), n, _ptr(succ), _ptr(pred), C.byref(cnt)),
                  "bft_b200_query_branching")

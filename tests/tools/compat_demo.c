@@ -1,0 +1,58 @@
+/* compat_demo — TEST TOOL: a caller written against the reference's public API names (include/bft.h) but compiled
+ * with include/bft_compat.h and linked with libbft_b200.so. Prints, for every k-mer of a text file:
+ *   presence, the ascending genome ids (get_annotation + get_list_id_genomes), get_count_id_genomes,
+ *   presence_genome of genome 0, and the presence flags of get_neighbors (4 predecessors, 4 successors);
+ * then for every line of a sequence file the ids query_sequence returns. */
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include "bft_compat.h"
+
+int main(int argc, char** argv) {
+    if (argc < 6) return 2;
+    BFT* g = load_BFT(argv[1]);
+    double thr = atof(argv[4]);
+    int canonical = atoi(argv[5]);
+    printf("k=%d genomes=%d first=%s\n", g->k, g->nb_genomes, g->nb_genomes ? g->filenames[0] : "");
+    char line[1 << 16];
+    FILE* f = fopen(argv[2], "r");
+    set_neighbors_traversal(g);
+    while (fgets(line, sizeof line, f)) {
+        line[strcspn(line, "\r\n")] = 0;
+        BFT_kmer* km = get_kmer(line, g);
+        if (!is_kmer_in_cdbg(km)) {
+            printf("K 0\n");
+        } else {
+            BFT_annotation* a = get_annotation(km);
+            uint32_t* ids = get_list_id_genomes(a, g);
+            printf("K 1 n=%u c=%u g0=%d ids", ids[0], get_count_id_genomes(a, g), (int)presence_genome(0, a, g));
+            for (uint32_t i = 1; i <= ids[0]; i++) printf(" %u", ids[i]);
+            BFT_kmer* nb = get_neighbors(km, g);
+            printf(" nb");
+            for (int i = 0; i < 8; i++) printf(" %d", (int)is_kmer_in_cdbg(&nb[i]));
+            BFT_kmer* pr = get_predecessors(km, g);
+            BFT_kmer* su = get_successors(km, g);
+            int same = 1;
+            for (int i = 0; i < 4; i++) same &= is_kmer_in_cdbg(&pr[i]) == is_kmer_in_cdbg(&nb[i]) && is_kmer_in_cdbg(&su[i]) == is_kmer_in_cdbg(&nb[4 + i]);
+            printf(" consistent=%d first_pred=%s\n", same, nb[0].kmer);
+            free_BFT_kmer(nb, 8); free_BFT_kmer(pr, 4); free_BFT_kmer(su, 4);
+            free(ids);
+            free_BFT_annotation(a);
+        }
+        free_BFT_kmer(km, 1);
+    }
+    unset_neighbors_traversal(g);
+    fclose(f);
+    f = fopen(argv[3], "r");
+    while (fgets(line, sizeof line, f)) {
+        line[strcspn(line, "\r\n")] = 0;
+        uint32_t* ids = query_sequence(g, line, thr, canonical);
+        printf("S n=%u ids", ids[0]);
+        for (uint32_t i = 1; i <= ids[0]; i++) printf(" %u", ids[i]);
+        printf("\n");
+        free(ids);
+    }
+    fclose(f);
+    free_cdbg(g);
+    return 0;
+}
