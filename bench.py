@@ -91,6 +91,8 @@ class ClockSampler:
 
 def pick_workload(args):
     from bloomfiltertrie_b200 import workloads as wl
+    if getattr(args, "pangenome", "c3") == "c5":  # informational: 1000 colours, wide rows (RW = 32)
+        return wl.C5, (args.genome_len or 100_000)
     cfg = wl.C3
     if args.genome_len:
         L = args.genome_len
@@ -276,6 +278,10 @@ def engine_arm(args):
     # A_min per k-mer: key words in + (presence byte + colour row) out + 32-byte sectors the walk must
     # touch: 6 per Node probed, ceil(log2(lines+1)) per suffix search, 1 for the annotation of a found k-mer
     a_min = 8 * W + (1 + 4 * RW) + 32.0 * (6 * nodes_pk + depth_pk + found_pk)
+    # A_ref: same, with the Bloom-chain term of the REFERENCE layout (2 bytes probed in each of the c CCs walked
+    # before one fires) instead of the single first-CC-table sector — context only
+    cc_pk = ws["cc_probed"] / n
+    a_ref = 8 * W + (1 + 4 * RW) + 32.0 * (5 * nodes_pk + 2 * cc_pk + depth_pk + found_pk)
     achieved = a_min * n / (k_ms / 1e3) / 1e9
     peak, peak_src = peaks()
     traffic = ncu_traffic()
@@ -287,6 +293,8 @@ def engine_arm(args):
                 "traffic": (traffic * n if traffic else None), "peak_source": peak_src, "kernel_ms": k_ms,
                 "kmers_per_sec_kernel": n / (k_ms / 1e3), "a_min_bytes_per_kmer": a_min,
                 "nodes_per_kmer": nodes_pk, "search_depth_per_kmer": depth_pk, "found_frac": found_pk,
+                "a_ref_bytes_per_kmer": a_ref, "cc_probed_per_node_reference_layout": cc_pk / max(nodes_pk, 1e-9),
+                "mean_suffix_block_lines": ws["block_lines"] / max(1, n),
                 "dram_bytes_per_kmer_ncu": traffic,
                 "random_gather_probe_loads_per_s": probe,
                 "note": "A_min counts the sectors of the REFERENCE layout's walk; the flattened arena serves the root probe from "
@@ -464,6 +472,8 @@ def main():
     ap.add_argument("--workload", default="kmers", choices=["kmers", "sequences", "branching"],
                     help="kmers = the headline metric (default); the other two print informational single-GPU lines")
     ap.add_argument("--reads", type=int, default=1_000_000)
+    ap.add_argument("--pangenome", default="c3", choices=["c3", "c5"],
+                    help="c3 = 100 genomes (headline); c5 = 1000 colours, 100 kbp genomes (informational)")
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3

@@ -317,7 +317,16 @@ BFT_HD void bft_shift18(uint64_t* cur, int W) {
  * kmer: W words (bits above 2k must be zero). Returns the colour class of the k-mer, or BFT_CLS_NONE if absent.
  * W is passed explicitly so device callers can make it a compile-time constant. */
 /* st (optional, NULL on the product path): walk statistics for the roofline accounting of SURVEY.md §8(d) —
- * st[0] += Nodes probed, st[1] += sum of ceil(log2(lines+1)) over the line searches, st[2] += 1 if found. */
+ * st[0] += Nodes probed, st[1] += sum of ceil(log2(lines+1)) over the line searches, st[2] += 1 if found,
+ * st[3] += CCs whose Bloom filter the REFERENCE would probe in those Nodes (index of the first CC that fires + 1, or
+ * all of them), st[4] += lines in the searched blocks. */
+BFT_HD uint32_t bft_cc_probed(const bft_view_t* v, uint32_t node_id, uint32_t low18) {
+    const bft_node_t* nd = v->nodes + node_id;
+    if (!nd->n_cc) return 0;
+    const uint32_t c = v->firstcc[nd->fc_off + bft_idx14(bft_msb_first18(low18))];
+    return c == BFT_FIRSTCC_NONE ? nd->n_cc : c + 1;
+}
+
 BFT_HD uint32_t bft_ceil_log2p1(uint32_t n) { /* ceil(log2(n + 1)) */
     uint32_t b = 0;
     while ((1u << b) < n + 1u) b++;
@@ -329,7 +338,7 @@ BFT_HD uint32_t bft_lookup_ex(const bft_view_t* v, const uint64_t* kmer, const i
     for (int w = 0; w < BFT_MAX_WORDS; w++) cur[w] = w < W ? kmer[w] : 0;
     int sz = v->k;
     bft_entry_t e = bft_ld_entry(v->rootdir + ((uint32_t)cur[0] & (BFT_ROOTDIR_SIZE - 1u)));
-    if (st) st[0]++;
+    if (st) { st[0]++; st[3] += bft_cc_probed(v, 0, (uint32_t)cur[0] & (BFT_ROOTDIR_SIZE - 1u)); }
     for (;;) {
         const uint32_t kind = e.b >> BFT_KIND_SHIFT;
         const uint32_t n = e.b & BFT_CNT_MASK;
@@ -340,7 +349,7 @@ BFT_HD uint32_t bft_lookup_ex(const bft_view_t* v, const uint64_t* kmer, const i
         }
         if (kind == BFT_KIND_UC) {
             if (n == 0) return BFT_CLS_NONE;
-            if (st) st[1] += bft_ceil_log2p1(n);
+            if (st) { st[1] += bft_ceil_log2p1(n); st[4] += n; }
             const uint32_t ln = bft_search_uc(v, e.a, n, cur, W);
             if (st && ln != 0xffffffffu) st[2]++;
             return ln == 0xffffffffu ? BFT_CLS_NONE : BFT_LD32(v->uccls + ln);
@@ -348,13 +357,13 @@ BFT_HD uint32_t bft_lookup_ex(const bft_view_t* v, const uint64_t* kmer, const i
         bft_shift18(cur, W);
         sz -= BFT_NB_CHAR_SUF_PREF;
         if (kind == BFT_KIND_INLINE) {
-            if (st) st[1] += bft_ceil_log2p1(n);
+            if (st) { st[1] += bft_ceil_log2p1(n); st[4] += n; }
             const uint32_t cls = bft_search_block(v, e.a, (e.b >> BFT_LB_SHIFT) & BFT_LB_MASK, cur, W);
             if (st && cls != BFT_CLS_NONE) st[2]++;
             return cls;
         }
         /* BFT_KIND_NODE */
-        if (st) st[0]++;
+        if (st) { st[0]++; st[3] += bft_cc_probed(v, e.a, (uint32_t)cur[0] & (BFT_ROOTDIR_SIZE - 1u)); }
         e = bft_node_probe(v, e.a, (uint32_t)cur[0] & (BFT_ROOTDIR_SIZE - 1u), succ_leaf_quirk && sz == BFT_NB_CHAR_SUF_PREF);
     }
 }

@@ -154,13 +154,6 @@ extern "C" int bft_b200_open(const char* path, int device, bft_b200_ctx** out) {
     if (device < 0 || device >= ndev) return set_err(BFT_B200_ERR_ARG, "bft_b200_open: device %d out of range (0..%d)", device, ndev - 1);
     CK(cudaSetDevice(device));
 
-    /* the walk reads isolated 32-byte sectors; ask L2 not to over-fetch their neighbours from HBM (a hint) */
-    {
-        const char* g = getenv("BFT_B200_L2_FETCH");
-        size_t gran = g ? (size_t)atoi(g) : 32;
-        if (gran == 32 || gran == 64 || gran == 128) cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, gran);
-    }
-
     char ferr[256];
     double t0 = now_s();
     bft_arena_t* a = bft_arena_from_file(path, ferr, sizeof ferr);
@@ -372,7 +365,9 @@ static int query_kmers_host(bft_b200_ctx* c, const uint64_t* kmers, const char* 
         ENSURE(sl->d_u8a, sl->cap_u8a, m);
         ENSURE(sl->d_cls, sl->cap_cls, m * sizeof(uint32_t));
         if (rows) ENSURE(sl->d_rows, sl->cap_rows, m * rw * sizeof(uint32_t));
-        int rc = enqueue_kmers(c, st, d_k, m, sl->d_u8a, rows ? sl->d_rows : NULL, sl->d_cls);
+        /* class ids are materialised only when asked for, or as the intermediate of the wide-row path */
+        const int fused = rows && (c->rw == 1 || c->rw == 2 || c->rw == 4);
+        int rc = enqueue_kmers(c, st, d_k, m, sl->d_u8a, rows ? sl->d_rows : NULL, (class_ids || (rows && !fused) || !rows) ? sl->d_cls : NULL);
         if (rc) return rc;
         if (present) CK(cudaMemcpyAsync(present + done, sl->d_u8a, m, cudaMemcpyDeviceToHost, st));
         if (valid) CK(cudaMemcpyAsync(valid + done, sl->d_u8b, m, cudaMemcpyDeviceToHost, st));
@@ -580,24 +575,24 @@ extern "C" int bft_b200_query_neighbors(bft_b200_ctx* c, const uint64_t* kmers, 
     return 0;
 }
 
-extern "C" int bft_b200_kmer_walk_stats_device(bft_b200_ctx* c, const uint64_t* d_kmers, size_t n, uint64_t out[3]) {
+extern "C" int bft_b200_kmer_walk_stats_device(bft_b200_ctx* c, const uint64_t* d_kmers, size_t n, uint64_t out[5]) {
     if (!c || !out || (!d_kmers && n)) return set_err(BFT_B200_ERR_ARG, "bft_b200_kmer_walk_stats_device: NULL argument");
     CK(cudaSetDevice(c->device));
     unsigned long long* d_acc = NULL;
-    CK(cudaMalloc((void**)&d_acc, 3 * sizeof(unsigned long long)));
-    cudaMemsetAsync(d_acc, 0, 3 * sizeof(unsigned long long), c->streams[0]);
+    CK(cudaMalloc((void**)&d_acc, 5 * sizeof(unsigned long long)));
+    cudaMemsetAsync(d_acc, 0, 5 * sizeof(unsigned long long), c->streams[0]);
     if (n) {
         const int grid = grid_for(c, n, BFT_TPB);
         if (c->W == 1) k_kmer_walk_stats<1><<<grid, BFT_TPB, 0, c->streams[0]>>>(c->dview, d_kmers, n, d_acc);
         else k_kmer_walk_stats<2><<<grid, BFT_TPB, 0, c->streams[0]>>>(c->dview, d_kmers, n, d_acc);
         c->launches++;
     }
-    unsigned long long h[3] = {0, 0, 0};
+    unsigned long long h[5] = {0, 0, 0, 0, 0};
     cudaError_t e = cudaMemcpyAsync(h, d_acc, sizeof h, cudaMemcpyDeviceToHost, c->streams[0]);
     if (e == cudaSuccess) e = cudaStreamSynchronize(c->streams[0]);
     cudaFree(d_acc);
     if (e != cudaSuccess) return set_err(BFT_B200_ERR_CUDA, "k_kmer_walk_stats failed: %s", cudaGetErrorString(e));
-    out[0] = h[0]; out[1] = h[1]; out[2] = h[2];
+    for (int j = 0; j < 5; j++) out[j] = h[j];
     return 0;
 }
 

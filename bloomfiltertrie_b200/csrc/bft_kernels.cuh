@@ -88,29 +88,25 @@ __global__ void __launch_bounds__(BFT_TPB) k_random_gather(const uint64_t* __res
 }
 
 /* Instrumented walk for the roofline accounting: sums over the batch of Nodes probed, binary-search
- * depths ceil(log2(lines+1)) and hits. Not on the product path; bench.py runs it once on the timed batch. */
+ * depths ceil(log2(lines+1)), hits, CCs the reference would probe and block sizes. Not on the product path; bench.py runs it once on the timed batch. */
 template <int W>
 __global__ void __launch_bounds__(BFT_TPB) k_kmer_walk_stats(const bft_view_t v, const uint64_t* __restrict__ kmers, size_t n,
                                                              unsigned long long* __restrict__ acc) {
     const size_t stride = (size_t)gridDim.x * blockDim.x;
-    unsigned long long a0 = 0, a1 = 0, a2 = 0;
+    unsigned long long a[5] = {0, 0, 0, 0, 0};
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
         uint64_t km[W];
 #pragma unroll
         for (int w = 0; w < W; w++) km[w] = kmers[i * W + w];
-        uint32_t st[3] = {0, 0, 0};
+        uint32_t st[5] = {0, 0, 0, 0, 0};
         bft_lookup_ex(&v, km, W, 0, st);
-        a0 += st[0]; a1 += st[1]; a2 += st[2];
+#pragma unroll
+        for (int j = 0; j < 5; j++) a[j] += st[j];
     }
-    for (int o = 16; o > 0; o >>= 1) {
-        a0 += __shfl_down_sync(0xffffffffu, a0, o);
-        a1 += __shfl_down_sync(0xffffffffu, a1, o);
-        a2 += __shfl_down_sync(0xffffffffu, a2, o);
-    }
-    if ((threadIdx.x & 31) == 0) {
-        atomicAdd(acc + 0, a0);
-        atomicAdd(acc + 1, a1);
-        atomicAdd(acc + 2, a2);
+#pragma unroll
+    for (int j = 0; j < 5; j++) {
+        for (int o = 16; o > 0; o >>= 1) a[j] += __shfl_down_sync(0xffffffffu, a[j], o);
+        if ((threadIdx.x & 31) == 0) atomicAdd(acc + j, a[j]);
     }
 }
 

@@ -84,7 +84,7 @@ def load_library() -> C.CDLL:
     lib.bft_b200_query_kmers_file.argtypes = [vp, C.c_char_p, C.c_int, C.c_char_p, C.POINTER(C.c_uint64)]
     lib.bft_b200_query_branching_file.argtypes = [vp, C.c_char_p, C.c_int, C.POINTER(C.c_uint64)]
     lib.bft_b200_query_sequences_file.argtypes = [vp, C.c_char_p, C.c_char_p, C.c_double, C.c_int]
-    lib.bft_b200_kmer_walk_stats_device.argtypes = [vp, u64p, sz, C.POINTER(C.c_uint64 * 3)]
+    lib.bft_b200_kmer_walk_stats_device.argtypes = [vp, u64p, sz, C.POINTER(C.c_uint64 * 5)]
     lib.bft_b200_random_gather_probe.argtypes = [vp, sz, sz, C.POINTER(C.c_double)]
     lib.bft_b200_sync.argtypes = [vp]
     lib.bft_b200_launch_count.argtypes = [vp]
@@ -220,10 +220,11 @@ class BFTEngine:
         return np.frombuffer(buf, dtype=np.uint32).copy()
 
     def kmer_walk_stats_device(self, d_kmers, n: int) -> dict:
-        out = (C.c_uint64 * 3)()
+        out = (C.c_uint64 * 5)()
         self._ck(self.lib.bft_b200_kmer_walk_stats_device(self.h, _ptr(d_kmers), n, C.byref(out)),
                  "bft_b200_kmer_walk_stats_device")
-        return dict(nodes=int(out[0]), search_depth=int(out[1]), found=int(out[2]), n=n)
+        return dict(nodes=int(out[0]), search_depth=int(out[1]), found=int(out[2]), cc_probed=int(out[3]),
+                    block_lines=int(out[4]), n=n)
 
     def random_gather_probe(self, table_bytes: int, n_loads: int) -> float:
         out = C.c_double()

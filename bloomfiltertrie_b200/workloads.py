@@ -23,6 +23,8 @@ REF_HARNESS = os.path.join(ROOT, "oracle", "_ref", "ref_harness")
 
 # config[2] of BASELINE.json: 100-genome synthetic bacterial pan-genome, tree-structured SNP/indel strains
 C3 = dict(name="c3_g100", n_genomes=100, snp=0.002, indel=0.0002, seed=12345, tree=True)
+# config[4]: 1000-colour pan-genome (annotation-compression heavy: mode-3 annotations + delta-coded colour pools)
+C5 = dict(name="c5_g1000", n_genomes=1000, snp=0.002, indel=0.0002, seed=54321, tree=True)
 # config[1]: 16-genome pan-genome, canonical k-mers inserted, queried with 150 bp reads (threshold 0.8, canonical)
 C2 = dict(name="c2_g16_canon", n_genomes=16, snp=0.005, indel=0.0005, seed=2345, tree=False, canonical=True)
 

@@ -131,9 +131,10 @@ int bft_b200_query_branching_file(bft_b200_ctx* ctx, const char* query_path, int
 int bft_b200_query_sequences_file(bft_b200_ctx* ctx, const char* query_path, const char* csv_path, double threshold,
                                   int canonical);
 
-/* Roofline accounting helper: over a device-resident batch, sums of Nodes probed, binary-search
- * depths ceil(log2(lines+1)) and found k-mers: out[0..2]. Diagnostic; synchronous. */
-int bft_b200_kmer_walk_stats_device(bft_b200_ctx* ctx, const uint64_t* d_kmers, size_t n, uint64_t out[3]);
+/* Roofline accounting helper: over a device-resident batch, sums of out[0] Nodes probed, out[1]
+ * binary-search depths ceil(log2(lines+1)), out[2] found k-mers, out[3] CC Bloom filters the reference layout would
+ * probe, out[4] lines in the searched suffix blocks. Diagnostic; synchronous. */
+int bft_b200_kmer_walk_stats_device(bft_b200_ctx* ctx, const uint64_t* d_kmers, size_t n, uint64_t out[5]);
 
 /* Random-access roofline probe: rate (loads/s) of independent 8-byte loads at random offsets of a table_bytes table
  * (choose it far larger than the 126 MB L2). Diagnostic; synchronous. */
