@@ -63,7 +63,9 @@ struct bft_b200_ctx {
     bft_view_t dview;
     bft_pools_t dpools;
     void* d_pool[4];
-    uint32_t* d_class_rows;
+    void* d_hot;              /* one allocation: rootdir | class_rows — the tables every lookup touches, pinned in L2 */
+    size_t hot_bytes;
+    uint32_t* d_class_rows;   /* inside d_hot */
     uint32_t* d_class_counts;
     uint32_t* h_class_rows;
     uint32_t* h_class_counts;
@@ -119,7 +121,7 @@ extern "C" void bft_b200_close(bft_b200_ctx* c) {
     cudaDeviceSynchronize();
     for (int i = 0; i < 13; i++) if (c->d_arena[i]) cudaFree(c->d_arena[i]);
     for (int i = 0; i < 4; i++) if (c->d_pool[i]) cudaFree(c->d_pool[i]);
-    if (c->d_class_rows) cudaFree(c->d_class_rows);
+    if (c->d_hot) cudaFree(c->d_hot);
     if (c->d_class_counts) cudaFree(c->d_class_counts);
     if (c->d_counter) cudaFree(c->d_counter);
     if (c->d_nbr) cudaFree(c->d_nbr);
@@ -176,7 +178,6 @@ extern "C" int bft_b200_open(const char* path, int device, bft_b200_ctx** out) {
 
     int rc = 0;
 #define UP(i, field, bytes) if (!rc) rc = upload(&c->d_arena[i], a->field, (bytes))
-    UP(0, rootdir, BFT_ROOTDIR_SIZE * sizeof(bft_entry_t));
     UP(1, nodes, a->n_nodes * sizeof(bft_node_t));
     UP(2, ccs, a->n_ccs * sizeof(bft_cc_t));
     UP(3, firstcc, a->firstcc_bytes);
@@ -199,7 +200,6 @@ extern "C" int bft_b200_open(const char* path, int device, bft_b200_ctx** out) {
     if (!rc) rc = upload(&c->d_pool[3], a->pool_bytes, a->pool_bytes_len);
     double t2 = now_s();
     if (!rc) {
-        c->dview.rootdir = (const bft_entry_t*)c->d_arena[0];
         c->dview.nodes = (const bft_node_t*)c->d_arena[1];
         c->dview.ccs = (const bft_cc_t*)c->d_arena[2];
         c->dview.firstcc = (const uint8_t*)c->d_arena[3];
@@ -226,12 +226,38 @@ extern "C" int bft_b200_open(const char* path, int device, bft_b200_ctx** out) {
     int* d_bad = NULL;
     int h_bad = 0;
     const size_t row_bytes = (a->n_classes + 1) * (size_t)c->rw * sizeof(uint32_t);
-    if (!rc && cudaMalloc((void**)&c->d_class_rows, row_bytes) != cudaSuccess) rc = set_err(BFT_B200_ERR_NOMEM, "cudaMalloc(class rows, %zu) failed", row_bytes);
+    /* hot block: rootdir followed by the class rows */
+    const size_t rootdir_bytes = BFT_ROOTDIR_SIZE * sizeof(bft_entry_t);
+    c->hot_bytes = rootdir_bytes + row_bytes;
+    if (!rc && cudaMalloc(&c->d_hot, c->hot_bytes + 32) != cudaSuccess) rc = set_err(BFT_B200_ERR_NOMEM, "cudaMalloc(hot tables, %zu) failed", c->hot_bytes);
+    if (!rc && cudaMemcpy(c->d_hot, a->rootdir, rootdir_bytes, cudaMemcpyHostToDevice) != cudaSuccess) rc = set_err(BFT_B200_ERR_CUDA, "rootdir upload failed");
+    if (!rc) {
+        c->d_class_rows = (uint32_t*)((char*)c->d_hot + rootdir_bytes);
+        c->dview.rootdir = (const bft_entry_t*)c->d_hot;
+    }
     if (!rc && cudaMalloc((void**)&c->d_class_counts, (a->n_classes + 1) * sizeof(uint32_t)) != cudaSuccess) rc = set_err(BFT_B200_ERR_NOMEM, "cudaMalloc(class counts) failed");
     if (!rc && cudaMalloc((void**)&d_bad, sizeof(int)) != cudaSuccess) rc = set_err(BFT_B200_ERR_NOMEM, "cudaMalloc failed");
     if (!rc && cudaMalloc((void**)&c->d_counter, sizeof(unsigned long long)) != cudaSuccess) rc = set_err(BFT_B200_ERR_NOMEM, "cudaMalloc failed");
     for (int s = 0; s < 2 && !rc; s++)
         if (cudaStreamCreateWithFlags(&c->streams[s], cudaStreamNonBlocking) != cudaSuccess) rc = set_err(BFT_B200_ERR_CUDA, "cudaStreamCreate failed");
+    if (!rc && !(getenv("BFT_B200_NO_L2_PERSIST") && getenv("BFT_B200_NO_L2_PERSIST")[0] == '1')) {
+        /* keep the hot block resident in L2 (persisting access-policy window on both streams); best effort */
+        size_t win = c->hot_bytes;
+        if (win > (size_t)prop.accessPolicyMaxWindowSize) win = (size_t)prop.accessPolicyMaxWindowSize;
+        size_t persist = win;
+        if (persist > (size_t)prop.persistingL2CacheMaxSize) persist = (size_t)prop.persistingL2CacheMaxSize;
+        if (win && persist && cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, persist) == cudaSuccess) {
+            cudaStreamAttrValue attr;
+            memset(&attr, 0, sizeof attr);
+            attr.accessPolicyWindow.base_ptr = c->d_hot;
+            attr.accessPolicyWindow.num_bytes = win;
+            attr.accessPolicyWindow.hitRatio = (float)((double)persist / (double)win);
+            attr.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+            attr.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+            for (int s2 = 0; s2 < 2; s2++) cudaStreamSetAttribute(c->streams[s2], cudaStreamAttributeAccessPolicyWindow, &attr);
+        }
+        cudaGetLastError(); /* a refusal only costs performance */
+    }
     if (!rc) {
         cudaMemsetAsync(d_bad, 0, sizeof(int), c->streams[0]);
         k_decode_classes<<<grid_for(c, a->n_classes, BFT_TPB), BFT_TPB, 0, c->streams[0]>>>(
