@@ -342,7 +342,10 @@ static int enqueue_kmers(bft_b200_ctx* c, cudaStream_t st, const uint64_t* d_kme
     else k_query_kmers<2><<<grid, BFT_TPB, 0, st>>>(c->dview, d_kmers, n, d_present, d_cls);
     c->launches++;
     if (d_rows) {
-        k_expand_rows<<<grid_for(c, n * (size_t)c->rw, BFT_TPB), BFT_TPB, 0, st>>>(d_cls, n, c->d_class_rows, c->rw, d_rows);
+        if (c->rw % 4 == 0 && ((uintptr_t)d_rows & 15) == 0 && ((uintptr_t)c->d_class_rows & 15) == 0)
+            k_expand_rows_v4<<<grid_for(c, n * (size_t)(c->rw / 4), BFT_TPB), BFT_TPB, 0, st>>>(d_cls, n, (const uint4*)c->d_class_rows, c->rw / 4, (uint4*)d_rows);
+        else
+            k_expand_rows<<<grid_for(c, n * (size_t)c->rw, BFT_TPB), BFT_TPB, 0, st>>>(d_cls, n, c->d_class_rows, c->rw, d_rows);
         c->launches++;
     }
     CK(cudaGetLastError());

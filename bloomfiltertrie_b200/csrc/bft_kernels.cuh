@@ -123,6 +123,22 @@ __global__ void __launch_bounds__(BFT_TPB) k_expand_rows(const uint32_t* __restr
     }
 }
 
+/* same, for RW a multiple of 4 (wide colour sets, e.g. 1000 genomes = 32 words): one 16-byte vector per thread,
+ * class rows read through the read-only path (L2), output rows written with streaming stores */
+__global__ void __launch_bounds__(BFT_TPB) k_expand_rows_v4(const uint32_t* __restrict__ cls, size_t n, const uint4* __restrict__ class_rows,
+                                                            int rw4, uint4* __restrict__ rows) {
+    const size_t total = n * (size_t)rw4;
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += stride) {
+        const size_t i = t / (size_t)rw4;
+        const int w = (int)(t - i * (size_t)rw4);
+        const uint32_t c = __ldg(cls + i);
+        uint4 r = make_uint4(0, 0, 0, 0);
+        if (c != BFT_CLS_NONE) r = __ldg(class_rows + (size_t)c * rw4 + w);
+        __stcs(rows + t, r);
+    }
+}
+
 /* a9/a10: decode every distinct annotation once (get_id_genomes_from_annot, src/annotation.c:2086-2250) */
 __global__ void __launch_bounds__(BFT_TPB) k_decode_classes(const uint32_t* __restrict__ cls_off, const uint8_t* __restrict__ cls_bytes,
                                                             size_t n_classes, const bft_pools_t pools, uint32_t* __restrict__ rows,
