@@ -111,6 +111,13 @@ typedef struct {
     uint8_t pad;
 } bft_cc_t;
 
+typedef struct {
+    uint64_t acc[BFT_MAX_WORDS]; /* nucleotides of the 9-nt prefixes above this Node, at their final bit positions */
+    uint32_t depth;              /* number of prefixes above (0 for the root) */
+    uint32_t uc_out_lo, uc_out_hi; /* enumeration index of this Node's first own-UC k-mer (64 bits, split) */
+    uint32_t pad;
+} bft_path_t;
+
 /* Read-only view of an arena; pointers are host pointers on the host and device pointers in kernels. */
 typedef struct {
     const bft_entry_t* rootdir;
@@ -126,6 +133,11 @@ typedef struct {
     const uint32_t* ovfcls;   /* n_ovf, only when cls_shift == 0 */
     const uint64_t* uckeys;   /* n_uc_lines * W words (Node-UC lines) */
     const uint32_t* uccls;    /* n_uc_lines */
+    /* enumeration side tables (iterate_over_kmers / -extract_kmers): where each stored prefix sits in the trie */
+    const uint32_t* pref_low18;  /* per stored prefix: its 9 nucleotides as they appear in the packed k-mer */
+    const uint32_t* pref_node;   /* per stored prefix: the Node whose CC holds it */
+    const bft_path_t* node_path; /* per Node: the k-mer bits fixed by the path from the root, and the depth */
+    const uint64_t* pref_out;    /* per stored prefix: index of its first k-mer in the enumeration order */
     int k;
     int W;             /* 64-bit words per key: 1 for k <= 27, 2 for k <= 63 */
     int cls_shift;     /* != 0: class id of an inline line = (top word >> cls_shift) & cls_mask, suffix = the bits below */

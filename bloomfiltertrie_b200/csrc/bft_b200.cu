@@ -59,7 +59,8 @@ struct bft_b200_ctx {
     char** names;
     bft_b200_stats stats;
     /* device arena */
-    void* d_arena[13];
+    void* d_arena[17];
+    size_t n_pref, n_nodes;
     bft_view_t dview;
     bft_pools_t dpools;
     void* d_pool[4];
@@ -119,7 +120,7 @@ extern "C" void bft_b200_close(bft_b200_ctx* c) {
     if (!c) return;
     cudaSetDevice(c->device);
     cudaDeviceSynchronize();
-    for (int i = 0; i < 13; i++) if (c->d_arena[i]) cudaFree(c->d_arena[i]);
+    for (int i = 0; i < 17; i++) if (c->d_arena[i]) cudaFree(c->d_arena[i]);
     for (int i = 0; i < 4; i++) if (c->d_pool[i]) cudaFree(c->d_pool[i]);
     if (c->d_hot) cudaFree(c->d_hot);
     if (c->d_class_counts) cudaFree(c->d_class_counts);
@@ -190,6 +191,12 @@ extern "C" int bft_b200_open(const char* path, int device, bft_b200_ctx** out) {
     UP(10, ovfcls, a->ovfcls ? a->n_ovf * sizeof(uint32_t) : 0);
     UP(11, uckeys, a->n_uc_lines * (size_t)a->W * sizeof(uint64_t));
     UP(12, uccls, a->n_uc_lines * sizeof(uint32_t));
+    UP(13, pref_low18, a->n_pref * sizeof(uint32_t));
+    UP(14, pref_node, a->n_pref * sizeof(uint32_t));
+    UP(15, node_path, a->n_nodes * sizeof(bft_path_t));
+    UP(16, pref_out, (a->n_pref + 1) * sizeof(uint64_t));
+    c->n_pref = a->n_pref;
+    c->n_nodes = a->n_nodes;
 #undef UP
     void* d_cls_off = NULL; void* d_cls_bytes = NULL;
     if (!rc) rc = upload(&d_cls_off, a->cls_off, (a->n_classes + 1) * sizeof(uint32_t));
@@ -212,6 +219,10 @@ extern "C" int bft_b200_open(const char* path, int device, bft_b200_ctx** out) {
         c->dview.ovfcls = (const uint32_t*)c->d_arena[10];
         c->dview.uckeys = (const uint64_t*)c->d_arena[11];
         c->dview.uccls = (const uint32_t*)c->d_arena[12];
+        c->dview.pref_low18 = (const uint32_t*)c->d_arena[13];
+        c->dview.pref_node = (const uint32_t*)c->d_arena[14];
+        c->dview.node_path = (const bft_path_t*)c->d_arena[15];
+        c->dview.pref_out = (const uint64_t*)c->d_arena[16];
         c->dview.cls_shift = a->cls_shift;
         c->dview.cls_mask = a->cls_mask;
         c->dview.k = a->k;
@@ -656,6 +667,92 @@ extern "C" int bft_b200_random_gather_probe(bft_b200_ctx* c, size_t table_bytes,
     if (e != cudaSuccess) return set_err(BFT_B200_ERR_CUDA, "k_random_gather failed: %s", cudaGetErrorString(e));
     *loads_per_sec = (double)n_loads / (best * 1e-3);
     return 0;
+}
+
+/* ---- enumeration --------------------------------------------------------------------------------------------- */
+extern "C" int bft_b200_extract_kmers_device(bft_b200_ctx* c, uint64_t* d_kmers, uint32_t* d_cls, size_t capacity) {
+    if (!c || !d_kmers) return set_err(BFT_B200_ERR_ARG, "bft_b200_extract_kmers_device: NULL argument");
+    if (capacity < c->stats.n_kmers) return set_err(BFT_B200_ERR_ARG, "bft_b200_extract_kmers: capacity %zu < %llu stored k-mers", capacity, (unsigned long long)c->stats.n_kmers);
+    CK(cudaSetDevice(c->device));
+    cudaStream_t st = c->streams[0];
+    if (c->n_pref) {
+        const int grid = grid_for(c, c->n_pref * 32, BFT_TPB);
+        if (c->W == 1) k_extract_prefix_kmers<1><<<grid, BFT_TPB, 0, st>>>(c->dview, c->n_pref, d_kmers, d_cls);
+        else k_extract_prefix_kmers<2><<<grid, BFT_TPB, 0, st>>>(c->dview, c->n_pref, d_kmers, d_cls);
+        c->launches++;
+    }
+    if (c->W == 1) k_extract_uc_kmers<1><<<grid_for(c, c->n_nodes, BFT_TPB), BFT_TPB, 0, st>>>(c->dview, c->n_nodes, d_kmers, d_cls);
+    else k_extract_uc_kmers<2><<<grid_for(c, c->n_nodes, BFT_TPB), BFT_TPB, 0, st>>>(c->dview, c->n_nodes, d_kmers, d_cls);
+    c->launches++;
+    CK(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int bft_b200_extract_kmers(bft_b200_ctx* c, uint64_t* kmers, uint32_t* class_ids, uint32_t* rows, size_t capacity, uint64_t* n_written) {
+    if (!c || !kmers) return set_err(BFT_B200_ERR_ARG, "bft_b200_extract_kmers: NULL argument");
+    const size_t n = (size_t)c->stats.n_kmers, W = (size_t)c->W, rw = (size_t)c->rw;
+    if (capacity < n) return set_err(BFT_B200_ERR_ARG, "bft_b200_extract_kmers: capacity %zu < %zu stored k-mers", capacity, n);
+    CK(cudaSetDevice(c->device));
+    CK(cudaStreamSynchronize(c->streams[0]));
+    uint64_t* d_k = NULL;
+    uint32_t* d_c = NULL;
+    uint32_t* d_r = NULL;
+    int rc = 0;
+    if (cudaMalloc((void**)&d_k, (n + 1) * W * 8) != cudaSuccess || cudaMalloc((void**)&d_c, (n + 1) * 4) != cudaSuccess)
+        rc = set_err(BFT_B200_ERR_NOMEM, "bft_b200_extract_kmers: cudaMalloc failed for %zu k-mers", n);
+    if (!rc) rc = bft_b200_extract_kmers_device(c, d_k, d_c, n);
+    if (!rc && cudaMemcpyAsync(kmers, d_k, n * W * 8, cudaMemcpyDeviceToHost, c->streams[0]) != cudaSuccess) rc = set_err(BFT_B200_ERR_CUDA, "copy failed");
+    if (!rc && class_ids && cudaMemcpyAsync(class_ids, d_c, n * 4, cudaMemcpyDeviceToHost, c->streams[0]) != cudaSuccess) rc = set_err(BFT_B200_ERR_CUDA, "copy failed");
+    if (!rc && rows && n) { /* rows in slices so the device buffer stays bounded */
+        const size_t slice = BFT_CHUNK_KMERS;
+        if (cudaMalloc((void**)&d_r, slice * rw * 4) != cudaSuccess) rc = set_err(BFT_B200_ERR_NOMEM, "bft_b200_extract_kmers: cudaMalloc failed");
+        for (size_t done = 0; !rc && done < n; done += slice) {
+            const size_t m = n - done < slice ? n - done : slice;
+            k_expand_rows<<<grid_for(c, m * rw, BFT_TPB), BFT_TPB, 0, c->streams[0]>>>(d_c + done, m, c->d_class_rows, c->rw, d_r);
+            c->launches++;
+            if (cudaMemcpyAsync(rows + done * rw, d_r, m * rw * 4, cudaMemcpyDeviceToHost, c->streams[0]) != cudaSuccess) rc = set_err(BFT_B200_ERR_CUDA, "copy failed");
+            if (!rc && cudaStreamSynchronize(c->streams[0]) != cudaSuccess) rc = set_err(BFT_B200_ERR_CUDA, "k_expand_rows failed");
+        }
+    }
+    if (!rc) {
+        cudaError_t e = cudaStreamSynchronize(c->streams[0]);
+        if (e != cudaSuccess) rc = set_err(BFT_B200_ERR_CUDA, "extraction kernels failed: %s", cudaGetErrorString(e));
+    }
+    if (d_k) cudaFree(d_k);
+    if (d_c) cudaFree(d_c);
+    if (d_r) cudaFree(d_r);
+    if (!rc && n_written) *n_written = n;
+    return rc;
+}
+
+extern "C" int bft_b200_extract_kmers_file(bft_b200_ctx* c, const char* path, int compressed_output) {
+    if (!c || !path) return set_err(BFT_B200_ERR_ARG, "bft_b200_extract_kmers_file: NULL argument");
+    const size_t n = (size_t)c->stats.n_kmers, W = (size_t)c->W;
+    uint64_t* km = (uint64_t*)malloc((n + 1) * W * 8);
+    if (!km) return set_err(BFT_B200_ERR_NOMEM, "out of host memory");
+    int rc = bft_b200_extract_kmers(c, km, NULL, NULL, n, NULL);
+    if (!rc) {
+        FILE* f = fopen(path, "w");
+        if (!f) rc = set_err(BFT_B200_ERR_FILE, "extract_kmers_to_disk(): failed to create/open output file %s", path);
+        else {
+            const int k = c->k;
+            const size_t nb = (size_t)(2 * k + 7) / 8;
+            if (compressed_output) {
+                fprintf(f, "%d\n%d\n", k, (int)n);
+                for (size_t i = 0; i < n; i++) fwrite(km + i * W, 1, nb, f);
+            } else {
+                char line[132];
+                for (size_t i = 0; i < n; i++) {
+                    for (int j = 0; j < k; j++) line[j] = "ACGT"[(km[i * W + (size_t)(j >> 5)] >> (2 * (j & 31))) & 3];
+                    line[k] = '\n';
+                    fwrite(line, 1, (size_t)k + 1, f);
+                }
+            }
+            fclose(f);
+        }
+    }
+    free(km);
+    return rc;
 }
 
 /* ---- file-level drivers ------------------------------------------------------------------------------------- */

@@ -1,8 +1,8 @@
 /* bft_cli.c — `bft_b200`: the query half of the reference CLI (src/main.c:204-316) on the GPU engine.
  *   bft_b200 load file_bft [-query_kmers {kmers|kmers_comp} list] [-query_sequences thr {canonical|non_canonical} list]
- *                          [-query_branching {kmers|kmers_comp} list]
+ *                          [-query_branching {kmers|kmers_comp} list] [-extract_kmers {kmers|kmers_comp} file]
  * Output files are named and placed as the reference does (basename with extension replaced by .csv in the cwd,
- * src/main.c:258-264). `build` / -add_genomes / -extract_kmers stay with the reference binary. */
+ * src/main.c:258-264). `build` / -add_genomes stay with the reference binary. */
 #define _GNU_SOURCE
 #include <libgen.h>
 #include <stdio.h>
@@ -25,7 +25,8 @@ int main(int argc, char** argv) {
         fprintf(stderr, "Usage:\nbft_b200 load file_bft [-query_sequences threshold {canonical|non_canonical} list_sequence_files]\n"
                         "                       [-query_kmers {kmers|kmers_comp} list_kmer_files]\n"
                         "                       [-query_branching {kmers|kmers_comp} list_kmer_files]\n"
-                        "Graph construction (build, -add_genomes) and -extract_kmers are served by the reference `bft` binary.\n");
+                        "                       [-extract_kmers {kmers|kmers_comp} kmers_file]\n"
+                        "Graph construction (build, -add_genomes) is served by the reference `bft` binary.\n");
         return EXIT_FAILURE;
     }
     BFT* bft = load_BFT(argv[2]);
@@ -70,6 +71,10 @@ int main(int argc, char** argv) {
                 printf("\nNb branching k-mers = %d\n", queryBFT_kmerBranching_from_KmerFiles(bft, buffer, binary));
             }
             fclose(fl);
+            i += 3;
+        } else if (strcmp(argv[i], "-extract_kmers") == 0 && i + 2 < argc) { /* src/main.c:317, write_kmers_2disk */
+            printf("\nExtraction of k-mers from the BFT to file %s\n\n", argv[i + 2]);
+            extract_kmers_to_disk(bft, argv[i + 2], strcmp(argv[i + 1], "kmers_comp") == 0);
             i += 3;
         } else {
             fprintf(stderr, "Unrecognized command %s.\n", argv[i]);

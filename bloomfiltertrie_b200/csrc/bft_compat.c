@@ -3,6 +3,7 @@
 #include "bft_compat.h"
 #include "bft_b200.h"
 
+#include <stdarg.h>
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
@@ -244,6 +245,69 @@ static BFT_kmer* neighbours(BFT_kmer* km, BFT* bft, int first, int count, const 
 BFT_kmer* get_neighbors(BFT_kmer* km, BFT* bft) { return neighbours(km, bft, 0, 8, "get_neighbors()"); }
 BFT_kmer* get_predecessors(BFT_kmer* km, BFT* bft) { return neighbours(km, bft, 0, 4, "get_predecessors()"); }
 BFT_kmer* get_successors(BFT_kmer* km, BFT* bft) { return neighbours(km, bft, 4, 4, "get_successors()"); }
+
+void v_iterate_over_kmers(BFT* bft, BFT_func_ptr f, va_list args) { /* src/bft.c:1014-1034 */
+    NOT_NULL(bft, "v_iterate_over_kmers()");
+    bft_b200_stats st;
+    ENGINE_OK(bft_b200_get_stats(bft->engine, &st), "v_iterate_over_kmers()");
+    const size_t n = (size_t)st.n_kmers, W = (size_t)bft_b200_kmer_words(bft->engine);
+    const int k = bft->k, nb = nb_bytes(k);
+    uint64_t* km = (uint64_t*)malloc((n + 1) * W * sizeof(uint64_t));
+    uint32_t* cls = (uint32_t*)malloc((n + 1) * sizeof(uint32_t));
+    NOT_NULL(km, "v_iterate_over_kmers()");
+    NOT_NULL(cls, "v_iterate_over_kmers()");
+    ENGINE_OK(bft_b200_extract_kmers(bft->engine, km, cls, NULL, n, NULL), "v_iterate_over_kmers()");
+    BFT_kmer cur;
+    resultPresence res;
+    cur.kmer = (char*)malloc((size_t)k + 2);
+    cur.kmer_comp = (uint8_t*)calloc((size_t)nb + 8, 1);
+    cur.res = &res;
+    for (size_t i = 0; i < n; i++) {
+        for (int j = 0; j < k; j++) cur.kmer[j] = "ACGT"[(km[i * W + (size_t)(j >> 5)] >> (2 * (j & 31))) & 3];
+        cur.kmer[k] = '\0';
+        memcpy(cur.kmer_comp, km + i * W, (size_t)nb);
+        res.present = 1;
+        res.class_id = cls[i];
+        res.bft = bft;
+        va_list copy;
+        va_copy(copy, args);
+        const size_t go_on = f(&cur, bft, copy);
+        va_end(copy);
+        if (go_on == 0) break;
+    }
+    free(cur.kmer);
+    free(cur.kmer_comp);
+    free(km);
+    free(cls);
+}
+
+void iterate_over_kmers(BFT* bft, BFT_func_ptr f, ...) { /* src/bft.c:1043-1075 */
+    va_list args;
+    va_start(args, f);
+    v_iterate_over_kmers(bft, f, args);
+    va_end(args);
+}
+
+size_t write_kmer_ascii_to_disk(BFT_kmer* bft_kmer, BFT* bft, va_list args) { /* src/bft.c:291-300 */
+    FILE* file = va_arg(args, FILE*);
+    bft_kmer->kmer[bft->k] = '\n';
+    fwrite(bft_kmer->kmer, sizeof(char), (size_t)bft->k + 1, file);
+    return 1;
+}
+
+size_t write_kmer_comp_to_disk(BFT_kmer* bft_kmer, BFT* bft, va_list args) { /* src/bft.c:308-318 */
+    (void)bft;
+    int nb_bytes_kmer_comp = va_arg(args, int);
+    FILE* file = va_arg(args, FILE*);
+    fwrite(bft_kmer->kmer_comp, sizeof(uint8_t), (size_t)nb_bytes_kmer_comp, file);
+    return 1;
+}
+
+void extract_kmers_to_disk(BFT* bft, char* filename_output, bool compressed_output) { /* src/bft.c:255-283 */
+    NOT_NULL(bft, "extract_kmers_to_disk()");
+    NOT_NULL(filename_output, "extract_kmers_to_disk()");
+    ENGINE_OK(bft_b200_extract_kmers_file(bft->engine, filename_output, compressed_output), "extract_kmers_to_disk()");
+}
 
 int queryBFT_kmerPresences_from_KmerFiles(BFT_Root* root, char* query_filename, int binary_file, char* output_filename) {
     NOT_NULL(root, "queryBFT_kmerPresences_from_KmerFiles()");

@@ -531,6 +531,10 @@ void bft_arena_view(const bft_arena_t* a, bft_view_t* v) {
     v->ovfcls = a->ovfcls;
     v->uckeys = a->uckeys;
     v->uccls = a->uccls;
+    v->pref_low18 = a->pref_low18;
+    v->pref_node = a->pref_node;
+    v->node_path = a->node_path;
+    v->pref_out = a->pref_out;
     v->cls_shift = a->cls_shift;
     v->cls_mask = a->cls_mask;
     v->k = a->k;
@@ -544,6 +548,7 @@ void bft_arena_free(bft_arena_t* a) {
         free(a->filenames);
     }
     free(a->rootdir); free(a->nodes); free(a->ccs); free(a->firstcc); free(a->csr); free(a->filter3);
+    free(a->pref_low18); free(a->pref_node); free(a->node_path); free(a->pref_out);
     free(a->pref); free(a->buckets); free(a->slotcls); free(a->ovf); free(a->ovfcls); free(a->uckeys); free(a->uccls); free(a->cls_off); free(a->cls_bytes);
     free(a->pool_last_index); free(a->pool_size_annot); free(a->pool_off); free(a->pool_bytes);
     free(a);
@@ -553,7 +558,8 @@ size_t bft_arena_bytes(const bft_arena_t* a) {
     return BFT_ROOTDIR_SIZE * sizeof(bft_entry_t) + a->n_nodes * sizeof(bft_node_t) + a->n_ccs * sizeof(bft_cc_t) +
            a->firstcc_bytes + a->n_csr * 2 + a->filter3_bytes + a->n_pref * sizeof(bft_entry_t) +
            (a->n_buckets * BFT_BUCKET_KEYS + a->n_ovf) * ((size_t)a->W * 8 + (a->cls_shift ? 0 : 4)) +
-           a->n_uc_lines * ((size_t)a->W * 8 + 4) + (a->n_classes + 1) * 4 + a->cls_bytes_len + a->pool_bytes_len;
+           a->n_uc_lines * ((size_t)a->W * 8 + 4) + (a->n_classes + 1) * 4 + a->cls_bytes_len + a->pool_bytes_len +
+           a->n_pref * 16 + a->n_nodes * sizeof(bft_path_t);
 }
 
 bft_arena_t* bft_arena_from_memory(const uint8_t* buf, size_t len, char* err, size_t errlen) {
@@ -689,6 +695,61 @@ bft_arena_t* bft_arena_from_memory(const uint8_t* buf, size_t len, char* err, si
             a->slotcls = NULL;
             a->ovfcls = NULL;
         }
+    }
+
+    /* enumeration side tables: Nodes are numbered parent-before-child, so one forward sweep fixes every Node's
+     * path. Enumeration order = stored prefixes in arena order (each followed by its inline suffixes in bucket
+     * order), then the Nodes' own UC lines. */
+    a->pref_low18 = (uint32_t*)xrealloc(c, NULL, (a->n_pref + 1) * sizeof(uint32_t));
+    a->pref_node = (uint32_t*)xrealloc(c, NULL, (a->n_pref + 1) * sizeof(uint32_t));
+    a->pref_out = (uint64_t*)xrealloc(c, NULL, (a->n_pref + 1) * sizeof(uint64_t));
+    a->node_path = (bft_path_t*)xrealloc(c, NULL, (a->n_nodes + 1) * sizeof(bft_path_t));
+    memset(a->node_path, 0, (a->n_nodes + 1) * sizeof(bft_path_t));
+    for (size_t nid = 0; nid < a->n_nodes; nid++) {
+        const bft_node_t* nd = &a->nodes[nid];
+        const bft_path_t pp = a->node_path[nid];
+        for (uint32_t ci = 0; ci < nd->n_cc; ci++) {
+            const bft_cc_t* cc = &a->ccs[nd->cc_begin + ci];
+            const uint16_t* csr = a->csr + cc->csr_off;
+            const uint8_t* f3 = a->filter3 + cc->f3_off;
+            const int n_pu = 1 << (BFT_PREFIX_BITS - cc->s);
+            for (int pu = 0; pu < n_pu; pu++) {
+                for (uint32_t j = csr[pu]; j < csr[pu + 1]; j++) {
+                    const uint32_t pv = cc->s == 8 ? f3[j] : ((j & 1) ? (uint32_t)(f3[j / 2] >> 4) : (uint32_t)(f3[j / 2] & 0xf));
+                    const uint32_t rot = ((uint32_t)pu << cc->s) | pv;              /* nuc1..nuc8,nuc0 */
+                    const uint32_t r18 = (rot >> 2) | ((rot & 3u) << 16);           /* nuc0..nuc8, MSB first */
+                    uint32_t low18 = 0;
+                    for (int q = 0; q < 9; q++) low18 |= ((r18 >> (2 * (8 - q))) & 3u) << (2 * q);
+                    const size_t pj = (size_t)cc->pref_off + j;
+                    a->pref_low18[pj] = low18;
+                    a->pref_node[pj] = (uint32_t)nid;
+                    if ((a->pref[pj].b >> BFT_KIND_SHIFT) == BFT_KIND_NODE) {
+                        bft_path_t* cp = &a->node_path[a->pref[pj].a];
+                        *cp = pp;
+                        const unsigned sh = BFT_PREFIX_BITS * pp.depth;
+                        cp->acc[sh >> 6] |= (uint64_t)low18 << (sh & 63);
+                        if ((sh & 63) > 64 - BFT_PREFIX_BITS && (sh >> 6) + 1 < BFT_MAX_WORDS) cp->acc[(sh >> 6) + 1] |= (uint64_t)low18 >> (64 - (sh & 63));
+                        cp->depth = pp.depth + 1;
+                    }
+                }
+            }
+        }
+    }
+    {
+        uint64_t run = 0;
+        for (size_t pj = 0; pj < a->n_pref; pj++) {
+            a->pref_out[pj] = run;
+            const uint32_t kind = a->pref[pj].b >> BFT_KIND_SHIFT;
+            if (kind == BFT_KIND_INLINE) run += a->pref[pj].b & BFT_CNT_MASK;
+            else if (kind == BFT_KIND_LEAF) run += 1;
+        }
+        a->pref_out[a->n_pref] = run;
+        for (size_t nid = 0; nid < a->n_nodes; nid++) {
+            a->node_path[nid].uc_out_lo = (uint32_t)run;
+            a->node_path[nid].uc_out_hi = (uint32_t)(run >> 32);
+            run += a->nodes[nid].uc_n;
+        }
+        if (run != a->n_kmers) fail(c, "bft_flatten: enumeration order counts %llu k-mers, the arena %zu", (unsigned long long)run, a->n_kmers);
     }
 
     /* root directory: the root probe for every 9-nt prefix */

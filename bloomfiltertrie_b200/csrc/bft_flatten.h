@@ -30,6 +30,11 @@ typedef struct bft_arena {
     uint32_t* uccls;     size_t n_uc_lines;
     int cls_shift;
     uint32_t cls_mask;
+    /* enumeration side tables (see bft_arena.h) */
+    uint32_t* pref_low18; /* n_pref */
+    uint32_t* pref_node;  /* n_pref */
+    bft_path_t* node_path; /* n_nodes */
+    uint64_t* pref_out;   /* n_pref */
 
     /* colour classes: distinct annotation byte strings (annotation ‖ extended byte, reference src/UC.c:171-239) */
     uint32_t* cls_off;   /* n_classes + 1 */

@@ -187,6 +187,123 @@ __global__ void __launch_bounds__(BFT_TPB) k_encode_ascii(const char* __restrict
     }
 }
 
+/* ---- enumeration: iterate_over_kmers / -extract_kmers (include/bft.h:88,164; src/extract_kmers.c:3-597) ------------
+ * One warp per stored prefix. The k-mer is re-assembled from the Node's path (the prefixes above it), the prefix's own
+ * 9 nucleotides and the suffix found in its buckets; the output slot of every k-mer is fixed by the exclusive counts
+ * the serializer stored (pref_out), so the result is deterministic and needs no atomics. */
+template <int W>
+__device__ __forceinline__ void bft_emit_kmer(const uint64_t* base, const uint64_t* suffix, int shift_bits, uint64_t* out) {
+    /* out = base | suffix << shift_bits (shift_bits = 18 * (depth + 1), 18..126) */
+    if (W == 1) {
+        out[0] = base[0] | (suffix[0] << shift_bits);
+    } else {
+        uint64_t lo, hi;
+        if (shift_bits >= 64) { lo = 0; hi = suffix[0] << (shift_bits - 64); }
+        else { lo = suffix[0] << shift_bits; hi = (suffix[W - 1] << shift_bits) | (suffix[0] >> (64 - shift_bits)); }
+        out[0] = base[0] | lo;
+        out[W - 1] = base[W - 1] | hi;
+    }
+}
+
+template <int W>
+__global__ void __launch_bounds__(BFT_TPB) k_extract_prefix_kmers(const bft_view_t v, size_t n_pref, uint64_t* __restrict__ kmers,
+                                                                  uint32_t* __restrict__ cls_out) {
+    const int lane = threadIdx.x & 31;
+    const size_t warp_stride = ((size_t)gridDim.x * blockDim.x) >> 5;
+    const int shift = v.cls_shift;
+    const uint64_t top_mask = shift ? ((1ULL << shift) - 1ULL) : ~BFT_SLOT_SPECIAL;
+    for (size_t j = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5; j < n_pref; j += warp_stride) {
+        const bft_entry_t e = v.pref[j];
+        const uint32_t kind = e.b >> BFT_KIND_SHIFT;
+        if (kind != BFT_KIND_INLINE && kind != BFT_KIND_LEAF) continue;
+        const bft_path_t path = v.node_path[v.pref_node[j]];
+        uint64_t base[W];
+        {
+            const uint64_t low18 = v.pref_low18[j];
+            const unsigned sh = BFT_PREFIX_BITS * path.depth;
+            base[0] = path.acc[0];
+            if (W > 1) base[W - 1] = path.acc[W - 1];
+            if (W == 1) base[0] |= low18 << sh;
+            else if (sh >= 64) base[W - 1] |= low18 << (sh - 64);
+            else { base[0] |= low18 << sh; if (sh > 64 - BFT_PREFIX_BITS) base[W - 1] |= low18 >> (64 - sh); }
+        }
+        uint64_t out = v.pref_out[j];
+        if (kind == BFT_KIND_LEAF) {
+            if (lane == 0) {
+                for (int w = 0; w < W; w++) kmers[out * W + w] = base[w];
+                if (cls_out) cls_out[out] = e.a;
+            }
+            continue;
+        }
+        const int shift_bits = BFT_PREFIX_BITS * (int)(path.depth + 1);
+        const uint32_t n_slots = BFT_BUCKET_KEYS << ((e.b >> BFT_LB_SHIFT) & BFT_LB_MASK);
+        for (uint32_t s0 = 0; s0 < n_slots; s0 += 32) {
+            const uint32_t slot = s0 + lane;
+            uint64_t key[W];
+            uint32_t n_emit = 0, ovf_start = 0;
+            size_t gslot = 0;
+            if (slot < n_slots) {
+                gslot = (size_t)e.a * BFT_BUCKET_KEYS + slot;
+                for (int w = 0; w < W; w++) key[w] = v.buckets[gslot * W + w];
+                const uint64_t top = key[W - 1];
+                if (!(top & BFT_SLOT_SPECIAL)) n_emit = 1;
+                else if (top != BFT_SLOT_EMPTY) { n_emit = (uint32_t)(top >> 32) & 0x7fffffffu; ovf_start = (uint32_t)top; }
+            }
+            /* exclusive scan of n_emit over the warp */
+            uint32_t incl = n_emit;
+            for (int o = 1; o < 32; o <<= 1) {
+                const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
+                if (lane >= o) incl += t;
+            }
+            const uint64_t my = out + incl - n_emit;
+            out += __shfl_sync(0xffffffffu, incl, 31);
+            if (n_emit == 1 && !(key[W - 1] & BFT_SLOT_SPECIAL)) {
+                const uint32_t c = shift ? ((uint32_t)(key[W - 1] >> shift) & v.cls_mask) : v.slotcls[gslot];
+                key[W - 1] &= top_mask;
+                uint64_t km[W];
+                bft_emit_kmer<W>(base, key, shift_bits, km);
+                for (int w = 0; w < W; w++) kmers[my * W + w] = km[w];
+                if (cls_out) cls_out[my] = c;
+            } else if (n_emit) { /* overflow run of this bucket */
+                for (uint32_t i = 0; i < n_emit; i++) {
+                    uint64_t ok[W];
+                    for (int w = 0; w < W; w++) ok[w] = v.ovf[((size_t)ovf_start + i) * W + w];
+                    const uint32_t c = shift ? ((uint32_t)(ok[W - 1] >> shift) & v.cls_mask) : v.ovfcls[ovf_start + i];
+                    ok[W - 1] &= top_mask;
+                    uint64_t km[W];
+                    bft_emit_kmer<W>(base, ok, shift_bits, km);
+                    for (int w = 0; w < W; w++) kmers[(my + i) * W + w] = km[w];
+                    if (cls_out) cls_out[my + i] = c;
+                }
+            }
+        }
+    }
+}
+
+/* the Nodes' own UC lines: whole remainders below the Node's path (one thread per Node, <= 255 lines each) */
+template <int W>
+__global__ void __launch_bounds__(BFT_TPB) k_extract_uc_kmers(const bft_view_t v, size_t n_nodes, uint64_t* __restrict__ kmers,
+                                                              uint32_t* __restrict__ cls_out) {
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (size_t nid = (size_t)blockIdx.x * blockDim.x + threadIdx.x; nid < n_nodes; nid += stride) {
+        const bft_node_t nd = v.nodes[nid];
+        if (!nd.uc_n) continue;
+        const bft_path_t path = v.node_path[nid];
+        const uint64_t out = ((uint64_t)path.uc_out_hi << 32) | path.uc_out_lo;
+        uint64_t base[W];
+        base[0] = path.acc[0];
+        if (W > 1) base[W - 1] = path.acc[W - 1];
+        for (uint32_t i = 0; i < nd.uc_n; i++) {
+            uint64_t key[W], km[W];
+            for (int w = 0; w < W; w++) key[w] = v.uckeys[((size_t)nd.uc_begin + i) * W + w];
+            if (path.depth == 0) { for (int w = 0; w < W; w++) km[w] = key[w]; }
+            else bft_emit_kmer<W>(base, key, BFT_PREFIX_BITS * (int)path.depth, km);
+            for (int w = 0; w < W; w++) kmers[(out + i) * W + w] = km[w];
+            if (cls_out) cls_out[out + i] = v.uccls[nd.uc_begin + i];
+        }
+    }
+}
+
 /* ---- a13/a14: branching ------------------------------------------------------------------------------------
  * 8 lanes per query: lanes 0-3 look up the four successors (drop nuc 0, append c), lanes 4-7 the four
  * predecessors (prepend c, drop the last nuc) — isBranchingRight / isBranchingLeft (src/branchingNode.c:16-110,

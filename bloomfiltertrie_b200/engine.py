@@ -28,6 +28,7 @@ ABI_SYMBOLS = [
     "bft_b200_query_branching_device", "bft_b200_query_neighbors", "bft_b200_set_reference_exact_branching",
     "bft_b200_query_kmers_file", "bft_b200_query_branching_file",
     "bft_b200_query_sequences_file", "bft_b200_sync", "bft_b200_launch_count", "bft_b200_kmer_walk_stats_device", "bft_b200_random_gather_probe",
+    "bft_b200_extract_kmers", "bft_b200_extract_kmers_device", "bft_b200_extract_kmers_file",
 ]
 
 
@@ -86,6 +87,9 @@ def load_library() -> C.CDLL:
     lib.bft_b200_query_sequences_file.argtypes = [vp, C.c_char_p, C.c_char_p, C.c_double, C.c_int]
     lib.bft_b200_kmer_walk_stats_device.argtypes = [vp, u64p, sz, C.POINTER(C.c_uint64 * 5)]
     lib.bft_b200_random_gather_probe.argtypes = [vp, sz, sz, C.POINTER(C.c_double)]
+    lib.bft_b200_extract_kmers.argtypes = [vp, u64p, u32p, u32p, sz, C.POINTER(C.c_uint64)]
+    lib.bft_b200_extract_kmers_device.argtypes = [vp, u64p, u32p, sz]
+    lib.bft_b200_extract_kmers_file.argtypes = [vp, C.c_char_p, C.c_int]
     lib.bft_b200_sync.argtypes = [vp]
     lib.bft_b200_launch_count.argtypes = [vp]
     lib.bft_b200_launch_count.restype = C.c_uint64
@@ -280,6 +284,23 @@ class BFTEngine:
     def query_branching_device(self, d_kmers, n: int, d_succ=None, d_pred=None, d_count=None):
         self._ck(self.lib.bft_b200_query_branching_device(self.h, _ptr(d_kmers), n, _ptr(d_succ), _ptr(d_pred),
                                                           _ptr(d_count)), "bft_b200_query_branching_device")
+
+    # -- enumeration
+    def extract_kmers(self, want_classes: bool = True, want_rows: bool = False):
+        """Every stored k-mer: (uint64 [n, W], class ids uint32 [n] | None, rows uint32 [n, RW] | None), arena order."""
+        n = int(self.stats()["n_kmers"])
+        kmers = np.empty((n, self.W), dtype=np.uint64)
+        cls = np.empty(n, dtype=np.uint32) if want_classes else None
+        rows = np.empty((n, self.RW), dtype=np.uint32) if want_rows else None
+        out = C.c_uint64()
+        self._ck(self.lib.bft_b200_extract_kmers(self.h, _ptr(kmers), _ptr(cls), _ptr(rows), n, C.byref(out)),
+                 "bft_b200_extract_kmers")
+        assert out.value == n
+        return kmers, cls, rows
+
+    def extract_kmers_file(self, path: str, compressed_output: bool = True):
+        self._ck(self.lib.bft_b200_extract_kmers_file(self.h, os.fsencode(path), int(bool(compressed_output))),
+                 "bft_b200_extract_kmers_file")
 
     # -- file-level drivers
     def query_kmers_file(self, query_path: str, binary: bool, csv_path: str) -> int:

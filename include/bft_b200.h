@@ -121,6 +121,20 @@ int bft_b200_query_neighbors(bft_b200_ctx* ctx, const uint64_t* kmers, size_t n,
  * exact == 0 switches to plain set membership of the four successors. */
 int bft_b200_set_reference_exact_branching(bft_b200_ctx* ctx, int exact);
 
+/* ---- enumeration --------------------------------------------------------------------------------------------------
+ * Batch form of iterate_over_kmers / extract_kmers_to_disk (include/bft.h:88,164; src/bft.c:255-283,
+ * src/extract_kmers.c): every k-mer stored in the BFT (bft_b200_get_stats().n_kmers of them) with its colour class
+ * and, optionally, its colour row. The k-mers come out in arena order — deterministic for a given .bft, but not the
+ * reference's trie order; the SET of (k-mer, colours) pairs is identical. capacity = room in the output arrays, in
+ * k-mers; kmers is required, class_ids and rows may be NULL. */
+int bft_b200_extract_kmers(bft_b200_ctx* ctx, uint64_t* kmers, uint32_t* class_ids, uint32_t* rows, size_t capacity,
+                           uint64_t* n_written);
+int bft_b200_extract_kmers_device(bft_b200_ctx* ctx, uint64_t* d_kmers, uint32_t* d_class_ids, size_t capacity);
+/* extract_kmers_to_disk (src/bft.c:255-283): compressed_output != 0 writes the `kmers_comp` layout (two header lines:
+ * k, count; then ceil(2k/8)-byte records), else one ASCII k-mer per line. Same records as the reference's file, in
+ * arena order. */
+int bft_b200_extract_kmers_file(bft_b200_ctx* ctx, const char* path, int compressed_output);
+
 /* ---- file-level drivers (the CLI-visible bytes) ---------------------------------------------------------------
  * queryBFT_kmerPresences_from_KmerFiles (src/file_io.c:651-895): CSV of colour rows; returns #present via out.
  * queryBFT_kmerBranching_from_KmerFiles (src/file_io.c:897-1020): count of branching k-mers.

@@ -9,13 +9,15 @@
  * Reference declarations replaced (include/bft.h): load_BFT :176, free_cdbg :63, get_kmer :125,
  * is_kmer_in_cdbg :126, query_sequence :127, get_annotation :97, presence_genome :98, get_list_id_genomes :115,
  * get_count_id_genomes :116, free_BFT_annotation :96, create_kmer/free_BFT_kmer/free_BFT_kmer_content :78-82,
- * set/unset_neighbors_traversal :154-155, get_neighbors/get_predecessors/get_successors :156-158; and the
+ * set/unset_neighbors_traversal :154-155, get_neighbors/get_predecessors/get_successors :156-158,
+ * iterate_over_kmers/v_iterate_over_kmers :164-165, extract_kmers_to_disk + write_kmer_{ascii,comp}_to_disk :88-90; and the
  * file-level drivers of include/file_io.h (queryBFT_kmerPresences_from_KmerFiles, queryBFT_kmerBranching_from_KmerFiles,
  * query_sequences_outputCSV).
  */
 #ifndef BFT_COMPAT_H
 #define BFT_COMPAT_H
 
+#include <stdarg.h>
 #include <stdbool.h>
 #include <stdint.h>
 #include <stddef.h>
@@ -83,6 +85,16 @@ void unset_neighbors_traversal(BFT* bft);
 BFT_kmer* get_neighbors(BFT_kmer* bft_kmer, BFT* bft);
 BFT_kmer* get_predecessors(BFT_kmer* bft_kmer, BFT* bft);
 BFT_kmer* get_successors(BFT_kmer* bft_kmer, BFT* bft);
+
+/* Iteration (src/bft.c:1014-1075, src/extract_kmers.c): f is called once per stored k-mer with its ASCII and 2-bit
+ * forms and a locator usable with get_annotation(); iteration stops when f returns 0. The k-mers are produced by the
+ * device enumeration (bft_b200_extract_kmers) in arena order, not the reference's trie order. */
+typedef size_t (*BFT_func_ptr)(BFT_kmer* bft_kmer, BFT* bft, va_list args);
+void iterate_over_kmers(BFT* bft, BFT_func_ptr f, ...);
+void v_iterate_over_kmers(BFT* bft, BFT_func_ptr f, va_list args);
+void extract_kmers_to_disk(BFT* bft, char* filename_output, bool compressed_output);
+size_t write_kmer_ascii_to_disk(BFT_kmer* bft_kmer, BFT* bft, va_list args);
+size_t write_kmer_comp_to_disk(BFT_kmer* bft_kmer, BFT* bft, va_list args);
 
 int queryBFT_kmerPresences_from_KmerFiles(BFT_Root* root, char* query_filename, int binary_file, char* output_filename);
 int queryBFT_kmerBranching_from_KmerFiles(BFT_Root* root, char* query_filename, int binary_file);

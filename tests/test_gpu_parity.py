@@ -150,3 +150,50 @@ def test_file_drivers_match_reference_cli(built, workdir):
     assert counts[0] == n_present
     if k > 9:
         assert refutil.parse_count(out, "Nb branching k-mers") == n_branching
+
+
+def _sort_rows(words):
+    order = np.lexsort([words[:, w] for w in range(words.shape[1])])
+    return order
+
+
+def test_enumeration_matches_inserted_sets_and_reference_extract(built, workdir):
+    """iterate_over_kmers / -extract_kmers on the device: the set of (k-mer, colour set) pairs must equal what was
+    inserted, and the k-mer records must equal the reference's own -extract_kmers output (as a set: the engine
+    enumerates in arena order, the reference in trie order)."""
+    c, path, eng = built
+    k, G = c["k"], c["n_genomes"]
+    kmers, cls, rows = eng.extract_kmers(want_classes=True, want_rows=True)
+    # expected: union of the genome k-mer sets, colours by membership
+    allw = np.concatenate(c["genome_words"])
+    gid = np.concatenate([np.full(len(w), g, dtype=np.int64) for g, w in enumerate(c["genome_words"])])
+    uniq, inv = np.unique(allw, axis=0, return_inverse=True)
+    inv = inv.reshape(-1)
+    assert len(kmers) == len(uniq) == int(eng.stats()["n_kmers"])
+    want_rows = np.zeros((len(uniq), eng.RW), dtype=np.uint32)
+    np.bitwise_or.at(want_rows, (inv, gid >> 5), (np.uint32(1) << (gid & 31).astype(np.uint32)))
+    o = _sort_rows(kmers)
+    ou = _sort_rows(uniq)
+    np.testing.assert_array_equal(kmers[o], uniq[ou])
+    np.testing.assert_array_equal(rows[o], want_rows[ou])
+    np.testing.assert_array_equal(eng.class_rows()[cls], rows)
+    # the reference's own extraction, and the engine's file writer
+    d = os.path.join(workdir, c["name"], "extract")
+    os.makedirs(d, exist_ok=True)
+    refutil.ref_cli(path, ["-extract_kmers", "kmers_comp", os.path.join(d, "ref.kc")], cwd=d)
+    eng.extract_kmers_file(os.path.join(d, "mine.kc"), True)
+    nb = synth.kmer_nbytes(k)
+
+    def records(p):
+        raw = open(p, "rb").read()
+        l1 = raw.index(b"\n")
+        l2 = raw.index(b"\n", l1 + 1)
+        assert int(raw[:l1]) == k and int(raw[l1 + 1:l2]) == len(uniq)
+        rec = np.frombuffer(raw[l2 + 1:], dtype=np.uint8).reshape(-1, nb)
+        return rec[np.lexsort(rec.T[::-1])]
+
+    np.testing.assert_array_equal(records(os.path.join(d, "mine.kc")), records(os.path.join(d, "ref.kc")))
+    eng.extract_kmers_file(os.path.join(d, "mine.txt"), False)
+    lines = open(os.path.join(d, "mine.txt"), "rb").read().split(b"\n")[:-1]
+    assert len(lines) == len(uniq) and all(len(x) == k for x in lines[:50])
+    np.testing.assert_array_equal(synth.words_to_ascii(kmers[:50], k), np.array([list(x) for x in lines[:50]], dtype=np.uint8))

@@ -129,7 +129,8 @@ def test_abi_library_loads_and_exports_every_declared_symbol():
     for s in ["load_BFT", "free_cdbg", "get_kmer", "is_kmer_in_cdbg", "get_annotation", "get_list_id_genomes",
               "get_count_id_genomes", "presence_genome", "query_sequence", "get_neighbors", "get_predecessors",
               "get_successors", "queryBFT_kmerPresences_from_KmerFiles", "queryBFT_kmerBranching_from_KmerFiles",
-              "query_sequences_outputCSV", "free_BFT_kmer", "free_BFT_annotation", "create_kmer"]:
+              "query_sequences_outputCSV", "free_BFT_kmer", "free_BFT_annotation", "create_kmer", "iterate_over_kmers",
+              "v_iterate_over_kmers", "extract_kmers_to_disk", "write_kmer_ascii_to_disk", "write_kmer_comp_to_disk"]:
         assert s in compat and hasattr(lib, s), s
 
 

@@ -8,6 +8,16 @@
 #include <string.h>
 #include "bft_compat.h"
 
+static size_t count_and_check(BFT_kmer* km, BFT* g, va_list args) { /* a BFT_func_ptr, as in the reference's snippets */
+    size_t* n = va_arg(args, size_t*);
+    size_t* colours = va_arg(args, size_t*);
+    BFT_annotation* a = get_annotation(km);
+    *colours += get_count_id_genomes(a, g);
+    free_BFT_annotation(a);
+    (*n)++;
+    return 1;
+}
+
 int main(int argc, char** argv) {
     if (argc < 6) return 2;
     BFT* g = load_BFT(argv[1]);
@@ -53,6 +63,9 @@ int main(int argc, char** argv) {
         free(ids);
     }
     fclose(f);
+    size_t n_iter = 0, n_colours = 0;
+    iterate_over_kmers(g, count_and_check, &n_iter, &n_colours);
+    printf("I kmers=%zu colours=%zu\n", n_iter, n_colours);
     free_cdbg(g);
     return 0;
 }
