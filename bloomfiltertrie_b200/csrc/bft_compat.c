@@ -123,6 +123,7 @@ BFT_annotation* create_BFT_annotation(void) {
 
 void free_BFT_annotation(BFT_annotation* a) {
     NOT_NULL(a, "free_BFT_annotation()");
+    if (!a->from_BFT) free(a->row);
     free(a);
 }
 
@@ -133,6 +134,73 @@ BFT_annotation* get_annotation(BFT_kmer* km) { /* src/bft.c:363-387 */
     a->class_id = km->res->class_id;
     a->from_BFT = 1;
     return a;
+}
+
+static const uint32_t* class_row(BFT* bft, uint32_t cls, int* rw);
+
+/* the colour bitmap behind an annotation: a class row of the engine, or the owned row of a computed annotation */
+static const uint32_t* annot_row(BFT* bft, const BFT_annotation* a, int* rw) {
+    if (!a->from_BFT && a->row) { *rw = bft_b200_row_words(bft->engine); return a->row; }
+    return class_row(bft, a->class_id, rw);
+}
+
+static BFT_annotation* combine_annotations(BFT* bft, uint32_t nb, va_list args, int op, const char* who) { /* src/bft.c:421-613 */
+    if (nb == 0) DIE("%s: no annotations given as parameters.\n", who);
+    const int rw = bft_b200_row_words(bft->engine);
+    BFT_annotation* out = create_BFT_annotation();
+    out->row = (uint32_t*)calloc((size_t)rw, sizeof(uint32_t));
+    NOT_NULL(out->row, who);
+    for (uint32_t i = 0; i < nb; i++) {
+        BFT_annotation* a = va_arg(args, BFT_annotation*);
+        NOT_NULL(a, who);
+        int rw2;
+        const uint32_t* r = annot_row(bft, a, &rw2);
+        for (int w = 0; w < rw; w++) {
+            if (i == 0) out->row[w] = r[w];
+            else if (op == 0) out->row[w] &= r[w];
+            else if (op == 1) out->row[w] |= r[w];
+            else out->row[w] ^= r[w];
+        }
+    }
+    return out;
+}
+
+BFT_annotation* intersection_annotations(BFT* bft, uint32_t nb_annotations, ...) {
+    va_list args;
+    va_start(args, nb_annotations);
+    BFT_annotation* r = combine_annotations(bft, nb_annotations, args, 0, "intersection_annotations()");
+    va_end(args);
+    return r;
+}
+BFT_annotation* union_annotations(BFT* bft, uint32_t nb_annotations, ...) {
+    va_list args;
+    va_start(args, nb_annotations);
+    BFT_annotation* r = combine_annotations(bft, nb_annotations, args, 1, "union_annotations()");
+    va_end(args);
+    return r;
+}
+BFT_annotation* sym_difference_annotations(BFT* bft, uint32_t nb_annotations, ...) {
+    va_list args;
+    va_start(args, nb_annotations);
+    BFT_annotation* r = combine_annotations(bft, nb_annotations, args, 2, "sym_difference_annotations()");
+    va_end(args);
+    return r;
+}
+
+uint32_t* intersection_list_id_genomes(uint32_t* list_a, uint32_t* list_b) { /* src/bft.c:656-690: sorted [count, ids...] lists */
+    NOT_NULL(list_a, "intersection_list_id_genomes()");
+    NOT_NULL(list_b, "intersection_list_id_genomes()");
+    const uint32_t na = list_a[0], nb = list_b[0];
+    uint32_t* out = (uint32_t*)malloc(((size_t)(na < nb ? na : nb) + 1) * sizeof(uint32_t));
+    NOT_NULL(out, "intersection_list_id_genomes()");
+    uint32_t i = 1, j = 1, n = 0;
+    while (i <= na && j <= nb) {
+        if (list_a[i] < list_b[j]) i++;
+        else if (list_a[i] > list_b[j]) j++;
+        else { out[++n] = list_a[i]; i++; j++; }
+    }
+    out[0] = n;
+    return out;
 }
 
 static const uint32_t* class_row(BFT* bft, uint32_t cls, int* rw) {
@@ -148,7 +216,7 @@ uint32_t* get_list_id_genomes(BFT_annotation* a, BFT* bft) { /* src/bft.c:622-64
     NOT_NULL(a, "get_list_id_genomes()");
     NOT_NULL(bft, "get_list_id_genomes()");
     int rw;
-    const uint32_t* row = class_row(bft, a->class_id, &rw);
+    const uint32_t* row = annot_row(bft, a, &rw);
     uint32_t cnt = 0;
     for (int w = 0; w < rw; w++) cnt += (uint32_t)__builtin_popcount(row[w]);
     uint32_t* ids = (uint32_t*)malloc(((size_t)cnt + 1) * sizeof(uint32_t));
@@ -163,6 +231,11 @@ uint32_t* get_list_id_genomes(BFT_annotation* a, BFT* bft) { /* src/bft.c:622-64
 uint32_t get_count_id_genomes(BFT_annotation* a, BFT* bft) { /* src/bft.c:648 */
     NOT_NULL(a, "get_count_id_genomes()");
     NOT_NULL(bft, "get_count_id_genomes()");
+    if (!a->from_BFT && a->row) {
+        uint32_t cnt = 0;
+        for (int w = 0; w < bft_b200_row_words(bft->engine); w++) cnt += (uint32_t)__builtin_popcount(a->row[w]);
+        return cnt;
+    }
     const uint32_t* counts;
     uint64_t n;
     ENGINE_OK(bft_b200_class_counts(bft->engine, &counts, &n), "get_count_id_genomes()");
@@ -175,7 +248,7 @@ bool presence_genome(uint32_t id_genome, BFT_annotation* a, BFT* bft) { /* src/b
     NOT_NULL(bft, "is_genome_present()");
     if (id_genome >= (uint32_t)bft->nb_genomes) return false;
     int rw;
-    const uint32_t* row = class_row(bft, a->class_id, &rw);
+    const uint32_t* row = annot_row(bft, a, &rw);
     return (row[id_genome >> 5] >> (id_genome & 31)) & 1u;
 }
 
@@ -246,8 +319,25 @@ BFT_kmer* get_neighbors(BFT_kmer* km, BFT* bft) { return neighbours(km, bft, 0, 
 BFT_kmer* get_predecessors(BFT_kmer* km, BFT* bft) { return neighbours(km, bft, 0, 4, "get_predecessors()"); }
 BFT_kmer* get_successors(BFT_kmer* km, BFT* bft) { return neighbours(km, bft, 4, 4, "get_successors()"); }
 
+/* shared by iteration and prefix matching: prefix == NULL iterates everything; returns the number of k-mers visited */
+static size_t iterate_filtered(BFT* bft, const char* prefix, BFT_func_ptr f, va_list args);
+
 void v_iterate_over_kmers(BFT* bft, BFT_func_ptr f, va_list args) { /* src/bft.c:1014-1034 */
     NOT_NULL(bft, "v_iterate_over_kmers()");
+    iterate_filtered(bft, NULL, f, args);
+}
+
+static size_t iterate_filtered(BFT* bft, const char* prefix, BFT_func_ptr f, va_list args) {
+    size_t matched = 0;
+    uint64_t pmask[2] = {0, 0}, pval[2] = {0, 0};
+    if (prefix) { /* compare the leading nucleotides in packed form */
+        const int len = (int)strlen(prefix);
+        uint8_t tmp[40];
+        memset(tmp, 0, sizeof tmp);
+        parse_kmer_bytes(prefix, len, tmp);
+        memcpy(pval, tmp, 16);
+        for (int j = 0; j < len; j++) pmask[j >> 5] |= 3ULL << (2 * (j & 31));
+    }
     bft_b200_stats st;
     ENGINE_OK(bft_b200_get_stats(bft->engine, &st), "v_iterate_over_kmers()");
     const size_t n = (size_t)st.n_kmers, W = (size_t)bft_b200_kmer_words(bft->engine);
@@ -263,6 +353,11 @@ void v_iterate_over_kmers(BFT* bft, BFT_func_ptr f, va_list args) { /* src/bft.c
     cur.kmer_comp = (uint8_t*)calloc((size_t)nb + 8, 1);
     cur.res = &res;
     for (size_t i = 0; i < n; i++) {
+        if (prefix) {
+            if ((km[i * W] & pmask[0]) != pval[0]) continue;
+            if (W > 1 && (km[i * W + 1] & pmask[1]) != pval[1]) continue;
+        }
+        matched++;
         for (int j = 0; j < k; j++) cur.kmer[j] = "ACGT"[(km[i * W + (size_t)(j >> 5)] >> (2 * (j & 31))) & 3];
         cur.kmer[k] = '\0';
         memcpy(cur.kmer_comp, km + i * W, (size_t)nb);
@@ -279,6 +374,23 @@ void v_iterate_over_kmers(BFT* bft, BFT_func_ptr f, va_list args) { /* src/bft.c
     free(cur.kmer_comp);
     free(km);
     free(cls);
+    return matched;
+}
+
+bool prefix_matching(BFT* bft, char* prefix, BFT_func_ptr f, ...) { /* src/bft.c:1093-1141 */
+    NOT_NULL(bft, "prefix_matching()");
+    NOT_NULL(prefix, "prefix_matching()");
+    const int len = (int)strlen(prefix);
+    if (len > bft->k) DIE("prefix_matching(): Prefix length is larger than k-mer length.\n");
+    if (len == 0) DIE("prefix_matching(): Prefix length is 0.\n");
+    uint8_t tmp[40];
+    memset(tmp, 0, sizeof tmp);
+    if (!parse_kmer_bytes(prefix, len, tmp)) DIE("prefix_matching(): Non-ACGT char. encountered in prefix.\n");
+    va_list args;
+    va_start(args, f);
+    const size_t matched = iterate_filtered(bft, prefix, f, args);
+    va_end(args);
+    return matched > 0;
 }
 
 void iterate_over_kmers(BFT* bft, BFT_func_ptr f, ...) { /* src/bft.c:1043-1075 */

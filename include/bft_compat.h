@@ -10,7 +10,7 @@
  * is_kmer_in_cdbg :126, query_sequence :127, get_annotation :97, presence_genome :98, get_list_id_genomes :115,
  * get_count_id_genomes :116, free_BFT_annotation :96, create_kmer/free_BFT_kmer/free_BFT_kmer_content :78-82,
  * set/unset_neighbors_traversal :154-155, get_neighbors/get_predecessors/get_successors :156-158,
- * iterate_over_kmers/v_iterate_over_kmers :164-165, extract_kmers_to_disk + write_kmer_{ascii,comp}_to_disk :88-90; and the
+ * intersection/union/sym_difference_annotations :99-113, prefix_matching :137, iterate_over_kmers/v_iterate_over_kmers :164-165, extract_kmers_to_disk + write_kmer_{ascii,comp}_to_disk :88-90; and the
  * file-level drivers of include/file_io.h (queryBFT_kmerPresences_from_KmerFiles, queryBFT_kmerBranching_from_KmerFiles,
  * query_sequences_outputCSV).
  */
@@ -58,7 +58,8 @@ typedef struct {
     int size_annot;
     int size_annot_cplx;
     uint8_t from_BFT;
-    uint32_t class_id;
+    uint32_t class_id;   /* from_BFT: the colour class of the k-mer */
+    uint32_t* row;       /* !from_BFT: an owned colour bitmap (result of the set operations below) */
 } BFT_annotation;
 
 BFT* load_BFT(char* filename);
@@ -80,6 +81,13 @@ bool presence_genome(uint32_t id_genome, BFT_annotation* bft_annot, BFT* bft);
 uint32_t* get_list_id_genomes(BFT_annotation* bft_annot, BFT* bft);
 uint32_t get_count_id_genomes(BFT_annotation* bft_annot, BFT* bft);
 
+/* Set algebra over colour sets (include/bft.h:99-113, src/bft.c:421-613): bitmap operations on the decoded class rows.
+ * nb_annotations BFT_annotation* follow; the result is a new annotation to free with free_BFT_annotation(). */
+BFT_annotation* intersection_annotations(BFT* bft, uint32_t nb_annotations, ...);
+BFT_annotation* union_annotations(BFT* bft, uint32_t nb_annotations, ...);
+BFT_annotation* sym_difference_annotations(BFT* bft, uint32_t nb_annotations, ...);
+uint32_t* intersection_list_id_genomes(uint32_t* list_a, uint32_t* list_b);
+
 void set_neighbors_traversal(BFT* bft);
 void unset_neighbors_traversal(BFT* bft);
 BFT_kmer* get_neighbors(BFT_kmer* bft_kmer, BFT* bft);
@@ -91,6 +99,9 @@ BFT_kmer* get_successors(BFT_kmer* bft_kmer, BFT* bft);
  * device enumeration (bft_b200_extract_kmers) in arena order, not the reference's trie order. */
 typedef size_t (*BFT_func_ptr)(BFT_kmer* bft_kmer, BFT* bft, va_list args);
 void iterate_over_kmers(BFT* bft, BFT_func_ptr f, ...);
+/* prefix_matching (include/bft.h:137, src/bft.c:1093-1141): f on every stored k-mer that starts with `prefix`
+ * (1 <= strlen(prefix) <= k); returns whether at least one k-mer matched. */
+bool prefix_matching(BFT* bft, char* prefix, BFT_func_ptr f, ...);
 void v_iterate_over_kmers(BFT* bft, BFT_func_ptr f, va_list args);
 void extract_kmers_to_disk(BFT* bft, char* filename_output, bool compressed_output);
 size_t write_kmer_ascii_to_disk(BFT_kmer* bft_kmer, BFT* bft, va_list args);

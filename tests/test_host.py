@@ -130,7 +130,9 @@ def test_abi_library_loads_and_exports_every_declared_symbol():
               "get_count_id_genomes", "presence_genome", "query_sequence", "get_neighbors", "get_predecessors",
               "get_successors", "queryBFT_kmerPresences_from_KmerFiles", "queryBFT_kmerBranching_from_KmerFiles",
               "query_sequences_outputCSV", "free_BFT_kmer", "free_BFT_annotation", "create_kmer", "iterate_over_kmers",
-              "v_iterate_over_kmers", "extract_kmers_to_disk", "write_kmer_ascii_to_disk", "write_kmer_comp_to_disk"]:
+              "v_iterate_over_kmers", "extract_kmers_to_disk", "write_kmer_ascii_to_disk", "write_kmer_comp_to_disk",
+              "prefix_matching", "intersection_annotations", "union_annotations", "sym_difference_annotations",
+              "intersection_list_id_genomes"]:
         assert s in compat and hasattr(lib, s), s
 
 

@@ -66,6 +66,38 @@ int main(int argc, char** argv) {
     size_t n_iter = 0, n_colours = 0;
     iterate_over_kmers(g, count_and_check, &n_iter, &n_colours);
     printf("I kmers=%zu colours=%zu\n", n_iter, n_colours);
+    /* prefix matching + set algebra on the first two k-mers of the query file that are present */
+    {
+        FILE* fq = fopen(argv[2], "r");
+        BFT_annotation* found[2] = {NULL, NULL};
+        int nf = 0;
+        char pfx[16];
+        while (nf < 2 && fgets(line, sizeof line, fq)) {
+            line[strcspn(line, "\r\n")] = 0;
+            BFT_kmer* km = get_kmer(line, g);
+            if (is_kmer_in_cdbg(km)) {
+                if (nf == 0) { memcpy(pfx, line, 5); pfx[5] = 0; }
+                found[nf++] = get_annotation(km);
+            }
+            free_BFT_kmer(km, 1);
+        }
+        fclose(fq);
+        if (nf == 2) {
+            size_t pn = 0, pc = 0;
+            bool any = prefix_matching(g, pfx, count_and_check, &pn, &pc);
+            BFT_annotation* ai = intersection_annotations(g, 2, found[0], found[1]);
+            BFT_annotation* au = union_annotations(g, 2, found[0], found[1]);
+            BFT_annotation* ax = sym_difference_annotations(g, 2, found[0], found[1]);
+            uint32_t* la = get_list_id_genomes(found[0], g);
+            uint32_t* lb = get_list_id_genomes(found[1], g);
+            uint32_t* li = intersection_list_id_genomes(la, lb);
+            printf("P prefix=%s any=%d n=%zu | A inter=%u union=%u xor=%u a=%u b=%u listinter=%u\n", pfx, (int)any, pn,
+                   get_count_id_genomes(ai, g), get_count_id_genomes(au, g), get_count_id_genomes(ax, g), la[0], lb[0], li[0]);
+            free(la); free(lb); free(li);
+            free_BFT_annotation(ai); free_BFT_annotation(au); free_BFT_annotation(ax);
+            free_BFT_annotation(found[0]); free_BFT_annotation(found[1]);
+        }
+    }
     free_cdbg(g);
     return 0;
 }
