@@ -297,6 +297,7 @@ def engine_arm(args):
                 "mean_suffix_block_lines": ws["block_lines"] / max(1, n),
                 "dram_bytes_per_kmer_ncu": traffic,
                 "random_gather_probe_loads_per_s": probe,
+                "random_access_frac": (n / (k_ms / 1e3) / probe) if probe else None,
                 "note": "A_min counts the sectors of the REFERENCE layout's walk; the flattened arena serves the root probe from "
                         "an L2-resident directory, so achieved can exceed the DRAM peak; dram_bytes_per_kmer_ncu is the physical traffic"}
 
