@@ -222,11 +222,17 @@ def engine_arm(args):
 
     pending = []
 
+    counted = RW in (1, 2, 4)
+    d_hits = torch.zeros(1, dtype=torch.int64, device=dev)
+
     def step():
-        eng.query_kmers_device(q, n, d_present, d_rows, None)
+        if counted:  # the kernel accumulates the batch's hit count itself
+            eng.query_kmers_device_counted(q, n, d_present, d_rows, d_hits)
+        else:
+            eng.query_kmers_device(q, n, d_present, d_rows, None)
         if world > 1:  # the only exchange the path has: a summary of each rank's results (no data-path collective);
             with torch.cuda.stream(es):  # enqueued asynchronously so ranks do not lock-step on it, awaited before the clock stops
-                s = d_present.sum(dtype=torch.int64).reshape(1)
+                s = d_hits.clone() if counted else d_present.sum(dtype=torch.int64).reshape(1)
                 pending.append((s, dist.all_reduce(s, async_op=True)))
 
     def drain():
@@ -263,11 +269,19 @@ def engine_arm(args):
     ms_step = float(t.item()) / args.steps
     value = n * world / (ms_step / 1e3)
     n_present = int(d_present.sum().item())
+    if counted:
+        assert int(d_hits.item()) == n_present, "kernel hit counter disagrees with the presence bytes"
     # size-independent property at full size: every window sampled from an inserted genome must be found, and a
     # found k-mer must carry at least one colour
     assert bool(d_present[q_kind == 0].all()), "a k-mer window of an inserted genome was reported absent"
     assert bool((d_rows[d_present.bool()] != 0).any(dim=1).all()), "a present k-mer came back without colours"
     assert not bool((d_rows[~d_present.bool()] != 0).any()), "an absent k-mer came back with colours"
+
+    def step_kernel():
+        if counted:
+            eng.query_kmers_device_counted(q, n, d_present, d_rows, d_hits)
+        else:
+            eng.query_kmers_device(q, n, d_present, d_rows, None)
 
     # ---- dominant kernel alone: the fused walk + colour-row kernel (k_query_kmers_rows for RW in {1,2,4}; for wider
     # rows k_query_kmers followed by k_expand_rows), CUDA events on the stream it is launched on
@@ -275,7 +289,7 @@ def engine_arm(args):
     for i in range(args.warmup + args.steps):
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         a.record(es)
-        eng.query_kmers_device(q, n, d_present, d_rows, None)
+        step_kernel()
         b.record(es)
         b.synchronize()
         if i >= args.warmup:

@@ -337,11 +337,11 @@ extern "C" int bft_b200_sync(bft_b200_ctx* c) {
 
 /* ---- enqueue helpers (device pointers, one stream) ---------------------------------------------------------- */
 static int enqueue_kmers(bft_b200_ctx* c, cudaStream_t st, const uint64_t* d_kmers, size_t n, uint8_t* d_present, uint32_t* d_rows,
-                         uint32_t* d_cls) {
+                         uint32_t* d_cls, unsigned long long* d_n_present = NULL) {
     if (n == 0) return 0;
     const int grid = grid_for(c, n, BFT_TPB);
     if (d_rows && (c->rw == 1 || c->rw == 2 || c->rw == 4) && ((uintptr_t)d_rows & 15) == 0) { /* narrow rows: one fused kernel */
-#define BFT_FUSED(W_, RW_) k_query_kmers_rows<W_, RW_><<<grid, BFT_TPB, 0, st>>>(c->dview, d_kmers, n, d_present, d_cls, c->d_class_rows, d_rows)
+#define BFT_FUSED(W_, RW_) k_query_kmers_rows<W_, RW_><<<grid, BFT_TPB, 0, st>>>(c->dview, d_kmers, n, d_present, d_cls, c->d_class_rows, d_rows, d_n_present)
         if (c->W == 1) { if (c->rw == 4) BFT_FUSED(1, 4); else if (c->rw == 2) BFT_FUSED(1, 2); else BFT_FUSED(1, 1); }
         else { if (c->rw == 4) BFT_FUSED(2, 4); else if (c->rw == 2) BFT_FUSED(2, 2); else BFT_FUSED(2, 1); }
 #undef BFT_FUSED
@@ -373,6 +373,16 @@ extern "C" int bft_b200_query_kmers_device(bft_b200_ctx* c, const uint64_t* d_km
         d_cls = sl->d_cls;
     }
     return enqueue_kmers(c, c->streams[0], d_kmers, n, d_present, d_rows, d_cls);
+}
+
+extern "C" int bft_b200_query_kmers_device_counted(bft_b200_ctx* c, const uint64_t* d_kmers, size_t n, uint8_t* d_present, uint32_t* d_rows,
+                                                   uint64_t* d_n_present) {
+    if (!c || (!d_kmers && n) || !d_rows || !d_n_present) return set_err(BFT_B200_ERR_ARG, "bft_b200_query_kmers_device_counted: NULL argument");
+    if (!((c->rw == 1 || c->rw == 2 || c->rw == 4) && ((uintptr_t)d_rows & 15) == 0))
+        return set_err(BFT_B200_ERR_ARG, "bft_b200_query_kmers_device_counted: needs colour rows of 1, 2 or 4 words (<= 128 genomes) and a 16-byte aligned row buffer");
+    CK(cudaSetDevice(c->device));
+    CK(cudaMemsetAsync(d_n_present, 0, sizeof(uint64_t), c->streams[0]));
+    return enqueue_kmers(c, c->streams[0], d_kmers, n, d_present, d_rows, NULL, (unsigned long long*)d_n_present);
 }
 
 static int query_kmers_host(bft_b200_ctx* c, const uint64_t* kmers, const char* ascii, size_t n, uint8_t* valid, uint8_t* present,

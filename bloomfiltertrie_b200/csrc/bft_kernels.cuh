@@ -42,8 +42,10 @@ __global__ void __launch_bounds__(BFT_TPB) k_query_kmers(const bft_view_t v, con
 template <int W, int RW>
 __global__ void __launch_bounds__(BFT_TPB) k_query_kmers_rows(const bft_view_t v, const uint64_t* __restrict__ kmers, size_t n,
                                                               uint8_t* __restrict__ present, uint32_t* __restrict__ cls_out,
-                                                              const uint32_t* __restrict__ class_rows, uint32_t* __restrict__ rows) {
+                                                              const uint32_t* __restrict__ class_rows, uint32_t* __restrict__ rows,
+                                                              unsigned long long* __restrict__ n_present) {
     const size_t stride = (size_t)gridDim.x * blockDim.x;
+    unsigned int hits = 0;
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
         uint64_t km[W];
         if (W == 1) {
@@ -54,6 +56,7 @@ __global__ void __launch_bounds__(BFT_TPB) k_query_kmers_rows(const bft_view_t v
             km[W - 1] = t.y;
         }
         const uint32_t cls = bft_lookup_w(&v, km, W);
+        hits += cls != BFT_CLS_NONE;
         if (present) present[i] = cls != BFT_CLS_NONE;
         if (cls_out) cls_out[i] = cls;
         if (RW == 4) {
@@ -69,6 +72,10 @@ __global__ void __launch_bounds__(BFT_TPB) k_query_kmers_rows(const bft_view_t v
             if (cls != BFT_CLS_NONE) r = __ldg(class_rows + cls);
             __stcs(rows + i, r);
         }
+    }
+    if (n_present) { /* the batch's hit count (the number `Nb k-mers present` of the reference driver): one atomic per warp */
+        for (int o = 16; o > 0; o >>= 1) hits += __shfl_down_sync(0xffffffffu, hits, o);
+        if ((threadIdx.x & 31) == 0 && hits) atomicAdd(n_present, (unsigned long long)hits);
     }
 }
 

@@ -23,7 +23,7 @@ ABI_SYMBOLS = [
     "bft_b200_last_error", "bft_b200_open", "bft_b200_close", "bft_b200_k", "bft_b200_n_genomes",
     "bft_b200_genome_name", "bft_b200_kmer_words", "bft_b200_row_words", "bft_b200_device", "bft_b200_stream",
     "bft_b200_get_stats", "bft_b200_host_alloc", "bft_b200_host_free", "bft_b200_query_kmers",
-    "bft_b200_query_kmers_device", "bft_b200_query_kmers_ascii", "bft_b200_class_rows", "bft_b200_class_counts",
+    "bft_b200_query_kmers_device", "bft_b200_query_kmers_device_counted", "bft_b200_query_kmers_ascii", "bft_b200_class_rows", "bft_b200_class_counts",
     "bft_b200_query_sequences", "bft_b200_query_sequences_device", "bft_b200_query_branching",
     "bft_b200_query_branching_device", "bft_b200_query_neighbors", "bft_b200_set_reference_exact_branching",
     "bft_b200_query_kmers_file", "bft_b200_query_branching_file",
@@ -73,6 +73,7 @@ def load_library() -> C.CDLL:
     lib.bft_b200_host_free.restype = None
     lib.bft_b200_query_kmers.argtypes = [vp, u64p, sz, u8p, u32p, u32p]
     lib.bft_b200_query_kmers_device.argtypes = [vp, u64p, sz, u8p, u32p, u32p]
+    lib.bft_b200_query_kmers_device_counted.argtypes = [vp, u64p, sz, u8p, u32p, u64p]
     lib.bft_b200_query_kmers_ascii.argtypes = [vp, C.c_void_p, sz, u8p, u8p, u32p, u32p]
     lib.bft_b200_class_rows.argtypes = [vp, C.POINTER(vp), C.POINTER(C.c_uint64)]
     lib.bft_b200_class_counts.argtypes = [vp, C.POINTER(vp), C.POINTER(C.c_uint64)]
@@ -208,6 +209,11 @@ class BFTEngine:
         """Device-resident variant: torch CUDA tensors (or raw device addresses); enqueues on self.stream."""
         self._ck(self.lib.bft_b200_query_kmers_device(self.h, _ptr(d_kmers), n, _ptr(d_present), _ptr(d_rows),
                                                       _ptr(d_classes)), "bft_b200_query_kmers_device")
+
+    def query_kmers_device_counted(self, d_kmers, n: int, d_present, d_rows, d_n_present):
+        """Device-resident k-mers -> presence, rows and the hit count in d_n_present (int64/uint64 tensor of 1)."""
+        self._ck(self.lib.bft_b200_query_kmers_device_counted(self.h, _ptr(d_kmers), n, _ptr(d_present), _ptr(d_rows),
+                                                              _ptr(d_n_present)), "bft_b200_query_kmers_device_counted")
 
     def class_rows(self) -> np.ndarray:
         p = C.c_void_p()

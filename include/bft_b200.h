@@ -81,6 +81,11 @@ int bft_b200_query_kmers(bft_b200_ctx* ctx, const uint64_t* kmers, size_t n, uin
                          uint32_t* class_ids);
 int bft_b200_query_kmers_device(bft_b200_ctx* ctx, const uint64_t* d_kmers, size_t n, uint8_t* d_present,
                                 uint32_t* d_rows, uint32_t* d_class_ids);
+/* Same as the _device call with rows, plus the batch's hit count accumulated by the kernel itself into *d_n_present (a
+ * device uint64, zeroed by the call): the "Nb k-mers present" of the reference driver (src/file_io.c:813) without a
+ * second pass over the presence bytes. Narrow rows only (RW in {1,2,4}, i.e. <= 128 genomes). */
+int bft_b200_query_kmers_device_counted(bft_b200_ctx* ctx, const uint64_t* d_kmers, size_t n, uint8_t* d_present,
+                                        uint32_t* d_rows, uint64_t* d_n_present);
 /* ASCII input, n k-mers of exactly k characters each, back to back: parseKmerCount (src/fasta.c:3-53) on the GPU.
  * valid[i] = 0 for a k-mer with a non-ACGTU character (the reference drops such lines, src/file_io.c:786-862);
  * its present/rows are zero. */
