@@ -41,6 +41,7 @@ typedef struct {
     uint8_t* scratch; size_t cap_scratch;   /* one annotation + extended byte */
     int16_t* extbuf; size_t cap_extbuf;     /* per line of the UC being read: extended byte or -1 */
     uint32_t* bkt; size_t cap_bkt;          /* bucketing scratch */
+    void** live; size_t n_live, cap_live;   /* registered short-lived buffers */
     int depth;
     char* err; size_t errlen;
     jmp_buf jb;
@@ -56,10 +57,34 @@ static void fail(ctx_t* c, const char* fmt, ...) {
     longjmp(c->jb, 1);
 }
 
+/* short-lived buffers of the recursive parse: registered so the failure path (longjmp) can release them */
+static void* tmp_alloc(ctx_t* c, size_t n);
+static void tmp_free(ctx_t* c, void* p);
+
 static void* xrealloc(ctx_t* c, void* p, size_t n) {
     void* q = realloc(p, n ? n : 1);
     if (!q) fail(c, "bft_flatten: out of memory (%zu bytes)", n);
     return q;
+}
+
+static void* tmp_alloc(ctx_t* c, size_t n) {
+    if (c->n_live == c->cap_live) {
+        size_t ncap = c->cap_live ? c->cap_live * 2 : 64;
+        void** t = (void**)realloc(c->live, ncap * sizeof(void*));
+        if (!t) fail(c, "bft_flatten: out of memory");
+        c->live = t;
+        c->cap_live = ncap;
+    }
+    void* p = malloc(n ? n : 1);
+    if (!p) fail(c, "bft_flatten: out of memory (%zu bytes)", n);
+    c->live[c->n_live++] = p;
+    return p;
+}
+
+static void tmp_free(ctx_t* c, void* p) {
+    for (size_t i = c->n_live; i-- > 0;)
+        if (c->live[i] == p) { c->live[i] = c->live[--c->n_live]; break; }
+    free(p);
 }
 
 #define GROW(c, arr, cap, need, type)                                   \
@@ -347,7 +372,7 @@ static void parse_cc(ctx_t* c, int sz, uint32_t cc_id, uint8_t* bf) {
     GROW(c, a->pref, c->cap_pref, a->n_pref + (size_t)nb_elem, bft_entry_t);
     a->n_pref += (size_t)nb_elem;
 
-    uint8_t* flags = (uint8_t*)xrealloc(c, NULL, (size_t)nb_elem + 1);
+    uint8_t* flags = (uint8_t*)tmp_alloc(c, (size_t)nb_elem + 1);
     memset(flags, 0, (size_t)nb_elem + 1);
     if (ef3)
         for (int j = 0; j < nb_elem; j++) flags[j] = (ef3[j / 8] >> (j % 8)) & 1;
@@ -407,7 +432,7 @@ static void parse_cc(ctx_t* c, int sz, uint32_t cc_id, uint8_t* bf) {
 
     /* cluster directory: rank over filter2 + select over the cluster-start flags (findCluster,
      * src/presenceNode.c:1578-1821) folded into exclusive prefix sums */
-    int* starts = (int*)xrealloc(c, NULL, ((size_t)nb_elem + 2) * sizeof(int));
+    int* starts = (int*)tmp_alloc(c, ((size_t)nb_elem + 2) * sizeof(int));
     int n_starts = 0;
     for (int j = 0; j < nb_elem; j++)
         if (flags[j]) starts[n_starts++] = j;
@@ -448,8 +473,8 @@ static void parse_cc(ctx_t* c, int sz, uint32_t cc_id, uint8_t* bf) {
     cc->nb_elem = (uint16_t)nb_elem;
     cc->s = (uint8_t)s;
     cc->pad = 0;
-    free(starts);
-    free(flags);
+    tmp_free(c, starts);
+    tmp_free(c, flags);
 }
 
 static uint32_t parse_node(ctx_t* c, int sz, int* cluster_flag) {
@@ -487,7 +512,7 @@ static uint32_t parse_node(ctx_t* c, int sz, int* cluster_flag) {
     uint32_t fc_off = 0;
     if (n_cc) {
         const int nbf = CEILDIV(li->modulo_hash, 8);
-        uint8_t* bfs = (uint8_t*)xrealloc(c, NULL, (size_t)n_cc * (size_t)nbf);
+        uint8_t* bfs = (uint8_t*)tmp_alloc(c, (size_t)n_cc * (size_t)nbf);
         for (uint32_t i = 0; i < n_cc; i++) parse_cc(c, sz, cc_begin + i, bfs + (size_t)i * nbf);
         /* first CC whose Bloom filter fires, per 14-bit hash index (src/presenceNode.c:1354-1362) */
         if (a->firstcc_bytes + BFT_N_IDX14 > 0xfffffff0u) fail(c, "bft_flatten: first-CC tables exceed 4 GiB");
@@ -505,7 +530,7 @@ static uint32_t parse_node(ctx_t* c, int sz, int* cluster_flag) {
             fc[idx] = hit;
         }
         a->firstcc_bytes += BFT_N_IDX14;
-        free(bfs);
+        tmp_free(c, bfs);
     }
     bft_node_t* nd = &a->nodes[id];
     nd->cc_begin = cc_begin;
@@ -569,6 +594,8 @@ bft_arena_t* bft_arena_from_memory(const uint8_t* buf, size_t len, char* err, si
     c->buf = buf; c->len = len; c->a = a; c->err = err; c->errlen = errlen;
     if (err && errlen) err[0] = 0;
     if (setjmp(c->jb)) {
+        for (size_t i = 0; i < c->n_live; i++) free(c->live[i]);
+        free(c->live);
         free(c->map); free(c->tmp); free(c->hv1); free(c->hv2); free(c->scratch); free(c->extbuf); free(c->bkt);
         free(c);
         bft_arena_free(a);
@@ -586,6 +613,9 @@ bft_arena_t* bft_arena_from_memory(const uint8_t* buf, size_t len, char* err, si
         a->pool_size_annot[i] = rd_i32(c);
         int64_t cnt = i ? a->pool_last_index[i] - a->pool_last_index[i - 1] : a->pool_last_index[i] + 1;
         if (cnt < 0 || a->pool_size_annot[i] < 0) fail(c, "bft_flatten: corrupt colour pool %d", i);
+        if ((uint64_t)cnt > c->len || (uint64_t)a->pool_size_annot[i] > c->len ||
+            (uint64_t)cnt * (uint64_t)a->pool_size_annot[i] > c->len - c->pos)
+            fail(c, "bft_flatten: colour pool %d is larger than the file", i);
         size_t nbytes = (size_t)cnt * (size_t)a->pool_size_annot[i];
         a->pool_off[i] = a->pool_bytes_len;
         GROW(c, a->pool_bytes, cap_pool, a->pool_bytes_len + nbytes + 1, uint8_t);
@@ -601,7 +631,8 @@ bft_arena_t* bft_arena_from_memory(const uint8_t* buf, size_t len, char* err, si
     if (a->k <= 0 || a->k % 9 != 0 || a->k > 126) fail(c, "bft_flatten: not a .bft file (k=%d)", a->k);
     if (a->k > 63) fail(c, "bft_flatten: k=%d is not supported by this build (k <= 63)", a->k);
     if (a->compressed) fail(c, "bft_flatten: root->compressed=%d files are not supported", a->compressed);
-    if (a->n_genomes < 0 || a->n_genomes > 100000000) fail(c, "bft_flatten: implausible genome count %d", a->n_genomes);
+    if (a->n_genomes < 0 || a->n_genomes > 100000000 || (size_t)a->n_genomes * 2 > c->len - c->pos)
+        fail(c, "bft_flatten: implausible genome count %d", a->n_genomes);
     a->W = a->k <= 27 ? 1 : 2;
     a->n_levels = a->k / 9;
     a->filenames = (char**)xrealloc(c, NULL, (size_t)(a->n_genomes + 1) * sizeof(char*));
@@ -758,6 +789,7 @@ bft_arena_t* bft_arena_from_memory(const uint8_t* buf, size_t len, char* err, si
     bft_arena_view(a, &v);
     for (uint32_t low18 = 0; low18 < BFT_ROOTDIR_SIZE; low18++) a->rootdir[low18] = bft_node_probe(&v, 0, low18, 0);
 
+    free(c->live);
     free(c->map); free(c->tmp); free(c->hv1); free(c->hv2); free(c->scratch); free(c->extbuf); free(c->bkt);
     free(c);
     return a;

@@ -210,3 +210,40 @@ def test_sharded_query_gathers_in_order_gloo_world2(tmp_path):
     outs = [p.communicate(timeout=600)[0].decode() for p in procs]
     assert all(p.returncode == 0 for p in procs), outs
     assert "SHARD_OK" in outs[0]
+
+
+def test_flattener_survives_mutated_files_under_asan(tmp_path):
+    """Corrupted .bft files (byte flips, truncations, header damage) must be rejected or parsed without any memory
+    error: the serializer and the arena walk are built with AddressSanitizer + UBSan and run over the mutations."""
+    exe = str(tmp_path / "ahq_asan")
+    try:
+        _gcc(["-O1", "-g", "-fsanitize=address,undefined", "-fno-omit-frame-pointer", "-std=c11", "-I", CSRC,
+              os.path.join(ROOT, "tests", "tools", "arena_host_query.c"), os.path.join(CSRC, "bft_flatten.c"),
+              os.path.join(CSRC, "bft_io.c"), "-o", exe])
+    except subprocess.CalledProcessError:
+        pytest.skip("sanitizer runtime not available")
+    rng = np.random.default_rng(11)
+    name = "golden_deep_k63_g12"
+    z = np.load(os.path.join(refutil.GOLDEN, name + ".npz"))
+    q = str(tmp_path / "q.kc")
+    synth.write_kmers_comp(q, z["queries"][:300], int(z["k"]))
+    data = open(os.path.join(refutil.GOLDEN, name + ".bft"), "rb").read()
+    env = dict(os.environ, ASAN_OPTIONS="detect_leaks=1")
+    outcomes = {"ok": 0, "rejected": 0}
+    for t in range(45):
+        d = bytearray(data)
+        if t % 3 == 0:
+            for _ in range(int(rng.integers(1, 8))):
+                d[int(rng.integers(0, len(d)))] = int(rng.integers(0, 256))
+        elif t % 3 == 1:
+            d = d[: int(rng.integers(1, len(d)))]
+        else:
+            d[int(rng.integers(0, 600))] = int(rng.integers(0, 256))
+        m = tmp_path / "m.bft"
+        m.write_bytes(bytes(d))
+        r = subprocess.run([exe, str(m), "kmers_comp", q, str(tmp_path / "o.csv")], stdout=subprocess.PIPE, stderr=subprocess.PIPE,
+                           env=env, timeout=120)
+        assert b"AddressSanitizer" not in r.stderr and b"LeakSanitizer" not in r.stderr and b"runtime error" not in r.stderr \
+            and r.returncode >= 0, r.stderr.decode(errors="replace")[:1500]
+        outcomes["ok" if r.returncode == 0 else "rejected"] += 1
+    assert outcomes["rejected"] > 0

@@ -40,5 +40,7 @@ int main(int argc, char** argv) {
     bft_csv_finish(f);
     fclose(f);
     printf("Nb k-mers present = %zu\n", present);
+    free(q); free(out); free(rows);
+    bft_arena_free(a);
     return 0;
 }
