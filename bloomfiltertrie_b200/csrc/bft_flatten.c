@@ -36,6 +36,7 @@ typedef struct {
     size_t cap_nodes, cap_ccs, cap_firstcc, cap_csr, cap_filter3, cap_pref, cap_buckets, cap_ovf, cap_uc_lines, cap_cls_off, cap_cls_bytes;
     /* class hash map */
     uint32_t* map; size_t map_cap, map_used;
+    struct { uint64_t h; uint32_t id; uint32_t valid; } hot[4096]; /* recently seen classes: most lines share a few */
     /* scratch */
     line_tmp_t* tmp; size_t cap_tmp;
     uint8_t* scratch; size_t cap_scratch;   /* one annotation + extended byte */
@@ -133,12 +134,23 @@ static uint32_t class_of(ctx_t* c, const uint8_t* s, size_t n) {
         c->map_cap = ncap;
     }
     uint64_t h = bft_xxh64(s, n, 0x5bd1e995);
+    {
+        const size_t slot = (size_t)(h >> 20) & 4095;
+        if (c->hot[slot].valid && c->hot[slot].h == h) {
+            const uint32_t id = c->hot[slot].id;
+            if (a->cls_off[id + 1] - a->cls_off[id] == n && memcmp(a->cls_bytes + a->cls_off[id], s, n) == 0) return id;
+        }
+    }
     size_t j = (size_t)h & (c->map_cap - 1);
     for (;;) {
         uint32_t id = c->map[j];
         if (id == 0xffffffffu) break;
         size_t ln = a->cls_off[id + 1] - a->cls_off[id];
-        if (ln == n && memcmp(a->cls_bytes + a->cls_off[id], s, n) == 0) return id;
+        if (ln == n && memcmp(a->cls_bytes + a->cls_off[id], s, n) == 0) {
+            const size_t slot = (size_t)(h >> 20) & 4095;
+            c->hot[slot].h = h; c->hot[slot].id = id; c->hot[slot].valid = 1;
+            return id;
+        }
         j = (j + 1) & (c->map_cap - 1);
     }
     if (a->n_classes >= 0xfffffff0u) fail(c, "bft_flatten: too many colour classes");
