@@ -484,22 +484,32 @@ __global__ void __launch_bounds__(32 * BFT_SEQ_WARPS) k_query_sequences(const bf
             const int n_here = (int)(n_win - t0 < BFT_SEQ_TILE ? n_win - t0 : BFT_SEQ_TILE); /* windows in this tile */
             const int n_chars = n_here + k - 1;
             /* stage + encode: 32 characters per step, up to one zeroed 64-base word past the data (the funnel
-             * shifts below may read one word beyond the last window) */
+             * shifts below may read one word beyond the last window). Upper-case A/C/G/T — all there is in ordinary
+             * reads — take a branch-free path: code = ((ch >> 1) ^ (ch >> 2)) & 3; anything else is classified in
+             * full, and a tile without such characters skips every mask test below (tile_special == 0). */
             const int stage_end = min(BFT_SEQ_SPAN + 64, ((n_chars + 63) & ~63) + 64);
+            uint32_t tile_special = 0;
             for (int c0 = 0; c0 < stage_end; c0 += 32) {
                 const int ci = c0 + lane;
                 uint32_t code = 0, cls = BFT_CH_ACGT, nonplain = 0;
                 if (ci < n_chars) {
-                    const char ch = chars[o0 + (uint64_t)t0 + (uint64_t)ci];
-                    tile_chars[ci] = ch;
-                    bft_classify_char((unsigned char)ch, code, cls, nonplain);
+                    const unsigned char ch = (unsigned char)chars[o0 + (uint64_t)t0 + (uint64_t)ci];
+                    tile_chars[ci] = (char)ch;
+                    const uint32_t d = (uint32_t)ch - 'A';
+                    if (d < 26u && ((0x00080045u >> d) & 1u)) code = ((ch >> 1) ^ (ch >> 2)) & 3u; /* A, C, G, T */
+                    else bft_classify_char(ch, code, cls, nonplain);
                 }
                 const uint32_t b0 = __ballot_sync(0xffffffffu, code & 1u);
                 const uint32_t b1 = __ballot_sync(0xffffffffu, code >> 1);
-                const uint32_t bi = __ballot_sync(0xffffffffu, cls == BFT_CH_IUPAC || cls == BFT_CH_DOTDASH);
-                const uint32_t br = __ballot_sync(0xffffffffu, cls == BFT_CH_DOTDASH || cls == BFT_CH_OTHER);
-                const uint32_t bo = __ballot_sync(0xffffffffu, cls == BFT_CH_OTHER);
-                const uint32_t bn = __ballot_sync(0xffffffffu, nonplain);
+                const uint32_t special = __ballot_sync(0xffffffffu, cls != BFT_CH_ACGT || nonplain);
+                uint32_t bi = 0, br = 0, bo = 0, bn = 0;
+                if (special) {
+                    bi = __ballot_sync(0xffffffffu, cls == BFT_CH_IUPAC || cls == BFT_CH_DOTDASH);
+                    br = __ballot_sync(0xffffffffu, cls == BFT_CH_DOTDASH || cls == BFT_CH_OTHER);
+                    bo = __ballot_sync(0xffffffffu, cls == BFT_CH_OTHER);
+                    bn = __ballot_sync(0xffffffffu, nonplain);
+                    tile_special = 1;
+                }
                 if (lane == 0 && (c0 >> 5) < n_code_words) codes[c0 >> 5] = bft_spread32(b0) | (bft_spread32(b1) << 1);
                 if (lane == 1 && (c0 >> 6) < n_mask_words) {
                     uint32_t* p;
@@ -515,9 +525,12 @@ __global__ void __launch_bounds__(32 * BFT_SEQ_WARPS) k_query_sequences(const bf
                 const int j = j0 + lane;
                 uint32_t cls = BFT_CLS_NONE;
                 if (j < n_here) {
-                    const uint64_t wi = bft_extract_bits(m_iupac, j, k);
-                    const uint64_t wr = bft_extract_bits(m_rcbad, j, k);
-                    const uint64_t wo = bft_extract_bits(m_other, j, k);
+                    uint64_t wi = 0, wr = 0, wo = 0;
+                    if (tile_special) {
+                        wi = bft_extract_bits(m_iupac, j, k);
+                        wr = bft_extract_bits(m_rcbad, j, k);
+                        wo = bft_extract_bits(m_other, j, k);
+                    }
                     int skip = 0;
                     if (canonical) {
                         if (wr) bad = 1;
@@ -543,7 +556,7 @@ __global__ void __launch_bounds__(32 * BFT_SEQ_WARPS) k_query_sequences(const bf
                                 rx[0] = bft_rev2_64(x[0]) >> (64 - 2 * k);
                                 nx[0] = ~x[0] & mask;
                                 use_rc = rx[0] >= nx[0];
-                                if (bft_extract_bits(m_nonpl, j, k)) { /* mixed case / U: ASCII order decides */
+                                if (tile_special && bft_extract_bits(m_nonpl, j, k)) { /* mixed case / U: ASCII order decides */
                                     use_rc = 1;
                                     for (int i = 0; i < k; i++) {
                                         const char a = tile_chars[j + i], b = bft_rc_char(tile_chars[j + k - 1 - i]);
@@ -560,7 +573,7 @@ __global__ void __launch_bounds__(32 * BFT_SEQ_WARPS) k_query_sequences(const bf
                                 nx[0] = ~x[0];
                                 nx[W - 1] = ~x[W - 1] & mask_hi;
                                 use_rc = rx[W - 1] > nx[W - 1] || (rx[W - 1] == nx[W - 1] && rx[0] >= nx[0]);
-                                if (bft_extract_bits(m_nonpl, j, k)) {
+                                if (tile_special && bft_extract_bits(m_nonpl, j, k)) {
                                     use_rc = 1;
                                     for (int i = 0; i < k; i++) {
                                         const char a = tile_chars[j + i], b = bft_rc_char(tile_chars[j + k - 1 - i]);
