@@ -21,8 +21,8 @@
  *   buckets[]  every CC inline suffix line, as W little-endian 64-bit words holding the suffix as an integer
  *              (nucleotide i at bits 2i; replaces memcmp in binary_search_UC, src/UC.c:81-124), hashed by its own
  *              top bits into fixed-size buckets: a prefix with cnt suffixes owns B = 2^lb consecutive buckets
- *              (B >= cnt/2, lb <= 8) of BFT_BUCKET_KEYS = 4 slots — one 32-byte sector for W = 1, one 64-byte pair
- *              for W = 2 — and suffix x lives in bucket hash(x) >> (64 - lb). A lookup therefore touches exactly one
+ *              (B >= cnt/2, lb <= 8) of BFT_BUCKET_KEYS = 4 slots — one 32-byte sector for W = 1, a 64-byte pair
+ *              for W = 2, a 128-byte line for W = 4 — and suffix x lives in bucket hash(x) >> (64 - lb). A lookup therefore touches exactly one
  *              aligned bucket: ONE random DRAM access per k-mer. Buckets that would hold more than 4 suffixes keep
  *              3 and an overflow descriptor pointing into ovf[] (rare: the load factor is <= 1/2).
  *              When the colour-class ids fit above the widest suffix (cls_shift != 0) the line's class is stored in
@@ -69,7 +69,7 @@
 #define BFT_N_IDX14 16384
 #define BFT_ROOTDIR_SIZE (1u << BFT_PREFIX_BITS)
 #define BFT_FIRSTCC_NONE 0xffu
-#define BFT_MAX_WORDS 2                /* k <= 63 (126 bits) */
+#define BFT_MAX_WORDS 4                /* k <= 126 (252 bits), the reference's KMER_LENGTH_MAX */
 #define BFT_BUCKET_KEYS 4              /* slots per bucket */
 #define BFT_MAX_LB 8                   /* at most 256 buckets per prefix */
 #define BFT_SLOT_EMPTY 0xffffffffffffffffULL
@@ -139,7 +139,7 @@ typedef struct {
     const bft_path_t* node_path; /* per Node: the k-mer bits fixed by the path from the root, and the depth */
     const uint64_t* pref_out;    /* per stored prefix: index of its first k-mer in the enumeration order */
     int k;
-    int W;             /* 64-bit words per key: 1 for k <= 27, 2 for k <= 63 */
+    int W;             /* 64-bit words per key: 1 for k <= 27, 2 for k <= 63, 4 for k <= 126 */
     int cls_shift;     /* != 0: class id of an inline line = (top word >> cls_shift) & cls_mask, suffix = the bits below */
     uint32_t cls_mask;
 } bft_view_t;
@@ -282,7 +282,7 @@ BFT_HD uint32_t bft_bucket_of(const uint64_t* key, const int W, const uint32_t l
     /* multiplicative hash of the whole suffix: the suffixes of one prefix are near-duplicates of each other in a
      * pan-genome (SNP variants share all but one nucleotide), so raw leading bits would pile them into one bucket */
     uint64_t x = key[0];
-    if (W > 1) x ^= key[W - 1] * 0xC2B2AE3D27D4EB4FULL;
+    for (int w = 1; w < W; w++) x = (x ^ (x >> 31)) * 0xC2B2AE3D27D4EB4FULL + key[w];
     x ^= x >> 29;
     return lb ? (uint32_t)((x * 0x9E3779B97F4A7C15ULL) >> (64 - lb)) : 0u;
 }
@@ -300,7 +300,7 @@ BFT_HD uint32_t bft_search_block(const bft_view_t* v, uint32_t base, uint32_t lb
     for (int j = 0; j < BFT_BUCKET_KEYS; j++) {
         const uint64_t top = s[j * W + W - 1];
         int eq = !(top & BFT_SLOT_SPECIAL) && (top & top_mask) == key[W - 1];
-        if (W > 1) eq = eq && s[j * W] == key[0];
+        for (int w = 0; w < W - 1; w++) eq = eq && s[j * W + w] == key[w];
         if (eq) found = shift ? ((uint32_t)(top >> shift) & v->cls_mask) : BFT_LD32(v->slotcls + bucket * BFT_BUCKET_KEYS + j);
     }
     const uint64_t last = s[(BFT_BUCKET_KEYS - 1) * W + W - 1];
@@ -310,7 +310,7 @@ BFT_HD uint32_t bft_search_block(const bft_view_t* v, uint32_t base, uint32_t lb
             const uint64_t* p = v->ovf + ((size_t)start + i) * W;
             const uint64_t top = BFT_LD64(p + W - 1);
             int eq = (top & top_mask) == key[W - 1];
-            if (W > 1) eq = eq && BFT_LD64(p) == key[0];
+            for (int w = 0; w < W - 1; w++) eq = eq && BFT_LD64(p + w) == key[w];
             if (eq) found = shift ? ((uint32_t)(top >> shift) & v->cls_mask) : BFT_LD32(v->ovfcls + start + i);
         }
     }

@@ -81,6 +81,14 @@ struct bft_b200_ctx {
 
 extern "C" const char* bft_b200_last_error(void) { return g_err; }
 
+/* instantiate a launch for the arena's key width (W = 1, 2 or 4 words) */
+#define BFT_BY_W(w_, LAUNCH)                 \
+    do {                                     \
+        if ((w_) == 1) { LAUNCH(1); }        \
+        else if ((w_) == 2) { LAUNCH(2); }   \
+        else { LAUNCH(4); }                  \
+    } while (0)
+
 static int ensure(void** p, size_t* cap, size_t need) {
     if (need <= *cap && *p) return 0;
     if (*p) cudaFree(*p);
@@ -299,6 +307,7 @@ extern "C" int bft_b200_open(const char* path, int device, bft_b200_ctx** out) {
         else {
             cudaFuncSetAttribute(k_query_sequences<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->seq_smem);
             cudaFuncSetAttribute(k_query_sequences<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->seq_smem);
+            cudaFuncSetAttribute(k_query_sequences<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->seq_smem);
         }
     }
     if (rc) { bft_b200_close(c); return rc; }
@@ -342,15 +351,17 @@ static int enqueue_kmers(bft_b200_ctx* c, cudaStream_t st, const uint64_t* d_kme
     const int grid = grid_for(c, n, BFT_TPB);
     if (d_rows && (c->rw == 1 || c->rw == 2 || c->rw == 4) && ((uintptr_t)d_rows & 15) == 0) { /* narrow rows: one fused kernel */
 #define BFT_FUSED(W_, RW_) k_query_kmers_rows<W_, RW_><<<grid, BFT_TPB, 0, st>>>(c->dview, d_kmers, n, d_present, d_cls, c->d_class_rows, d_rows, d_n_present)
-        if (c->W == 1) { if (c->rw == 4) BFT_FUSED(1, 4); else if (c->rw == 2) BFT_FUSED(1, 2); else BFT_FUSED(1, 1); }
-        else { if (c->rw == 4) BFT_FUSED(2, 4); else if (c->rw == 2) BFT_FUSED(2, 2); else BFT_FUSED(2, 1); }
+#define BFT_FUSED_W(W_) do { if (c->rw == 4) BFT_FUSED(W_, 4); else if (c->rw == 2) BFT_FUSED(W_, 2); else BFT_FUSED(W_, 1); } while (0)
+        BFT_BY_W(c->W, BFT_FUSED_W);
+#undef BFT_FUSED_W
 #undef BFT_FUSED
         c->launches++;
         CK(cudaGetLastError());
         return 0;
     }
-    if (c->W == 1) k_query_kmers<1><<<grid, BFT_TPB, 0, st>>>(c->dview, d_kmers, n, d_present, d_cls);
-    else k_query_kmers<2><<<grid, BFT_TPB, 0, st>>>(c->dview, d_kmers, n, d_present, d_cls);
+#define BFT_L(W_) k_query_kmers<W_><<<grid, BFT_TPB, 0, st>>>(c->dview, d_kmers, n, d_present, d_cls)
+    BFT_BY_W(c->W, BFT_L);
+#undef BFT_L
     c->launches++;
     if (d_rows) {
         if (c->rw % 4 == 0 && ((uintptr_t)d_rows & 15) == 0 && ((uintptr_t)c->d_class_rows & 15) == 0)
@@ -403,8 +414,9 @@ static int query_kmers_host(bft_b200_ctx* c, const uint64_t* kmers, const char* 
             ENSURE(sl->d_kmers, sl->cap_kmers, m * W * 8);
             ENSURE(sl->d_u8b, sl->cap_u8b, m);
             CK(cudaMemcpyAsync(sl->d_in, ascii + done * k, m * k, cudaMemcpyHostToDevice, st));
-            if (c->W == 1) k_encode_ascii<1><<<grid_for(c, m, BFT_TPB), BFT_TPB, 0, st>>>((const char*)sl->d_in, m, c->k, sl->d_kmers, sl->d_u8b);
-            else k_encode_ascii<2><<<grid_for(c, m, BFT_TPB), BFT_TPB, 0, st>>>((const char*)sl->d_in, m, c->k, sl->d_kmers, sl->d_u8b);
+#define BFT_L(W_) k_encode_ascii<W_><<<grid_for(c, m, BFT_TPB), BFT_TPB, 0, st>>>((const char*)sl->d_in, m, c->k, sl->d_kmers, sl->d_u8b)
+            BFT_BY_W(c->W, BFT_L);
+#undef BFT_L
             c->launches++;
             d_k = sl->d_kmers;
         } else {
@@ -478,12 +490,10 @@ static int enqueue_sequences(bft_b200_ctx* c, cudaStream_t st, const char* d_cha
     size_t blocks = (n_seq + BFT_SEQ_WARPS - 1) / BFT_SEQ_WARPS;
     const size_t cap = (size_t)c->sm_count * 16;
     if (blocks > cap) blocks = cap;
-    if (c->W == 1)
-        k_query_sequences<1><<<(int)blocks, 32 * BFT_SEQ_WARPS, c->seq_smem, st>>>(c->dview, d_chars, d_offs, n_seq, thr, canonical,
-                                                                                c->d_class_rows, c->rw, c->G, d_rows, d_status);
-    else
-        k_query_sequences<2><<<(int)blocks, 32 * BFT_SEQ_WARPS, c->seq_smem, st>>>(c->dview, d_chars, d_offs, n_seq, thr, canonical,
-                                                                                c->d_class_rows, c->rw, c->G, d_rows, d_status);
+#define BFT_L(W_) k_query_sequences<W_><<<(int)blocks, 32 * BFT_SEQ_WARPS, c->seq_smem, st>>>(c->dview, d_chars, d_offs, n_seq, thr, canonical, \
+                                                                                               c->d_class_rows, c->rw, c->G, d_rows, d_status)
+    BFT_BY_W(c->W, BFT_L);
+#undef BFT_L
     c->launches++;
     CK(cudaGetLastError());
     return 0;
@@ -545,8 +555,9 @@ static int enqueue_branching(bft_b200_ctx* c, cudaStream_t st, const uint64_t* d
                              unsigned long long* d_count, uint32_t* d_nbr) {
     if (n == 0) return 0;
     const int grid = grid_for(c, n * 8, BFT_TPB);
-    if (c->W == 1) k_query_branching<1><<<grid, BFT_TPB, 0, st>>>(c->dview, d_kmers, n, d_succ, d_pred, d_count, d_nbr, c->ref_quirks);
-    else k_query_branching<2><<<grid, BFT_TPB, 0, st>>>(c->dview, d_kmers, n, d_succ, d_pred, d_count, d_nbr, c->ref_quirks);
+#define BFT_L(W_) k_query_branching<W_><<<grid, BFT_TPB, 0, st>>>(c->dview, d_kmers, n, d_succ, d_pred, d_count, d_nbr, c->ref_quirks)
+    BFT_BY_W(c->W, BFT_L);
+#undef BFT_L
     c->launches++;
     CK(cudaGetLastError());
     return 0;
@@ -633,8 +644,9 @@ extern "C" int bft_b200_kmer_walk_stats_device(bft_b200_ctx* c, const uint64_t* 
     cudaMemsetAsync(d_acc, 0, 5 * sizeof(unsigned long long), c->streams[0]);
     if (n) {
         const int grid = grid_for(c, n, BFT_TPB);
-        if (c->W == 1) k_kmer_walk_stats<1><<<grid, BFT_TPB, 0, c->streams[0]>>>(c->dview, d_kmers, n, d_acc);
-        else k_kmer_walk_stats<2><<<grid, BFT_TPB, 0, c->streams[0]>>>(c->dview, d_kmers, n, d_acc);
+#define BFT_L(W_) k_kmer_walk_stats<W_><<<grid, BFT_TPB, 0, c->streams[0]>>>(c->dview, d_kmers, n, d_acc)
+        BFT_BY_W(c->W, BFT_L);
+#undef BFT_L
         c->launches++;
     }
     unsigned long long h[5] = {0, 0, 0, 0, 0};
@@ -687,12 +699,14 @@ extern "C" int bft_b200_extract_kmers_device(bft_b200_ctx* c, uint64_t* d_kmers,
     cudaStream_t st = c->streams[0];
     if (c->n_pref) {
         const int grid = grid_for(c, c->n_pref * 32, BFT_TPB);
-        if (c->W == 1) k_extract_prefix_kmers<1><<<grid, BFT_TPB, 0, st>>>(c->dview, c->n_pref, d_kmers, d_cls);
-        else k_extract_prefix_kmers<2><<<grid, BFT_TPB, 0, st>>>(c->dview, c->n_pref, d_kmers, d_cls);
+#define BFT_L(W_) k_extract_prefix_kmers<W_><<<grid, BFT_TPB, 0, st>>>(c->dview, c->n_pref, d_kmers, d_cls)
+        BFT_BY_W(c->W, BFT_L);
+#undef BFT_L
         c->launches++;
     }
-    if (c->W == 1) k_extract_uc_kmers<1><<<grid_for(c, c->n_nodes, BFT_TPB), BFT_TPB, 0, st>>>(c->dview, c->n_nodes, d_kmers, d_cls);
-    else k_extract_uc_kmers<2><<<grid_for(c, c->n_nodes, BFT_TPB), BFT_TPB, 0, st>>>(c->dview, c->n_nodes, d_kmers, d_cls);
+#define BFT_L(W_) k_extract_uc_kmers<W_><<<grid_for(c, c->n_nodes, BFT_TPB), BFT_TPB, 0, st>>>(c->dview, c->n_nodes, d_kmers, d_cls)
+    BFT_BY_W(c->W, BFT_L);
+#undef BFT_L
     c->launches++;
     CK(cudaGetLastError());
     return 0;

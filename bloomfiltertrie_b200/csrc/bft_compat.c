@@ -85,7 +85,7 @@ void free_BFT_kmer(BFT_kmer* km, int n) {
 
 static void lookup_into(BFT* bft, BFT_kmer* kms, int n) {
     const int W = bft_b200_kmer_words(bft->engine), nb = nb_bytes(bft->k);
-    uint64_t words[8 * 2];
+    uint64_t words[8 * 4];
     uint8_t present[8];
     uint32_t cls[8];
     memset(words, 0, sizeof words);
@@ -303,7 +303,7 @@ static BFT_kmer* neighbours(BFT_kmer* km, BFT* bft, int first, int count, const 
         parse_kmer_bytes(out[i].kmer, k, out[i].kmer_comp);
     }
     /* presence + class of the 8 neighbours in the reference's own order (and with its leaf-level successor rule) */
-    uint64_t words[2] = {0, 0};
+    uint64_t words[4] = {0, 0, 0, 0};
     uint32_t cls[8];
     memcpy(words, km->kmer_comp, (size_t)nb_bytes(k));
     ENGINE_OK(bft_b200_query_neighbors(bft->engine, words, 1, cls), who);
@@ -329,13 +329,13 @@ void v_iterate_over_kmers(BFT* bft, BFT_func_ptr f, va_list args) { /* src/bft.c
 
 static size_t iterate_filtered(BFT* bft, const char* prefix, BFT_func_ptr f, va_list args) {
     size_t matched = 0;
-    uint64_t pmask[2] = {0, 0}, pval[2] = {0, 0};
+    uint64_t pmask[4] = {0, 0, 0, 0}, pval[4] = {0, 0, 0, 0};
     if (prefix) { /* compare the leading nucleotides in packed form */
         const int len = (int)strlen(prefix);
         uint8_t tmp[40];
         memset(tmp, 0, sizeof tmp);
         parse_kmer_bytes(prefix, len, tmp);
-        memcpy(pval, tmp, 16);
+        memcpy(pval, tmp, 32);
         for (int j = 0; j < len; j++) pmask[j >> 5] |= 3ULL << (2 * (j & 31));
     }
     bft_b200_stats st;
@@ -354,8 +354,9 @@ static size_t iterate_filtered(BFT* bft, const char* prefix, BFT_func_ptr f, va_
     cur.res = &res;
     for (size_t i = 0; i < n; i++) {
         if (prefix) {
-            if ((km[i * W] & pmask[0]) != pval[0]) continue;
-            if (W > 1 && (km[i * W + 1] & pmask[1]) != pval[1]) continue;
+            int match = 1;
+            for (size_t w = 0; w < W; w++) match &= (km[i * W + w] & pmask[w]) == pval[w];
+            if (!match) continue;
         }
         matched++;
         for (int j = 0; j < k; j++) cur.kmer[j] = "ACGT"[(km[i * W + (size_t)(j >> 5)] >> (2 * (j & 31))) & 3];

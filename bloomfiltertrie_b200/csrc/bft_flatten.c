@@ -250,6 +250,13 @@ static void load_block(ctx_t* c, const uc_body_t* u, int first, int cnt, int key
             if (c->tmp[i].k[w]) fail(c, "bft_flatten: key wider than W words");
     }
     if (cnt > 1) qsort(c->tmp, (size_t)cnt, sizeof(line_tmp_t), cmp_line_tmp);
+    /* A well-formed BFT stores every k-mer once. The reference's own insertion breaks that for k > 63 (its
+     * -extract_kmers then lists more records than distinct k-mers) and its answers depend on which copy a search
+     * happens to meet; refuse such a file instead of answering differently. */
+    for (int i = 1; i < cnt; i++)
+        if (cmp_line_tmp(&c->tmp[i - 1], &c->tmp[i]) == 0)
+            fail(c, "bft_flatten: this BFT stores the same k-mer twice (k=%d; the reference's insertion does that for k > 63): "
+                    "its query results are not well defined, refusing to load it", c->a->k);
 }
 
 /* a Node's own UC -> uckeys/uccls (sorted, binary-searched); returns the index of its first line */
@@ -641,11 +648,10 @@ bft_arena_t* bft_arena_from_memory(const uint8_t* buf, size_t len, char* err, si
     a->k = rd_i32(c);
     a->compressed = *rd(c, 1);
     if (a->k <= 0 || a->k % 9 != 0 || a->k > 126) fail(c, "bft_flatten: not a .bft file (k=%d)", a->k);
-    if (a->k > 63) fail(c, "bft_flatten: k=%d is not supported by this build (k <= 63)", a->k);
     if (a->compressed) fail(c, "bft_flatten: root->compressed=%d files are not supported", a->compressed);
     if (a->n_genomes < 0 || a->n_genomes > 100000000 || (size_t)a->n_genomes * 2 > c->len - c->pos)
         fail(c, "bft_flatten: implausible genome count %d", a->n_genomes);
-    a->W = a->k <= 27 ? 1 : 2;
+    a->W = a->k <= 27 ? 1 : (a->k <= 63 ? 2 : 4);
     a->n_levels = a->k / 9;
     a->filenames = (char**)xrealloc(c, NULL, (size_t)(a->n_genomes + 1) * sizeof(char*));
     memset(a->filenames, 0, (size_t)(a->n_genomes + 1) * sizeof(char*));
@@ -712,7 +718,8 @@ bft_arena_t* bft_arena_from_memory(const uint8_t* buf, size_t len, char* err, si
     }
 
     /* colour class ids into the spare top bits of the inline keys when they fit between the widest suffix and the
-     * flag bit 63: k <= 27: 36 suffix bits + up to 27 class bits; k <= 63: 44 bits in the upper word + up to 19 */
+     * flag bit 63: k <= 27: 36 suffix bits + up to 27 class bits; k <= 63: 44 bits in the upper word + up to 19;
+     * k <= 126: 42 bits in the top word + up to 21 */
     {
         int cls_bits = 1;
         while (((size_t)1 << cls_bits) < a->n_classes) cls_bits++;

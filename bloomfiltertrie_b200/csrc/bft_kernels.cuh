@@ -16,6 +16,72 @@
 
 #define BFT_TPB 256
 
+/* ---- multi-word helpers (W = 1, 2 or 4 words, compile-time; loops unroll and runtime word indices become selects,
+ * so nothing lands in local memory) */
+template <int W>
+__device__ __forceinline__ void bft_load_kmer(const uint64_t* __restrict__ kmers, size_t i, uint64_t* km) {
+    if (W == 1) {
+        km[0] = __ldcs((const unsigned long long*)kmers + i);
+    } else {
+#pragma unroll
+        for (int w = 0; w < W; w += 2) {
+            const ulonglong2 t = __ldcs((const ulonglong2*)(kmers + i * W + w));
+            km[w] = t.x;
+            km[w + 1] = t.y;
+        }
+    }
+}
+
+/* mask of the bits of word w that belong to a value of n_bits bits */
+__device__ __forceinline__ uint64_t bft_word_mask(int n_bits, int w) {
+    const int b = n_bits - 64 * w;
+    return b >= 64 ? ~0ULL : (b <= 0 ? 0ULL : ((1ULL << b) - 1ULL));
+}
+
+/* out = in >> sh, 0 <= sh < 64*W */
+template <int W>
+__device__ __forceinline__ void bft_shr(const uint64_t* in, int sh, uint64_t* out) {
+    const int ws = sh >> 6, bs = sh & 63;
+#pragma unroll
+    for (int w = 0; w < W; w++) {
+        uint64_t lo = 0, hi = 0;
+#pragma unroll
+        for (int u = 0; u < W; u++) {
+            if (u == w + ws) lo = in[u];
+            if (u == w + ws + 1) hi = in[u];
+        }
+        out[w] = bs ? (lo >> bs) | (hi << (64 - bs)) : lo;
+    }
+}
+
+/* out = in << sh, 0 <= sh < 64*W (bits shifted past the top are dropped) */
+template <int W>
+__device__ __forceinline__ void bft_shl(const uint64_t* in, int sh, uint64_t* out) {
+    const int ws = sh >> 6, bs = sh & 63;
+#pragma unroll
+    for (int w = 0; w < W; w++) {
+        uint64_t lo = 0, hi = 0; /* hi: the word that lands at w, lo: the one below it */
+#pragma unroll
+        for (int u = 0; u < W; u++) {
+            if (u + ws == w) hi = in[u];
+            if (u + ws + 1 == w) lo = in[u];
+        }
+        out[w] = bs ? (hi << bs) | (lo >> (64 - bs)) : hi;
+    }
+}
+
+/* a >= b as W-word integers */
+template <int W>
+__device__ __forceinline__ bool bft_ge(const uint64_t* a, const uint64_t* b) {
+    bool ge = true; /* equal so far */
+#pragma unroll
+    for (int w = 0; w < W; w++) { /* from the least significant word up: a higher word overrides */
+        if (a[w] > b[w]) ge = true;
+        else if (a[w] < b[w]) ge = false;
+    }
+    return ge;
+}
+
 /* ---- a4/a5/a7/a8: k-mer lookup ---------------------------------------------------------------------------- */
 template <int W>
 __global__ void __launch_bounds__(BFT_TPB) k_query_kmers(const bft_view_t v, const uint64_t* __restrict__ kmers, size_t n,
@@ -23,13 +89,7 @@ __global__ void __launch_bounds__(BFT_TPB) k_query_kmers(const bft_view_t v, con
     const size_t stride = (size_t)gridDim.x * blockDim.x;
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
         uint64_t km[W];
-        if (W == 1) {
-            km[0] = __ldcs((const unsigned long long*)kmers + i);
-        } else {
-            const ulonglong2 t = __ldcs((const ulonglong2*)kmers + i);
-            km[0] = t.x;
-            km[W - 1] = t.y;
-        }
+        bft_load_kmer<W>(kmers, i, km);
         const uint32_t cls = bft_lookup_w(&v, km, W);
         if (present) present[i] = cls != BFT_CLS_NONE;
         if (cls_out) cls_out[i] = cls;
@@ -48,13 +108,7 @@ __global__ void __launch_bounds__(BFT_TPB) k_query_kmers_rows(const bft_view_t v
     unsigned int hits = 0;
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
         uint64_t km[W];
-        if (W == 1) {
-            km[0] = __ldcs((const unsigned long long*)kmers + i);
-        } else {
-            const ulonglong2 t = __ldcs((const ulonglong2*)kmers + i);
-            km[0] = t.x;
-            km[W - 1] = t.y;
-        }
+        bft_load_kmer<W>(kmers, i, km);
         const uint32_t cls = bft_lookup_w(&v, km, W);
         hits += cls != BFT_CLS_NONE;
         if (present) present[i] = cls != BFT_CLS_NONE;
@@ -200,16 +254,11 @@ __global__ void __launch_bounds__(BFT_TPB) k_encode_ascii(const char* __restrict
  * the serializer stored (pref_out), so the result is deterministic and needs no atomics. */
 template <int W>
 __device__ __forceinline__ void bft_emit_kmer(const uint64_t* base, const uint64_t* suffix, int shift_bits, uint64_t* out) {
-    /* out = base | suffix << shift_bits (shift_bits = 18 * (depth + 1), 18..126) */
-    if (W == 1) {
-        out[0] = base[0] | (suffix[0] << shift_bits);
-    } else {
-        uint64_t lo, hi;
-        if (shift_bits >= 64) { lo = 0; hi = suffix[0] << (shift_bits - 64); }
-        else { lo = suffix[0] << shift_bits; hi = (suffix[W - 1] << shift_bits) | (suffix[0] >> (64 - shift_bits)); }
-        out[0] = base[0] | lo;
-        out[W - 1] = base[W - 1] | hi;
-    }
+    /* out = base | suffix << shift_bits (shift_bits = 18 * (depth + 1), 18..234) */
+    uint64_t sh[W];
+    bft_shl<W>(suffix, shift_bits, sh);
+#pragma unroll
+    for (int w = 0; w < W; w++) out[w] = base[w] | sh[w];
 }
 
 template <int W>
@@ -226,13 +275,13 @@ __global__ void __launch_bounds__(BFT_TPB) k_extract_prefix_kmers(const bft_view
         const bft_path_t path = v.node_path[v.pref_node[j]];
         uint64_t base[W];
         {
-            const uint64_t low18 = v.pref_low18[j];
-            const unsigned sh = BFT_PREFIX_BITS * path.depth;
-            base[0] = path.acc[0];
-            if (W > 1) base[W - 1] = path.acc[W - 1];
-            if (W == 1) base[0] |= low18 << sh;
-            else if (sh >= 64) base[W - 1] |= low18 << (sh - 64);
-            else { base[0] |= low18 << sh; if (sh > 64 - BFT_PREFIX_BITS) base[W - 1] |= low18 >> (64 - sh); }
+            uint64_t lw[W], sh[W];
+#pragma unroll
+            for (int w = 0; w < W; w++) lw[w] = 0;
+            lw[0] = v.pref_low18[j];
+            bft_shl<W>(lw, (int)(BFT_PREFIX_BITS * path.depth), sh);
+#pragma unroll
+            for (int w = 0; w < W; w++) base[w] = path.acc[w] | sh[w];
         }
         uint64_t out = v.pref_out[j];
         if (kind == BFT_KIND_LEAF) {
@@ -298,8 +347,8 @@ __global__ void __launch_bounds__(BFT_TPB) k_extract_uc_kmers(const bft_view_t v
         const bft_path_t path = v.node_path[nid];
         const uint64_t out = ((uint64_t)path.uc_out_hi << 32) | path.uc_out_lo;
         uint64_t base[W];
-        base[0] = path.acc[0];
-        if (W > 1) base[W - 1] = path.acc[W - 1];
+#pragma unroll
+        for (int w = 0; w < W; w++) base[w] = path.acc[w];
         for (uint32_t i = 0; i < nd.uc_n; i++) {
             uint64_t key[W], km[W];
             for (int w = 0; w < W; w++) key[w] = v.uckeys[((size_t)nd.uc_begin + i) * W + w];
@@ -335,22 +384,16 @@ __global__ void __launch_bounds__(BFT_TPB) k_query_branching(const bft_view_t v,
 #pragma unroll
             for (int w = 0; w < W; w++) x[w] = kmers[q * W + w];
             if (sub < 4) { /* successor: (x >> 2) | c << 2(k-1) */
+                bft_shr<W>(x, 2, y);
+                const int top = 2 * (k - 1);
 #pragma unroll
-                for (int w = 0; w < W; w++) {
-                    y[w] = x[w] >> 2;
-                    if (w + 1 < W) y[w] |= x[w + 1] << 62;
-                }
-                const int top = 2 * (k - 1); /* W == 2 means k >= 36, i.e. top >= 70: always the upper word */
-                y[W - 1] |= (uint64_t)c << (top - 64 * (W - 1));
+                for (int w = 0; w < W; w++)
+                    if ((top >> 6) == w) y[w] |= (uint64_t)c << (top & 63);
             } else { /* predecessor: (x << 2 | c) masked to 2k bits */
-#pragma unroll
-                for (int w = W - 1; w >= 0; w--) {
-                    y[w] = x[w] << 2;
-                    if (w > 0) y[w] |= x[w - 1] >> 62;
-                }
+                bft_shl<W>(x, 2, y);
                 y[0] |= c;
-                const int bits_last = 2 * k - 64 * (W - 1);
-                if (bits_last < 64) y[W - 1] &= (1ULL << bits_last) - 1ULL;
+#pragma unroll
+                for (int w = 0; w < W; w++) y[w] &= bft_word_mask(2 * k, w);
             }
             /* the reference's successor search deviates from set membership at the leaf level; see bft_node_probe */
             const uint32_t cls = bft_lookup_ex(&v, y, W, ref_quirks && sub < 4, (uint32_t*)0);
@@ -380,7 +423,7 @@ __global__ void __launch_bounds__(BFT_TPB) k_query_branching(const bft_view_t v,
  * compares the nucleotide-lexicographic keys (strcmp rule, src/bft.c:1287-1293). Windows sharing a colour class are
  * merged with __match_any_sync before the per-genome counters in shared memory are bumped. */
 #define BFT_SEQ_TILE 512                       /* window start positions per tile */
-#define BFT_SEQ_SPAN (BFT_SEQ_TILE + 64)       /* characters held per tile (k <= 63 overlap, rounded to 64) */
+#define BFT_SEQ_SPAN (BFT_SEQ_TILE + 128)      /* characters held per tile (k <= 126 overlap, rounded to 64) */
 #define BFT_SEQ_WARPS 4
 
 /* shared memory one warp of k_query_sequences needs (codes + 4 masks + characters + per-genome counters) */
@@ -438,6 +481,13 @@ __device__ __forceinline__ uint64_t bft_extract_bits(const uint64_t* plane, int 
     uint64_t x = plane[w] >> sh;
     if (sh && sh + len > 64) x |= plane[w + 1] << (64 - sh);
     return len < 64 ? x & ((1ULL << len) - 1ULL) : x;
+}
+
+/* any bit set in [pos, pos+len) of a bit plane, len <= 128 */
+__device__ __forceinline__ bool bft_any_bits(const uint64_t* plane, int pos, int len) {
+    uint64_t x = bft_extract_bits(plane, pos, len < 64 ? len : 64);
+    if (len > 64) x |= bft_extract_bits(plane, pos + 64, len - 64);
+    return x != 0;
 }
 
 __device__ __forceinline__ char bft_rc_char(char c) { /* reverse_complement on ACGTU (src/fasta.c:396-405) */
@@ -525,11 +575,11 @@ __global__ void __launch_bounds__(32 * BFT_SEQ_WARPS) k_query_sequences(const bf
                 const int j = j0 + lane;
                 uint32_t cls = BFT_CLS_NONE;
                 if (j < n_here) {
-                    uint64_t wi = 0, wr = 0, wo = 0;
+                    bool wi = false, wr = false, wo = false;
                     if (tile_special) {
-                        wi = bft_extract_bits(m_iupac, j, k);
-                        wr = bft_extract_bits(m_rcbad, j, k);
-                        wo = bft_extract_bits(m_other, j, k);
+                        wi = bft_any_bits(m_iupac, j, k);
+                        wr = bft_any_bits(m_rcbad, j, k);
+                        wo = bft_any_bits(m_other, j, k);
                     }
                     int skip = 0;
                     if (canonical) {
@@ -541,46 +591,31 @@ __global__ void __launch_bounds__(32 * BFT_SEQ_WARPS) k_query_sequences(const bf
                     }
                     if (!skip) {
                         uint64_t x[W];
-                        if (W == 1) {
-                            x[0] = bft_extract_bits(codes, 2 * j, 2 * k);
-                        } else {
-                            x[0] = bft_extract_bits(codes, 2 * j, 64);
-                            x[W - 1] = bft_extract_bits(codes, 2 * j + 64, 2 * k - 64);
+#pragma unroll
+                        for (int w = 0; w < W; w++) {
+                            const int len = 2 * k - 64 * w;
+                            x[w] = len <= 0 ? 0ULL : bft_extract_bits(codes, 2 * j + 64 * w, len < 64 ? len : 64);
                         }
                         if (canonical) {
-                            /* key(fwd) = R(x), key(rc) = ~x (masked); rc = ~R(x) (masked). strcmp(fwd, rc) >= 0 -> rc */
-                            uint64_t rx[W], nx[W];
-                            int use_rc;
-                            if (W == 1) {
-                                const uint64_t mask = (1ULL << (2 * k)) - 1ULL;
-                                rx[0] = bft_rev2_64(x[0]) >> (64 - 2 * k);
-                                nx[0] = ~x[0] & mask;
-                                use_rc = rx[0] >= nx[0];
-                                if (tile_special && bft_extract_bits(m_nonpl, j, k)) { /* mixed case / U: ASCII order decides */
-                                    use_rc = 1;
-                                    for (int i = 0; i < k; i++) {
-                                        const char a = tile_chars[j + i], b = bft_rc_char(tile_chars[j + k - 1 - i]);
-                                        if (a != b) { use_rc = (unsigned char)a > (unsigned char)b; break; }
-                                    }
+                            /* key(fwd) = R(x) (2-bit-group reversal), key(rc) = ~x, rc = ~R(x), all within 2k bits.
+                             * strcmp(fwd, rc) >= 0 -> rc (src/bft.c:1287-1293) */
+                            uint64_t r[W], rx[W], nx[W];
+#pragma unroll
+                            for (int w = 0; w < W; w++) r[w] = bft_rev2_64(x[W - 1 - w]);
+                            bft_shr<W>(r, 64 * W - 2 * k, rx);
+#pragma unroll
+                            for (int w = 0; w < W; w++) nx[w] = ~x[w] & bft_word_mask(2 * k, w);
+                            int use_rc = bft_ge<W>(rx, nx);
+                            if (tile_special && bft_any_bits(m_nonpl, j, k)) { /* mixed case / U: ASCII order decides */
+                                use_rc = 1;
+                                for (int i = 0; i < k; i++) {
+                                    const char a = tile_chars[j + i], b = bft_rc_char(tile_chars[j + k - 1 - i]);
+                                    if (a != b) { use_rc = (unsigned char)a > (unsigned char)b; break; }
                                 }
-                                if (use_rc) x[0] = ~rx[0] & mask;
-                            } else {
-                                const int sh = 128 - 2 * k; /* 2..56 for 36 <= k <= 63 */
-                                const uint64_t hi = bft_rev2_64(x[0]), lo = bft_rev2_64(x[W - 1]); /* 128-bit reversal */
-                                rx[0] = (lo >> sh) | (hi << (64 - sh));
-                                rx[W - 1] = hi >> sh;
-                                const uint64_t mask_hi = (1ULL << (2 * k - 64)) - 1ULL;
-                                nx[0] = ~x[0];
-                                nx[W - 1] = ~x[W - 1] & mask_hi;
-                                use_rc = rx[W - 1] > nx[W - 1] || (rx[W - 1] == nx[W - 1] && rx[0] >= nx[0]);
-                                if (tile_special && bft_extract_bits(m_nonpl, j, k)) {
-                                    use_rc = 1;
-                                    for (int i = 0; i < k; i++) {
-                                        const char a = tile_chars[j + i], b = bft_rc_char(tile_chars[j + k - 1 - i]);
-                                        if (a != b) { use_rc = (unsigned char)a > (unsigned char)b; break; }
-                                    }
-                                }
-                                if (use_rc) { x[0] = ~rx[0]; x[W - 1] = ~rx[W - 1] & mask_hi; }
+                            }
+                            if (use_rc) {
+#pragma unroll
+                                for (int w = 0; w < W; w++) x[w] = ~rx[w] & bft_word_mask(2 * k, w);
                             }
                         }
                         cls = bft_lookup_w(&v, x, W);

@@ -31,7 +31,16 @@ def kmer_nbytes(k: int) -> int:
 
 
 def kmer_nwords(k: int) -> int:
-    return (2 * k + 63) // 64
+    """64-bit words per packed k-mer in the engine's convention: 1, 2 or 4 (k <= 32 / 64 / 126)."""
+    return 1 if 2 * k <= 64 else (2 if 2 * k <= 128 else 4)
+
+
+def mask_words(words: np.ndarray, k: int) -> None:
+    """Clear, in place, every bit above 2k in [n, nwords] packed k-mers."""
+    for w in range(words.shape[1]):
+        bits = min(64, max(0, 2 * k - 64 * w))
+        if bits < 64:
+            words[:, w] &= np.uint64((1 << bits) - 1)
 
 
 def random_genome(rng: np.random.Generator, length: int) -> np.ndarray:
@@ -235,9 +244,7 @@ def sample_kmer_queries(genomes: Sequence[np.ndarray], k: int, n: int, seed: int
     if n_r:
         r = rng.integers(0, 1 << 63, size=(n_r, nw), dtype=np.uint64) * np.uint64(2) + \
             rng.integers(0, 2, size=(n_r, nw), dtype=np.uint64)
-        bits_last = 2 * k - 64 * (nw - 1)
-        if bits_last < 64:
-            r[:, nw - 1] &= np.uint64((1 << bits_last) - 1)
+        mask_words(r, k)
         parts.append(r)
     q = np.concatenate(parts)
     return q[rng.permutation(len(q))]
@@ -322,8 +329,6 @@ def near_miss_queries(words: np.ndarray, k: int, n: int, seed: int) -> np.ndarra
     n_r = n - len(a) - len(m)
     r = rng.integers(0, 1 << 63, size=(n_r, nw), dtype=np.uint64) * np.uint64(2) + \
         rng.integers(0, 2, size=(n_r, nw), dtype=np.uint64)
-    bits_last = 2 * k - 64 * (nw - 1)
-    if bits_last < 64:
-        r[:, nw - 1] &= np.uint64((1 << bits_last) - 1)
+    mask_words(r, k)
     q = np.concatenate([a, m, r])
     return q[rng.permutation(len(q))]

@@ -115,7 +115,7 @@ def gen_kmer_queries(cat, starts, lens, k: int, n: int, seed: int, mix: Tuple[fl
     dev = cat.device
     g = torch.Generator(device=dev)
     g.manual_seed(seed)
-    W = (2 * k + 63) // 64
+    W = synth.kmer_nwords(k)
     n_p = int(n * mix[0])
     n_m = int(n * mix[1])
     n_r = n - n_p - n_m
@@ -140,9 +140,9 @@ def gen_kmer_queries(cat, starts, lens, k: int, n: int, seed: int, mix: Tuple[fl
     if n_r:
         r = torch.empty((n_r, W), dtype=torch.int64, device=dev)
         for w in range(W):
-            bits = min(64, 2 * k - 64 * w)
-            lo = torch.randint(0, 1 << 32, (n_r,), generator=g, device=dev)
-            hi = torch.randint(0, 1 << max(1, min(32, bits - 32)), (n_r,), generator=g, device=dev) if bits > 32 else torch.zeros_like(lo)
+            bits = max(0, min(64, 2 * k - 64 * w))
+            lo = torch.randint(0, 1 << min(32, max(bits, 1)), (n_r,), generator=g, device=dev) if bits > 0 else torch.zeros(n_r, dtype=torch.int64, device=dev)
+            hi = torch.randint(0, 1 << min(32, bits - 32), (n_r,), generator=g, device=dev) if bits > 32 else torch.zeros_like(lo)
             r[:, w] = lo | (hi << 32)
         parts.append(r)
     out = torch.cat(parts)

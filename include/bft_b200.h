@@ -6,7 +6,7 @@
  * reference's own query path on the same .bft and inputs.
  *
  * Conventions
- *   - packed k-mers: W = bft_b200_kmer_words() little-endian uint64 per k-mer, nucleotide i at bits 2i
+ *   - packed k-mers: W = bft_b200_kmer_words() (1, 2 or 4 for k <= 27 / 63 / 126) little-endian uint64 per k-mer, nucleotide i at bits 2i
  *     (A=0 C=1 G=2 T=3), i.e. the reference's byte layout (include/fasta.h:15, src/fasta.c:13-23) zero-padded to W
  *     words; bits above 2k must be zero.
  *   - colour rows: RW = bft_b200_row_words() uint32 per item, genome g = bit (g & 31) of word g >> 5. A row is the

@@ -139,6 +139,10 @@ CASES = {
     "lowcomplex_k45_g2": (case_lowcomplexity, dict(k=45, n_genomes=2, length=100_000, seed=406)),
     "pan_k27_g100": (case_pangenome, dict(k=27, n_genomes=100, seed=303)),
     "pan_k27_g1000": (case_pangenome, dict(k=27, n_genomes=1000, length=2_000, seed=304)),
+    # four-word keys (63 < k <= 126, the reference's KMER_LENGTH_MAX); only inputs on which the reference's own
+    # insertion stays consistent (see test_duplicate_kmers_are_refused)
+    "shallow_k72_g3": (case_shallow, dict(k=72, n_genomes=3, length=30_000, seed=141)),
+    "shallow_k126_g4": (case_shallow, dict(k=126, n_genomes=4, length=25_000, seed=143)),
     "pan_k63_g130": (case_pangenome, dict(k=63, n_genomes=130, length=6_000, seed=305)),
 }
 

@@ -88,10 +88,13 @@ def test_branching_set_semantics_mode(built):
     k = c["k"]
     q = c["queries"][:1500]
     allw = np.unique(np.concatenate(c["genome_words"]), axis=0)
-    two = q.shape[1] > 1
-    members = set((int(r[0]) | (int(r[1]) << 64 if two else 0)) for r in allw)
+
+    def as_int(r):
+        return sum(int(r[w]) << (64 * w) for w in range(len(r)))
+
+    members = set(as_int(r) for r in allw)
     mask = (1 << (2 * k)) - 1
-    ints = [int(r[0]) | (int(r[1]) << 64 if two else 0) for r in q]
+    ints = [as_int(r) for r in q]
 
     def has(x):
         return x in members
@@ -197,3 +200,23 @@ def test_enumeration_matches_inserted_sets_and_reference_extract(built, workdir)
     lines = open(os.path.join(d, "mine.txt"), "rb").read().split(b"\n")[:-1]
     assert len(lines) == len(uniq) and all(len(x) == k for x in lines[:50])
     np.testing.assert_array_equal(synth.words_to_ascii(kmers[:50], k), np.array([list(x) for x in lines[:50]], dtype=np.uint8))
+
+
+def test_duplicate_kmers_are_refused(workdir, engine_mod):
+    """For k > 63 the reference's insertion can store one k-mer several times (its -extract_kmers lists more records
+    than distinct k-mers), which makes its own query answers depend on the copy a search meets. The serializer
+    detects that and refuses the file."""
+    if not refutil.have_ref():
+        pytest.skip("needs the compiled reference to build the BFT")
+    c = cases.case_deep(k=99, n_genomes=4, n_kmers=100_000, pools=(20, 3, 3, 3, 3, 3), seed=211)
+    path = refutil.build_bft(workdir, "dup_k99", c["genome_words"], 99)
+    d = os.path.join(workdir, "dup_k99")
+    refutil.ref_cli(path, ["-extract_kmers", "kmers_comp", os.path.join(d, "ref.kc")], cwd=d)
+    raw = open(os.path.join(d, "ref.kc"), "rb").read()
+    l1 = raw.index(b"\n")
+    l2 = raw.index(b"\n", l1 + 1)
+    rec = np.frombuffer(raw[l2 + 1:], dtype=np.uint8).reshape(-1, synth.kmer_nbytes(99))
+    if len(np.unique(rec, axis=0)) == len(rec):
+        pytest.skip("this reference build produced no duplicates")
+    with pytest.raises(engine_mod.BFTError, match="same k-mer twice"):
+        engine_mod.BFTEngine(path)
