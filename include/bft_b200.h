@@ -18,6 +18,9 @@
  *     copy) and include the host<->device transfers; "_device" entry points take pointers into this context's GPU
  *     and only enqueue work on bft_b200_stream().
  *   - there is no CPU fallback: without a usable CUDA device every call fails with BFT_B200_ERR_CUDA.
+ *   - a context serves one caller at a time (the reference's query API is not re-entrant either); use one
+ *     context per thread / per GPU. bft_b200_open reserves part of the device's L2 as persisting cache for the tables
+ *     every lookup touches (cudaLimitPersistingL2CacheSize, a device-wide setting; BFT_B200_NO_L2_PERSIST=1 disables it).
  */
 #ifndef BFT_B200_H
 #define BFT_B200_H
