@@ -90,7 +90,7 @@ class ClockSampler:
 
 
 def pick_workload(args):
-    from bloomfiltertrie_b200 import workloads as wl
+    import bench_workloads as wl
     if getattr(args, "pangenome", "c3") == "c5":  # informational: 1000 colours, wide rows (RW = 32)
         return wl.C5, (args.genome_len or 100_000)
     cfg = wl.C3
@@ -130,7 +130,7 @@ def write_query_file(path, q_np, k):
 
 
 def run_reference_harness(bft, qfile, threads, passes):
-    from bloomfiltertrie_b200 import workloads as wl
+    import bench_workloads as wl
     out = qfile + ".out"
     p = subprocess.run([wl.REF_HARNESS, "kmers", bft, qfile, out, str(threads), str(passes)], stdout=subprocess.PIPE,
                        stderr=subprocess.STDOUT, text=True)
@@ -148,7 +148,7 @@ def reference_arm(args):
     if rank != 0:
         return
     import torch
-    from bloomfiltertrie_b200 import workloads as wl
+    import bench_workloads as wl
     cfg, L = pick_workload(args)
     genomes = wl.pangenome(cfg, L)
     bft = wl.ensure_bft(cfg, K, L, genomes)
@@ -179,7 +179,7 @@ def engine_arm(args):
     import torch
     import torch.distributed as dist
     from bloomfiltertrie_b200 import engine as E
-    from bloomfiltertrie_b200 import workloads as wl
+    import bench_workloads as wl
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -402,7 +402,7 @@ def side_workload(args):
     import numpy as np
     import torch
     from bloomfiltertrie_b200 import engine as E
-    from bloomfiltertrie_b200 import workloads as wl
+    import bench_workloads as wl
     dev = torch.device("cuda", 0)
     torch.cuda.set_device(0)
     seq = args.workload == "sequences"

@@ -1,4 +1,5 @@
-"""Benchmark workloads (BASELINE.json configs): synthetic pan-genome BFTs and query batches.
+"""Benchmark/test infrastructure (NOT part of the product package): the workloads of BASELINE.json's configs
+ — synthetic pan-genome BFTs and query batches.
 
 The BFT itself is always built by the UNMODIFIED reference (`oracle/_ref/bft build`, graph construction stays on the
 reference host path); this module only generates the seeded inputs, caches the resulting .bft under data/ and
@@ -14,9 +15,9 @@ from typing import List, Tuple
 
 import numpy as np
 
-from . import synth
+from bloomfiltertrie_b200 import synth
 
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.abspath(__file__))
 DATA = os.path.join(ROOT, "data")
 REF_BFT = os.path.join(ROOT, "oracle", "_ref", "bft")
 REF_HARNESS = os.path.join(ROOT, "oracle", "_ref", "ref_harness")

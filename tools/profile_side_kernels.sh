@@ -9,7 +9,8 @@ $NCU -k regex:k_query_kmers -s 3 -c 1 -o gpurun_out/prof_kmers_c5 python bench.p
 $NCU -k "regex:k_extract|k_decode" -c 3 -o gpurun_out/prof_extract python - <<'PY'
 import sys
 sys.path.insert(0, ".")
-from bloomfiltertrie_b200 import engine, workloads as wl
+from bloomfiltertrie_b200 import engine
+import bench_workloads as wl
 eng = engine.BFTEngine(wl.ensure_bft(wl.C5, 27, 100_000))
 km, cls, _ = eng.extract_kmers()
 print(len(km))
