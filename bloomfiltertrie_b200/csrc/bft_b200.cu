@@ -691,6 +691,50 @@ extern "C" int bft_b200_random_gather_probe(bft_b200_ctx* c, size_t table_bytes,
     return 0;
 }
 
+/* ---- peer (NVLink) result buffers --------------------------------------------------------------------------- */
+extern "C" int bft_b200_device_alloc(bft_b200_ctx* c, size_t bytes, void** d_ptr) {
+    if (!c || !d_ptr) return set_err(BFT_B200_ERR_ARG, "bft_b200_device_alloc: NULL argument");
+    CK(cudaSetDevice(c->device));
+    cudaError_t e = cudaMalloc(d_ptr, bytes ? bytes : 1);
+    if (e != cudaSuccess) return set_err(BFT_B200_ERR_NOMEM, "cudaMalloc(%zu) failed: %s", bytes, cudaGetErrorString(e));
+    CK(cudaMemset(*d_ptr, 0, bytes ? bytes : 1));
+    return 0;
+}
+
+extern "C" int bft_b200_device_free(bft_b200_ctx* c, void* d_ptr) {
+    if (!c) return set_err(BFT_B200_ERR_ARG, "bft_b200_device_free: NULL context");
+    CK(cudaSetDevice(c->device));
+    CK(cudaFree(d_ptr));
+    return 0;
+}
+
+extern "C" int bft_b200_peer_export(bft_b200_ctx* c, void* d_ptr, unsigned char handle[64]) {
+    if (!c || !d_ptr || !handle) return set_err(BFT_B200_ERR_ARG, "bft_b200_peer_export: NULL argument");
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "CUDA IPC handles are 64 bytes");
+    CK(cudaSetDevice(c->device));
+    cudaIpcMemHandle_t h;
+    CK(cudaIpcGetMemHandle(&h, d_ptr));
+    memcpy(handle, &h, 64);
+    return 0;
+}
+
+extern "C" int bft_b200_peer_import(bft_b200_ctx* c, const unsigned char handle[64], void** d_ptr) {
+    if (!c || !d_ptr || !handle) return set_err(BFT_B200_ERR_ARG, "bft_b200_peer_import: NULL argument");
+    CK(cudaSetDevice(c->device));
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle, 64);
+    CK(cudaIpcOpenMemHandle(d_ptr, h, cudaIpcMemLazyEnablePeerAccess)); /* maps the peer allocation; stores go over NVLink */
+    return 0;
+}
+
+extern "C" int bft_b200_peer_close(bft_b200_ctx* c, void* d_ptr) {
+    if (!c) return set_err(BFT_B200_ERR_ARG, "bft_b200_peer_close: NULL context");
+    CK(cudaSetDevice(c->device));
+    CK(cudaStreamSynchronize(c->streams[0]));
+    CK(cudaIpcCloseMemHandle(d_ptr));
+    return 0;
+}
+
 /* ---- enumeration --------------------------------------------------------------------------------------------- */
 extern "C" int bft_b200_extract_kmers_device(bft_b200_ctx* c, uint64_t* d_kmers, uint32_t* d_cls, size_t capacity) {
     if (!c || !d_kmers) return set_err(BFT_B200_ERR_ARG, "bft_b200_extract_kmers_device: NULL argument");

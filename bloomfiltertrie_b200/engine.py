@@ -29,6 +29,7 @@ ABI_SYMBOLS = [
     "bft_b200_query_kmers_file", "bft_b200_query_branching_file",
     "bft_b200_query_sequences_file", "bft_b200_sync", "bft_b200_launch_count", "bft_b200_kmer_walk_stats_device", "bft_b200_random_gather_probe",
     "bft_b200_extract_kmers", "bft_b200_extract_kmers_device", "bft_b200_extract_kmers_file",
+    "bft_b200_device_alloc", "bft_b200_device_free", "bft_b200_peer_export", "bft_b200_peer_import", "bft_b200_peer_close",
 ]
 
 
@@ -91,6 +92,11 @@ def load_library() -> C.CDLL:
     lib.bft_b200_extract_kmers.argtypes = [vp, u64p, u32p, u32p, sz, C.POINTER(C.c_uint64)]
     lib.bft_b200_extract_kmers_device.argtypes = [vp, u64p, u32p, sz]
     lib.bft_b200_extract_kmers_file.argtypes = [vp, C.c_char_p, C.c_int]
+    lib.bft_b200_device_alloc.argtypes = [vp, sz, C.POINTER(vp)]
+    lib.bft_b200_device_free.argtypes = [vp, vp]
+    lib.bft_b200_peer_export.argtypes = [vp, vp, C.c_char_p]
+    lib.bft_b200_peer_import.argtypes = [vp, C.c_char_p, C.POINTER(vp)]
+    lib.bft_b200_peer_close.argtypes = [vp, vp]
     lib.bft_b200_sync.argtypes = [vp]
     lib.bft_b200_launch_count.argtypes = [vp]
     lib.bft_b200_launch_count.restype = C.c_uint64
@@ -101,6 +107,8 @@ def load_library() -> C.CDLL:
 def _ptr(a) -> Optional[int]:
     if a is None:
         return None
+    if isinstance(a, int):
+        return a              # raw device address (e.g. a peer mapping)
     if isinstance(a, np.ndarray):
         return a.ctypes.data
     return int(a.data_ptr())  # torch tensor
@@ -290,6 +298,37 @@ class BFTEngine:
     def query_branching_device(self, d_kmers, n: int, d_succ=None, d_pred=None, d_count=None):
         self._ck(self.lib.bft_b200_query_branching_device(self.h, _ptr(d_kmers), n, _ptr(d_succ), _ptr(d_pred),
                                                           _ptr(d_count)), "bft_b200_query_branching_device")
+
+    # -- peer (NVLink) result buffers
+    def device_alloc(self, nbytes: int) -> int:
+        p = C.c_void_p()
+        self._ck(self.lib.bft_b200_device_alloc(self.h, nbytes, C.byref(p)), "bft_b200_device_alloc")
+        return int(p.value)
+
+    def device_free(self, ptr: int):
+        self._ck(self.lib.bft_b200_device_free(self.h, ptr), "bft_b200_device_free")
+
+    def peer_export(self, ptr: int) -> bytes:
+        buf = C.create_string_buffer(64)
+        self._ck(self.lib.bft_b200_peer_export(self.h, ptr, buf), "bft_b200_peer_export")
+        return buf.raw
+
+    def peer_import(self, handle: bytes) -> int:
+        p = C.c_void_p()
+        self._ck(self.lib.bft_b200_peer_import(self.h, handle, C.byref(p)), "bft_b200_peer_import")
+        return int(p.value)
+
+    def peer_close(self, ptr: int):
+        self._ck(self.lib.bft_b200_peer_close(self.h, ptr), "bft_b200_peer_close")
+
+    def copy_from_device(self, ptr: int, out: np.ndarray):
+        """Blocking device -> host copy of a raw device buffer into a NumPy array (test / gather helper)."""
+        rt = C.CDLL("libcudart.so.12")
+        rt.cudaMemcpy.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_int]
+        rc = rt.cudaMemcpy(out.ctypes.data, ptr, out.nbytes, 2)
+        if rc != 0:
+            raise BFTError(f"cudaMemcpy failed ({rc})")
+        return out
 
     # -- enumeration
     def extract_kmers(self, want_classes: bool = True, want_rows: bool = False):

@@ -104,3 +104,86 @@ class ShardedQuery:
         b, e = shard_range(n, self.rank, self.world)
         _, _, cnt = self.engine.query_branching(kmers[b:e])
         return sum_to_all(cnt, self._device(), self.group)
+
+
+class PeerGather:
+    """Gather fused into the query kernels: rank 0 owns the result arrays in its HBM, every other rank maps them
+    through CUDA IPC (bft_b200_peer_import) and passes the slice for its shard as the kernel's OUTPUT pointer, so the
+    result stores themselves cross NVLink/NVSwitch — no collective runs after the kernel. `torch.distributed` (any
+    backend) is used only to ship the 64-byte handles and for the closing barrier."""
+
+    def __init__(self, engine, group=None):
+        import torch.distributed as dist
+        self.engine = engine
+        self.group = group
+        self.rank = dist.get_rank(group)
+        self.world = dist.get_world_size(group)
+
+    def _shared(self, nbytes: int):
+        import torch.distributed as dist
+        box = [None]
+        base = None
+        if self.rank == 0:
+            base = self.engine.device_alloc(max(nbytes, 16))
+            box[0] = self.engine.peer_export(base)
+        dist.broadcast_object_list(box, src=0, group=self.group)
+        ptr = base if self.rank == 0 else self.engine.peer_import(box[0])
+        return base, ptr
+
+    def _release(self, base, ptr):
+        import torch.distributed as dist
+        self.engine.sync()
+        dist.barrier(group=self.group)          # every rank's stores have landed
+        if self.rank != 0:
+            self.engine.peer_close(ptr)
+
+    def query_sequences(self, chars: np.ndarray, offs: np.ndarray, threshold: float, canonical: bool):
+        """All ranks pass the FULL batch; returns the rows of every sequence on rank 0 (None elsewhere)."""
+        import torch
+        import torch.distributed as dist
+        eng = self.engine
+        offs = np.asarray(offs, dtype=np.uint64)
+        n = len(offs) - 1
+        base, ptr = self._shared(n * eng.RW * 4)
+        b, e = shard_sequences(offs, self.rank, self.world)
+        if e > b:
+            dev = torch.device("cuda", eng.device)
+            d_chars = torch.from_numpy(np.ascontiguousarray(chars[int(offs[b]):int(offs[e])])).to(dev)
+            d_offs = torch.from_numpy((offs[b:e + 1] - offs[b]).astype(np.int64)).to(dev)
+            eng.query_sequences_device(d_chars, d_offs, e - b, threshold, canonical, ptr + b * eng.RW * 4, None)
+        self._release(base, ptr)
+        out = None
+        if self.rank == 0:
+            out = eng.copy_from_device(base, np.empty((n, eng.RW), dtype=np.uint32))
+            dist.barrier(group=self.group)
+            eng.device_free(base)
+        else:
+            dist.barrier(group=self.group)
+        return out
+
+    def query_kmers(self, kmers: np.ndarray):
+        """Presence bytes and colour rows of the full batch on rank 0, written there by every rank's kernel."""
+        import torch
+        import torch.distributed as dist
+        eng = self.engine
+        n = kmers.shape[0]
+        base_r, ptr_r = self._shared(n * eng.RW * 4)
+        base_p, ptr_p = self._shared(n)
+        b, e = shard_range(n, self.rank, self.world)
+        if e > b:
+            dev = torch.device("cuda", eng.device)
+            d_k = torch.from_numpy(np.ascontiguousarray(kmers[b:e]).view(np.int64)).to(dev)
+            eng.query_kmers_device(d_k, e - b, ptr_p + b, ptr_r + b * eng.RW * 4, None)
+        self._release(base_r, ptr_r)
+        if self.rank != 0:
+            eng.peer_close(ptr_p)
+        out = (None, None)
+        if self.rank == 0:
+            out = (eng.copy_from_device(base_p, np.empty(n, dtype=np.uint8)),
+                   eng.copy_from_device(base_r, np.empty((n, eng.RW), dtype=np.uint32)))
+            dist.barrier(group=self.group)
+            eng.device_free(base_r)
+            eng.device_free(base_p)
+        else:
+            dist.barrier(group=self.group)
+        return out

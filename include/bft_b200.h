@@ -143,6 +143,20 @@ int bft_b200_extract_kmers_device(bft_b200_ctx* ctx, uint64_t* d_kmers, uint32_t
  * arena order. */
 int bft_b200_extract_kmers_file(bft_b200_ctx* ctx, const char* path, int compressed_output);
 
+/* ---- multi-GPU: results written straight into a peer GPU's memory over NVLink ------------------------------------
+ * The path shards by query with the arena replicated per GPU; the only exchange is the gather of results on one
+ * GPU. Instead of a collective after the kernel, a rank can hand the *_device entry points an output pointer that
+ * lives on ANOTHER GPU of the box (mapped through CUDA IPC, one process per GPU): the kernel's own result stores
+ * then travel over NVLink/NVSwitch into the right slice of the gathered array — compute and gather in one kernel.
+ *   owner rank:  bft_b200_device_alloc -> bft_b200_peer_export (64-byte handle, ship it with any host channel)
+ *   other ranks: bft_b200_peer_import -> pointer usable as d_rows / d_present / ... (+ element offset of the shard)
+ * Close imported mappings with bft_b200_peer_close and free the buffer with bft_b200_device_free on the owner. */
+int bft_b200_device_alloc(bft_b200_ctx* ctx, size_t bytes, void** d_ptr);
+int bft_b200_device_free(bft_b200_ctx* ctx, void* d_ptr);
+int bft_b200_peer_export(bft_b200_ctx* ctx, void* d_ptr, unsigned char handle[64]);
+int bft_b200_peer_import(bft_b200_ctx* ctx, const unsigned char handle[64], void** d_ptr);
+int bft_b200_peer_close(bft_b200_ctx* ctx, void* d_ptr);
+
 /* ---- file-level drivers (the CLI-visible bytes) ---------------------------------------------------------------
  * queryBFT_kmerPresences_from_KmerFiles (src/file_io.c:651-895): CSV of colour rows; returns #present via out.
  * queryBFT_kmerBranching_from_KmerFiles (src/file_io.c:897-1020): count of branching k-mers.
