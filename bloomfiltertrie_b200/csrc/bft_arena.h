@@ -142,6 +142,11 @@ typedef struct {
     int W;             /* 64-bit words per key: 1 for k <= 27, 2 for k <= 63, 4 for k <= 126 */
     int cls_shift;     /* != 0: class id of an inline line = (top word >> cls_shift) & cls_mask, suffix = the bits below */
     uint32_t cls_mask;
+    /* storage locations ("loc"): one number per place a k-mer can be stored — bucket slot g -> g, overflow line i ->
+     * loc_ovf + i, Node-UC line i -> loc_uc + i, leaf prefix i -> loc_leaf + i; n_loc = loc_leaf + n_pref. The graph
+     * traversals (bft_graph.cuh) key their vertex table and marks on it, the way the reference keeps its marks inside
+     * the UC a k-mer is stored in (src/marking.c). */
+    uint32_t loc_ovf, loc_uc, loc_leaf;
 } bft_view_t;
 
 /* ---- prefix bit manipulation --------------------------------------------------------------------------------
@@ -195,7 +200,7 @@ BFT_HD void bft_ld_bucket(const uint64_t* p, uint64_t* out, const int W) {
  * src/presenceNode.c:719-723): the reference clears nucleotide 7 of the prefix (`& 0xfc` on the second byte) before
  * hashing and before forming p_u/p_v, so the CC path answers for the prefix with nuc 7 = A; the Node-UC path
  * (:1164-1208) compares the unmodified k-mer. Only the successor lookups of the branching queries pass it. */
-BFT_HD bft_entry_t bft_node_probe(const bft_view_t* v, uint32_t node_id, uint32_t low18, int succ_leaf_quirk) {
+BFT_HD bft_entry_t bft_node_probe_ex(const bft_view_t* v, uint32_t node_id, uint32_t low18, int succ_leaf_quirk, uint32_t* pref_idx) {
     bft_node_t nd;
 #ifdef __CUDA_ARCH__
     {
@@ -246,10 +251,15 @@ BFT_HD bft_entry_t bft_node_probe(const bft_view_t* v, uint32_t node_id, uint32_
                 uint32_t t = (lo & 1u) ? (uint32_t)(BFT_LD8(f3 + (lo >> 1)) >> 4) : (uint32_t)(BFT_LD8(f3 + (lo >> 1)) & 0xf);
                 if (t != pv) return bft_mk_entry(BFT_KIND_ABSENT, 0, 0);
             }
+            if (pref_idx) *pref_idx = cc.pref_off + lo;
             return bft_ld_entry(v->pref + cc.pref_off + lo);
         }
     }
     return bft_mk_entry(BFT_KIND_UC, nd.uc_begin, nd.uc_n);
+}
+
+BFT_HD bft_entry_t bft_node_probe(const bft_view_t* v, uint32_t node_id, uint32_t low18, int succ_leaf_quirk) {
+    return bft_node_probe_ex(v, node_id, low18, succ_leaf_quirk, (uint32_t*)0);
 }
 
 /* Search the Node-UC lines [begin, begin+n) for `key` (W words, word W-1 most significant); returns the line index
@@ -287,7 +297,7 @@ BFT_HD uint32_t bft_bucket_of(const uint64_t* key, const int W, const uint32_t l
     return lb ? (uint32_t)((x * 0x9E3779B97F4A7C15ULL) >> (64 - lb)) : 0u;
 }
 
-BFT_HD uint32_t bft_search_block(const bft_view_t* v, uint32_t base, uint32_t lb, const uint64_t* key, const int W) {
+BFT_HD uint32_t bft_search_block_ex(const bft_view_t* v, uint32_t base, uint32_t lb, const uint64_t* key, const int W, uint32_t* loc) {
     const size_t bucket = (size_t)base + bft_bucket_of(key, W, lb);
     uint64_t s[BFT_BUCKET_KEYS * BFT_MAX_WORDS];
     bft_ld_bucket(v->buckets + bucket * (size_t)(BFT_BUCKET_KEYS * W), s, W);
@@ -301,7 +311,10 @@ BFT_HD uint32_t bft_search_block(const bft_view_t* v, uint32_t base, uint32_t lb
         const uint64_t top = s[j * W + W - 1];
         int eq = !(top & BFT_SLOT_SPECIAL) && (top & top_mask) == key[W - 1];
         for (int w = 0; w < W - 1; w++) eq = eq && s[j * W + w] == key[w];
-        if (eq) found = shift ? ((uint32_t)(top >> shift) & v->cls_mask) : BFT_LD32(v->slotcls + bucket * BFT_BUCKET_KEYS + j);
+        if (eq) {
+            found = shift ? ((uint32_t)(top >> shift) & v->cls_mask) : BFT_LD32(v->slotcls + bucket * BFT_BUCKET_KEYS + j);
+            if (loc) *loc = (uint32_t)(bucket * BFT_BUCKET_KEYS + j);
+        }
     }
     const uint64_t last = s[(BFT_BUCKET_KEYS - 1) * W + W - 1];
     if (found == BFT_CLS_NONE && (last & BFT_SLOT_SPECIAL) && last != BFT_SLOT_EMPTY) { /* overflow run */
@@ -311,10 +324,17 @@ BFT_HD uint32_t bft_search_block(const bft_view_t* v, uint32_t base, uint32_t lb
             const uint64_t top = BFT_LD64(p + W - 1);
             int eq = (top & top_mask) == key[W - 1];
             for (int w = 0; w < W - 1; w++) eq = eq && BFT_LD64(p + w) == key[w];
-            if (eq) found = shift ? ((uint32_t)(top >> shift) & v->cls_mask) : BFT_LD32(v->ovfcls + start + i);
+            if (eq) {
+                found = shift ? ((uint32_t)(top >> shift) & v->cls_mask) : BFT_LD32(v->ovfcls + start + i);
+                if (loc) *loc = v->loc_ovf + start + i;
+            }
         }
     }
     return found;
+}
+
+BFT_HD uint32_t bft_search_block(const bft_view_t* v, uint32_t base, uint32_t lb, const uint64_t* key, const int W) {
+    return bft_search_block_ex(v, base, lb, key, W, (uint32_t*)0);
 }
 
 BFT_HD void bft_shift18(uint64_t* cur, int W) {
@@ -345,11 +365,16 @@ BFT_HD uint32_t bft_ceil_log2p1(uint32_t n) { /* ceil(log2(n + 1)) */
     return b;
 }
 
-BFT_HD uint32_t bft_lookup_ex(const bft_view_t* v, const uint64_t* kmer, const int W, const int succ_leaf_quirk, uint32_t* st) {
+/* loc (optional): receives the storage location of the k-mer when it is found (see bft_view_t). */
+BFT_HD uint32_t bft_lookup_loc(const bft_view_t* v, const uint64_t* kmer, const int W, const int succ_leaf_quirk, uint32_t* st, uint32_t* loc) {
     uint64_t cur[BFT_MAX_WORDS];
     for (int w = 0; w < BFT_MAX_WORDS; w++) cur[w] = w < W ? kmer[w] : 0;
     int sz = v->k;
-    bft_entry_t e = bft_ld_entry(v->rootdir + ((uint32_t)cur[0] & (BFT_ROOTDIR_SIZE - 1u)));
+    uint32_t pref_idx = 0;
+    bft_entry_t e;
+    /* a 9-mer trie keeps its k-mers as leaf prefixes of the root: rootdir holds the entry but not its index */
+    if (loc && sz == BFT_NB_CHAR_SUF_PREF) e = bft_node_probe_ex(v, 0, (uint32_t)cur[0] & (BFT_ROOTDIR_SIZE - 1u), 0, &pref_idx);
+    else e = bft_ld_entry(v->rootdir + ((uint32_t)cur[0] & (BFT_ROOTDIR_SIZE - 1u)));
     if (st) { st[0]++; st[3] += bft_cc_probed(v, 0, (uint32_t)cur[0] & (BFT_ROOTDIR_SIZE - 1u)); }
     for (;;) {
         const uint32_t kind = e.b >> BFT_KIND_SHIFT;
@@ -357,6 +382,7 @@ BFT_HD uint32_t bft_lookup_ex(const bft_view_t* v, const uint64_t* kmer, const i
         if (kind == BFT_KIND_ABSENT) return BFT_CLS_NONE;
         if (kind == BFT_KIND_LEAF) {
             if (st) st[2]++;
+            if (loc) *loc = v->loc_leaf + pref_idx;
             return e.a;
         }
         if (kind == BFT_KIND_UC) {
@@ -364,20 +390,26 @@ BFT_HD uint32_t bft_lookup_ex(const bft_view_t* v, const uint64_t* kmer, const i
             if (st) { st[1] += bft_ceil_log2p1(n); st[4] += n; }
             const uint32_t ln = bft_search_uc(v, e.a, n, cur, W);
             if (st && ln != 0xffffffffu) st[2]++;
+            if (loc && ln != 0xffffffffu) *loc = v->loc_uc + ln;
             return ln == 0xffffffffu ? BFT_CLS_NONE : BFT_LD32(v->uccls + ln);
         }
         bft_shift18(cur, W);
         sz -= BFT_NB_CHAR_SUF_PREF;
         if (kind == BFT_KIND_INLINE) {
             if (st) { st[1] += bft_ceil_log2p1(n); st[4] += n; }
-            const uint32_t cls = bft_search_block(v, e.a, (e.b >> BFT_LB_SHIFT) & BFT_LB_MASK, cur, W);
+            const uint32_t cls = bft_search_block_ex(v, e.a, (e.b >> BFT_LB_SHIFT) & BFT_LB_MASK, cur, W, loc);
             if (st && cls != BFT_CLS_NONE) st[2]++;
             return cls;
         }
         /* BFT_KIND_NODE */
         if (st) { st[0]++; st[3] += bft_cc_probed(v, e.a, (uint32_t)cur[0] & (BFT_ROOTDIR_SIZE - 1u)); }
-        e = bft_node_probe(v, e.a, (uint32_t)cur[0] & (BFT_ROOTDIR_SIZE - 1u), succ_leaf_quirk && sz == BFT_NB_CHAR_SUF_PREF);
+        e = bft_node_probe_ex(v, e.a, (uint32_t)cur[0] & (BFT_ROOTDIR_SIZE - 1u), succ_leaf_quirk && sz == BFT_NB_CHAR_SUF_PREF,
+                              loc ? &pref_idx : (uint32_t*)0);
     }
+}
+
+BFT_HD uint32_t bft_lookup_ex(const bft_view_t* v, const uint64_t* kmer, const int W, const int succ_leaf_quirk, uint32_t* st) {
+    return bft_lookup_loc(v, kmer, W, succ_leaf_quirk, st, (uint32_t*)0);
 }
 
 BFT_HD uint32_t bft_lookup_w(const bft_view_t* v, const uint64_t* kmer, const int W) { return bft_lookup_ex(v, kmer, W, 0, (uint32_t*)0); }

@@ -14,6 +14,8 @@
 #include "bft_flatten.h"
 #include "bft_io.h"
 #include "bft_kernels.cuh"
+#include "bft_graph.cuh"
+#include <cub/device/device_scan.cuh>
 
 static __thread char g_err[512];
 
@@ -77,6 +79,15 @@ struct bft_b200_ctx {
     size_t seq_smem;
     int ref_quirks;
     uint32_t* d_nbr; size_t cap_nbr;
+    /* device graph (bft_graph.cuh), built on first use */
+    struct {
+        int ready;
+        size_t n;            /* vertices = stored k-mers */
+        uint64_t* d_vk;      /* n * W: the k-mer of each vertex, in enumeration order */
+        uint32_t* d_vcls;    /* n: its colour class */
+        uint32_t* d_adj;     /* n * 8: predecessors 0-3, successors 4-7 (vertex ids or BFT_V_NONE) */
+        size_t bytes;
+    } graph;
 };
 
 extern "C" const char* bft_b200_last_error(void) { return g_err; }
@@ -134,6 +145,7 @@ extern "C" void bft_b200_close(bft_b200_ctx* c) {
     if (c->d_class_counts) cudaFree(c->d_class_counts);
     if (c->d_counter) cudaFree(c->d_counter);
     if (c->d_nbr) cudaFree(c->d_nbr);
+    bft_b200_graph_release(c);
     for (int s = 0; s < 2; s++) {
         slot_t* sl = &c->slot[s];
         if (sl->d_in) cudaFree(sl->d_in);
@@ -235,6 +247,9 @@ extern "C" int bft_b200_open(const char* path, int device, bft_b200_ctx** out) {
         c->dview.cls_mask = a->cls_mask;
         c->dview.k = a->k;
         c->dview.W = a->W;
+        c->dview.loc_ovf = (uint32_t)(a->n_buckets * BFT_BUCKET_KEYS);
+        c->dview.loc_uc = c->dview.loc_ovf + (uint32_t)a->n_ovf;
+        c->dview.loc_leaf = c->dview.loc_uc + (uint32_t)a->n_uc_lines;
         c->dpools.n_pools = a->n_pools;
         c->dpools.last_index = (const int64_t*)c->d_pool[0];
         c->dpools.size_annot = (const int32_t*)c->d_pool[1];
@@ -736,24 +751,28 @@ extern "C" int bft_b200_peer_close(bft_b200_ctx* c, void* d_ptr) {
 }
 
 /* ---- enumeration --------------------------------------------------------------------------------------------- */
-extern "C" int bft_b200_extract_kmers_device(bft_b200_ctx* c, uint64_t* d_kmers, uint32_t* d_cls, size_t capacity) {
-    if (!c || !d_kmers) return set_err(BFT_B200_ERR_ARG, "bft_b200_extract_kmers_device: NULL argument");
-    if (capacity < c->stats.n_kmers) return set_err(BFT_B200_ERR_ARG, "bft_b200_extract_kmers: capacity %zu < %llu stored k-mers", capacity, (unsigned long long)c->stats.n_kmers);
-    CK(cudaSetDevice(c->device));
+static int enqueue_extract(bft_b200_ctx* c, uint64_t* d_kmers, uint32_t* d_cls, uint32_t* d_loc2vid) {
     cudaStream_t st = c->streams[0];
     if (c->n_pref) {
         const int grid = grid_for(c, c->n_pref * 32, BFT_TPB);
-#define BFT_L(W_) k_extract_prefix_kmers<W_><<<grid, BFT_TPB, 0, st>>>(c->dview, c->n_pref, d_kmers, d_cls)
+#define BFT_L(W_) k_extract_prefix_kmers<W_><<<grid, BFT_TPB, 0, st>>>(c->dview, c->n_pref, d_kmers, d_cls, d_loc2vid)
         BFT_BY_W(c->W, BFT_L);
 #undef BFT_L
         c->launches++;
     }
-#define BFT_L(W_) k_extract_uc_kmers<W_><<<grid_for(c, c->n_nodes, BFT_TPB), BFT_TPB, 0, st>>>(c->dview, c->n_nodes, d_kmers, d_cls)
+#define BFT_L(W_) k_extract_uc_kmers<W_><<<grid_for(c, c->n_nodes, BFT_TPB), BFT_TPB, 0, st>>>(c->dview, c->n_nodes, d_kmers, d_cls, d_loc2vid)
     BFT_BY_W(c->W, BFT_L);
 #undef BFT_L
     c->launches++;
     CK(cudaGetLastError());
     return 0;
+}
+
+extern "C" int bft_b200_extract_kmers_device(bft_b200_ctx* c, uint64_t* d_kmers, uint32_t* d_cls, size_t capacity) {
+    if (!c || !d_kmers) return set_err(BFT_B200_ERR_ARG, "bft_b200_extract_kmers_device: NULL argument");
+    if (capacity < c->stats.n_kmers) return set_err(BFT_B200_ERR_ARG, "bft_b200_extract_kmers: capacity %zu < %llu stored k-mers", capacity, (unsigned long long)c->stats.n_kmers);
+    CK(cudaSetDevice(c->device));
+    return enqueue_extract(c, d_kmers, d_cls, NULL);
 }
 
 extern "C" int bft_b200_extract_kmers(bft_b200_ctx* c, uint64_t* kmers, uint32_t* class_ids, uint32_t* rows, size_t capacity, uint64_t* n_written) {
@@ -881,5 +900,236 @@ extern "C" int bft_b200_query_sequences_file(bft_b200_ctx* c, const char* query_
         }
     }
     free(chars); free(offs); free(rows); free(status);
+    return rc;
+}
+
+/* ---- graph traversals (reference src/snippets.c) --------------------------------------------------------------- */
+extern "C" int bft_b200_graph_release(bft_b200_ctx* c) {
+    if (!c) return set_err(BFT_B200_ERR_ARG, "bft_b200_graph_release: NULL context");
+    cudaSetDevice(c->device);
+    if (c->graph.d_vk) cudaFree(c->graph.d_vk);
+    if (c->graph.d_vcls) cudaFree(c->graph.d_vcls);
+    if (c->graph.d_adj) cudaFree(c->graph.d_adj);
+    memset(&c->graph, 0, sizeof c->graph);
+    return 0;
+}
+
+/* scratch device arrays of one traversal call, freed together */
+struct dev_scratch {
+    void* p[24];
+    int n;
+    dev_scratch() : n(0) {}
+    ~dev_scratch() { for (int i = 0; i < n; i++) cudaFree(p[i]); }
+    template <typename T>
+    int get(T** out, size_t count) {
+        void* q = NULL;
+        const size_t bytes = (count ? count : 1) * sizeof(T) + 32;
+        if (n >= 24 || cudaMalloc(&q, bytes) != cudaSuccess) return set_err(BFT_B200_ERR_NOMEM, "graph traversal: cudaMalloc(%zu) failed", bytes);
+        p[n++] = q;
+        *out = (T*)q;
+        return 0;
+    }
+};
+
+extern "C" int bft_b200_graph_prepare(bft_b200_ctx* c) {
+    if (!c) return set_err(BFT_B200_ERR_ARG, "bft_b200_graph_prepare: NULL context");
+    if (c->graph.ready) return 0;
+    CK(cudaSetDevice(c->device));
+    const size_t n = (size_t)c->stats.n_kmers, W = (size_t)c->W;
+    const uint64_t n_loc = (uint64_t)c->dview.loc_leaf + c->n_pref;
+    if (n >= BFT_V_NONE || n_loc >= BFT_V_NONE) return set_err(BFT_B200_ERR_ARG, "graph traversal: %zu k-mers exceed the 32-bit vertex ids", n);
+    cudaStream_t st = c->streams[0];
+    CK(cudaStreamSynchronize(st));
+    bft_b200_graph_release(c);
+    dev_scratch tmp;
+    uint32_t* d_loc2vid = NULL;
+    int rc = tmp.get(&d_loc2vid, (size_t)n_loc);
+    if (rc) return rc;
+    if (cudaMalloc((void**)&c->graph.d_vk, (n + 1) * W * 8) != cudaSuccess || cudaMalloc((void**)&c->graph.d_vcls, (n + 1) * 4) != cudaSuccess ||
+        cudaMalloc((void**)&c->graph.d_adj, (n + 1) * 8 * 4) != cudaSuccess) {
+        bft_b200_graph_release(c);
+        return set_err(BFT_B200_ERR_NOMEM, "graph traversal: cudaMalloc failed for %zu vertices", n);
+    }
+    c->graph.n = n;
+    c->graph.bytes = (n + 1) * (W * 8 + 4 + 32);
+    rc = enqueue_extract(c, c->graph.d_vk, c->graph.d_vcls, d_loc2vid);
+    if (!rc && n) {
+        const int grid = grid_for(c, n * 8, BFT_TPB);
+#define BFT_L(W_) k_graph_adjacency<W_><<<grid, BFT_TPB, 0, st>>>(c->dview, c->graph.d_vk, n, d_loc2vid, c->graph.d_adj)
+        BFT_BY_W(c->W, BFT_L);
+#undef BFT_L
+        c->launches++;
+    }
+    cudaError_t e = cudaStreamSynchronize(st);
+    if (!rc && e != cudaSuccess) rc = set_err(BFT_B200_ERR_CUDA, "graph construction failed: %s", cudaGetErrorString(e));
+    if (rc) { bft_b200_graph_release(c); return rc; }
+    c->graph.ready = 1;
+    return 0;
+}
+
+extern "C" int bft_b200_graph_adjacency(bft_b200_ctx* c, uint32_t* adj, size_t capacity) {
+    if (!c || !adj) return set_err(BFT_B200_ERR_ARG, "bft_b200_graph_adjacency: NULL argument");
+    if (capacity < c->stats.n_kmers) return set_err(BFT_B200_ERR_ARG, "bft_b200_graph_adjacency: capacity %zu < %llu stored k-mers", capacity, (unsigned long long)c->stats.n_kmers);
+    int rc = bft_b200_graph_prepare(c);
+    if (rc) return rc;
+    CK(cudaMemcpy(adj, c->graph.d_adj, c->graph.n * 8 * sizeof(uint32_t), cudaMemcpyDeviceToHost));
+    return 0;
+}
+
+extern "C" int bft_b200_connected_components(bft_b200_ctx* c, const uint32_t* genome_ids, int n_ids, uint64_t* n_components, uint32_t* labels) {
+    if (!c || !n_components || n_ids < 0 || (n_ids && !genome_ids)) return set_err(BFT_B200_ERR_ARG, "bft_b200_connected_components: bad argument");
+    for (int i = 1; i < n_ids; i++)
+        if (genome_ids[i] <= genome_ids[i - 1])
+            return set_err(BFT_B200_ERR_ARG, "bft_b200_connected_components: genome ids must be strictly ascending (is_in_subgraph() walks them in order)");
+    int rc = bft_b200_graph_prepare(c);
+    if (rc) return rc;
+    const size_t n = c->graph.n;
+    cudaStream_t st = c->streams[0];
+    *n_components = 0;
+    if (n_ids && genome_ids[n_ids - 1] >= (uint32_t)c->G) { /* no k-mer carries a genome that was never inserted */
+        if (labels) memset(labels, 0xff, n * sizeof(uint32_t));
+        return 0;
+    }
+    dev_scratch tmp;
+    uint32_t *d_parent = NULL, *d_labels = NULL, *d_want = NULL;
+    uint8_t* d_in = NULL;
+    unsigned long long* d_cnt = NULL;
+    if ((rc = tmp.get(&d_parent, n)) || (rc = tmp.get(&d_cnt, 1)) || (labels && (rc = tmp.get(&d_labels, n)))) return rc;
+    if (n_ids) {
+        if ((rc = tmp.get(&d_want, (size_t)c->rw)) || (rc = tmp.get(&d_in, c->n_classes + 1))) return rc;
+        CK(cudaMemsetAsync(d_want, 0, (size_t)c->rw * 4, st));
+        for (int i = 0; i < n_ids; i++) { /* a handful of ids: set their bits one by one */
+            uint32_t word = 0;
+            for (int j = 0; j < n_ids; j++)
+                if ((genome_ids[j] >> 5) == (genome_ids[i] >> 5)) word |= 1u << (genome_ids[j] & 31);
+            CK(cudaMemcpyAsync(d_want + (genome_ids[i] >> 5), &word, 4, cudaMemcpyHostToDevice, st));
+            CK(cudaStreamSynchronize(st));
+        }
+        k_graph_class_filter<<<grid_for(c, c->n_classes, BFT_TPB), BFT_TPB, 0, st>>>(c->d_class_rows, c->rw, c->n_classes, d_want, d_in);
+        c->launches++;
+    }
+    CK(cudaMemsetAsync(d_cnt, 0, sizeof(unsigned long long), st));
+    if (n) {
+        const int grid = grid_for(c, n, BFT_TPB);
+        k_graph_iota<<<grid, BFT_TPB, 0, st>>>(d_parent, n);
+        k_graph_hook<<<grid, BFT_TPB, 0, st>>>(c->graph.d_adj, c->graph.d_vcls, d_in, n, d_parent);
+        k_graph_labels<<<grid, BFT_TPB, 0, st>>>(d_parent, c->graph.d_vcls, d_in, n, d_labels, d_cnt);
+        c->launches += 3;
+    }
+    unsigned long long h = 0;
+    CK(cudaMemcpyAsync(&h, d_cnt, sizeof h, cudaMemcpyDeviceToHost, st));
+    if (labels && n) CK(cudaMemcpyAsync(labels, d_labels, n * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    *n_components = h;
+    return 0;
+}
+
+extern "C" void bft_b200_free(void* p) { free(p); }
+
+extern "C" int bft_b200_simple_paths(bft_b200_ctx* c, double core_ratio, char** paths, size_t* n_bytes, uint64_t* n_paths, uint64_t* longest) {
+    if (!c || !paths || !n_bytes) return set_err(BFT_B200_ERR_ARG, "bft_b200_simple_paths: NULL argument");
+    if (!(core_ratio >= 0.0 && core_ratio <= 1.0)) return set_err(BFT_B200_ERR_ARG, "bft_b200_simple_paths: core_ratio %g outside [0, 1]", core_ratio);
+    *paths = NULL;
+    *n_bytes = 0;
+    int rc = bft_b200_graph_prepare(c);
+    if (rc) return rc;
+    const size_t n = c->graph.n;
+    const uint32_t core = (uint32_t)(int)(core_ratio * c->G); /* nb_genomes_core, src/snippets.c:366 */
+    cudaStream_t st = c->streams[0];
+    dev_scratch tmp;
+    uint8_t* d_chain = NULL;
+    uint32_t *d_usucc = NULL, *d_next = NULL, *d_prev = NULL, *d_to[2] = {NULL, NULL}, *d_dist[2] = {NULL, NULL}, *d_low[2] = {NULL, NULL};
+    unsigned long long *d_size = NULL, *d_offs = NULL, *d_stats = NULL;
+    int* d_pending = NULL;
+    if ((rc = tmp.get(&d_chain, n)) || (rc = tmp.get(&d_usucc, n)) || (rc = tmp.get(&d_next, n)) || (rc = tmp.get(&d_prev, n)) ||
+        (rc = tmp.get(&d_to[0], n)) || (rc = tmp.get(&d_to[1], n)) || (rc = tmp.get(&d_dist[0], n)) || (rc = tmp.get(&d_dist[1], n)) ||
+        (rc = tmp.get(&d_size, n + 1)) || (rc = tmp.get(&d_offs, n + 1)) || (rc = tmp.get(&d_stats, 2)) || (rc = tmp.get(&d_pending, 1)))
+        return rc;
+    const int grid = grid_for(c, n ? n : 1, BFT_TPB);
+    CK(cudaMemsetAsync(d_prev, 0xff, (n + 1) * 4, st));
+    CK(cudaMemsetAsync(d_size, 0, (n + 1) * 8, st));
+    CK(cudaMemsetAsync(d_stats, 0, 16, st));
+    k_paths_vertices<<<grid, BFT_TPB, 0, st>>>(c->graph.d_adj, c->graph.d_vcls, c->d_class_counts, core, n, d_chain, d_usucc);
+    k_paths_link<<<grid, BFT_TPB, 0, st>>>(d_chain, d_usucc, c->graph.d_vcls, c->d_class_rows, c->rw, core, n, d_next, d_prev);
+    c->launches += 2;
+    int max_rounds = 2;
+    while (((size_t)1 << (max_rounds - 2)) < n + 1) max_rounds++; /* ceil(log2(n + 1)) + 2 */
+    int cur = 0;
+    for (int attempt = 0; attempt < 2; attempt++) {
+        /* attempt 0: rank the chains; pointers still short of a head after max_rounds sit on cycles of chain vertices:
+         * redo the doubling carrying the smallest vertex id, open each cycle there, rank again */
+        cur = 0;
+        k_paths_rank_init<<<grid, BFT_TPB, 0, st>>>(d_chain, d_prev, n, d_to[0], d_dist[0], (uint32_t*)NULL);
+        c->launches++;
+        int pending = 1;
+        for (int r = 0; r < max_rounds && pending; r++) {
+            CK(cudaMemsetAsync(d_pending, 0, sizeof(int), st));
+            k_paths_rank_step<<<grid, BFT_TPB, 0, st>>>(d_to[cur], d_dist[cur], (const uint32_t*)NULL, d_prev, n, d_to[cur ^ 1], d_dist[cur ^ 1],
+                                                        (uint32_t*)NULL, d_pending);
+            c->launches++;
+            CK(cudaMemcpyAsync(&pending, d_pending, sizeof(int), cudaMemcpyDeviceToHost, st));
+            CK(cudaStreamSynchronize(st));
+            cur ^= 1;
+        }
+        if (!pending) break;
+        if (attempt == 1) return set_err(BFT_B200_ERR_CUDA, "bft_b200_simple_paths: chain ranking did not converge");
+        uint8_t* d_cut = NULL;
+        if ((rc = tmp.get(&d_low[0], n)) || (rc = tmp.get(&d_low[1], n)) || (rc = tmp.get(&d_cut, n))) return rc;
+        int lc = 0;
+        k_paths_rank_init<<<grid, BFT_TPB, 0, st>>>(d_chain, d_prev, n, d_to[0], d_dist[0], d_low[0]);
+        for (int r = 0; r < max_rounds; r++, lc ^= 1)
+            k_paths_rank_step<<<grid, BFT_TPB, 0, st>>>(d_to[lc], d_dist[lc], d_low[lc], d_prev, n, d_to[lc ^ 1], d_dist[lc ^ 1], d_low[lc ^ 1], d_pending);
+        k_paths_find_cuts<<<grid, BFT_TPB, 0, st>>>(d_chain, d_to[lc], d_low[lc], d_prev, n, d_cut);
+        k_paths_apply_cuts<<<grid, BFT_TPB, 0, st>>>(d_cut, n, d_next, d_prev);
+        c->launches += 3 + (uint64_t)max_rounds;
+    }
+    k_paths_sizes<<<grid, BFT_TPB, 0, st>>>(d_chain, d_next, d_to[cur], d_dist[cur], n, c->k, d_size, d_stats);
+    c->launches++;
+    {
+        void* d_tmp = NULL;
+        size_t tmp_bytes = 0;
+        cub::DeviceScan::ExclusiveSum(d_tmp, tmp_bytes, d_size, d_offs, (int64_t)(n + 1), st);
+        unsigned char* d_scan = NULL;
+        if ((rc = tmp.get(&d_scan, tmp_bytes))) return rc;
+        CK(cub::DeviceScan::ExclusiveSum((void*)d_scan, tmp_bytes, d_size, d_offs, (int64_t)(n + 1), st));
+    }
+    unsigned long long total = 0, stats[2] = {0, 0};
+    CK(cudaMemcpyAsync(&total, d_offs + n, 8, cudaMemcpyDeviceToHost, st)); /* size[n] == 0, so offs[n] is the grand total */
+    CK(cudaMemcpyAsync(stats, d_stats, 16, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    char* d_out = NULL;
+    if ((rc = tmp.get(&d_out, (size_t)total))) return rc;
+    if (n) {
+#define BFT_L(W_) k_paths_write<W_><<<grid, BFT_TPB, 0, st>>>(d_chain, d_next, d_to[cur], d_dist[cur], d_offs, c->graph.d_vk, n, c->k, d_out)
+        BFT_BY_W(c->W, BFT_L);
+#undef BFT_L
+        c->launches++;
+    }
+    char* h = (char*)malloc((size_t)total + 1);
+    if (!h) return set_err(BFT_B200_ERR_NOMEM, "bft_b200_simple_paths: out of host memory (%llu bytes)", total);
+    cudaError_t e = cudaMemcpyAsync(h, d_out, (size_t)total, cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+    if (e != cudaSuccess) { free(h); return set_err(BFT_B200_ERR_CUDA, "bft_b200_simple_paths: %s", cudaGetErrorString(e)); }
+    h[total] = 0;
+    *paths = h;
+    *n_bytes = (size_t)total;
+    if (n_paths) *n_paths = stats[0];
+    if (longest) *longest = stats[1];
+    return 0;
+}
+
+extern "C" int bft_b200_simple_paths_file(bft_b200_ctx* c, double core_ratio, const char* out_path, uint64_t* n_paths, uint64_t* longest) {
+    if (!c || !out_path) return set_err(BFT_B200_ERR_ARG, "bft_b200_simple_paths_file: NULL argument");
+    char* buf = NULL;
+    size_t nb = 0;
+    int rc = bft_b200_simple_paths(c, core_ratio, &buf, &nb, n_paths, longest);
+    if (rc) return rc;
+    FILE* f = fopen(out_path, "w");
+    if (!f) rc = set_err(BFT_B200_ERR_FILE, "extract_simple_paths_to_disk(): failed to create output file %s", out_path);
+    else {
+        if (fwrite(buf, 1, nb, f) != nb) rc = set_err(BFT_B200_ERR_FILE, "could not write %s", out_path);
+        fclose(f);
+    }
+    free(buf);
     return rc;
 }

@@ -583,6 +583,9 @@ void bft_arena_view(const bft_arena_t* a, bft_view_t* v) {
     v->cls_mask = a->cls_mask;
     v->k = a->k;
     v->W = a->W;
+    v->loc_ovf = (uint32_t)(a->n_buckets * BFT_BUCKET_KEYS);
+    v->loc_uc = v->loc_ovf + (uint32_t)a->n_ovf;
+    v->loc_leaf = v->loc_uc + (uint32_t)a->n_uc_lines;
 }
 
 void bft_arena_free(bft_arena_t* a) {

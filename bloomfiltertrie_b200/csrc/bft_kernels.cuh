@@ -263,7 +263,7 @@ __device__ __forceinline__ void bft_emit_kmer(const uint64_t* base, const uint64
 
 template <int W>
 __global__ void __launch_bounds__(BFT_TPB) k_extract_prefix_kmers(const bft_view_t v, size_t n_pref, uint64_t* __restrict__ kmers,
-                                                                  uint32_t* __restrict__ cls_out) {
+                                                                  uint32_t* __restrict__ cls_out, uint32_t* __restrict__ loc2vid) {
     const int lane = threadIdx.x & 31;
     const size_t warp_stride = ((size_t)gridDim.x * blockDim.x) >> 5;
     const int shift = v.cls_shift;
@@ -288,6 +288,7 @@ __global__ void __launch_bounds__(BFT_TPB) k_extract_prefix_kmers(const bft_view
             if (lane == 0) {
                 for (int w = 0; w < W; w++) kmers[out * W + w] = base[w];
                 if (cls_out) cls_out[out] = e.a;
+                if (loc2vid) loc2vid[v.loc_leaf + j] = (uint32_t)out;
             }
             continue;
         }
@@ -320,6 +321,7 @@ __global__ void __launch_bounds__(BFT_TPB) k_extract_prefix_kmers(const bft_view
                 bft_emit_kmer<W>(base, key, shift_bits, km);
                 for (int w = 0; w < W; w++) kmers[my * W + w] = km[w];
                 if (cls_out) cls_out[my] = c;
+                if (loc2vid) loc2vid[gslot] = (uint32_t)my;
             } else if (n_emit) { /* overflow run of this bucket */
                 for (uint32_t i = 0; i < n_emit; i++) {
                     uint64_t ok[W];
@@ -330,6 +332,7 @@ __global__ void __launch_bounds__(BFT_TPB) k_extract_prefix_kmers(const bft_view
                     bft_emit_kmer<W>(base, ok, shift_bits, km);
                     for (int w = 0; w < W; w++) kmers[(my + i) * W + w] = km[w];
                     if (cls_out) cls_out[my + i] = c;
+                    if (loc2vid) loc2vid[v.loc_ovf + ovf_start + i] = (uint32_t)(my + i);
                 }
             }
         }
@@ -339,7 +342,7 @@ __global__ void __launch_bounds__(BFT_TPB) k_extract_prefix_kmers(const bft_view
 /* the Nodes' own UC lines: whole remainders below the Node's path (one thread per Node, <= 255 lines each) */
 template <int W>
 __global__ void __launch_bounds__(BFT_TPB) k_extract_uc_kmers(const bft_view_t v, size_t n_nodes, uint64_t* __restrict__ kmers,
-                                                              uint32_t* __restrict__ cls_out) {
+                                                              uint32_t* __restrict__ cls_out, uint32_t* __restrict__ loc2vid) {
     const size_t stride = (size_t)gridDim.x * blockDim.x;
     for (size_t nid = (size_t)blockIdx.x * blockDim.x + threadIdx.x; nid < n_nodes; nid += stride) {
         const bft_node_t nd = v.nodes[nid];
@@ -356,6 +359,7 @@ __global__ void __launch_bounds__(BFT_TPB) k_extract_uc_kmers(const bft_view_t v
             else bft_emit_kmer<W>(base, key, BFT_PREFIX_BITS * (int)path.depth, km);
             for (int w = 0; w < W; w++) kmers[(out + i) * W + w] = km[w];
             if (cls_out) cls_out[out + i] = v.uccls[nd.uc_begin + i];
+            if (loc2vid) loc2vid[v.loc_uc + nd.uc_begin + i] = (uint32_t)(out + i);
         }
     }
 }

@@ -30,6 +30,8 @@ ABI_SYMBOLS = [
     "bft_b200_query_sequences_file", "bft_b200_sync", "bft_b200_launch_count", "bft_b200_kmer_walk_stats_device", "bft_b200_random_gather_probe",
     "bft_b200_extract_kmers", "bft_b200_extract_kmers_device", "bft_b200_extract_kmers_file",
     "bft_b200_device_alloc", "bft_b200_device_free", "bft_b200_peer_export", "bft_b200_peer_import", "bft_b200_peer_close",
+    "bft_b200_graph_prepare", "bft_b200_graph_release", "bft_b200_graph_adjacency", "bft_b200_connected_components",
+    "bft_b200_simple_paths", "bft_b200_simple_paths_file", "bft_b200_free",
 ]
 
 
@@ -97,6 +99,14 @@ def load_library() -> C.CDLL:
     lib.bft_b200_peer_export.argtypes = [vp, vp, C.c_char_p]
     lib.bft_b200_peer_import.argtypes = [vp, C.c_char_p, C.POINTER(vp)]
     lib.bft_b200_peer_close.argtypes = [vp, vp]
+    lib.bft_b200_graph_prepare.argtypes = [vp]
+    lib.bft_b200_graph_release.argtypes = [vp]
+    lib.bft_b200_graph_adjacency.argtypes = [vp, u32p, sz]
+    lib.bft_b200_connected_components.argtypes = [vp, u32p, C.c_int, C.POINTER(C.c_uint64), u32p]
+    lib.bft_b200_simple_paths.argtypes = [vp, C.c_double, C.POINTER(vp), C.POINTER(sz), C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
+    lib.bft_b200_simple_paths_file.argtypes = [vp, C.c_double, C.c_char_p, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
+    lib.bft_b200_free.argtypes = [vp]
+    lib.bft_b200_free.restype = None
     lib.bft_b200_sync.argtypes = [vp]
     lib.bft_b200_launch_count.argtypes = [vp]
     lib.bft_b200_launch_count.restype = C.c_uint64
@@ -346,6 +356,49 @@ class BFTEngine:
     def extract_kmers_file(self, path: str, compressed_output: bool = True):
         self._ck(self.lib.bft_b200_extract_kmers_file(self.h, os.fsencode(path), int(bool(compressed_output))),
                  "bft_b200_extract_kmers_file")
+
+    # -- graph traversals (reference src/snippets.c)
+    def graph_prepare(self):
+        self._ck(self.lib.bft_b200_graph_prepare(self.h), "bft_b200_graph_prepare")
+
+    def graph_release(self):
+        self._ck(self.lib.bft_b200_graph_release(self.h), "bft_b200_graph_release")
+
+    def graph_adjacency(self) -> np.ndarray:
+        """uint32 [n_kmers, 8]: vertex index of each possible neighbour (0-3 predecessors, 4-7 successors) or 0xffffffff."""
+        n = int(self.stats()["n_kmers"])
+        adj = np.empty((n, 8), dtype=np.uint32)
+        self._ck(self.lib.bft_b200_graph_adjacency(self.h, _ptr(adj), n), "bft_b200_graph_adjacency")
+        return adj
+
+    def connected_components(self, genome_ids=(), want_labels: bool = False):
+        """Number of connected components of the graph (or of the colour subgraph); optionally the per-k-mer labels."""
+        ids = np.asarray(list(genome_ids), dtype=np.uint32)
+        n = int(self.stats()["n_kmers"])
+        labels = np.empty(n, dtype=np.uint32) if want_labels else None
+        out = C.c_uint64()
+        self._ck(self.lib.bft_b200_connected_components(self.h, _ptr(ids) if len(ids) else None, len(ids), C.byref(out), _ptr(labels)),
+                 "bft_b200_connected_components")
+        return (int(out.value), labels) if want_labels else int(out.value)
+
+    def simple_paths(self, core_ratio: float = 0.0):
+        """(list of path strings as bytes, longest length). core_ratio 0: all simple paths."""
+        buf, nb, n_paths, longest = C.c_void_p(), C.c_size_t(), C.c_uint64(), C.c_uint64()
+        self._ck(self.lib.bft_b200_simple_paths(self.h, float(core_ratio), C.byref(buf), C.byref(nb), C.byref(n_paths), C.byref(longest)),
+                 "bft_b200_simple_paths")
+        try:
+            raw = C.string_at(buf.value, nb.value) if nb.value else b""
+        finally:
+            self.lib.bft_b200_free(buf)
+        lines = raw.split(b"\n")[:-1] if raw else []
+        assert len(lines) == n_paths.value
+        return lines, int(longest.value)
+
+    def simple_paths_file(self, path: str, core_ratio: float = 0.0):
+        n_paths, longest = C.c_uint64(), C.c_uint64()
+        self._ck(self.lib.bft_b200_simple_paths_file(self.h, float(core_ratio), os.fsencode(path), C.byref(n_paths), C.byref(longest)),
+                 "bft_b200_simple_paths_file")
+        return int(n_paths.value), int(longest.value)
 
     # -- file-level drivers
     def query_kmers_file(self, query_path: str, binary: bool, csv_path: str) -> int:

@@ -182,6 +182,42 @@ int bft_b200_sync(bft_b200_ctx* ctx);
 /* number of kernels this context has launched (bench.py's gpu_launches) */
 uint64_t bft_b200_launch_count(const bft_b200_ctx* ctx);
 
+/* ---- graph traversals (reference src/snippets.c) ----------------------------------------------
+ * The coloured de Bruijn graph is materialised on the device once (one vertex per stored k-mer, in the order of
+ * bft_b200_extract_kmers; 8 neighbour look-ups per vertex) and the reference's traversal snippets run on it as
+ * data-parallel kernels. Neighbourhood is plain set membership of the 8 possible neighbours (get_neighbors,
+ * include/bft.h:156). Results that do not depend on the reference's iteration order are identical to its own. */
+
+/* Build the device graph now (otherwise the first traversal call does). bft_b200_graph_release frees it. */
+int bft_b200_graph_prepare(bft_b200_ctx* ctx);
+int bft_b200_graph_release(bft_b200_ctx* ctx);
+
+/* adj[8 * i + j]: vertex index of the j-th possible neighbour of k-mer i (j = 0-3 predecessors prepending A,C,G,T;
+ * 4-7 successors appending A,C,G,T — the order of get_neighbors), or 0xffffffff when it is not in the graph.
+ * capacity in k-mers, >= stats.n_kmers. */
+int bft_b200_graph_adjacency(bft_b200_ctx* ctx, uint32_t* adj, size_t capacity);
+
+/* get_nb_connected_component (src/snippets.c:937-958) with BFS / DFS (n_ids == 0: the whole graph) or with
+ * BFS_subgraph / DFS_subgraph (n_ids > 0: the subgraph of the k-mers whose colour set holds every listed genome id,
+ * is_in_subgraph :824-881; ids strictly ascending, as that function requires). labels (optional, stats.n_kmers
+ * entries, order of bft_b200_extract_kmers): smallest vertex index of the k-mer's component, 0xffffffff for k-mers
+ * outside the subgraph. */
+int bft_b200_connected_components(bft_b200_ctx* ctx, const uint32_t* genome_ids, int n_ids, uint64_t* n_components,
+                                  uint32_t* labels);
+
+/* extract_simple_core_paths_to_disk (src/snippets.c:346-596): every maximal non-branching path over k-mers with fewer
+ * than two successors and fewer than two predecessors, consecutive k-mers sharing at least (int)(core_ratio * genomes)
+ * genomes; one line per path (first k-mer, then the last character of each following k-mer, then a newline).
+ * core_ratio = 0 is extract_simple_paths_to_disk (:115-344). The lines come in vertex order of their first k-mer, not
+ * in the reference's trie order; a cycle of non-branching k-mers is opened at its smallest vertex.
+ * *paths is malloc'd by the library (release with bft_b200_free), *n_bytes its length; n_paths / longest (characters
+ * of the longest line, the reference's "Longest simple path has %d nuc.") are optional. */
+int bft_b200_simple_paths(bft_b200_ctx* ctx, double core_ratio, char** paths, size_t* n_bytes, uint64_t* n_paths,
+                          uint64_t* longest);
+int bft_b200_simple_paths_file(bft_b200_ctx* ctx, double core_ratio, const char* out_path, uint64_t* n_paths,
+                               uint64_t* longest);
+void bft_b200_free(void* p);
+
 #ifdef __cplusplus
 }
 #endif

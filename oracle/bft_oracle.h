@@ -35,4 +35,11 @@ int o_branching_left(o_bft* b, const uint8_t* kmer);
  * ids as in o_query_kmer. */
 int o_query_sequence(o_bft* b, const char* seq, double threshold, int canonical, uint32_t* ids);
 
+
+/* ---- graph traversals (bft_graph_oracle.c; reference src/snippets.c) ------------------------------------------------
+ * kmers: every stored k-mer as ASCII, n * k characters, in the order iterate_over_kmers visits them. */
+int64_t o_connected_components(o_bft* b, const char* kmers, size_t n, const uint32_t* ids, int n_ids, uint32_t* labels);
+char* o_simple_paths(o_bft* b, const char* kmers, size_t n, double core_ratio, int faithful, size_t* n_bytes, int* longest);
+void o_free_buf(void* p);
+
 #endif

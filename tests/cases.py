@@ -115,6 +115,37 @@ def case_structured(k: int, n_genomes: int, vocab: int, n_units: int, seed: int)
     return dict(k=k, genome_words=per, queries=q, seqs=_reads_with_edge_cases(genomes, k, seed + 3, n_reads=150), canonical=False)
 
 
+def case_cycles(k: int, n_genomes: int, seed: int) -> Dict:
+    """Graph shapes for the traversal tests: closed loops of non-branching k-mers (circular replicons: every window of
+    the circle including the ones across the junction), a loop with a tail, linear pieces with SNP bubbles, a tandem
+    repeat, isolated k-mers and a homopolymer self-loop."""
+    rng = np.random.default_rng(seed)
+
+    def circ_windows(codes):
+        return synth.pack_windows(np.concatenate([codes, codes[: k - 1]]), k)
+
+    circles = [rng.integers(0, 4, size=n, dtype=np.uint8) for n in (k + 5, 300, 1200, 2 * k)]
+    base = synth.make_pangenome(n_genomes, 6000, 0.01, indel=0.001, seed=seed + 1)
+    unit = rng.integers(0, 4, size=40, dtype=np.uint8)
+    tandem = np.concatenate([rng.integers(0, 4, size=100, dtype=np.uint8), np.tile(unit, 6), rng.integers(0, 4, size=100, dtype=np.uint8)])
+    lollipop = rng.integers(0, 4, size=500, dtype=np.uint8)
+    lollipop = np.concatenate([lollipop, lollipop[200: 200 + k + 30]])   # runs back into itself: a loop with a tail
+    homo = np.zeros(k + 3, dtype=np.uint8)                                 # AAAA...: one k-mer, its own neighbour
+    singles = [rng.integers(0, 4, size=k, dtype=np.uint8) for _ in range(20)]
+    per = []
+    for g in range(n_genomes):
+        parts = [synth.pack_windows(base[g], k), synth.pack_windows(tandem, k)]
+        parts += [circ_windows(c) for i, c in enumerate(circles) if (i + g) % 2 == 0 or g == 0]
+        if g != 1:
+            parts += [synth.pack_windows(lollipop, k), synth.pack_windows(homo, k)]
+        parts += [synth.pack_windows(s, k) for s in singles[g::n_genomes]]
+        per.append(np.unique(np.concatenate(parts), axis=0))
+    allw = np.unique(np.concatenate(per), axis=0)
+    q = np.concatenate([synth.sample_kmer_queries(base, k, 3000, seed + 2, frac_present=0.6, frac_mismatch=0.3),
+                        synth.near_miss_queries(allw, k, 2000, seed + 3)])
+    return dict(k=k, genome_words=per, queries=q, seqs=_reads_with_edge_cases(base, k, seed + 4, n_reads=80), canonical=False)
+
+
 CASES = {
     # name: (factory, kwargs)
     "shallow_k27_g4": (case_shallow, dict(k=27, n_genomes=4, seed=101)),
@@ -137,6 +168,8 @@ CASES = {
     "structured_k27_g2": (case_structured, dict(k=27, n_genomes=2, vocab=3, n_units=5_000, seed=408)),
     "lowcomplex_k27_g3": (case_lowcomplexity, dict(k=27, n_genomes=3, length=100_000, seed=405)),
     "lowcomplex_k45_g2": (case_lowcomplexity, dict(k=45, n_genomes=2, length=100_000, seed=406)),
+    "cycles_k27_g3": (case_cycles, dict(k=27, n_genomes=3, seed=601)),
+    "cycles_k63_g2": (case_cycles, dict(k=63, n_genomes=2, seed=602)),
     "pan_k27_g100": (case_pangenome, dict(k=27, n_genomes=100, seed=303)),
     "pan_k27_g1000": (case_pangenome, dict(k=27, n_genomes=1000, length=2_000, seed=304)),
     # four-word keys (63 < k <= 126, the reference's KMER_LENGTH_MAX); only inputs on which the reference's own

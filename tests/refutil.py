@@ -170,3 +170,98 @@ def oracle_sequences(bft_path: str, seqs: Sequence[bytes], threshold: float, can
 def split_seqs(chars: np.ndarray, offs: np.ndarray) -> List[bytes]:
     b = chars.tobytes()
     return [b[int(offs[i]):int(offs[i + 1])] for i in range(len(offs) - 1)]
+
+
+# ---- graph traversals (reference src/snippets.c) ------------------------------------------------------------------
+REF_GRAPH = os.path.join(REF_DIR, "ref_graph")
+ORACLE_LIB = os.path.join(ROOT, "oracle", "liboracle_bft.so")
+
+
+def have_ref_graph() -> bool:
+    return os.access(REF_GRAPH, os.X_OK)
+
+
+def ref_extract_ascii(bft_path: str, workdir: str) -> bytes:
+    """Every stored k-mer in the reference's iterate_over_kmers order (`-extract_kmers kmers`), concatenated (n * k chars)."""
+    out = os.path.join(workdir, f"extract_{os.getpid()}.txt")
+    ref_cli(bft_path, ["-extract_kmers", "kmers", out], cwd=workdir)
+    with open(out, "rb") as f:
+        data = f.read()
+    os.remove(out)
+    return data.replace(b"\n", b"")
+
+
+def ref_components(bft_path: str, mode: str = "bfs", ids: Sequence[int] = ()) -> int:
+    out = _run([REF_GRAPH, "components", bft_path, mode] + [str(i) for i in ids], cwd=os.path.dirname(bft_path))
+    m = re.search(r"REF_COMPONENTS (\d+)", out)
+    return int(m.group(1))
+
+
+def ref_core_paths(bft_path: str, ratio: float, workdir: str) -> Tuple[bytes, int]:
+    """Bytes extract_simple_core_paths_to_disk writes, and the length it prints."""
+    out = os.path.join(workdir, f"paths_{os.getpid()}.txt")
+    log = _run([REF_GRAPH, "core_paths", bft_path, repr(float(ratio)), out], cwd=workdir)
+    with open(out, "rb") as f:
+        data = f.read()
+    os.remove(out)
+    m = re.search(r"Longest simple core path has (\d+) nuc", log)
+    return data, int(m.group(1))
+
+
+_olib = None
+
+
+def oracle_lib():
+    import ctypes as C
+    global _olib
+    if _olib is None:
+        ensure_oracle()
+        lib = C.CDLL(ORACLE_LIB)
+        lib.o_load.restype = C.c_void_p
+        lib.o_load.argtypes = [C.c_char_p, C.c_char_p, C.c_size_t]
+        lib.o_free.argtypes = [C.c_void_p]
+        lib.o_k.argtypes = [C.c_void_p]
+        lib.o_connected_components.restype = C.c_int64
+        lib.o_connected_components.argtypes = [C.c_void_p, C.c_char_p, C.c_size_t, C.c_void_p, C.c_int, C.c_void_p]
+        lib.o_simple_paths.restype = C.c_void_p
+        lib.o_simple_paths.argtypes = [C.c_void_p, C.c_char_p, C.c_size_t, C.c_double, C.c_int, C.POINTER(C.c_size_t), C.POINTER(C.c_int)]
+        lib.o_free_buf.argtypes = [C.c_void_p]
+        _olib = lib
+    return _olib
+
+
+class OracleGraph:
+    """The oracle's sequential restatement of src/snippets.c over a given k-mer list (ASCII, n * k characters)."""
+
+    def __init__(self, bft_path: str, kmers_ascii: bytes):
+        import ctypes as C
+        self.lib = oracle_lib()
+        err = C.create_string_buffer(256)
+        self.h = self.lib.o_load(os.fsencode(bft_path), err, 256)
+        if not self.h:
+            raise RuntimeError(err.value.decode())
+        self.k = self.lib.o_k(self.h)
+        self.kmers = kmers_ascii
+        self.n = len(kmers_ascii) // self.k
+
+    def close(self):
+        if self.h:
+            self.lib.o_free(self.h)
+            self.h = None
+
+    def components(self, ids: Sequence[int] = (), want_labels: bool = False):
+        arr = np.asarray(list(ids), dtype=np.uint32)
+        labels = np.empty(self.n, dtype=np.uint32) if want_labels else None
+        r = self.lib.o_connected_components(self.h, self.kmers, self.n, arr.ctypes.data if len(arr) else None, len(arr),
+                                            labels.ctypes.data if want_labels else None)
+        assert r >= 0
+        return (int(r), labels) if want_labels else int(r)
+
+    def simple_paths(self, ratio: float, faithful: bool) -> Tuple[bytes, int]:
+        import ctypes as C
+        nb, longest = C.c_size_t(), C.c_int()
+        p = self.lib.o_simple_paths(self.h, self.kmers, self.n, float(ratio), int(faithful), C.byref(nb), C.byref(longest))
+        assert p
+        data = C.string_at(p, nb.value)
+        self.lib.o_free_buf(p)
+        return data, int(longest.value)

@@ -14,7 +14,7 @@ from bloomfiltertrie_b200 import shard, synth
 
 ROOT = refutil.ROOT
 CSRC = os.path.join(ROOT, "bloomfiltertrie_b200", "csrc")
-NAMES = sorted(os.path.basename(p)[:-4] for p in glob.glob(os.path.join(refutil.GOLDEN, "*.npz")))
+NAMES = sorted(os.path.basename(p)[:-4] for p in glob.glob(os.path.join(refutil.GOLDEN, "golden_*.npz")))
 
 
 def _gcc(args, **kw):

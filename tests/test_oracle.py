@@ -10,7 +10,7 @@ import pytest
 import cases
 import refutil
 
-NAMES = sorted(os.path.basename(p)[:-4] for p in glob.glob(os.path.join(refutil.GOLDEN, "*.npz")))
+NAMES = sorted(os.path.basename(p)[:-4] for p in glob.glob(os.path.join(refutil.GOLDEN, "golden_*.npz")))
 
 
 @pytest.mark.parametrize("name", NAMES)
@@ -50,3 +50,54 @@ def test_oracle_matches_compiled_reference(name, workdir):
     for canonical in (False, True):
         np.testing.assert_array_equal(refutil.oracle_sequences(bft, seqs, 0.8, canonical, G, workdir),
                                       refutil.ref_sequences(bft, seqs, 0.8, canonical, G))
+
+
+# ---- graph traversals (src/snippets.c): oracle/bft_graph_oracle.c ----------------------------------------------------
+import graphutil  # noqa: E402
+
+GRAPH_NAMES = sorted(os.path.basename(p)[len("graph_"):-4] for p in glob.glob(os.path.join(refutil.GOLDEN, "graph_*.npz")))
+
+
+@pytest.mark.parametrize("name", GRAPH_NAMES)
+def test_graph_oracle_reproduces_golden(name):
+    """Component counts equal the reference's; its path lines, with a branching end k-mer dropped (graphutil), are the
+    oracle's order-independent paths — the k-mer list here comes from the case generator, not from the reference."""
+    z = np.load(os.path.join(refutil.GOLDEN, "graph_" + name + ".npz"))
+    c = cases.make_golden_case(name)
+    k = c["k"]
+    asc = graphutil.case_kmers_ascii(c)
+    og = refutil.OracleGraph(os.path.join(refutil.GOLDEN, name + ".bft"), asc)
+    try:
+        assert og.components() == int(z["n_components"])
+        kset = set(graphutil.kmer_list(asc, k))
+        for r in z["ratios"]:
+            ref_lines = z[f"paths_r{r}"].tobytes().split(b"\n")
+            mine, longest = og.simple_paths(float(r), faithful=False)
+            assert graphutil.normal_paths(graphutil.trim_branching_ends(ref_lines, kset, k), k) == graphutil.normal_paths(mine.split(b"\n"), k)
+            assert longest <= int(z[f"longest_r{r}"]) <= longest + 2
+    finally:
+        og.close()
+
+
+@pytest.mark.skipif(not (refutil.have_ref() and refutil.have_ref_graph()), reason="compiled reference (oracle/_ref) not present")
+@pytest.mark.parametrize("name", ["cycles_k27_g3", "cycles_k63_g2", "canon_k45_g3", "repeats_k36_g3"])
+def test_graph_oracle_matches_compiled_reference(name, workdir):
+    """Same iteration order as the reference (its own -extract_kmers output): the statement-by-statement restatement
+    must write the very bytes extract_simple_core_paths_to_disk writes, and count the components BFS and DFS count."""
+    c = cases.make_case(name)
+    k = c["k"]
+    bft = refutil.build_bft(workdir, "og_" + name, c["genome_words"], k)
+    asc = refutil.ref_extract_ascii(bft, workdir)
+    assert sorted(graphutil.kmer_list(asc, k)) == sorted(graphutil.kmer_list(graphutil.case_kmers_ascii(c), k))
+    og = refutil.OracleGraph(bft, asc)
+    try:
+        n = og.components()
+        assert n == refutil.ref_components(bft, "bfs") == refutil.ref_components(bft, "dfs")
+        ref_bytes, ref_longest = refutil.ref_core_paths(bft, 0.0, workdir)
+        mine, longest = og.simple_paths(0.0, faithful=True)
+        assert mine == ref_bytes and longest == ref_longest
+        kset = set(graphutil.kmer_list(asc, k))
+        clean, _ = og.simple_paths(0.0, faithful=False)
+        assert graphutil.normal_paths(graphutil.trim_branching_ends(ref_bytes.split(b"\n"), kset, k), k) == graphutil.normal_paths(clean.split(b"\n"), k)
+    finally:
+        og.close()
