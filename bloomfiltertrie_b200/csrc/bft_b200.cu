@@ -86,6 +86,7 @@ struct bft_b200_ctx {
         uint64_t* d_vk;      /* n * W: the k-mer of each vertex, in enumeration order */
         uint32_t* d_vcls;    /* n: its colour class */
         uint32_t* d_adj;     /* n * 8: predecessors 0-3, successors 4-7 (vertex ids or BFT_V_NONE) */
+        uint32_t* d_loc2vid; /* storage location (bft_view_t) -> vertex id */
         size_t bytes;
     } graph;
 };
@@ -910,6 +911,7 @@ extern "C" int bft_b200_graph_release(bft_b200_ctx* c) {
     if (c->graph.d_vk) cudaFree(c->graph.d_vk);
     if (c->graph.d_vcls) cudaFree(c->graph.d_vcls);
     if (c->graph.d_adj) cudaFree(c->graph.d_adj);
+    if (c->graph.d_loc2vid) cudaFree(c->graph.d_loc2vid);
     memset(&c->graph, 0, sizeof c->graph);
     return 0;
 }
@@ -941,18 +943,16 @@ extern "C" int bft_b200_graph_prepare(bft_b200_ctx* c) {
     cudaStream_t st = c->streams[0];
     CK(cudaStreamSynchronize(st));
     bft_b200_graph_release(c);
-    dev_scratch tmp;
-    uint32_t* d_loc2vid = NULL;
-    int rc = tmp.get(&d_loc2vid, (size_t)n_loc);
-    if (rc) return rc;
     if (cudaMalloc((void**)&c->graph.d_vk, (n + 1) * W * 8) != cudaSuccess || cudaMalloc((void**)&c->graph.d_vcls, (n + 1) * 4) != cudaSuccess ||
-        cudaMalloc((void**)&c->graph.d_adj, (n + 1) * 8 * 4) != cudaSuccess) {
+        cudaMalloc((void**)&c->graph.d_adj, (n + 1) * 8 * 4) != cudaSuccess || cudaMalloc((void**)&c->graph.d_loc2vid, ((size_t)n_loc + 1) * 4) != cudaSuccess) {
         bft_b200_graph_release(c);
         return set_err(BFT_B200_ERR_NOMEM, "graph traversal: cudaMalloc failed for %zu vertices", n);
     }
+    uint32_t* d_loc2vid = c->graph.d_loc2vid;
     c->graph.n = n;
-    c->graph.bytes = (n + 1) * (W * 8 + 4 + 32);
-    rc = enqueue_extract(c, c->graph.d_vk, c->graph.d_vcls, d_loc2vid);
+    c->graph.bytes = (n + 1) * (W * 8 + 4 + 32) + ((size_t)n_loc + 1) * 4;
+    CK(cudaMemsetAsync(d_loc2vid, 0xff, ((size_t)n_loc + 1) * 4, st));
+    int rc = enqueue_extract(c, c->graph.d_vk, c->graph.d_vcls, d_loc2vid);
     if (!rc && n) {
         const int grid = grid_for(c, n * 8, BFT_TPB);
 #define BFT_L(W_) k_graph_adjacency<W_><<<grid, BFT_TPB, 0, st>>>(c->dview, c->graph.d_vk, n, d_loc2vid, c->graph.d_adj)
@@ -964,6 +964,30 @@ extern "C" int bft_b200_graph_prepare(bft_b200_ctx* c) {
     if (!rc && e != cudaSuccess) rc = set_err(BFT_B200_ERR_CUDA, "graph construction failed: %s", cudaGetErrorString(e));
     if (rc) { bft_b200_graph_release(c); return rc; }
     c->graph.ready = 1;
+    return 0;
+}
+
+extern "C" int bft_b200_query_vertex_ids(bft_b200_ctx* c, const uint64_t* kmers, size_t n, uint32_t* vertex_ids) {
+    if (!c || !vertex_ids || (!kmers && n)) return set_err(BFT_B200_ERR_ARG, "bft_b200_query_vertex_ids: NULL argument");
+    int rc = bft_b200_graph_prepare(c);
+    if (rc) return rc;
+    const size_t W = (size_t)c->W;
+    cudaStream_t st = c->streams[0];
+    CK(cudaStreamSynchronize(st));
+    slot_t* sl = &c->slot[0];
+    for (size_t done = 0; done < n;) {
+        const size_t m = n - done < BFT_CHUNK_KMERS ? n - done : BFT_CHUNK_KMERS;
+        ENSURE(sl->d_in, sl->cap_in, m * W * 8);
+        ENSURE(sl->d_cls, sl->cap_cls, m * sizeof(uint32_t));
+        CK(cudaMemcpyAsync(sl->d_in, kmers + done * W, m * W * 8, cudaMemcpyHostToDevice, st));
+#define BFT_L(W_) k_query_vertex_ids<W_><<<grid_for(c, m, BFT_TPB), BFT_TPB, 0, st>>>(c->dview, (const uint64_t*)sl->d_in, m, c->graph.d_loc2vid, (uint32_t*)sl->d_cls)
+        BFT_BY_W(c->W, BFT_L);
+#undef BFT_L
+        c->launches++;
+        CK(cudaMemcpyAsync(vertex_ids + done, sl->d_cls, m * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
+        done += m;
+    }
     return 0;
 }
 

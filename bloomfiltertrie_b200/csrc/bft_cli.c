@@ -1,6 +1,8 @@
 /* bft_cli.c — `bft_b200`: the query half of the reference CLI (src/main.c:204-316) on the GPU engine.
  *   bft_b200 load file_bft [-query_kmers {kmers|kmers_comp} list] [-query_sequences thr {canonical|non_canonical} list]
  *                          [-query_branching {kmers|kmers_comp} list] [-extract_kmers {kmers|kmers_comp} file]
+ *                          [-connected_components] [-simple_paths core_ratio file]
+ * (the last two expose the library's src/snippets.c traversals, which the reference binary has no option for)
  * Output files are named and placed as the reference does (basename with extension replaced by .csv in the cwd,
  * src/main.c:258-264). `build` / -add_genomes stay with the reference binary. */
 #define _GNU_SOURCE
@@ -26,6 +28,7 @@ int main(int argc, char** argv) {
                         "                       [-query_kmers {kmers|kmers_comp} list_kmer_files]\n"
                         "                       [-query_branching {kmers|kmers_comp} list_kmer_files]\n"
                         "                       [-extract_kmers {kmers|kmers_comp} kmers_file]\n"
+                        "                       [-connected_components] [-simple_paths core_ratio paths_file]\n"
                         "Graph construction (build, -add_genomes) is served by the reference `bft` binary.\n");
         return EXIT_FAILURE;
     }
@@ -75,6 +78,16 @@ int main(int argc, char** argv) {
         } else if (strcmp(argv[i], "-extract_kmers") == 0 && i + 2 < argc) { /* src/main.c:317, write_kmers_2disk */
             printf("\nExtraction of k-mers from the BFT to file %s\n\n", argv[i + 2]);
             extract_kmers_to_disk(bft, argv[i + 2], strcmp(argv[i + 1], "kmers_comp") == 0);
+            i += 3;
+        } else if (strcmp(argv[i], "-connected_components") == 0) { /* get_nb_connected_component(graph, &n, BFS) */
+            int n = 0;
+            get_nb_connected_component(bft, &n, BFS);
+            printf("\nNb connected components = %d\n", n);
+            i += 1;
+        } else if (strcmp(argv[i], "-simple_paths") == 0 && i + 2 < argc) { /* extract_simple[_core]_paths_to_disk */
+            const double ratio = atof(argv[i + 1]);
+            if (ratio > 0) extract_simple_core_paths_to_disk(bft, ratio, argv[i + 2]);
+            else extract_simple_paths_to_disk(bft, argv[i + 2]);
             i += 3;
         } else {
             fprintf(stderr, "Unrecognized command %s.\n", argv[i]);

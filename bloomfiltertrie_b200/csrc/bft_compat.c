@@ -46,6 +46,7 @@ void free_cdbg(BFT* bft) {
     NOT_NULL(bft, "free_cdbg()");
     for (int i = 0; i < bft->nb_genomes; i++) free(bft->filenames[i]);
     free(bft->filenames);
+    free(bft->marks);
     bft_b200_close(bft->engine);
     free(bft);
 }
@@ -365,6 +366,7 @@ static size_t iterate_filtered(BFT* bft, const char* prefix, BFT_func_ptr f, va_
         res.present = 1;
         res.class_id = cls[i];
         res.bft = bft;
+        res.vertex1 = (uint32_t)i + 1;
         va_list copy;
         va_copy(copy, args);
         const size_t go_on = f(&cur, bft, copy);
@@ -448,4 +450,139 @@ void query_sequences_outputCSV(BFT_Root* root, char* query_filename, char* outpu
     if (threshold > 1) DIE("query_sequences_outputCSV(): the threshold must be inferior or equal to 1.\n");
     ENGINE_OK(bft_b200_query_sequences_file(root->engine, query_filename, output_filename, threshold, canonical_search), "query_sequences_outputCSV()");
     printf("\nFile %s has been processed.\n", query_filename);
+}
+
+/* ---- marking (include/bft.h:143-146) -------------------------------------------------------------------------------
+ * The reference appends 2-bit marks to the UCs of the trie (src/marking.c); here a k-mer's vertex index keys a host
+ * array, so marks cost one byte per stored k-mer and nothing in device memory. */
+void set_marking(BFT* bft) { /* src/bft.c:700-712 */
+    NOT_NULL(bft, "set_marking()");
+    bft_b200_stats st;
+    ENGINE_OK(bft_b200_get_stats(bft->engine, &st), "set_marking()");
+    free(bft->marks);
+    bft->marks = (uint8_t*)calloc((size_t)st.n_kmers + 1, 1);
+    NOT_NULL(bft->marks, "set_marking()");
+}
+
+void unset_marking(BFT* bft) { /* src/bft.c:717-729 */
+    NOT_NULL(bft, "unset_marking()");
+    free(bft->marks);
+    bft->marks = NULL;
+}
+
+static uint32_t vertex_of(BFT_kmer* km, BFT* bft, const char* who) {
+    NOT_NULL(km, who);
+    NOT_NULL(bft, who);
+    if (!bft->marks) DIE("%s: graph is not locked for marking (set_marking() must be called first).\n", who);
+    if (!is_kmer_in_cdbg(km)) DIE("%s: k-mer is not present in the graph.\n", who);
+    if (!km->res->vertex1) {
+        uint64_t words[4] = {0, 0, 0, 0};
+        uint32_t vid = 0xffffffffu;
+        memcpy(words, km->kmer_comp, (size_t)nb_bytes(bft->k));
+        ENGINE_OK(bft_b200_query_vertex_ids(bft->engine, words, 1, &vid), who);
+        if (vid == 0xffffffffu) DIE("%s: k-mer is not present in the graph.\n", who);
+        km->res->vertex1 = vid + 1;
+    }
+    return km->res->vertex1 - 1;
+}
+
+void set_flag_kmer(uint8_t flag, BFT_kmer* km, BFT* bft) { /* src/bft.c:737-763 */
+    bft->marks[vertex_of(km, bft, "set_flag_kmer()")] = flag & 3u;
+}
+
+uint8_t get_flag_kmer(BFT_kmer* km, BFT* bft) { /* src/bft.c:770-796 */
+    return bft->marks[vertex_of(km, bft, "get_flag_kmer()")];
+}
+
+/* ---- src/snippets.c ------------------------------------------------------------------------------------------------ */
+static size_t write_if_count(BFT_kmer* kmer, BFT* graph, va_list args, int want) { /* want: 0 core, 1 dispensable, 2 singleton */
+    FILE* file = va_arg(args, FILE*);
+    int* nb_kmers = va_arg(args, int*);
+    BFT_annotation* a = get_annotation(kmer);
+    const uint32_t cnt = get_count_id_genomes(a, graph);
+    free_BFT_annotation(a);
+    const uint32_t all = (uint32_t)graph->nb_genomes;
+    if ((want == 0 && cnt == all) || (want == 1 && cnt < all) || (want == 2 && cnt == 1)) {
+        fwrite(kmer->kmer, sizeof(char), strlen(kmer->kmer) + 1, file); /* the k-mer and its NUL, as the reference writes it */
+        *nb_kmers += 1;
+    }
+    return 1;
+}
+size_t extract_core_kmers(BFT_kmer* kmer, BFT* graph, va_list args) { return write_if_count(kmer, graph, args, 0); }        /* src/snippets.c:10-27 */
+size_t extract_dispensable_kmers(BFT_kmer* kmer, BFT* graph, va_list args) { return write_if_count(kmer, graph, args, 1); } /* :35-52 */
+size_t extract_singleton_kmers(BFT_kmer* kmer, BFT* graph, va_list args) { return write_if_count(kmer, graph, args, 2); }   /* :60-76 */
+
+void extract_pangenome_kmers_to_disk(BFT* graph, char* filename_output, BFT_func_ptr f) { /* src/snippets.c:86-107 */
+    NOT_NULL(graph, "extract_pangenome_kmers_to_disk()");
+    NOT_NULL(filename_output, "extract_pangenome_kmers_to_disk()");
+    FILE* file = fopen(filename_output, "w");
+    if (!file) DIE("extract_pangenome_kmers_to_disk(): failed to create/open output file.\n");
+    int nb_kmers = 0;
+    iterate_over_kmers(graph, f, file, &nb_kmers);
+    fclose(file);
+    printf("Number of extracted k-mers is %d.\n", nb_kmers);
+}
+
+void extract_simple_paths_to_disk(BFT* graph, char* filename_output) { /* src/snippets.c:310-338 */
+    NOT_NULL(graph, "extract_simple_paths_to_disk()");
+    NOT_NULL(filename_output, "extract_simple_paths_to_disk()");
+    uint64_t longest = 0;
+    ENGINE_OK(bft_b200_simple_paths_file(graph->engine, 0.0, filename_output, NULL, &longest), "extract_simple_paths_to_disk()");
+    printf("Longest simple path has %d nuc.\n", (int)longest);
+}
+
+void extract_simple_core_paths_to_disk(BFT* graph, double core_ratio, char* filename_output) { /* src/snippets.c:572-597 */
+    NOT_NULL(graph, "extract_simple_core_paths_to_disk()");
+    NOT_NULL(filename_output, "extract_simple_core_paths_to_disk()");
+    uint64_t longest = 0;
+    ENGINE_OK(bft_b200_simple_paths_file(graph->engine, core_ratio, filename_output, NULL, &longest), "extract_simple_core_paths_to_disk()");
+    printf("Longest simple core path has %d nuc.\n", (int)longest);
+}
+
+/* The four traversal callbacks only name the traversal wanted; the traversal itself is a device kernel. */
+static size_t traversal_tag(const char* who) {
+    DIE("%s: per-k-mer traversal callbacks are not run on the host; pass this function to cdbg_traversal() or get_nb_connected_component().\n", who);
+    return 0;
+}
+size_t BFS(BFT_kmer* kmer, BFT* graph, va_list args) { (void)kmer; (void)graph; (void)args; return traversal_tag("BFS()"); }
+size_t DFS(BFT_kmer* kmer, BFT* graph, va_list args) { (void)kmer; (void)graph; (void)args; return traversal_tag("DFS()"); }
+size_t BFS_subgraph(BFT_kmer* kmer, BFT* graph, va_list args) { (void)kmer; (void)graph; (void)args; return traversal_tag("BFS_subgraph()"); }
+size_t DFS_subgraph(BFT_kmer* kmer, BFT* graph, va_list args) { (void)kmer; (void)graph; (void)args; return traversal_tag("DFS_subgraph()"); }
+
+/* counts the components the traversal `f` (with its genome-id arguments still in args) would start */
+static uint64_t run_traversal(BFT* graph, BFT_func_ptr f, va_list args, const char* who) {
+    uint64_t n = 0;
+    if (f == BFS || f == DFS) {
+        ENGINE_OK(bft_b200_connected_components(graph->engine, NULL, 0, &n, NULL), who);
+    } else if (f == BFS_subgraph || f == DFS_subgraph) {
+        const int nb_id_genomes = va_arg(args, int);
+        if (nb_id_genomes <= 0) return 0; /* is_in_subgraph() is false for every k-mer (src/snippets.c:848) */
+        uint32_t* ids = (uint32_t*)malloc((size_t)nb_id_genomes * sizeof(uint32_t));
+        NOT_NULL(ids, who);
+        for (int i = 0; i < nb_id_genomes; i++) ids[i] = va_arg(args, uint32_t);
+        ENGINE_OK(bft_b200_connected_components(graph->engine, ids, nb_id_genomes, &n, NULL), who);
+        free(ids);
+    } else {
+        DIE("%s: only BFS, DFS, BFS_subgraph and DFS_subgraph run on the device; use iterate_over_kmers() for other callbacks.\n", who);
+    }
+    return n;
+}
+
+void cdbg_traversal(BFT* graph, BFT_func_ptr f, ...) { /* src/snippets.c:883-907: visits every k-mer; nothing is returned */
+    NOT_NULL(graph, "cdbg_traversal()");
+    va_list args;
+    va_start(args, f);
+    (void)run_traversal(graph, f, args, "cdbg_traversal()");
+    va_end(args);
+}
+
+void get_nb_connected_component(BFT* graph, ...) { /* src/snippets.c:915-958: args = int* count, traversal, its arguments */
+    NOT_NULL(graph, "get_nb_connected_component()");
+    va_list args;
+    va_start(args, graph);
+    int* nb_connected_comp = va_arg(args, int*);
+    BFT_func_ptr f = va_arg(args, BFT_func_ptr);
+    NOT_NULL(nb_connected_comp, "get_nb_connected_component()");
+    *nb_connected_comp += (int)run_traversal(graph, f, args, "get_nb_connected_component()");
+    va_end(args);
 }

@@ -62,6 +62,22 @@ __global__ void __launch_bounds__(BFT_TPB) k_graph_adjacency(const bft_view_t v,
     }
 }
 
+/* vertex id of each queried k-mer (BFT_V_NONE when it is not stored): the handle under which callers keep their own
+ * per-k-mer state — the reference keeps such state as marks inside the trie (set_flag_kmer / get_flag_kmer,
+ * src/marking.c, include/bft.h:143-146) */
+template <int W>
+__global__ void __launch_bounds__(BFT_TPB) k_query_vertex_ids(const bft_view_t v, const uint64_t* __restrict__ kmers, size_t n,
+                                                              const uint32_t* __restrict__ loc2vid, uint32_t* __restrict__ vids) {
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        uint64_t km[W];
+        bft_load_kmer<W>(kmers, i, km);
+        uint32_t loc = 0;
+        const uint32_t cls = bft_lookup_loc(&v, km, W, 0, (uint32_t*)0, &loc);
+        vids[i] = cls != BFT_CLS_NONE ? __ldg(loc2vid + loc) : BFT_V_NONE;
+    }
+}
+
 /* is_in_subgraph (src/snippets.c:824-881) per colour class: the class holds every requested genome id */
 __global__ void __launch_bounds__(BFT_TPB) k_graph_class_filter(const uint32_t* __restrict__ class_rows, int rw, size_t n_classes,
                                                                 const uint32_t* __restrict__ want_row, uint8_t* __restrict__ cls_in) {

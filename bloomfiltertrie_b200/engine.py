@@ -31,7 +31,7 @@ ABI_SYMBOLS = [
     "bft_b200_extract_kmers", "bft_b200_extract_kmers_device", "bft_b200_extract_kmers_file",
     "bft_b200_device_alloc", "bft_b200_device_free", "bft_b200_peer_export", "bft_b200_peer_import", "bft_b200_peer_close",
     "bft_b200_graph_prepare", "bft_b200_graph_release", "bft_b200_graph_adjacency", "bft_b200_connected_components",
-    "bft_b200_simple_paths", "bft_b200_simple_paths_file", "bft_b200_free",
+    "bft_b200_simple_paths", "bft_b200_simple_paths_file", "bft_b200_free", "bft_b200_query_vertex_ids",
 ]
 
 
@@ -102,6 +102,7 @@ def load_library() -> C.CDLL:
     lib.bft_b200_graph_prepare.argtypes = [vp]
     lib.bft_b200_graph_release.argtypes = [vp]
     lib.bft_b200_graph_adjacency.argtypes = [vp, u32p, sz]
+    lib.bft_b200_query_vertex_ids.argtypes = [vp, u64p, sz, u32p]
     lib.bft_b200_connected_components.argtypes = [vp, u32p, C.c_int, C.POINTER(C.c_uint64), u32p]
     lib.bft_b200_simple_paths.argtypes = [vp, C.c_double, C.POINTER(vp), C.POINTER(sz), C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
     lib.bft_b200_simple_paths_file.argtypes = [vp, C.c_double, C.c_char_p, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
@@ -363,6 +364,13 @@ class BFTEngine:
 
     def graph_release(self):
         self._ck(self.lib.bft_b200_graph_release(self.h), "bft_b200_graph_release")
+
+    def query_vertex_ids(self, kmers: np.ndarray) -> np.ndarray:
+        """Index of each k-mer in the order of extract_kmers (0xffffffff if absent): the key for caller-side marks."""
+        kmers = np.ascontiguousarray(kmers, dtype=np.uint64).reshape(-1, self.W)
+        out = np.empty(kmers.shape[0], dtype=np.uint32)
+        self._ck(self.lib.bft_b200_query_vertex_ids(self.h, _ptr(kmers), kmers.shape[0], _ptr(out)), "bft_b200_query_vertex_ids")
+        return out
 
     def graph_adjacency(self) -> np.ndarray:
         """uint32 [n_kmers, 8]: vertex index of each possible neighbour (0-3 predecessors, 4-7 successors) or 0xffffffff."""

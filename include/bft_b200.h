@@ -192,6 +192,11 @@ uint64_t bft_b200_launch_count(const bft_b200_ctx* ctx);
 int bft_b200_graph_prepare(bft_b200_ctx* ctx);
 int bft_b200_graph_release(bft_b200_ctx* ctx);
 
+/* Vertex index of each k-mer (its position in the order of bft_b200_extract_kmers), 0xffffffff when the k-mer is not
+ * stored. This is the handle for per-k-mer state kept by the caller — what the reference stores as marks inside the
+ * trie (set_marking / set_flag_kmer / get_flag_kmer, include/bft.h:143-146, src/marking.c). */
+int bft_b200_query_vertex_ids(bft_b200_ctx* ctx, const uint64_t* kmers, size_t n, uint32_t* vertex_ids);
+
 /* adj[8 * i + j]: vertex index of the j-th possible neighbour of k-mer i (j = 0-3 predecessors prepending A,C,G,T;
  * 4-7 successors appending A,C,G,T — the order of get_neighbors), or 0xffffffff when it is not in the graph.
  * capacity in k-mers, >= stats.n_kmers. */

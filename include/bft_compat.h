@@ -12,7 +12,10 @@
  * set/unset_neighbors_traversal :154-155, get_neighbors/get_predecessors/get_successors :156-158,
  * intersection/union/sym_difference_annotations :99-113, prefix_matching :137, iterate_over_kmers/v_iterate_over_kmers :164-165, extract_kmers_to_disk + write_kmer_{ascii,comp}_to_disk :88-90; and the
  * file-level drivers of include/file_io.h (queryBFT_kmerPresences_from_KmerFiles, queryBFT_kmerBranching_from_KmerFiles,
- * query_sequences_outputCSV).
+ * query_sequences_outputCSV); set_marking/unset_marking/set_flag_kmer/get_flag_kmer :143-146; and include/snippets.h:
+ * extract_{core,dispensable,singleton}_kmers + extract_pangenome_kmers_to_disk :39-42, extract_simple_paths_to_disk :50,
+ * extract_simple_core_paths_to_disk :52, BFS/DFS/BFS_subgraph/DFS_subgraph + cdbg_traversal +
+ * get_nb_connected_component :60-67.
  */
 #ifndef BFT_COMPAT_H
 #define BFT_COMPAT_H
@@ -34,6 +37,7 @@ typedef struct {
     int k;            /* size of k-mers */
     int nb_genomes;   /* number of genomes inserted */
     struct bft_b200_ctx* engine;
+    uint8_t* marks;   /* set_marking(): one flag per stored k-mer */
 } BFT_Root;
 typedef BFT_Root BFT;
 
@@ -43,6 +47,7 @@ typedef struct {
     uint32_t present;
     uint32_t class_id;
     BFT* bft;
+    uint32_t vertex1; /* 1 + index of the k-mer among the stored k-mers once marking looked it up; 0 = not yet */
 } resultPresence;
 
 typedef struct {
@@ -110,6 +115,32 @@ size_t write_kmer_comp_to_disk(BFT_kmer* bft_kmer, BFT* bft, va_list args);
 int queryBFT_kmerPresences_from_KmerFiles(BFT_Root* root, char* query_filename, int binary_file, char* output_filename);
 int queryBFT_kmerBranching_from_KmerFiles(BFT_Root* root, char* query_filename, int binary_file);
 void query_sequences_outputCSV(BFT_Root* root, char* query_filename, char* output_filename, double threshold, bool canonical_search);
+
+/* ---- marking (include/bft.h:143-146, src/marking.c): one 2-bit flag per stored k-mer, kept on the host and keyed by
+ * the k-mer's vertex index (bft_b200_query_vertex_ids) */
+void set_marking(BFT* bft);
+void unset_marking(BFT* bft);
+void set_flag_kmer(uint8_t flag, BFT_kmer* bft_kmer, BFT* bft);
+uint8_t get_flag_kmer(BFT_kmer* bft_kmer, BFT* bft);
+
+/* ---- src/snippets.c (include/snippets.h): pan-genome k-mer classes, simple paths, traversals ------------------------
+ * BFS / DFS / BFS_subgraph / DFS_subgraph are accepted by cdbg_traversal and get_nb_connected_component as the
+ * reference's callers pass them; the traversal itself runs on the device (bft_b200_connected_components,
+ * bft_b200_simple_paths), so calling them directly on one k-mer is not supported (exit(1), like any reference ERROR). */
+#define V_NOT_VISITED 0
+#define V_VISITED 1
+size_t extract_core_kmers(BFT_kmer* kmer, BFT* graph, va_list args);
+size_t extract_dispensable_kmers(BFT_kmer* kmer, BFT* graph, va_list args);
+size_t extract_singleton_kmers(BFT_kmer* kmer, BFT* graph, va_list args);
+void extract_pangenome_kmers_to_disk(BFT* graph, char* filename_output, BFT_func_ptr f);
+void extract_simple_paths_to_disk(BFT* graph, char* filename_output);
+void extract_simple_core_paths_to_disk(BFT* graph, double core_ratio, char* filename_output);
+size_t BFS(BFT_kmer* kmer, BFT* graph, va_list args);
+size_t BFS_subgraph(BFT_kmer* kmer, BFT* graph, va_list args);
+size_t DFS(BFT_kmer* kmer, BFT* graph, va_list args);
+size_t DFS_subgraph(BFT_kmer* kmer, BFT* graph, va_list args);
+void cdbg_traversal(BFT* graph, BFT_func_ptr f, ...);
+void get_nb_connected_component(BFT* graph, ...);
 
 #ifdef __cplusplus
 }

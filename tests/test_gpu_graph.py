@@ -154,3 +154,72 @@ def test_graph_golden(name):
             assert longest <= int(z[f"longest_r{r}"]) <= longest + 2
     finally:
         eng.close()
+
+
+SNIPPETS_REF = os.path.join(refutil.REF_DIR, "snippets_demo_ref")
+
+
+@pytest.mark.skipif(not os.access(SNIPPETS_REF, os.X_OK), reason="oracle/_ref/snippets_demo_ref not built")
+@pytest.mark.parametrize("name,ratio", [("golden_shallow_k27_g4", 0.5), ("golden_canon_k27_g8", 0.0)])
+def test_snippets_drop_in(name, ratio, tmp_path):
+    """tests/tools/snippets_demo.c — written against the reference's traversal and marking API — compiled once with the
+    reference (prebuilt in oracle/_ref) and once with bft_compat.h + libbft_b200.so: same counts, same k-mer classes,
+    same marks, same paths (up to line order and the reference's branching end k-mers)."""
+    import subprocess
+    root = refutil.ROOT
+    z = np.load(os.path.join(refutil.GOLDEN, name + ".npz"))
+    k = int(z["k"])
+    bft = os.path.join(refutil.GOLDEN, name + ".bft")
+    exe = str(tmp_path / "snippets_demo_compat")
+    env = {kk: v for kk, v in os.environ.items() if kk not in ("CC", "CXX")}
+    subprocess.run(["gcc", "-O1", "-DUSE_COMPAT", "-I", os.path.join(root, "include"), os.path.join(root, "tests", "tools", "snippets_demo.c"),
+                    "-o", exe, "-L", os.path.join(root, "bloomfiltertrie_b200"), "-lbft_b200",
+                    "-Wl,-rpath," + os.path.join(root, "bloomfiltertrie_b200")], check=True, env=env)
+    qf = tmp_path / "q.txt"
+    synth.write_kmers_text(str(qf), z["queries"][:300], k)
+    outs = {}
+    for tag, prog in (("ref", SNIPPETS_REF), ("mine", exe)):
+        d = tmp_path / tag
+        d.mkdir()
+        p = subprocess.run([prog, bft, str(qf), str(d), repr(ratio)], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, timeout=900)
+        assert p.returncode == 0, p.stdout.decode(errors="replace")[-2000:]
+        outs[tag] = (p.stdout.decode().splitlines(), d)
+    ref_lines, ref_dir = outs["ref"]
+    my_lines, my_dir = outs["mine"]
+
+    def pick(lines, prefix):
+        return [l for l in lines if l.startswith(prefix)]
+
+    for prefix in ("C ", "T ", "Number of extracted k-mers", "M "):
+        assert pick(my_lines, prefix) == pick(ref_lines, prefix) and pick(ref_lines, prefix), prefix
+    for fn in ("core.txt", "dispensable.txt", "singleton.txt"):
+        a = sorted((ref_dir / fn).read_bytes().split(b"\0"))
+        b = sorted((my_dir / fn).read_bytes().split(b"\0"))
+        assert a == b, fn
+    from bloomfiltertrie_b200 import engine
+    eng = engine.BFTEngine(bft)
+    km, _, _ = eng.extract_kmers()
+    eng.close()
+    kset = set(graphutil.kmer_list(synth.words_to_ascii(km, k).tobytes(), k))
+    files = ["paths_core0.txt"] + (["paths_core.txt"] if ratio > 0 else [])
+    for fn in files:
+        ref_paths = graphutil.trim_branching_ends((ref_dir / fn).read_bytes().split(b"\n"), kset, k)
+        mine = [l for l in (my_dir / fn).read_bytes().split(b"\n") if l]
+        assert graphutil.normal_paths(ref_paths, k) == graphutil.normal_paths(mine, k), fn
+    lr = [int(l.split()[5]) for l in pick(ref_lines, "Longest simple core path")]
+    lm = [int(l.split()[5]) for l in pick(my_lines, "Longest simple core path")]
+    assert len(lr) == len(lm) == len(files) and all(m <= r <= m + 2 for r, m in zip(lr, lm))
+
+
+def test_vertex_ids_and_marking_key(graph):
+    c, path, eng, kmers, og = graph
+    km, _, _ = eng.extract_kmers()
+    rng = np.random.default_rng(5)
+    pick = rng.integers(0, len(km), size=min(5000, len(km)))
+    np.testing.assert_array_equal(eng.query_vertex_ids(km[pick]), pick.astype(np.uint32))
+    q = c["queries"][:3000]
+    present, _, _ = eng.query_kmers(q, want_rows=False)
+    vid = eng.query_vertex_ids(q)
+    np.testing.assert_array_equal(vid != NONE, present.astype(bool))
+    hit = vid != NONE
+    np.testing.assert_array_equal(km[vid[hit]], q[hit])
