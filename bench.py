@@ -496,6 +496,66 @@ def side_workload(args):
     eng.close()
 
 
+def graph_workload(args):
+    """Informational single-GPU line for the traversal snippets: build the device graph of the
+    100-genome BFT, count its connected components, extract its simple paths; beside it the reference's own
+    get_nb_connected_component(BFS) / extract_simple_core_paths_to_disk on one host core (they cannot thread)."""
+    import numpy as np
+    import torch
+    from bloomfiltertrie_b200 import engine as E
+    import bench_workloads as wl
+    torch.cuda.set_device(0)
+    cfg, k, L = wl.C3, 27, args.genome_len or 1_000_000
+    genomes = wl.pangenome(cfg, L)
+    bft = wl.ensure_bft(cfg, k, L, genomes)
+    eng = E.BFTEngine(bft, device=0)
+    st = eng.stats()
+    n = int(st["n_kmers"])
+    t = {"build": [], "components": [], "paths": []}
+    n_comp = n_paths = longest = path_bytes = 0
+    l0 = 0
+    for it in range(args.warmup + args.steps):
+        if it == args.warmup:
+            t = {kk: [] for kk in t}
+            l0 = eng.launch_count()
+        eng.graph_release()
+        eng.sync()
+        t0 = time.perf_counter()
+        eng.graph_prepare()
+        t1 = time.perf_counter()
+        n_comp = eng.connected_components()
+        t2 = time.perf_counter()
+        _, n_paths, longest, path_bytes = eng.simple_paths_raw(0.0, copy=False)   # the C call: kernels + copy to a host buffer
+        t3 = time.perf_counter()
+        t["build"].append(t1 - t0); t["components"].append(t2 - t1); t["paths"].append(t3 - t2)
+    launches = eng.launch_count() - l0
+    ms = {kk: 1e3 * sum(v) / len(v) for kk, v in t.items()}
+    step_ms = ms["build"] + ms["components"]
+    cpu = None
+    ref_graph = os.path.join(os.path.dirname(wl.REF_HARNESS), "ref_graph")
+    if not args.no_cpu_baseline and os.access(ref_graph, os.X_OK):
+        t0 = time.perf_counter()
+        out = subprocess.run([ref_graph, "components", bft, "bfs"], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True).stdout
+        dt = time.perf_counter() - t0 - st["flatten_seconds"] * 0  # includes the reference's own load of the file
+        m = re.search(r"REF_COMPONENTS (\d+)", out)
+        assert m and int(m.group(1)) == n_comp, f"GPU and reference disagree: {n_comp} vs {out[-200:]}"
+        cpu = {"value": n / dt, "unit": "k-mers/s", "cores": 1, "kind": "reference",
+               "sample": f"get_nb_connected_component(BFS) over the whole BFT incl. load_BFT: {dt:.1f} s; same count as the GPU ({n_comp})"}
+    line = {"metric": "k-mers traversed/sec (graph build + connected components)", "value": n / (step_ms / 1e3), "unit": "k-mers/s",
+            "n_gpus": 1, "steps": args.steps, "warmup": args.warmup, "ms_per_step": step_ms, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "u64", "data": "synthetic",
+            "config": {"workload": "graph: get_nb_connected_component + extract_simple_paths_to_disk on the 100-genome BFT",
+                       "k": k, "n_genomes": cfg["n_genomes"], "genome_len": L, "kmers_in_bft": n, "graph_build_ms": ms["build"],
+                       "components_ms": ms["components"], "simple_paths_ms": ms["paths"], "n_components": n_comp, "n_paths": n_paths,
+                       "longest_path": longest, "path_bytes": path_bytes,
+                       "timing": "host clock around the blocking C-ABI calls (each ends with a stream synchronize)"},
+            "e2e": {"value": n / ((step_ms + ms["paths"]) / 1e3), "unit": "k-mers/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": path_bytes + 8,
+                    "ms_per_step": step_ms + ms["paths"], "note": "build + components + simple paths copied to the host"},
+            "gpu_launches": launches, "cpu_baseline": cpu}
+    print(json.dumps(line), flush=True)
+    eng.close()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -508,7 +568,7 @@ def main():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-probe", action="store_true")
-    ap.add_argument("--workload", default="kmers", choices=["kmers", "sequences", "branching"],
+    ap.add_argument("--workload", default="kmers", choices=["kmers", "sequences", "branching", "graph"],
                     help="kmers = the headline metric (default); the other two print informational single-GPU lines")
     ap.add_argument("--reads", type=int, default=1_000_000)
     ap.add_argument("--pangenome", default="c3", choices=["c3", "c5"],
@@ -516,7 +576,9 @@ def main():
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3
-    if args.workload != "kmers":
+    if args.workload == "graph":
+        graph_workload(args)
+    elif args.workload != "kmers":
         if args.queries_per_gpu == 125_000_000:
             args.queries_per_gpu = 20_000_000
         side_workload(args)

@@ -913,20 +913,30 @@ extern "C" int bft_b200_graph_release(bft_b200_ctx* c) {
     if (c->graph.d_adj) cudaFree(c->graph.d_adj);
     if (c->graph.d_loc2vid) cudaFree(c->graph.d_loc2vid);
     memset(&c->graph, 0, sizeof c->graph);
+    cudaMemPool_t pool;
+    if (cudaDeviceGetDefaultMemPool(&pool, c->device) == cudaSuccess) { /* hand the traversal scratch back to the device */
+        cudaStreamSynchronize(c->streams[0]);
+        cudaMemPoolTrimTo(pool, 0);
+    }
     return 0;
 }
 
-/* scratch device arrays of one traversal call, freed together */
+/* scratch device arrays of one traversal call, freed together. Stream-ordered allocations: after the first call the
+ * blocks come back from the device's memory pool without a driver round trip (bft_b200_graph_release trims the pool). */
 struct dev_scratch {
     void* p[24];
     int n;
-    dev_scratch() : n(0) {}
-    ~dev_scratch() { for (int i = 0; i < n; i++) cudaFree(p[i]); }
+    cudaStream_t st;
+    explicit dev_scratch(cudaStream_t s) : n(0), st(s) {}
+    ~dev_scratch() { for (int i = 0; i < n; i++) cudaFreeAsync(p[i], st); }
     template <typename T>
     int get(T** out, size_t count) {
         void* q = NULL;
         const size_t bytes = (count ? count : 1) * sizeof(T) + 32;
-        if (n >= 24 || cudaMalloc(&q, bytes) != cudaSuccess) return set_err(BFT_B200_ERR_NOMEM, "graph traversal: cudaMalloc(%zu) failed", bytes);
+        if (n >= 24 || cudaMallocAsync(&q, bytes, st) != cudaSuccess) {
+            (void)cudaGetLastError();
+            return set_err(BFT_B200_ERR_NOMEM, "graph traversal: cudaMallocAsync(%zu) failed", bytes);
+        }
         p[n++] = q;
         *out = (T*)q;
         return 0;
@@ -964,6 +974,11 @@ extern "C" int bft_b200_graph_prepare(bft_b200_ctx* c) {
     if (!rc && e != cudaSuccess) rc = set_err(BFT_B200_ERR_CUDA, "graph construction failed: %s", cudaGetErrorString(e));
     if (rc) { bft_b200_graph_release(c); return rc; }
     c->graph.ready = 1;
+    cudaMemPool_t pool;
+    if (cudaDeviceGetDefaultMemPool(&pool, c->device) == cudaSuccess) { /* keep traversal scratch cached between calls */
+        uint64_t keep = ~0ULL;
+        cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+    }
     return 0;
 }
 
@@ -1014,7 +1029,7 @@ extern "C" int bft_b200_connected_components(bft_b200_ctx* c, const uint32_t* ge
         if (labels) memset(labels, 0xff, n * sizeof(uint32_t));
         return 0;
     }
-    dev_scratch tmp;
+    dev_scratch tmp(st);
     uint32_t *d_parent = NULL, *d_labels = NULL, *d_want = NULL;
     uint8_t* d_in = NULL;
     unsigned long long* d_cnt = NULL;
@@ -1060,7 +1075,7 @@ extern "C" int bft_b200_simple_paths(bft_b200_ctx* c, double core_ratio, char** 
     const size_t n = c->graph.n;
     const uint32_t core = (uint32_t)(int)(core_ratio * c->G); /* nb_genomes_core, src/snippets.c:366 */
     cudaStream_t st = c->streams[0];
-    dev_scratch tmp;
+    dev_scratch tmp(st);
     uint8_t* d_chain = NULL;
     uint32_t *d_usucc = NULL, *d_next = NULL, *d_prev = NULL, *d_to[2] = {NULL, NULL}, *d_dist[2] = {NULL, NULL}, *d_low[2] = {NULL, NULL};
     unsigned long long *d_size = NULL, *d_offs = NULL, *d_stats = NULL;

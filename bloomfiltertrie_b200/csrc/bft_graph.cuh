@@ -252,17 +252,27 @@ __global__ void __launch_bounds__(BFT_TPB) k_paths_apply_cuts(const uint8_t* __r
     }
 }
 
-/* the tail of each path tells its head how many vertices the path has; heads get their output size */
+/* the tail of each path tells its head how many vertices the path has; heads get their output size.
+ * stats[0] += paths, stats[1] = max(characters of a path) — reduced per warp before the atomics */
 __global__ void __launch_bounds__(BFT_TPB) k_paths_sizes(const uint8_t* __restrict__ chain, const uint32_t* __restrict__ next,
                                                          const uint32_t* __restrict__ to, const uint32_t* __restrict__ dist, size_t n, int k,
                                                          unsigned long long* __restrict__ size, unsigned long long* __restrict__ stats) {
     const size_t stride = (size_t)gridDim.x * blockDim.x;
+    unsigned long long count = 0, longest = 0;
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
         if (!chain[i] || next[i] != BFT_V_NONE) continue;
         const unsigned long long chars = (unsigned long long)k + dist[i];
         size[to[i]] = chars + 1; /* + '\n' */
-        atomicAdd(stats, 1ULL);
-        atomicMax(stats + 1, chars);
+        count++;
+        longest = max(longest, chars);
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+        count += __shfl_down_sync(0xffffffffu, count, o);
+        longest = max(longest, __shfl_down_sync(0xffffffffu, longest, o));
+    }
+    if ((threadIdx.x & 31) == 0 && count) {
+        atomicAdd(stats, count);
+        atomicMax(stats + 1, longest);
     }
 }
 

@@ -389,18 +389,23 @@ class BFTEngine:
                  "bft_b200_connected_components")
         return (int(out.value), labels) if want_labels else int(out.value)
 
-    def simple_paths(self, core_ratio: float = 0.0):
-        """(list of path strings as bytes, longest length). core_ratio 0: all simple paths."""
+    def simple_paths_raw(self, core_ratio: float = 0.0, copy: bool = True):
+        """(newline-terminated path lines as one bytes object, number of paths, longest length)."""
         buf, nb, n_paths, longest = C.c_void_p(), C.c_size_t(), C.c_uint64(), C.c_uint64()
         self._ck(self.lib.bft_b200_simple_paths(self.h, float(core_ratio), C.byref(buf), C.byref(nb), C.byref(n_paths), C.byref(longest)),
                  "bft_b200_simple_paths")
         try:
-            raw = C.string_at(buf.value, nb.value) if nb.value else b""
+            raw = C.string_at(buf.value, nb.value) if (nb.value and copy) else b""
         finally:
             self.lib.bft_b200_free(buf)
+        return raw, int(n_paths.value), int(longest.value), int(nb.value)
+
+    def simple_paths(self, core_ratio: float = 0.0):
+        """(list of path strings as bytes, longest length). core_ratio 0: all simple paths."""
+        raw, n_paths, longest, _ = self.simple_paths_raw(core_ratio)
         lines = raw.split(b"\n")[:-1] if raw else []
-        assert len(lines) == n_paths.value
-        return lines, int(longest.value)
+        assert len(lines) == n_paths
+        return lines, longest
 
     def simple_paths_file(self, path: str, core_ratio: float = 0.0):
         n_paths, longest = C.c_uint64(), C.c_uint64()
