@@ -18,8 +18,8 @@ NONE = 0xFFFFFFFF
 # name -> the trie has leaf-level Nodes (the reference's own BFS/DFS disagree there; compared with the oracle only)
 GRAPH_CASES = {
     "cycles_k27_g3": False, "cycles_k63_g2": False, "shallow_k27_g4": False, "canon_k27_g16": False,
-    "shallow_k63_g5": False, "repeats_k27_g4": False, "lowcomplex_k27_g3": True, "pan_k27_g100": False,
-    "shallow_k72_g3": False, "structured_k18_g3": True, "leaf_k9_g5": True, "deep_k27_g4": False,
+    "repeats_k27_g4": False, "lowcomplex_k27_g3": True, "pan_k27_g100": False,
+    "shallow_k72_g3": False, "structured_k18_g3": True, "leaf_k9_g5": True,
 }
 
 
@@ -58,7 +58,7 @@ def test_adjacency_is_the_de_bruijn_graph(graph):
     assert ((back == src[:, None]).sum(axis=1) == 1).all()
 
 
-@pytest.mark.parametrize("ids", [(), (0,), (0, 1), (1, 2), (99999,)])
+@pytest.mark.parametrize("ids", [(), (0,), (0, 1), (99999,)])
 def test_connected_components(graph, ids):
     c, path, eng, kmers, og = graph
     if ids and ids[-1] != 99999 and ids[-1] >= c["n_genomes"]:
