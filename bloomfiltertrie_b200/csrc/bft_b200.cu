@@ -464,6 +464,79 @@ extern "C" int bft_b200_query_kmers(bft_b200_ctx* c, const uint64_t* kmers, size
     return query_kmers_host(c, kmers, NULL, n, NULL, present, rows, class_ids);
 }
 
+/* ---- the reference's record format in, byte rows out ------------------------------------------------------------ */
+static int enqueue_records(bft_b200_ctx* c, cudaStream_t st, const uint8_t* d_records, size_t n, uint8_t* d_present, uint8_t* d_rows,
+                           unsigned long long* d_n_present) {
+    if (n == 0) return 0;
+    const int nb = (2 * c->k + 7) / 8, rb = (c->G + 7) / 8 > 0 ? (c->G + 7) / 8 : 1;
+    const size_t smem = ((size_t)BFT_TPB * (size_t)(nb > rb ? nb : rb) + 15) & ~(size_t)15;
+    if (smem > 227 * 1024) return set_err(BFT_B200_ERR_ARG, "bft_b200_query_records: %d genomes exceed the shared-memory tile; use bft_b200_query_kmers", c->G);
+    if (smem > 48 * 1024) { /* opt in to large dynamic shared memory (wide colour rows) */
+#define BFT_L(W_) CK(cudaFuncSetAttribute(k_query_records<W_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem))
+        BFT_BY_W(c->W, BFT_L);
+#undef BFT_L
+    }
+    const size_t n_tiles = (n + BFT_TPB - 1) / BFT_TPB;
+    const size_t want = (size_t)c->sm_count * 8;
+    const int grid = (int)(n_tiles < want ? n_tiles : want);
+#define BFT_L(W_) k_query_records<W_><<<grid, BFT_TPB, smem, st>>>(c->dview, d_records, n, nb, rb, c->rw, c->d_class_rows, d_present, d_rows, d_n_present)
+    BFT_BY_W(c->W, BFT_L);
+#undef BFT_L
+    c->launches++;
+    CK(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int bft_b200_row_bytes(const bft_b200_ctx* c) { return c ? ((c->G + 7) / 8 > 0 ? (c->G + 7) / 8 : 1) : 0; }
+extern "C" int bft_b200_record_bytes(const bft_b200_ctx* c) { return c ? (2 * c->k + 7) / 8 : 0; }
+
+extern "C" int bft_b200_query_records_device(bft_b200_ctx* c, const uint8_t* d_records, size_t n, uint8_t* d_present, uint8_t* d_rows,
+                                             uint64_t* d_n_present) {
+    if (!c || (!d_records && n) || !d_rows) return set_err(BFT_B200_ERR_ARG, "bft_b200_query_records_device: NULL argument");
+    if (((uintptr_t)d_records & 15) || ((uintptr_t)d_rows & 15))
+        return set_err(BFT_B200_ERR_ARG, "bft_b200_query_records_device: record and row buffers must be 16-byte aligned");
+    CK(cudaSetDevice(c->device));
+    if (d_n_present) CK(cudaMemsetAsync(d_n_present, 0, sizeof(uint64_t), c->streams[0]));
+    return enqueue_records(c, c->streams[0], d_records, n, d_present, d_rows, (unsigned long long*)d_n_present);
+}
+
+extern "C" int bft_b200_query_records(bft_b200_ctx* c, const uint8_t* records, size_t n, uint8_t* present, uint8_t* rows, uint64_t* n_present) {
+    if (!c || (!records && n) || !rows) return set_err(BFT_B200_ERR_ARG, "bft_b200_query_records: NULL argument");
+    CK(cudaSetDevice(c->device));
+    const size_t nb = (size_t)bft_b200_record_bytes(c), rb = (size_t)bft_b200_row_bytes(c);
+    CK(cudaStreamSynchronize(c->streams[0]));
+    CK(cudaStreamSynchronize(c->streams[1]));
+    CK(cudaMemsetAsync(c->d_counter, 0, sizeof(unsigned long long), c->streams[0]));
+    CK(cudaStreamSynchronize(c->streams[0]));
+    size_t done = 0;
+    int it = 0;
+    while (done < n) {
+        const size_t m = n - done < BFT_CHUNK_KMERS ? n - done : BFT_CHUNK_KMERS;
+        const int s = it & 1;
+        slot_t* sl = &c->slot[s];
+        cudaStream_t st = c->streams[s];
+        CK(cudaStreamSynchronize(st)); /* slot buffers free again */
+        ENSURE(sl->d_in, sl->cap_in, m * nb);
+        ENSURE(sl->d_u8a, sl->cap_u8a, m);
+        ENSURE(sl->d_rows, sl->cap_rows, m * rb);
+        CK(cudaMemcpyAsync(sl->d_in, records + done * nb, m * nb, cudaMemcpyHostToDevice, st));
+        int rc = enqueue_records(c, st, (const uint8_t*)sl->d_in, m, present ? sl->d_u8a : NULL, (uint8_t*)sl->d_rows, n_present ? c->d_counter : NULL);
+        if (rc) return rc;
+        if (present) CK(cudaMemcpyAsync(present + done, sl->d_u8a, m, cudaMemcpyDeviceToHost, st));
+        CK(cudaMemcpyAsync(rows + done * rb, sl->d_rows, m * rb, cudaMemcpyDeviceToHost, st));
+        done += m;
+        it++;
+    }
+    CK(cudaStreamSynchronize(c->streams[0]));
+    CK(cudaStreamSynchronize(c->streams[1]));
+    if (n_present) {
+        unsigned long long h = 0;
+        CK(cudaMemcpy(&h, c->d_counter, sizeof h, cudaMemcpyDeviceToHost));
+        *n_present = h;
+    }
+    return 0;
+}
+
 extern "C" int bft_b200_query_kmers_ascii(bft_b200_ctx* c, const char* ascii, size_t n, uint8_t* valid, uint8_t* present, uint32_t* rows,
                                           uint32_t* class_ids) {
     if (!c || (!ascii && n)) return set_err(BFT_B200_ERR_ARG, "bft_b200_query_kmers_ascii: NULL argument");

@@ -133,6 +133,67 @@ __global__ void __launch_bounds__(BFT_TPB) k_query_kmers_rows(const bft_view_t v
     }
 }
 
+/* The same look-up on the reference's own record format: k-mers as ceil(2k/8)-byte records (a kmers_comp file,
+ * BFT_kmer.kmer_comp; src/file_io.c:721-774) in, colour rows of ceil(n_genomes/8) bytes out (bit g = genome g; an absent
+ * k-mer has an all-zero row). For k = 27 and 100 genomes that is 7 + 13 bytes per k-mer over PCIe instead of 8 + 17,
+ * which is what bounds the host-facing call. A block handles tiles of BFT_TPB k-mers; BFT_TPB * anything is a multiple
+ * of 16, so with 16-byte aligned buffers every tile is moved with 128-bit accesses through shared memory. */
+__device__ __forceinline__ void bft_tile_copy(uint8_t* dst, const uint8_t* src, size_t bytes, bool to_global) {
+    const size_t n16 = bytes >> 4;
+    for (size_t i = threadIdx.x; i < n16; i += blockDim.x) {
+        if (to_global) __stcs((uint4*)dst + i, ((const uint4*)src)[i]);
+        else ((uint4*)dst)[i] = __ldg((const uint4*)src + i);
+    }
+    for (size_t i = (n16 << 4) + threadIdx.x; i < bytes; i += blockDim.x) dst[i] = src[i];
+}
+
+template <int W>
+__global__ void __launch_bounds__(BFT_TPB) k_query_records(const bft_view_t v, const uint8_t* __restrict__ records, size_t n, int nb, int rb,
+                                                           int rw, const uint32_t* __restrict__ class_rows, uint8_t* __restrict__ present,
+                                                           uint8_t* __restrict__ rows, unsigned long long* __restrict__ n_present) {
+    extern __shared__ uint4 bft_tile_smem[];
+    uint8_t* sm = (uint8_t*)bft_tile_smem;
+    const size_t n_tiles = (n + BFT_TPB - 1) / BFT_TPB;
+    unsigned int hits = 0;
+    for (size_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        const size_t base = tile * BFT_TPB;
+        const size_t cnt = n - base < BFT_TPB ? n - base : BFT_TPB;
+        bft_tile_copy(sm, records + base * (size_t)nb, cnt * (size_t)nb, false);
+        __syncthreads();
+        uint64_t km[W];
+#pragma unroll
+        for (int w = 0; w < W; w++) km[w] = 0;
+        if (threadIdx.x < cnt) {
+            const uint8_t* r = sm + (size_t)threadIdx.x * nb;
+#pragma unroll
+            for (int w = 0; w < W; w++)
+                for (int b = 0; b < 8; b++)
+                    if (w * 8 + b < nb) km[w] |= (uint64_t)r[w * 8 + b] << (8 * b);
+#pragma unroll
+            for (int w = 0; w < W; w++) km[w] &= bft_word_mask(2 * v.k, w); /* the reference ignores the pad bits of the last byte */
+        }
+        __syncthreads(); /* the tile buffer is reused for the rows */
+        if (threadIdx.x < cnt) {
+            const uint32_t cls = bft_lookup_w(&v, km, W);
+            const bool hit = cls != BFT_CLS_NONE;
+            hits += hit;
+            if (present) present[base + threadIdx.x] = hit;
+            uint8_t* o = sm + (size_t)threadIdx.x * rb;
+            for (int j = 0; j < rb; j += 4) {
+                const uint32_t word = hit ? __ldg(class_rows + (size_t)cls * rw + (j >> 2)) : 0u;
+                for (int b = 0; b < 4 && j + b < rb; b++) o[j + b] = (uint8_t)(word >> (8 * b));
+            }
+        }
+        __syncthreads();
+        bft_tile_copy(rows + base * (size_t)rb, sm, cnt * (size_t)rb, true);
+        __syncthreads();
+    }
+    if (n_present) {
+        for (int o = 16; o > 0; o >>= 1) hits += __shfl_down_sync(0xffffffffu, hits, o);
+        if ((threadIdx.x & 31) == 0 && hits) atomicAdd(n_present, (unsigned long long)hits);
+    }
+}
+
 /* Random-access roofline probe: n independent 8-byte loads at pseudo-random offsets of a table far
  * larger than L2, one per thread per iteration — the rate the memory system sustains for dependent-free random
  * sectors. Not on the product path; bench.py runs it to put the walk's sector rate in context. */

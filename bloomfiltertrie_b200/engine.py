@@ -32,6 +32,7 @@ ABI_SYMBOLS = [
     "bft_b200_device_alloc", "bft_b200_device_free", "bft_b200_peer_export", "bft_b200_peer_import", "bft_b200_peer_close",
     "bft_b200_graph_prepare", "bft_b200_graph_release", "bft_b200_graph_adjacency", "bft_b200_connected_components",
     "bft_b200_simple_paths", "bft_b200_simple_paths_file", "bft_b200_free", "bft_b200_query_vertex_ids",
+    "bft_b200_record_bytes", "bft_b200_row_bytes", "bft_b200_query_records", "bft_b200_query_records_device",
 ]
 
 
@@ -99,6 +100,10 @@ def load_library() -> C.CDLL:
     lib.bft_b200_peer_export.argtypes = [vp, vp, C.c_char_p]
     lib.bft_b200_peer_import.argtypes = [vp, C.c_char_p, C.POINTER(vp)]
     lib.bft_b200_peer_close.argtypes = [vp, vp]
+    lib.bft_b200_record_bytes.argtypes = [vp]
+    lib.bft_b200_row_bytes.argtypes = [vp]
+    lib.bft_b200_query_records.argtypes = [vp, u8p, sz, u8p, u8p, C.POINTER(C.c_uint64)]
+    lib.bft_b200_query_records_device.argtypes = [vp, u8p, sz, u8p, u8p, u64p]
     lib.bft_b200_graph_prepare.argtypes = [vp]
     lib.bft_b200_graph_release.argtypes = [vp]
     lib.bft_b200_graph_adjacency.argtypes = [vp, u32p, sz]
@@ -213,6 +218,23 @@ class BFTEngine:
         self._ck(self.lib.bft_b200_query_kmers(self.h, _ptr(kmers), n, _ptr(present), _ptr(rows), _ptr(cls)),
                  "bft_b200_query_kmers")
         return present, rows, cls
+
+    def query_records(self, records: np.ndarray, want_present: bool = True, out_rows: Optional[np.ndarray] = None,
+                      out_present: Optional[np.ndarray] = None):
+        """The reference's record format: uint8 [n, ceil(2k/8)] in -> (present uint8 [n] | None, rows uint8 [n, ceil(G/8)],
+        number of k-mers present)."""
+        nb, rb = self.lib.bft_b200_record_bytes(self.h), self.lib.bft_b200_row_bytes(self.h)
+        records = np.ascontiguousarray(records, dtype=np.uint8).reshape(-1, nb)
+        n = records.shape[0]
+        rows = out_rows if out_rows is not None else np.empty((n, rb), dtype=np.uint8)
+        present = out_present if out_present is not None else (np.empty(n, dtype=np.uint8) if want_present else None)
+        cnt = C.c_uint64()
+        self._ck(self.lib.bft_b200_query_records(self.h, _ptr(records), n, _ptr(present), _ptr(rows), C.byref(cnt)), "bft_b200_query_records")
+        return present, rows, int(cnt.value)
+
+    def query_records_device(self, d_records, n: int, d_present, d_rows, d_n_present=None):
+        self._ck(self.lib.bft_b200_query_records_device(self.h, _ptr(d_records), n, _ptr(d_present), _ptr(d_rows), _ptr(d_n_present)),
+                 "bft_b200_query_records_device")
 
     def query_kmers_ascii(self, ascii_kmers: bytes, want_rows: bool = True):
         n = len(ascii_kmers) // self.k

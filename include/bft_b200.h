@@ -182,6 +182,21 @@ int bft_b200_sync(bft_b200_ctx* ctx);
 /* number of kernels this context has launched (bench.py's gpu_launches) */
 uint64_t bft_b200_launch_count(const bft_b200_ctx* ctx);
 
+/* ---- the reference's own record format ------------------------------------------------------------------------------
+ * records: n k-mers of bft_b200_record_bytes() = ceil(2k/8) bytes each, nucleotide i at bits 2(i%4) of byte i/4 — the
+ * records of a kmers_comp file and BFT_kmer.kmer_comp (src/fasta.c:3-53, src/file_io.c:721-774); pad bits ignored.
+ * rows: bft_b200_row_bytes() = ceil(n_genomes/8) bytes per k-mer, bit (g % 8) of byte g/8 = genome g; all zero for an
+ * absent k-mer (a stored k-mer always has at least one genome). present (optional): 1 byte per k-mer.
+ * n_present (optional): the number the reference driver prints as "Nb k-mers present".
+ * Same answers as bft_b200_query_kmers; 7 + 13 instead of 8 + 17 bytes per k-mer cross PCIe at k = 27 / 100 genomes,
+ * and that transfer is what bounds the host-facing call. The _device variant takes 16-byte aligned device buffers. */
+int bft_b200_record_bytes(const bft_b200_ctx* ctx);
+int bft_b200_row_bytes(const bft_b200_ctx* ctx);
+int bft_b200_query_records(bft_b200_ctx* ctx, const uint8_t* records, size_t n, uint8_t* present, uint8_t* rows,
+                           uint64_t* n_present);
+int bft_b200_query_records_device(bft_b200_ctx* ctx, const uint8_t* d_records, size_t n, uint8_t* d_present,
+                                  uint8_t* d_rows, uint64_t* d_n_present);
+
 /* ---- graph traversals (reference src/snippets.c) ----------------------------------------------
  * The coloured de Bruijn graph is materialised on the device once (one vertex per stored k-mer, in the order of
  * bft_b200_extract_kmers; 8 neighbour look-ups per vertex) and the reference's traversal snippets run on it as
