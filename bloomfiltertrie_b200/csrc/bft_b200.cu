@@ -445,8 +445,13 @@ static int query_kmers_host(bft_b200_ctx* c, const uint64_t* kmers, const char* 
         if (rows) ENSURE(sl->d_rows, sl->cap_rows, m * rw * sizeof(uint32_t));
         /* class ids are materialised only when asked for, or as the intermediate of the wide-row path */
         const int fused = rows && (c->rw == 1 || c->rw == 2 || c->rw == 4);
-        int rc = enqueue_kmers(c, st, d_k, m, sl->d_u8a, rows ? sl->d_rows : NULL, (class_ids || (rows && !fused) || !rows) ? sl->d_cls : NULL);
+        uint32_t* d_cls = (class_ids || (rows && !fused) || !rows) ? sl->d_cls : NULL;
+        int rc = enqueue_kmers(c, st, d_k, m, sl->d_u8a, rows ? sl->d_rows : NULL, d_cls);
         if (rc) return rc;
+        if (ascii) {
+            k_blank_invalid<<<grid_for(c, m, BFT_TPB), BFT_TPB, 0, st>>>(sl->d_u8b, m, c->rw, sl->d_u8a, d_cls, rows ? sl->d_rows : NULL);
+            c->launches++;
+        }
         if (present) CK(cudaMemcpyAsync(present + done, sl->d_u8a, m, cudaMemcpyDeviceToHost, st));
         if (valid) CK(cudaMemcpyAsync(valid + done, sl->d_u8b, m, cudaMemcpyDeviceToHost, st));
         if (class_ids) CK(cudaMemcpyAsync(class_ids + done, sl->d_cls, m * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));

@@ -309,6 +309,19 @@ __global__ void __launch_bounds__(BFT_TPB) k_encode_ascii(const char* __restrict
     }
 }
 
+/* k-mers that failed to parse were looked up as AAA...A (which may well be stored): blank their answers */
+__global__ void __launch_bounds__(BFT_TPB) k_blank_invalid(const uint8_t* __restrict__ valid, size_t n, int rw, uint8_t* __restrict__ present,
+                                                           uint32_t* __restrict__ cls, uint32_t* __restrict__ rows) {
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        if (valid[i]) continue;
+        if (present) present[i] = 0;
+        if (cls) cls[i] = BFT_CLS_NONE;
+        if (rows)
+            for (int w = 0; w < rw; w++) rows[i * (size_t)rw + w] = 0;
+    }
+}
+
 /* ---- enumeration: iterate_over_kmers / -extract_kmers (include/bft.h:88,164; src/extract_kmers.c:3-597) ------------
  * One warp per stored prefix. The k-mer is re-assembled from the Node's path (the prefixes above it), the prefix's own
  * 9 nucleotides and the suffix found in its buckets; the output slot of every k-mer is fixed by the exclusive counts

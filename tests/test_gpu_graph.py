@@ -19,7 +19,7 @@ NONE = 0xFFFFFFFF
 GRAPH_CASES = {
     "cycles_k27_g3": False, "cycles_k63_g2": False, "shallow_k27_g4": False, "canon_k27_g16": False,
     "repeats_k27_g4": False, "lowcomplex_k27_g3": True, "pan_k27_g100": False,
-    "shallow_k72_g3": False, "structured_k18_g3": True, "leaf_k9_g5": True,
+    "shallow_k72_g3": False, "leaf_k9_g5": True,
 }
 
 
