@@ -347,31 +347,6 @@ def engine_arm(args):
         word_api = {"value": n * world / (e2e_ms / 1e3), "unit": UNIT, "h2d_bytes_per_step": n * W * 8 * world,
                     "d2h_bytes_per_step": n * (1 + 4 * RW) * world, "ms_per_step": e2e_ms,
                     "api": "bft_b200_query_kmers (host pointers, pinned): 8*W-byte words in, presence byte + 4*RW-byte colour row out"}
-        # the headline e2e: the same batch in the reference's own record format (ceil(2k/8)-byte kmers_comp records in,
-        # ceil(G/8)-byte colour rows + the present count out) — fewer bytes over the link that bounds this call
-        nb, rb = (2 * K + 7) // 8, (cfg["n_genomes"] + 7) // 8
-        hrec = E.PinnedBuffer((n, nb), np.uint8)
-        hrow = E.PinnedBuffer((n, rb), np.uint8)
-        hrec.array[:] = hq.array.view(np.uint8).reshape(n, 8 * W)[:, :nb]
-        _, _, cnt = eng.query_records(hrec.array, want_present=False, out_rows=hrow.array)
-        assert cnt == n_present, "record-format and device-resident paths disagree"
-        ns = min(n, 1 << 20)
-        assert np.array_equal(hrow.array[:ns], hr.array[:ns].view(np.uint8).reshape(ns, 4 * RW)[:, :rb]), "record-format rows differ"
-        barrier()
-        t0 = time.perf_counter()
-        for _ in range(args.steps):
-            eng.query_records(hrec.array, want_present=False, out_rows=hrow.array)
-        torch.cuda.synchronize()
-        tt = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
-        if world > 1:
-            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-        r_ms = float(tt.item()) / args.steps * 1e3
-        e2e = {"value": n * world / (r_ms / 1e3), "unit": UNIT, "h2d_bytes_per_step": n * nb * world,
-               "d2h_bytes_per_step": (n * rb + 8) * world, "ms_per_step": r_ms,
-               "api": "bft_b200_query_records (host pointers, pinned): the reference's ceil(2k/8)-byte k-mer records in, "
-                      "ceil(G/8)-byte colour row per k-mer + the number of k-mers present out",
-               "word_api": word_api}
-        hrec.free(); hrow.free()
         # the same call asking for colour-class ids instead of rows (4 B instead of 4*RW B back per k-mer; the class ->
         # row table is downloaded once per context): information for link-bound deployments, not the headline
         hc = E.PinnedBuffer((n,), np.uint32)
@@ -385,9 +360,35 @@ def engine_arm(args):
         if world > 1:
             dist.all_reduce(tt, op=dist.ReduceOp.MAX)
         c_ms = float(tt.item()) / args.steps * 1e3
-        e2e["class_id_mode"] = {"value": n * world / (c_ms / 1e3), "unit": UNIT, "ms_per_step": c_ms,
+        class_id_mode = {"value": n * world / (c_ms / 1e3), "unit": UNIT, "ms_per_step": c_ms,
                                 "d2h_bytes_per_step": n * 5 * world}
-        hq.free(); hp.free(); hr.free(); hc.free()
+        # the headline e2e: the same batch in the reference's own record format (ceil(2k/8)-byte kmers_comp records in,
+        # ceil(G/8)-byte colour rows + the present count out) — fewer bytes over the link that bounds this call
+        nb, rb = (2 * K + 7) // 8, (cfg["n_genomes"] + 7) // 8
+        hrec = E.PinnedBuffer((n, nb), np.uint8)
+        hrec.array[:] = hq.array.view(np.uint8).reshape(n, 8 * W)[:, :nb]
+        ns = min(n, 1 << 20)
+        want_sample = hr.array[:ns].view(np.uint8).reshape(ns, 4 * RW)[:, :rb].copy()
+        hq.free(); hp.free(); hr.free(); hc.free()          # keep the pinned footprint per rank small
+        hrow = E.PinnedBuffer((n, rb), np.uint8)
+        _, _, cnt = eng.query_records(hrec.array, want_present=False, out_rows=hrow.array)
+        assert cnt == n_present, "record-format and device-resident paths disagree"
+        assert np.array_equal(hrow.array[:ns], want_sample), "record-format rows differ"
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            eng.query_records(hrec.array, want_present=False, out_rows=hrow.array)
+        torch.cuda.synchronize()
+        tt = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        r_ms = float(tt.item()) / args.steps * 1e3
+        e2e = {"value": n * world / (r_ms / 1e3), "unit": UNIT, "h2d_bytes_per_step": n * nb * world,
+               "d2h_bytes_per_step": (n * rb + 8) * world, "ms_per_step": r_ms,
+               "api": "bft_b200_query_records (host pointers, pinned): the reference's ceil(2k/8)-byte k-mer records in, "
+                      "ceil(G/8)-byte colour row per k-mer + the number of k-mers present out",
+               "word_api": word_api, "class_id_mode": class_id_mode}
+        hrec.free(); hrow.free()
 
     # ---- CPU baseline beside it: the unmodified reference on a bounded sample (rank 0, N=1 only)
     cpu = None

@@ -41,8 +41,8 @@ static double now_s(void) {
 }
 
 #define BFT_CHUNK_KMERS ((size_t)1 << 22)
-#define BFT_CHUNK_SEQ_CHARS ((size_t)1 << 28)
-#define BFT_CHUNK_SEQS ((size_t)1 << 21)
+#define BFT_CHUNK_SEQ_CHARS ((size_t)1 << 25) /* 32 MB of characters per chunk: small enough for the two slots to overlap copies and kernels on a 1 M-read batch */
+#define BFT_CHUNK_SEQS ((size_t)1 << 18)
 
 typedef struct {
     void* d_in;        size_t cap_in;

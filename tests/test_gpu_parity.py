@@ -39,6 +39,12 @@ def test_kmer_presence_and_colours(built):
     assert ref_present.sum() > 0 and (ref_present == 0).sum() > 0
     np.testing.assert_array_equal(present, ref_present)
     np.testing.assert_array_equal(rows, ref_rows)
+    # the reference's record format in, byte rows out: same answers
+    rb = (c["n_genomes"] + 7) // 8
+    p_rec, r_rec, n_rec = eng.query_records(synth.words_to_bytes(q, c["k"]))
+    np.testing.assert_array_equal(p_rec, ref_present)
+    np.testing.assert_array_equal(r_rec, np.ascontiguousarray(ref_rows).view(np.uint8).reshape(len(q), -1)[:, :rb])
+    assert n_rec == int(ref_present.sum())
     # class ids are consistent with rows and counts
     table = eng.class_rows()
     counts = eng.class_counts()
