@@ -132,8 +132,32 @@ def test_abi_library_loads_and_exports_every_declared_symbol():
               "query_sequences_outputCSV", "free_BFT_kmer", "free_BFT_annotation", "create_kmer", "iterate_over_kmers",
               "v_iterate_over_kmers", "extract_kmers_to_disk", "write_kmer_ascii_to_disk", "write_kmer_comp_to_disk",
               "prefix_matching", "intersection_annotations", "union_annotations", "sym_difference_annotations",
-              "intersection_list_id_genomes"]:
+              "intersection_list_id_genomes", "set_marking", "unset_marking", "set_flag_kmer", "get_flag_kmer",
+              "extract_core_kmers", "extract_dispensable_kmers", "extract_singleton_kmers", "extract_pangenome_kmers_to_disk",
+              "extract_simple_paths_to_disk", "extract_simple_core_paths_to_disk", "BFS", "DFS", "BFS_subgraph", "DFS_subgraph",
+              "cdbg_traversal", "get_nb_connected_component"]:
         assert s in compat and hasattr(lib, s), s
+
+
+def test_graph_normal_forms():
+    """The order-independent normal forms the traversal tests compare in (tests/graphutil.py)."""
+    import graphutil
+    k = 4
+    circ = b"ACGTTGCA"                                   # a closed loop of 8 k-mers, written from two different starts
+    a = circ + circ[:k - 1]
+    b = circ[3:] + circ[:3] + (circ[3:] + circ[:3])[:k - 1]
+    assert graphutil.canon_cycle(a, k) == graphutil.canon_cycle(b, k) and len(graphutil.canon_cycle(a, k)) == len(a)
+    assert graphutil.canon_cycle(b"ACGTAC", k) == b"ACGTAC"       # an open path is left alone
+    short = b"ACAC" + b"A"                                # 2-k-mer loop ACAC <-> CACA, shorter than k - 1
+    other = b"CACA" + b"C"
+    assert graphutil.canon_cycle(short, k) == graphutil.canon_cycle(other, k)
+    kset = {b"AAAC", b"AACG", b"ACGT", b"ACGA", b"CGTT"}  # AACG -> ACGT / ACGA would need 2 successors of AACG? no: ACGT, ACGA follow AACG
+    assert graphutil.out_degree(b"AACG", kset) == 2 and graphutil.in_degree(b"ACGT", kset) == 1
+    # a reference line that ends in a branching k-mer is cut back to the order-independent path
+    assert graphutil.trim_branching_ends([b"AAACG"], kset, k) == [b"AAAC"]
+    assert graphutil.trim_branching_ends([b"ACGTT"], kset, k) == [b"ACGTT"]
+    labels = np.array([0, 0, 5, 0xFFFFFFFF], dtype=np.uint32)
+    assert graphutil.partition(labels, [b"a", b"b", b"c", b"d"]) == {frozenset([b"a", b"b"]), frozenset([b"c"])}
 
 
 def test_engine_fails_loudly_without_a_gpu():
