@@ -189,6 +189,9 @@ def engine_arm(args):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
+        # NCCL writes its banner ("NCCL version ...", when NCCL_DEBUG is set on the box) to stdout; stdout carries the
+        # one JSON line only
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=dev)
 
     cfg, L = pick_workload(args)
