@@ -33,6 +33,28 @@ def log(*a):
     print("[bench]", *a, file=sys.stderr, flush=True)
 
 
+# stdout carries the one JSON line and nothing else: libraries that write to fd 1 on their own (NCCL prints its version
+# banner there) are pointed at stderr for the whole run, and the line goes to the saved descriptor.
+_JSON_FD = None
+
+
+def claim_stdout():
+    global _JSON_FD
+    if _JSON_FD is None:
+        sys.stdout.flush()
+        _JSON_FD = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit(line: dict):
+    data = (json.dumps(line) + "\n").encode()
+    if _JSON_FD is None:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
+    else:
+        os.write(_JSON_FD, data)
+
+
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md clocks line)."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
@@ -171,7 +193,7 @@ def reference_arm(args):
             "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "reference",
                              "sample": f"{n} k-mers per step (same generator and mix as the GPU batch), all {cores} host threads"},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 def engine_arm(args):
@@ -191,7 +213,7 @@ def engine_arm(args):
     if world > 1:
         # NCCL writes its banner ("NCCL version ...", when NCCL_DEBUG is set on the box) to stdout; stdout carries the
         # one JSON line only
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
+        claim_stdout()
         dist.init_process_group("nccl", device_id=dev)
 
     cfg, L = pick_workload(args)
@@ -418,7 +440,7 @@ def engine_arm(args):
                            "query_mix_present_mismatch_random": MIX, "present_frac": n_present / n,
                            "l2": "inputs larger than L2 (no flush needed)", "sharding": f"arena replicated, queries sharded x{world}"},
                 "clocks": clocks, "e2e": e2e, "gpu_launches": launches * world, "roofline": roofline, "cpu_baseline": cpu}
-        print(json.dumps(line), flush=True)
+        emit(line)
     eng.close()
     if world > 1:
         dist.destroy_process_group()
@@ -521,7 +543,7 @@ def side_workload(args):
                        "reads_per_sec": (n / (ms / 1e3)) if seq else None},
             "e2e": {"value": units / (e2e_ms / 1e3), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms},
             "gpu_launches": launches, "cpu_baseline": cpu}
-    print(json.dumps(line), flush=True)
+    emit(line)
     eng.close()
 
 
@@ -581,7 +603,7 @@ def graph_workload(args):
             "e2e": {"value": n / ((step_ms + ms["paths"]) / 1e3), "unit": "k-mers/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": path_bytes + 8,
                     "ms_per_step": step_ms + ms["paths"], "note": "build + components + simple paths copied to the host"},
             "gpu_launches": launches, "cpu_baseline": cpu}
-    print(json.dumps(line), flush=True)
+    emit(line)
     eng.close()
 
 
