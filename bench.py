@@ -344,10 +344,14 @@ def engine_arm(args):
                 "a_ref_bytes_per_kmer": a_ref, "cc_probed_per_node_reference_layout": cc_pk / max(nodes_pk, 1e-9),
                 "mean_suffix_block_lines": ws["block_lines"] / max(1, n),
                 "dram_bytes_per_kmer_ncu": traffic,
+                "dram_gbps_physical": (traffic * n / (k_ms / 1e3) / 1e9) if traffic else None,
+                "dram_frac_physical": (traffic * n / (k_ms / 1e3) / 1e9 / peak) if traffic else None,
                 "random_gather_probe_loads_per_s": probe,
                 "random_access_frac": (n / (k_ms / 1e3) / probe) if probe else None,
                 "note": "A_min counts the sectors of the REFERENCE layout's walk; the flattened arena serves the root probe from "
-                        "an L2-resident directory, so achieved can exceed the DRAM peak; dram_bytes_per_kmer_ncu is the physical traffic"}
+                        "an L2-resident directory, so achieved can exceed the DRAM peak; dram_bytes_per_kmer_ncu / dram_gbps_physical are the "
+                        "physical traffic (ncu), and random_access_frac compares the kernel with the measured rate of independent "
+                        "random HBM accesses, which is what bounds it"}
 
     # ---- e2e: host C-ABI call with pinned host buffers, copies inside the timed region
     e2e = None
