@@ -474,7 +474,7 @@ static int enqueue_records(bft_b200_ctx* c, cudaStream_t st, const uint8_t* d_re
                            unsigned long long* d_n_present) {
     if (n == 0) return 0;
     const int nb = (2 * c->k + 7) / 8, rb = (c->G + 7) / 8 > 0 ? (c->G + 7) / 8 : 1;
-    const size_t smem = ((size_t)BFT_TPB * (size_t)(nb > rb ? nb : rb) + 15) & ~(size_t)15;
+    const size_t smem = bft_records_smem(nb, rb);
     if (smem > 227 * 1024) return set_err(BFT_B200_ERR_ARG, "bft_b200_query_records: %d genomes exceed the shared-memory tile; use bft_b200_query_kmers", c->G);
     if (smem > 48 * 1024) { /* opt in to large dynamic shared memory (wide colour rows) */
 #define BFT_L(W_) CK(cudaFuncSetAttribute(k_query_records<W_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem))

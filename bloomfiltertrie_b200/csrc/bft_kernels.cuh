@@ -136,58 +136,119 @@ __global__ void __launch_bounds__(BFT_TPB) k_query_kmers_rows(const bft_view_t v
 /* The same look-up on the reference's own record format: k-mers as ceil(2k/8)-byte records (a kmers_comp file,
  * BFT_kmer.kmer_comp; src/file_io.c:721-774) in, colour rows of ceil(n_genomes/8) bytes out (bit g = genome g; an absent
  * k-mer has an all-zero row). For k = 27 and 100 genomes that is 7 + 13 bytes per k-mer over PCIe instead of 8 + 17,
- * which is what bounds the host-facing call. A block handles tiles of BFT_TPB k-mers; BFT_TPB * anything is a multiple
- * of 16, so with 16-byte aligned buffers every tile is moved with 128-bit accesses through shared memory. */
-__device__ __forceinline__ void bft_tile_copy(uint8_t* dst, const uint8_t* src, size_t bytes, bool to_global) {
-    const size_t n16 = bytes >> 4;
-    for (size_t i = threadIdx.x; i < n16; i += blockDim.x) {
-        if (to_global) __stcs((uint4*)dst + i, ((const uint4*)src)[i]);
-        else ((uint4*)dst)[i] = __ldg((const uint4*)src + i);
-    }
-    for (size_t i = (n16 << 4) + threadIdx.x; i < bytes; i += blockDim.x) dst[i] = src[i];
+ * which is what bounds the host-facing call.
+ *
+ * A block handles tiles of BFT_TPB k-mers. BFT_TPB * anything is a multiple of 16, so with 16-byte aligned buffers a
+ * full tile of records is ONE bulk asynchronous copy global -> shared (cp.async.bulk + mbarrier transaction count, the
+ * TMA engine's 1-D form; SASS UBLKCP) and a full tile of rows ONE bulk copy shared -> global. Both are double
+ * buffered: the records of tile t+1 arrive while the threads look tile t up, and the rows of tile t drain while
+ * tile t+1 is looked up. The last, partial tile of a batch is moved by the threads themselves. */
+__device__ __forceinline__ uint32_t bft_smem_addr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void bft_mbar_init(uint64_t* bar, uint32_t arrivals) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bft_smem_addr(bar)), "r"(arrivals) : "memory");
 }
+__device__ __forceinline__ void bft_mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bft_smem_addr(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bft_mbar_wait(uint64_t* bar, uint32_t parity) {
+    uint32_t done;
+    do {
+        asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}"
+                     : "=r"(done) : "r"(bft_smem_addr(bar)), "r"(parity) : "memory");
+    } while (!done);
+}
+__device__ __forceinline__ void bft_bulk_load(void* smem_dst, const void* gmem_src, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(bft_smem_addr(smem_dst)), "l"(gmem_src), "r"(bytes), "r"(bft_smem_addr(bar)) : "memory");
+}
+__device__ __forceinline__ void bft_bulk_store(void* gmem_dst, const void* smem_src, uint32_t bytes) {
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gmem_dst), "r"(bft_smem_addr(smem_src)), "r"(bytes) : "memory");
+    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+}
+
+/* dynamic shared memory of k_query_records: two record tiles, two row tiles, two mbarriers */
+__host__ __device__ inline size_t bft_records_smem(int nb, int rb) { return 2 * (size_t)BFT_TPB * (size_t)(nb + rb) + 16; }
 
 template <int W>
 __global__ void __launch_bounds__(BFT_TPB) k_query_records(const bft_view_t v, const uint8_t* __restrict__ records, size_t n, int nb, int rb,
                                                            int rw, const uint32_t* __restrict__ class_rows, uint8_t* __restrict__ present,
                                                            uint8_t* __restrict__ rows, unsigned long long* __restrict__ n_present) {
     extern __shared__ uint4 bft_tile_smem[];
-    uint8_t* sm = (uint8_t*)bft_tile_smem;
+    uint8_t* const sm = (uint8_t*)bft_tile_smem;
+    const uint32_t in_bytes = (uint32_t)BFT_TPB * (uint32_t)nb, out_bytes = (uint32_t)BFT_TPB * (uint32_t)rb;
+    uint8_t* const out_base = sm + 2 * (size_t)in_bytes;
+#define BFT_IN_BUF(i_) (sm + (size_t)(i_) * in_bytes)
+#define BFT_OUT_BUF(i_) (out_base + (size_t)(i_) * out_bytes)
+    uint64_t* const bar = (uint64_t*)(sm + 2 * (size_t)in_bytes + 2 * (size_t)out_bytes);
     const size_t n_tiles = (n + BFT_TPB - 1) / BFT_TPB;
+    const bool lead = threadIdx.x == 0;
+    if (lead) {
+        bft_mbar_init(bar, 1);
+        bft_mbar_init(bar + 1, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
     unsigned int hits = 0;
-    for (size_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    uint32_t it = 0;
+    size_t tile = blockIdx.x;
+    if (lead && tile < n_tiles && n - tile * BFT_TPB >= BFT_TPB) { /* first tile of this block */
+        bft_mbar_expect_tx(bar, in_bytes);
+        bft_bulk_load(BFT_IN_BUF(0), records + tile * (size_t)in_bytes, in_bytes, bar);
+    }
+    for (; tile < n_tiles; tile += gridDim.x, it++) {
+        const uint32_t b = it & 1u;
         const size_t base = tile * BFT_TPB;
-        const size_t cnt = n - base < BFT_TPB ? n - base : BFT_TPB;
-        bft_tile_copy(sm, records + base * (size_t)nb, cnt * (size_t)nb, false);
-        __syncthreads();
-        uint64_t km[W];
-#pragma unroll
-        for (int w = 0; w < W; w++) km[w] = 0;
+        const bool full = n - base >= BFT_TPB;
+        const size_t cnt = full ? BFT_TPB : n - base;
+        const size_t next = tile + gridDim.x;
+        if (lead && next < n_tiles && n - next * BFT_TPB >= BFT_TPB) { /* prefetch; the other record buffer was released at the last barrier of it-1 */
+            bft_mbar_expect_tx(bar + (b ^ 1u), in_bytes);
+            bft_bulk_load(BFT_IN_BUF(b ^ 1u), records + next * (size_t)in_bytes, in_bytes, bar + (b ^ 1u));
+        }
+        if (full) {
+            bft_mbar_wait(bar + b, (it >> 1) & 1u); /* buffer b is filled for the (it / 2)-th time */
+        } else {
+            for (size_t i = threadIdx.x; i < cnt * (size_t)nb; i += blockDim.x) BFT_IN_BUF(b)[i] = records[base * (size_t)nb + i];
+            __syncthreads();
+        }
+        uint32_t cls = BFT_CLS_NONE;
         if (threadIdx.x < cnt) {
-            const uint8_t* r = sm + (size_t)threadIdx.x * nb;
+            uint64_t km[W];
+#pragma unroll
+            for (int w = 0; w < W; w++) km[w] = 0;
+            const uint8_t* r = BFT_IN_BUF(b) + (size_t)threadIdx.x * nb;
 #pragma unroll
             for (int w = 0; w < W; w++)
-                for (int b = 0; b < 8; b++)
-                    if (w * 8 + b < nb) km[w] |= (uint64_t)r[w * 8 + b] << (8 * b);
+                for (int j = 0; j < 8; j++)
+                    if (w * 8 + j < nb) km[w] |= (uint64_t)r[w * 8 + j] << (8 * j);
 #pragma unroll
             for (int w = 0; w < W; w++) km[w] &= bft_word_mask(2 * v.k, w); /* the reference ignores the pad bits of the last byte */
+            cls = bft_lookup_w(&v, km, W);
         }
-        __syncthreads(); /* the tile buffer is reused for the rows */
+        /* the rows of tile it-2 must have left this row buffer before it is written again */
+        if (lead) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+        __syncthreads();
         if (threadIdx.x < cnt) {
-            const uint32_t cls = bft_lookup_w(&v, km, W);
             const bool hit = cls != BFT_CLS_NONE;
             hits += hit;
             if (present) present[base + threadIdx.x] = hit;
-            uint8_t* o = sm + (size_t)threadIdx.x * rb;
+            uint8_t* o = BFT_OUT_BUF(b) + (size_t)threadIdx.x * rb;
             for (int j = 0; j < rb; j += 4) {
                 const uint32_t word = hit ? __ldg(class_rows + (size_t)cls * rw + (j >> 2)) : 0u;
-                for (int b = 0; b < 4 && j + b < rb; b++) o[j + b] = (uint8_t)(word >> (8 * b));
+                for (int q = 0; q < 4 && j + q < rb; q++) o[j + q] = (uint8_t)(word >> (8 * q));
             }
         }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); /* generic-proxy writes -> visible to the bulk copy */
         __syncthreads();
-        bft_tile_copy(rows + base * (size_t)rb, sm, cnt * (size_t)rb, true);
-        __syncthreads();
+        if (full) {
+            if (lead) bft_bulk_store(rows + base * (size_t)rb, BFT_OUT_BUF(b), out_bytes);
+        } else {
+            for (size_t i = threadIdx.x; i < cnt * (size_t)rb; i += blockDim.x) rows[base * (size_t)rb + i] = BFT_OUT_BUF(b)[i];
+        }
     }
+#undef BFT_IN_BUF
+#undef BFT_OUT_BUF
+    if (lead) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); /* shared memory must outlive the copies reading it */
     if (n_present) {
         for (int o = 16; o > 0; o >>= 1) hits += __shfl_down_sync(0xffffffffu, hits, o);
         if ((threadIdx.x & 31) == 0 && hits) atomicAdd(n_present, (unsigned long long)hits);
