@@ -229,3 +229,28 @@ def test_vertex_ids_and_marking_key(graph):
     np.testing.assert_array_equal(vid != NONE, present.astype(bool))
     hit = vid != NONE
     np.testing.assert_array_equal(km[vid[hit]], q[hit])
+
+
+def test_cli_traversal_options(tmp_path):
+    """`bft_b200 load f.bft -connected_components -simple_paths ratio out`: the library's traversals from the command line."""
+    import subprocess
+    from bloomfiltertrie_b200 import engine
+    name = "golden_shallow_k27_g4"
+    bft = os.path.join(refutil.GOLDEN, name + ".bft")
+    cli = os.path.join(refutil.ROOT, "bloomfiltertrie_b200", "bft_b200")
+    out0, out5 = str(tmp_path / "p0.txt"), str(tmp_path / "p5.txt")
+    p = subprocess.run([cli, "load", bft, "-connected_components", "-simple_paths", "0", out0, "-simple_paths", "0.5", out5],
+                       stdout=subprocess.PIPE, stderr=subprocess.STDOUT, timeout=600)
+    text = p.stdout.decode(errors="replace")
+    assert p.returncode == 0, text
+    z = np.load(os.path.join(refutil.GOLDEN, "graph_" + name + ".npz"))
+    assert f"Nb connected components = {int(z['n_components'])}" in text
+    eng = engine.BFTEngine(bft)
+    try:
+        for path, ratio, label in ((out0, 0.0, "simple path"), (out5, 0.5, "simple core path")):
+            lines, longest = eng.simple_paths(ratio)
+            with open(path, "rb") as f:
+                assert f.read() == b"".join(l + b"\n" for l in lines)
+            assert f"Longest {label} has {longest} nuc." in text
+    finally:
+        eng.close()
