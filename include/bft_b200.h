@@ -9,6 +9,7 @@
  *   - packed k-mers: W = bft_b200_kmer_words() (1, 2 or 4 for k <= 27 / 63 / 126) little-endian uint64 per k-mer, nucleotide i at bits 2i
  *     (A=0 C=1 G=2 T=3), i.e. the reference's byte layout (include/fasta.h:15, src/fasta.c:13-23) zero-padded to W
  *     words; bits above 2k must be zero.
+ *     bft_b200_query_records takes the same k-mers as the reference's own ceil(2k/8)-byte records instead.
  *   - colour rows: RW = bft_b200_row_words() uint32 per item, genome g = bit (g & 31) of word g >> 5. A row is the
  *     reference's ascending id list (src/bft.c:622-641) as a bitmap; an absent k-mer has an all-zero row.
  *   - every function returns BFT_B200_OK (0) or a negative status; bft_b200_last_error() gives the message of the
