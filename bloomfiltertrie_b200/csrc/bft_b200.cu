@@ -44,6 +44,8 @@ static double now_s(void) {
 #define BFT_CHUNK_SEQ_CHARS ((size_t)1 << 25) /* 32 MB of characters per chunk: small enough for the two slots to overlap copies and kernels on a 1 M-read batch */
 #define BFT_CHUNK_SEQS ((size_t)1 << 18)
 
+#define BFT_N_SLOTS 4
+
 typedef struct {
     void* d_in;        size_t cap_in;
     uint64_t* d_offs;  size_t cap_offs;
@@ -52,11 +54,13 @@ typedef struct {
     uint8_t* d_u8b;    size_t cap_u8b;
     uint32_t* d_cls;   size_t cap_cls;
     uint32_t* d_rows;  size_t cap_rows;
+    uint32_t* d_tile;  size_t cap_tile;  /* compact form: per-tile hit counts, their prefix sums, the chunk total */
+    uint32_t* h_total;                   /* pinned: where the chunk total lands */
 } slot_t;
 
 struct bft_b200_ctx {
     int device, sm_count;
-    cudaStream_t streams[2];
+    cudaStream_t streams[BFT_N_SLOTS]; /* 0 and 1 serve every host pipeline; 2 and 3 only the compact form's deeper one */
     int k, W, G, rw;
     char** names;
     bft_b200_stats stats;
@@ -74,7 +78,7 @@ struct bft_b200_ctx {
     uint32_t* h_class_counts;
     size_t n_classes;
     unsigned long long* d_counter;
-    slot_t slot[2];
+    slot_t slot[BFT_N_SLOTS];
     uint64_t launches;
     size_t seq_smem;
     int ref_quirks;
@@ -147,7 +151,7 @@ extern "C" void bft_b200_close(bft_b200_ctx* c) {
     if (c->d_counter) cudaFree(c->d_counter);
     if (c->d_nbr) cudaFree(c->d_nbr);
     bft_b200_graph_release(c);
-    for (int s = 0; s < 2; s++) {
+    for (int s = 0; s < BFT_N_SLOTS; s++) {
         slot_t* sl = &c->slot[s];
         if (sl->d_in) cudaFree(sl->d_in);
         if (sl->d_offs) cudaFree(sl->d_offs);
@@ -156,6 +160,8 @@ extern "C" void bft_b200_close(bft_b200_ctx* c) {
         if (sl->d_u8b) cudaFree(sl->d_u8b);
         if (sl->d_cls) cudaFree(sl->d_cls);
         if (sl->d_rows) cudaFree(sl->d_rows);
+        if (sl->d_tile) cudaFree(sl->d_tile);
+        if (sl->h_total) cudaFreeHost(sl->h_total);
         if (c->streams[s]) cudaStreamDestroy(c->streams[s]);
     }
     if (c->names) {
@@ -273,7 +279,7 @@ extern "C" int bft_b200_open(const char* path, int device, bft_b200_ctx** out) {
     if (!rc && cudaMalloc((void**)&c->d_class_counts, (a->n_classes + 1) * sizeof(uint32_t)) != cudaSuccess) rc = set_err(BFT_B200_ERR_NOMEM, "cudaMalloc(class counts) failed");
     if (!rc && cudaMalloc((void**)&d_bad, sizeof(int)) != cudaSuccess) rc = set_err(BFT_B200_ERR_NOMEM, "cudaMalloc failed");
     if (!rc && cudaMalloc((void**)&c->d_counter, sizeof(unsigned long long)) != cudaSuccess) rc = set_err(BFT_B200_ERR_NOMEM, "cudaMalloc failed");
-    for (int s = 0; s < 2 && !rc; s++)
+    for (int s = 0; s < BFT_N_SLOTS && !rc; s++)
         if (cudaStreamCreateWithFlags(&c->streams[s], cudaStreamNonBlocking) != cudaSuccess) rc = set_err(BFT_B200_ERR_CUDA, "cudaStreamCreate failed");
     if (!rc && !(getenv("BFT_B200_NO_L2_PERSIST") && getenv("BFT_B200_NO_L2_PERSIST")[0] == '1')) {
         /* keep the hot block resident in L2 (persisting access-policy window on both streams); best effort */
@@ -289,7 +295,7 @@ extern "C" int bft_b200_open(const char* path, int device, bft_b200_ctx** out) {
             attr.accessPolicyWindow.hitRatio = persist >= win ? 1.0f : (float)((double)persist / (double)win);
             attr.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
             attr.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
-            for (int s2 = 0; s2 < 2; s2++) cudaStreamSetAttribute(c->streams[s2], cudaStreamAttributeAccessPolicyWindow, &attr);
+            for (int s2 = 0; s2 < BFT_N_SLOTS; s2++) cudaStreamSetAttribute(c->streams[s2], cudaStreamAttributeAccessPolicyWindow, &attr);
         }
         cudaGetLastError(); /* a refusal only costs performance */
     }
@@ -355,8 +361,7 @@ extern "C" void bft_b200_host_free(void* p) { if (p) cudaFreeHost(p); }
 extern "C" int bft_b200_sync(bft_b200_ctx* c) {
     if (!c) return set_err(BFT_B200_ERR_ARG, "bft_b200_sync: NULL context");
     CK(cudaSetDevice(c->device));
-    CK(cudaStreamSynchronize(c->streams[0]));
-    CK(cudaStreamSynchronize(c->streams[1]));
+    for (int s = 0; s < BFT_N_SLOTS; s++) CK(cudaStreamSynchronize(c->streams[s]));
     return 0;
 }
 
@@ -477,17 +482,41 @@ static int enqueue_records(bft_b200_ctx* c, cudaStream_t st, const uint8_t* d_re
     const size_t smem = bft_records_smem(nb, rb);
     if (smem > 227 * 1024) return set_err(BFT_B200_ERR_ARG, "bft_b200_query_records: %d genomes exceed the shared-memory tile; use bft_b200_query_kmers", c->G);
     if (smem > 48 * 1024) { /* opt in to large dynamic shared memory (wide colour rows) */
-#define BFT_L(W_) CK(cudaFuncSetAttribute(k_query_records<W_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem))
+#define BFT_L(W_) CK(cudaFuncSetAttribute(k_query_records<W_, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem))
         BFT_BY_W(c->W, BFT_L);
 #undef BFT_L
     }
     const size_t n_tiles = (n + BFT_TPB - 1) / BFT_TPB;
     const size_t want = (size_t)c->sm_count * 8;
     const int grid = (int)(n_tiles < want ? n_tiles : want);
-#define BFT_L(W_) k_query_records<W_><<<grid, BFT_TPB, smem, st>>>(c->dview, d_records, n, nb, rb, c->rw, c->d_class_rows, d_present, d_rows, d_n_present)
+#define BFT_L(W_) k_query_records<W_, false><<<grid, BFT_TPB, smem, st>>>(c->dview, d_records, n, nb, rb, c->rw, c->d_class_rows, d_present, d_rows, d_n_present, NULL, NULL, NULL)
     BFT_BY_W(c->W, BFT_L);
 #undef BFT_L
     c->launches++;
+    CK(cudaGetLastError());
+    return 0;
+}
+
+/* compact form, device side of one chunk: class ids + presence bits + per-tile counts, prefix sums, rows of the present
+ * k-mers back to back. d_tile holds [counts | offsets | total]. */
+static int enqueue_records_compact(bft_b200_ctx* c, cudaStream_t st, slot_t* sl, size_t n) {
+    const int nb = (2 * c->k + 7) / 8, rb = bft_b200_row_bytes(c);
+    const size_t n_tiles = (n + BFT_TPB - 1) / BFT_TPB;
+    const size_t smem_in = 2 * (size_t)BFT_TPB * (size_t)nb + 16, smem_rows = (size_t)BFT_TPB * (size_t)rb + 16;
+    if (smem_rows > 227 * 1024) return set_err(BFT_B200_ERR_ARG, "bft_b200_query_records_compact: %d genomes exceed the shared-memory tile", c->G);
+    if (smem_rows > 48 * 1024) CK(cudaFuncSetAttribute(k_compact_rows, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_rows));
+    const size_t want = (size_t)c->sm_count * 8;
+    const int grid = (int)(n_tiles < want ? n_tiles : want);
+    uint32_t* d_cnt = sl->d_tile;
+    uint32_t* d_off = sl->d_tile + n_tiles;
+    uint32_t* d_total = sl->d_tile + 2 * n_tiles;
+    /* rb = 0 in the first pass: no row tiles in shared memory */
+#define BFT_L(W_) k_query_records<W_, true><<<grid, BFT_TPB, smem_in, st>>>(c->dview, (const uint8_t*)sl->d_in, n, nb, 0, c->rw, c->d_class_rows, NULL, NULL, NULL, sl->d_cls, (uint32_t*)sl->d_u8a, d_cnt)
+    BFT_BY_W(c->W, BFT_L);
+#undef BFT_L
+    k_scan_tile_counts<<<1, 1024, 0, st>>>(d_cnt, (uint32_t)n_tiles, d_off, d_total);
+    k_compact_rows<<<grid, BFT_TPB, smem_rows, st>>>(sl->d_cls, n, d_off, c->d_class_rows, c->rw, rb, (uint8_t*)sl->d_rows);
+    c->launches += 3;
     CK(cudaGetLastError());
     return 0;
 }
@@ -539,6 +568,54 @@ extern "C" int bft_b200_query_records(bft_b200_ctx* c, const uint8_t* records, s
         CK(cudaMemcpy(&h, c->d_counter, sizeof h, cudaMemcpyDeviceToHost));
         *n_present = h;
     }
+    return 0;
+}
+
+/* Rows of a chunk can only be copied once its hit count is known on the host. Four slots on four streams, and the
+ * copy of chunk i - 2 is issued after the front half of chunk i has been enqueued: by then the count is there, so the
+ * host does not wait and neither copy engine idles. */
+extern "C" int bft_b200_query_records_compact(bft_b200_ctx* c, const uint8_t* records, size_t n, uint8_t* present_bits, uint8_t* rows,
+                                              uint64_t* n_present) {
+    if (!c || (!records && n) || !present_bits || !rows || !n_present) return set_err(BFT_B200_ERR_ARG, "bft_b200_query_records_compact: NULL argument");
+    CK(cudaSetDevice(c->device));
+    const size_t nb = (size_t)bft_b200_record_bytes(c), rb = (size_t)bft_b200_row_bytes(c);
+    for (int s = 0; s < BFT_N_SLOTS; s++) CK(cudaStreamSynchronize(c->streams[s]));
+    const size_t n_chunks = (n + BFT_CHUNK_KMERS - 1) / BFT_CHUNK_KMERS;
+    const size_t lag = 2;
+    size_t rows_done = 0;
+    *n_present = 0;
+    for (size_t i = 0; i < n_chunks + lag; i++) {
+        if (i < n_chunks) { /* front half of chunk i: records in, look-ups, compaction, presence bits and hit count out */
+            slot_t* sl = &c->slot[i % BFT_N_SLOTS];
+            cudaStream_t st = c->streams[i % BFT_N_SLOTS];
+            const size_t first = i * BFT_CHUNK_KMERS;
+            const size_t m = n - first < BFT_CHUNK_KMERS ? n - first : BFT_CHUNK_KMERS;
+            const size_t n_tiles = (m + BFT_TPB - 1) / BFT_TPB;
+            CK(cudaStreamSynchronize(st)); /* the slot's rows of four chunks ago reached the host long ago */
+            ENSURE(sl->d_in, sl->cap_in, m * nb);
+            ENSURE(sl->d_cls, sl->cap_cls, m * sizeof(uint32_t));
+            ENSURE(sl->d_u8a, sl->cap_u8a, (m + 31) / 32 * 4);
+            ENSURE(sl->d_rows, sl->cap_rows, m * rb);
+            ENSURE(sl->d_tile, sl->cap_tile, (2 * n_tiles + 1) * sizeof(uint32_t));
+            if (!sl->h_total) CK(cudaMallocHost((void**)&sl->h_total, 16));
+            CK(cudaMemcpyAsync(sl->d_in, records + first * nb, m * nb, cudaMemcpyHostToDevice, st));
+            int rc = enqueue_records_compact(c, st, sl, m);
+            if (rc) return rc;
+            CK(cudaMemcpyAsync(present_bits + first / 8, sl->d_u8a, (m + 7) / 8, cudaMemcpyDeviceToHost, st)); /* chunks are multiples of 8 */
+            CK(cudaMemcpyAsync(sl->h_total, sl->d_tile + 2 * n_tiles, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+        }
+        if (i >= lag) { /* back half of chunk i - lag: its rows, now that their number is known */
+            const size_t j = i - lag;
+            slot_t* pl = &c->slot[j % BFT_N_SLOTS];
+            cudaStream_t pst = c->streams[j % BFT_N_SLOTS];
+            CK(cudaStreamSynchronize(pst));
+            const size_t hits = pl->h_total[0];
+            if (hits) CK(cudaMemcpyAsync(rows + rows_done * rb, pl->d_rows, hits * rb, cudaMemcpyDeviceToHost, pst));
+            rows_done += hits;
+        }
+    }
+    for (int s = 0; s < BFT_N_SLOTS; s++) CK(cudaStreamSynchronize(c->streams[s]));
+    *n_present = rows_done;
     return 0;
 }
 

@@ -169,10 +169,16 @@ __device__ __forceinline__ void bft_bulk_store(void* gmem_dst, const void* smem_
 /* dynamic shared memory of k_query_records: two record tiles, two row tiles, two mbarriers */
 __host__ __device__ inline size_t bft_records_smem(int nb, int rb) { return 2 * (size_t)BFT_TPB * (size_t)(nb + rb) + 16; }
 
-template <int W>
+/* COMPACT = false: rows of every k-mer, fixed stride (bft_b200_query_records).
+ * COMPACT = true : first pass of bft_b200_query_records_compact — class id per k-mer, presence as one bit per k-mer
+ *                  (a warp ballot is 32 of them) and the number of hits of every tile; k_scan_tile_counts and
+ *                  k_compact_rows then lay the rows of the present k-mers out back to back, in query order. */
+template <int W, bool COMPACT>
 __global__ void __launch_bounds__(BFT_TPB) k_query_records(const bft_view_t v, const uint8_t* __restrict__ records, size_t n, int nb, int rb,
                                                            int rw, const uint32_t* __restrict__ class_rows, uint8_t* __restrict__ present,
-                                                           uint8_t* __restrict__ rows, unsigned long long* __restrict__ n_present) {
+                                                           uint8_t* __restrict__ rows, unsigned long long* __restrict__ n_present,
+                                                           uint32_t* __restrict__ cls_out, uint32_t* __restrict__ present_bits,
+                                                           uint32_t* __restrict__ tile_cnt) {
     extern __shared__ uint4 bft_tile_smem[];
     uint8_t* const sm = (uint8_t*)bft_tile_smem;
     const uint32_t in_bytes = (uint32_t)BFT_TPB * (uint32_t)nb, out_bytes = (uint32_t)BFT_TPB * (uint32_t)rb;
@@ -187,6 +193,8 @@ __global__ void __launch_bounds__(BFT_TPB) k_query_records(const bft_view_t v, c
         bft_mbar_init(bar + 1, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
+    __shared__ unsigned int tile_hits[2];
+    if (threadIdx.x < 2) tile_hits[threadIdx.x] = 0;
     __syncthreads();
     unsigned int hits = 0;
     uint32_t it = 0;
@@ -225,6 +233,21 @@ __global__ void __launch_bounds__(BFT_TPB) k_query_records(const bft_view_t v, c
             for (int w = 0; w < W; w++) km[w] &= bft_word_mask(2 * v.k, w); /* the reference ignores the pad bits of the last byte */
             cls = bft_lookup_w(&v, km, W);
         }
+        if constexpr (COMPACT) {
+            const bool hit = cls != BFT_CLS_NONE;
+            const uint32_t ball = __ballot_sync(0xffffffffu, hit);
+            if (threadIdx.x < cnt) cls_out[base + threadIdx.x] = cls;
+            if ((threadIdx.x & 31) == 0) {
+                if (base + threadIdx.x < n) present_bits[(base + threadIdx.x) >> 5] = ball;
+                if (ball) atomicAdd(&tile_hits[b], (unsigned int)__popc(ball));
+            }
+            __syncthreads(); /* every warp has read its records and added its hits */
+            if (lead) {
+                tile_cnt[tile] = tile_hits[b];
+                tile_hits[b] = 0; /* next used two tiles from now, behind another barrier */
+            }
+            continue;
+        }
         /* the rows of tile it-2 must have left this row buffer before it is written again */
         if (lead) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
         __syncthreads();
@@ -252,6 +275,65 @@ __global__ void __launch_bounds__(BFT_TPB) k_query_records(const bft_view_t v, c
     if (n_present) {
         for (int o = 16; o > 0; o >>= 1) hits += __shfl_down_sync(0xffffffffu, hits, o);
         if ((threadIdx.x & 31) == 0 && hits) atomicAdd(n_present, (unsigned long long)hits);
+    }
+}
+
+/* exclusive prefix sum of the per-tile hit counts of one chunk (at most a few thousand tiles): one block */
+__global__ void __launch_bounds__(1024) k_scan_tile_counts(const uint32_t* __restrict__ tile_cnt, uint32_t n_tiles, uint32_t* __restrict__ tile_off,
+                                                           uint32_t* __restrict__ total) {
+    __shared__ uint32_t part[1024];
+    const uint32_t per = (n_tiles + 1023u) / 1024u;
+    const uint32_t lo = threadIdx.x * per, hi = min(n_tiles, lo + per);
+    uint32_t sum = 0;
+    for (uint32_t i = lo; i < hi; i++) sum += tile_cnt[i];
+    part[threadIdx.x] = sum;
+    __syncthreads();
+    for (uint32_t o = 1; o < 1024; o <<= 1) { /* Hillis-Steele inclusive scan of the 1024 partial sums */
+        const uint32_t t = threadIdx.x >= o ? part[threadIdx.x - o] : 0u;
+        __syncthreads();
+        part[threadIdx.x] += t;
+        __syncthreads();
+    }
+    uint32_t run = part[threadIdx.x] - sum;
+    for (uint32_t i = lo; i < hi; i++) {
+        tile_off[i] = run;
+        run += tile_cnt[i];
+    }
+    if (threadIdx.x == 1023) *total = part[1023];
+}
+
+/* second pass of the compact form: the rows of a tile's present k-mers, in order, to rows[tile_off[tile] ...] */
+__global__ void __launch_bounds__(BFT_TPB) k_compact_rows(const uint32_t* __restrict__ cls, size_t n, const uint32_t* __restrict__ tile_off,
+                                                          const uint32_t* __restrict__ class_rows, int rw, int rb, uint8_t* __restrict__ rows) {
+    extern __shared__ uint4 bft_tile_smem[];
+    uint8_t* const sm = (uint8_t*)bft_tile_smem;
+    __shared__ uint32_t warp_hits[BFT_TPB / 32];
+    const size_t n_tiles = (n + BFT_TPB - 1) / BFT_TPB;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (size_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        const size_t i = tile * BFT_TPB + threadIdx.x;
+        const uint32_t c = i < n ? __ldg(cls + i) : BFT_CLS_NONE;
+        const bool hit = c != BFT_CLS_NONE;
+        const uint32_t ball = __ballot_sync(0xffffffffu, hit);
+        if (lane == 0) warp_hits[warp] = (uint32_t)__popc(ball);
+        __syncthreads();
+        uint32_t before = 0, total = 0;
+        for (int w = 0; w < BFT_TPB / 32; w++) {
+            const uint32_t h = warp_hits[w];
+            before += w < warp ? h : 0u;
+            total += h;
+        }
+        if (hit) {
+            uint8_t* o = sm + (size_t)(before + (uint32_t)__popc(ball & ((1u << lane) - 1u))) * rb;
+            for (int j = 0; j < rb; j += 4) {
+                const uint32_t word = __ldg(class_rows + (size_t)c * rw + (j >> 2));
+                for (int q = 0; q < 4 && j + q < rb; q++) o[j + q] = (uint8_t)(word >> (8 * q));
+            }
+        }
+        __syncthreads();
+        uint8_t* dst = rows + (size_t)tile_off[tile] * rb;
+        for (size_t q = threadIdx.x; q < (size_t)total * rb; q += blockDim.x) dst[q] = sm[q];
+        __syncthreads();
     }
 }
 

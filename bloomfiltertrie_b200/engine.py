@@ -33,6 +33,7 @@ ABI_SYMBOLS = [
     "bft_b200_graph_prepare", "bft_b200_graph_release", "bft_b200_graph_adjacency", "bft_b200_connected_components",
     "bft_b200_simple_paths", "bft_b200_simple_paths_file", "bft_b200_free", "bft_b200_query_vertex_ids",
     "bft_b200_record_bytes", "bft_b200_row_bytes", "bft_b200_query_records", "bft_b200_query_records_device",
+    "bft_b200_query_records_compact",
 ]
 
 
@@ -104,6 +105,7 @@ def load_library() -> C.CDLL:
     lib.bft_b200_row_bytes.argtypes = [vp]
     lib.bft_b200_query_records.argtypes = [vp, u8p, sz, u8p, u8p, C.POINTER(C.c_uint64)]
     lib.bft_b200_query_records_device.argtypes = [vp, u8p, sz, u8p, u8p, u64p]
+    lib.bft_b200_query_records_compact.argtypes = [vp, u8p, sz, u8p, u8p, C.POINTER(C.c_uint64)]
     lib.bft_b200_graph_prepare.argtypes = [vp]
     lib.bft_b200_graph_release.argtypes = [vp]
     lib.bft_b200_graph_adjacency.argtypes = [vp, u32p, sz]
@@ -231,6 +233,18 @@ class BFTEngine:
         cnt = C.c_uint64()
         self._ck(self.lib.bft_b200_query_records(self.h, _ptr(records), n, _ptr(present), _ptr(rows), C.byref(cnt)), "bft_b200_query_records")
         return present, rows, int(cnt.value)
+
+    def query_records_compact(self, records: np.ndarray, out_bits: Optional[np.ndarray] = None, out_rows: Optional[np.ndarray] = None):
+        """(presence bits uint8 [(n+7)//8], rows of the present k-mers uint8 [n_present, ceil(G/8)] in query order, n_present)."""
+        nb, rb = self.lib.bft_b200_record_bytes(self.h), self.lib.bft_b200_row_bytes(self.h)
+        records = np.ascontiguousarray(records, dtype=np.uint8).reshape(-1, nb)
+        n = records.shape[0]
+        bits = out_bits if out_bits is not None else np.empty((n + 7) // 8, dtype=np.uint8)
+        rows = out_rows if out_rows is not None else np.empty((n, rb), dtype=np.uint8)
+        cnt = C.c_uint64()
+        self._ck(self.lib.bft_b200_query_records_compact(self.h, _ptr(records), n, _ptr(bits), _ptr(rows), C.byref(cnt)),
+                 "bft_b200_query_records_compact")
+        return bits, rows[:cnt.value], int(cnt.value)
 
     def query_records_device(self, d_records, n: int, d_present, d_rows, d_n_present=None):
         self._ck(self.lib.bft_b200_query_records_device(self.h, _ptr(d_records), n, _ptr(d_present), _ptr(d_rows), _ptr(d_n_present)),

@@ -197,6 +197,13 @@ int bft_b200_query_records(bft_b200_ctx* ctx, const uint8_t* records, size_t n, 
                            uint64_t* n_present);
 int bft_b200_query_records_device(bft_b200_ctx* ctx, const uint8_t* d_records, size_t n, uint8_t* d_present,
                                   uint8_t* d_rows, uint64_t* d_n_present);
+/* The same answers without the zeros: present_bits = one bit per k-mer (bit i % 8 of byte i / 8; (n + 7) / 8 bytes),
+ * rows = the bft_b200_row_bytes()-byte rows of the PRESENT k-mers only, back to back in query order (capacity: n rows),
+ * *n_present = how many there are. The row of k-mer i is rows[r * row_bytes] with r = number of set bits before i —
+ * a CSV writer (src/file_io.c:740-752) walks both with one running index. On a batch where half the k-mers are absent
+ * half the row bytes never cross PCIe. */
+int bft_b200_query_records_compact(bft_b200_ctx* ctx, const uint8_t* records, size_t n, uint8_t* present_bits,
+                                   uint8_t* rows, uint64_t* n_present);
 
 /* ---- graph traversals (reference src/snippets.c) ----------------------------------------------
  * The coloured de Bruijn graph is materialised on the device once (one vertex per stored k-mer, in the order of

@@ -45,6 +45,10 @@ def test_kmer_presence_and_colours(built):
     np.testing.assert_array_equal(p_rec, ref_present)
     np.testing.assert_array_equal(r_rec, np.ascontiguousarray(ref_rows).view(np.uint8).reshape(len(q), -1)[:, :rb])
     assert n_rec == int(ref_present.sum())
+    bits, crows, n_c = eng.query_records_compact(synth.words_to_bytes(q, c["k"]))
+    np.testing.assert_array_equal(np.unpackbits(bits, bitorder="little")[:len(q)], ref_present)
+    np.testing.assert_array_equal(crows, r_rec[ref_present.astype(bool)])
+    assert n_c == n_rec
     # class ids are consistent with rows and counts
     table = eng.class_rows()
     counts = eng.class_counts()
