@@ -35,8 +35,11 @@ typedef struct {
     /* capacities */
     size_t cap_nodes, cap_ccs, cap_firstcc, cap_csr, cap_filter3, cap_pref, cap_buckets, cap_ovf, cap_uc_lines, cap_cls_off, cap_cls_bytes;
     /* class hash map */
-    uint32_t* map; size_t map_cap, map_used;
-    struct { uint64_t h; uint32_t id; uint32_t valid; } hot[4096]; /* recently seen classes: most lines share a few */
+    /* colour-class dedup: open addressing; a slot carries the hash and (for annotations up to 16 bytes — nearly all
+     * of them) the bytes themselves, so a look-up that hits costs one cache line instead of three dependent misses */
+    struct cls_slot { uint64_t h; uint32_t id; uint32_t len; uint8_t inl[16]; }* map;
+    size_t map_cap, map_used;
+    struct cls_slot hot[4096]; /* recently seen classes (direct mapped): most lines of a UC share a few */
     /* scratch */
     line_tmp_t* tmp; size_t cap_tmp;
     uint8_t* scratch; size_t cap_scratch;   /* one annotation + extended byte */
@@ -119,37 +122,32 @@ static uint32_t class_of(ctx_t* c, const uint8_t* s, size_t n) {
     bft_arena_t* a = c->a;
     if ((c->map_used + 1) * 2 > c->map_cap) {
         size_t ncap = c->map_cap ? c->map_cap * 2 : (1u << 16);
-        uint32_t* nm = (uint32_t*)xrealloc(c, NULL, ncap * sizeof(uint32_t));
-        memset(nm, 0xff, ncap * sizeof(uint32_t));
+        struct cls_slot* nm = (struct cls_slot*)xrealloc(c, NULL, ncap * sizeof(struct cls_slot));
+        memset(nm, 0xff, ncap * sizeof(struct cls_slot)); /* id 0xffffffff = empty */
         for (size_t i = 0; i < c->map_cap; i++) {
-            uint32_t id = c->map[i];
-            if (id == 0xffffffffu) continue;
-            uint64_t h = bft_xxh64(a->cls_bytes + a->cls_off[id], a->cls_off[id + 1] - a->cls_off[id], 0x5bd1e995);
-            size_t j = (size_t)h & (ncap - 1);
-            while (nm[j] != 0xffffffffu) j = (j + 1) & (ncap - 1);
-            nm[j] = id;
+            if (c->map[i].id == 0xffffffffu) continue;
+            size_t j = (size_t)c->map[i].h & (ncap - 1);
+            while (nm[j].id != 0xffffffffu) j = (j + 1) & (ncap - 1);
+            nm[j] = c->map[i];
         }
         free(c->map);
         c->map = nm;
         c->map_cap = ncap;
     }
-    uint64_t h = bft_xxh64(s, n, 0x5bd1e995);
-    {
-        const size_t slot = (size_t)(h >> 20) & 4095;
-        if (c->hot[slot].valid && c->hot[slot].h == h) {
-            const uint32_t id = c->hot[slot].id;
-            if (a->cls_off[id + 1] - a->cls_off[id] == n && memcmp(a->cls_bytes + a->cls_off[id], s, n) == 0) return id;
-        }
-    }
+    const uint64_t h = bft_xxh64(s, n, 0x5bd1e995);
+    struct cls_slot* const hot = &c->hot[(size_t)(h >> 20) & 4095];
+    if (hot->h == h && hot->len == (uint32_t)n && hot->id != 0xffffffffu &&
+        (n <= sizeof hot->inl ? memcmp(hot->inl, s, n) == 0 : memcmp(a->cls_bytes + a->cls_off[hot->id], s, n) == 0))
+        return hot->id;
     size_t j = (size_t)h & (c->map_cap - 1);
     for (;;) {
-        uint32_t id = c->map[j];
-        if (id == 0xffffffffu) break;
-        size_t ln = a->cls_off[id + 1] - a->cls_off[id];
-        if (ln == n && memcmp(a->cls_bytes + a->cls_off[id], s, n) == 0) {
-            const size_t slot = (size_t)(h >> 20) & 4095;
-            c->hot[slot].h = h; c->hot[slot].id = id; c->hot[slot].valid = 1;
-            return id;
+        const struct cls_slot* e = &c->map[j];
+        if (e->id == 0xffffffffu) break;
+        if (e->h == h && e->len == (uint32_t)n) {
+            if (n <= sizeof e->inl ? memcmp(e->inl, s, n) == 0 : memcmp(a->cls_bytes + a->cls_off[e->id], s, n) == 0) {
+                *hot = *e;
+                return e->id;
+            }
         }
         j = (j + 1) & (c->map_cap - 1);
     }
@@ -163,8 +161,13 @@ static uint32_t class_of(ctx_t* c, const uint8_t* s, size_t n) {
     a->n_classes++;
     a->cls_off[a->n_classes] = (uint32_t)a->cls_bytes_len;
     if (n > a->max_cls_len) a->max_cls_len = n;
-    c->map[j] = id;
+    c->map[j].h = h;
+    c->map[j].id = id;
+    c->map[j].len = (uint32_t)n;
+    memset(c->map[j].inl, 0, sizeof c->map[j].inl);
+    memcpy(c->map[j].inl, s, n < sizeof c->map[j].inl ? n : sizeof c->map[j].inl);
     c->map_used++;
+    *hot = c->map[j];
     return id;
 }
 
@@ -611,6 +614,7 @@ size_t bft_arena_bytes(const bft_arena_t* a) {
 
 bft_arena_t* bft_arena_from_memory(const uint8_t* buf, size_t len, char* err, size_t errlen) {
     ctx_t* c = (ctx_t*)calloc(1, sizeof(ctx_t));
+    if (c) memset(c->hot, 0xff, sizeof c->hot); /* id 0xffffffff = empty */
     bft_arena_t* a = (bft_arena_t*)calloc(1, sizeof(bft_arena_t));
     if (!c || !a) { free(c); free(a); if (err) snprintf(err, errlen, "bft_flatten: out of memory"); return NULL; }
     c->buf = buf; c->len = len; c->a = a; c->err = err; c->errlen = errlen;
