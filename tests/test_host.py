@@ -10,6 +10,7 @@ import numpy as np
 import pytest
 
 import refutil
+import cases
 from bloomfiltertrie_b200 import shard, synth
 
 ROOT = refutil.ROOT
@@ -101,6 +102,29 @@ def test_flattened_arena_walk_reproduces_golden(name, host_tool, tmp_path):
     assert int(p.stdout.split(b"=")[1]) == int(z["present"].sum())
     names = [f"genome_{i:04d}.kc" for i in range(G)]
     assert open(out, "rb").read() == _csv_bytes(names, z["rows"], G)
+
+
+@pytest.mark.parametrize("name", NAMES)
+def test_storage_locations_are_unique_per_stored_kmer(name, tmp_path):
+    """The traversal kernels key their vertex table on the storage location a look-up ends in (bft_lookup_loc): every
+    stored k-mer must end in its own location below n_loc, absent k-mers in none, and asking for the location must
+    not change the answer. Host build of the same walk the kernels compile."""
+    import re
+    exe = str(tmp_path / "arena_loc_check")
+    _gcc(["-O2", "-std=c11", "-I", CSRC, os.path.join(ROOT, "tests", "tools", "arena_loc_check.c"),
+          os.path.join(CSRC, "bft_flatten.c"), os.path.join(CSRC, "bft_io.c"), "-o", exe])
+    c = cases.make_golden_case(name)
+    k = c["k"]
+    stored = np.unique(np.concatenate(c["genome_words"]), axis=0)
+    z = np.load(os.path.join(refutil.GOLDEN, name + ".npz"))
+    absent = z["queries"][z["present"] == 0]
+    q = str(tmp_path / "all.kc")
+    synth.write_kmers_comp(q, np.concatenate([stored, absent]), k)
+    out = subprocess.run([exe, os.path.join(refutil.GOLDEN, name + ".bft"), q], stdout=subprocess.PIPE, check=True).stdout.decode()
+    f = {m.group(1): int(m.group(2)) for m in re.finditer(r"(\w+)=(\d+)", out)}
+    assert f["queries"] == len(stored) + len(absent)
+    assert f["found"] == f["distinct_locs"] == f["stored"] == len(stored)
+    assert f["max_loc"] < f["n_loc"] and f["answer_mismatch"] == 0
 
 
 def test_flattener_rejects_garbage(host_tool, tmp_path):
