@@ -414,6 +414,55 @@ static int find_kmer(const o_bft* b, const o_node* nd, const uint8_t* kmer_in, i
     return 1;
 }
 
+/* ---- enumeration: iterate_over_kmers_from_node (src/extract_kmers.c:3-597) --------------------------------------
+ * Order of the reference: the CCs of a Node in order; inside a CC the stored prefixes in order (clusters by ascending
+ * p_u, inside a cluster ascending p_v); for a prefix its inline suffix lines in order, or the k-mers of its child
+ * Node; after the CCs the Node's own UC lines. K-mers are rebuilt as ASCII: the path above the Node, the prefix
+ * un-rotated from (p_u, p_v) (:84-85), the suffix nucleotides of the line. */
+typedef struct { char* out; size_t n, cap; int k; } o_emit;
+
+static void emit_kmer(o_emit* e, const char* acc, int acc_len, const uint8_t* packed, int n_nuc) {
+    if (e->n < e->cap) {
+        char* d = e->out + e->n * (size_t)e->k;
+        memcpy(d, acc, (size_t)acc_len);
+        for (int j = 0; j < n_nuc; j++) d[acc_len + j] = "ACGT"[(packed[j >> 2] >> (2 * (j & 3))) & 3];
+    }
+    e->n++;
+}
+
+static void extract_node(const o_bft* b, const o_node* nd, int size, char* acc, int acc_len, o_emit* e) {
+    const o_level* l = &b->lvl[size / 9 - 1];
+    for (int i = 0; i < nd->n_cc; i++) {
+        const o_cc* cc = &nd->ccs[i];
+        int pu = -1;
+        for (int pos = 0; pos < cc->nb_elem; pos++) {
+            if (cluster_flag(b, cc, size, pos)) { /* first prefix of the next cluster: the next set bit of filter2 */
+                do pu++; while (pu < (1 << cc->p) && !((cc->f2[pu / 8] >> (pu % 8)) & 1));
+            }
+            const uint32_t pv = cc->s == 8 ? cc->f3[pos] : ((pos & 1) ? cc->f3[pos / 2] >> 4 : cc->f3[pos / 2] & 0xf);
+            const uint32_t rot = ((uint32_t)pu << cc->s) | pv;             /* nuc1..nuc8, nuc0 */
+            const uint32_t r18 = (rot >> 2) | ((rot & 3u) << 16);          /* nuc0..nuc8, MSB first */
+            for (int j = 0; j < 9; j++) acc[acc_len + j] = "ACGT"[(r18 >> (2 * (8 - j))) & 3];
+            if (size == NB_CHAR_SUF_PREF) { emit_kmer(e, acc, acc_len + 9, NULL, 0); continue; }
+            if (cc->node_of[pos] >= 0) { extract_node(b, &cc->nodes[cc->node_of[pos]], size - 9, acc, acc_len + 9, e); continue; }
+            const o_uc* u = &cc->buckets[pos / l->nb_ucs_skp];
+            const int nb = l->size_kmer_in_bytes_minus_1, first = cc->first_line[pos], ne = get_nb_elts(cc, pos);
+            for (int q = first; q < first + ne; q++)
+                emit_kmer(e, acc, acc_len + 9, &u->suffixes[(size_t)q * (nb + u->size_annot)], size - 9);
+        }
+    }
+    const o_uc* u = &nd->uc;
+    for (int q = 0; q < u->n; q++)
+        emit_kmer(e, acc, acc_len, &u->suffixes[(size_t)q * (l->size_kmer_in_bytes + u->size_annot)], size);
+}
+
+size_t o_extract_kmers(o_bft* b, char* out, size_t cap) {
+    char acc[160];
+    o_emit e = {out, 0, out ? cap : 0, b->k};
+    extract_node(b, &b->root, b->k, acc, 0, &e);
+    return e.n;
+}
+
 /* ---- annotation -------------------------------------------------------------------------------------------- */
 /* get_annot + get_extend_annot, src/UC.c:171-239, 501-521 */
 static void get_annot(const o_hit* h, const uint8_t** annot, int* size_annot, const uint8_t** ext) {

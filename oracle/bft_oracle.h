@@ -36,6 +36,10 @@ int o_branching_left(o_bft* b, const uint8_t* kmer);
 int o_query_sequence(o_bft* b, const char* seq, double threshold, int canonical, uint32_t* ids);
 
 
+/* iterate_over_kmers / -extract_kmers (src/extract_kmers.c:3-597): every stored k-mer as ASCII (k characters each, no
+ * separators) in the reference's own iteration order. Writes at most cap k-mers; returns how many the BFT holds. */
+size_t o_extract_kmers(o_bft* b, char* out, size_t cap);
+
 /* ---- graph traversals (bft_graph_oracle.c; reference src/snippets.c) ------------------------------------------------
  * kmers: every stored k-mer as ASCII, n * k characters, in the order iterate_over_kmers visits them. */
 int64_t o_connected_components(o_bft* b, const char* kmers, size_t n, const uint32_t* ids, int n_ids, uint32_t* labels);

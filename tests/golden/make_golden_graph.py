@@ -7,10 +7,15 @@ src/snippets.c driven by oracle/ref_graph.c (oracle/_ref/ref_graph):
   paths_r<ratio> the bytes extract_simple_core_paths_to_disk(graph, ratio, file) wrote, for the ratios on which the
                  reference runs to completion and its intersection_annotations returns the true intersection
                  (it drops genome ids for some annotation encodings)
-The leaf-level fixture (golden_lowcomplex_k18_g3) is left out: the reference's BFS and DFS disagree on it."""
+The leaf-level fixture (golden_lowcomplex_k18_g3) is left out: the reference's BFS and DFS disagree on it.
+Also writes extract_sha256.json (see extract_digests)."""
 import os
 import sys
 import tempfile
+
+import glob
+import hashlib
+import json
 
 import numpy as np
 
@@ -43,5 +48,21 @@ def main():
         print(name, n_bfs, {r: int(out[f"longest_r{r}"]) for r in ratios}, os.path.getsize(os.path.join(HERE, "graph_" + name + ".npz")))
 
 
+def extract_digests():
+    """extract_sha256.json: per golden .bft the number of k-mers and the SHA-256 of the reference's own
+    `-extract_kmers kmers` output (k-mers in iterate_over_kmers order, newlines removed)."""
+    wd = tempfile.mkdtemp()
+    out = {}
+    for bft in sorted(glob.glob(os.path.join(HERE, "golden_*.bft"))):
+        name = os.path.basename(bft)[:-4]
+        data = refutil.ref_extract_ascii(bft, wd)
+        k = int(np.load(os.path.join(HERE, name + ".npz"))["k"])
+        out[name] = {"n_kmers": len(data) // k, "sha256": hashlib.sha256(data).hexdigest()}
+    with open(os.path.join(HERE, "extract_sha256.json"), "w") as f:
+        json.dump(out, f, indent=1, sort_keys=True)
+    print(out)
+
+
 if __name__ == "__main__":
+    extract_digests()
     main()

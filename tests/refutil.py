@@ -226,8 +226,28 @@ def oracle_lib():
         lib.o_simple_paths.restype = C.c_void_p
         lib.o_simple_paths.argtypes = [C.c_void_p, C.c_char_p, C.c_size_t, C.c_double, C.c_int, C.POINTER(C.c_size_t), C.POINTER(C.c_int)]
         lib.o_free_buf.argtypes = [C.c_void_p]
+        lib.o_extract_kmers.restype = C.c_size_t
+        lib.o_extract_kmers.argtypes = [C.c_void_p, C.c_char_p, C.c_size_t]
         _olib = lib
     return _olib
+
+
+def oracle_extract_ascii(bft_path: str) -> bytes:
+    """Every stored k-mer in iterate_over_kmers order from the oracle's own restatement (n * k characters)."""
+    import ctypes as C
+    lib = oracle_lib()
+    err = C.create_string_buffer(256)
+    h = lib.o_load(os.fsencode(bft_path), err, 256)
+    if not h:
+        raise RuntimeError(err.value.decode())
+    try:
+        k = lib.o_k(h)
+        n = lib.o_extract_kmers(h, None, 0)
+        buf = C.create_string_buffer(max(1, n * k))
+        assert lib.o_extract_kmers(h, buf, n) == n
+        return buf.raw[:n * k]
+    finally:
+        lib.o_free(h)
 
 
 class OracleGraph:

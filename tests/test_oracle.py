@@ -37,6 +37,7 @@ def test_oracle_matches_compiled_reference(name, workdir):
     c = cases.make_case(name)
     k, G = c["k"], c["n_genomes"]
     bft = refutil.build_bft(workdir, "o_" + name, c["genome_words"], k)
+    assert refutil.oracle_extract_ascii(bft) == refutil.ref_extract_ascii(bft, workdir)   # iterate_over_kmers order
     q = c["queries"][:1500]
     rp, rr = refutil.ref_kmers(bft, q, k, G)
     op, orow = refutil.oracle_kmers(bft, q, k, G, workdir)
@@ -56,6 +57,38 @@ def test_oracle_matches_compiled_reference(name, workdir):
 import graphutil  # noqa: E402
 
 GRAPH_NAMES = sorted(os.path.basename(p)[len("graph_"):-4] for p in glob.glob(os.path.join(refutil.GOLDEN, "graph_*.npz")))
+
+
+@pytest.mark.parametrize("name", NAMES)
+def test_oracle_enumeration_reproduces_golden(name):
+    """o_extract_kmers (iterate_over_kmers restated): the same k-mers in the same order as the reference's own
+    `-extract_kmers kmers` output, whose SHA-256 is committed (tests/golden/extract_sha256.json)."""
+    import hashlib
+    import json
+    want = json.load(open(os.path.join(refutil.GOLDEN, "extract_sha256.json")))[name]
+    data = refutil.oracle_extract_ascii(os.path.join(refutil.GOLDEN, name + ".bft"))
+    k = int(np.load(os.path.join(refutil.GOLDEN, name + ".npz"))["k"])
+    assert len(data) == want["n_kmers"] * k
+    assert hashlib.sha256(data).hexdigest() == want["sha256"]
+    c = cases.make_golden_case(name)           # and they are exactly the k-mers the case inserted
+    assert sorted(graphutil.kmer_list(data, k)) == sorted(graphutil.kmer_list(graphutil.case_kmers_ascii(c), k))
+
+
+@pytest.mark.parametrize("name", GRAPH_NAMES)
+def test_graph_oracle_reproduces_golden_bytes(name):
+    """With the oracle's own enumeration as the iteration order, the statement-by-statement path extraction must write
+    the very bytes the reference wrote (committed in graph_<name>.npz) — no reference needed at run time."""
+    z = np.load(os.path.join(refutil.GOLDEN, "graph_" + name + ".npz"))
+    bft = os.path.join(refutil.GOLDEN, name + ".bft")
+    og = refutil.OracleGraph(bft, refutil.oracle_extract_ascii(bft))
+    try:
+        assert og.components() == int(z["n_components"])
+        for r in z["ratios"]:
+            mine, longest = og.simple_paths(float(r), faithful=True)
+            assert mine == z[f"paths_r{r}"].tobytes()
+            assert longest == int(z[f"longest_r{r}"])
+    finally:
+        og.close()
 
 
 @pytest.mark.parametrize("name", GRAPH_NAMES)
@@ -88,6 +121,7 @@ def test_graph_oracle_matches_compiled_reference(name, workdir):
     k = c["k"]
     bft = refutil.build_bft(workdir, "og_" + name, c["genome_words"], k)
     asc = refutil.ref_extract_ascii(bft, workdir)
+    assert refutil.oracle_extract_ascii(bft) == asc        # the oracle's enumeration, same k-mers in the same order
     assert sorted(graphutil.kmer_list(asc, k)) == sorted(graphutil.kmer_list(graphutil.case_kmers_ascii(c), k))
     og = refutil.OracleGraph(bft, asc)
     try:
