@@ -134,15 +134,68 @@ def peaks():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
-def ncu_traffic():
-    """dram bytes per launch of the dominant kernel from the committed ncu --set full capture, if any."""
+def ncu_capture():
+    """Summary of the committed ncu --set full capture of the dominant kernel (tools/ncu_summary.py writes it), if any."""
     p = os.path.join(ROOT, "profiles", "ncu_k_query_kmers.json")
     if os.path.exists(p):
         try:
-            return json.load(open(p)).get("dram_bytes_per_kmer")
+            return json.load(open(p))
         except Exception:
             return None
     return None
+
+
+def kmer_roofline(eng, ws, n, k_ms, W, RW, args, traffic_ok, kernel=None):
+    """Roofline record of the k-mer query kernel (HBM-bound, random access).
+
+    achieved = ALGORITHMIC bytes of the ARENA's walk per launch / CUDA-event time: per k-mer the key words in (8*W), the
+    presence byte + colour row out (1 + 4*RW) and one 32*W-byte bucket for every k-mer whose walk reaches a bucket
+    (measured on the timed batch by k_kmer_walk_stats; k-mers cut short by the root directory or by the L2-resident
+    stored-k-mer filter touch no HBM). The root directory entry, the filter sector and the class row come from L2 and
+    are listed as l2_bytes_per_kmer. traffic = ncu dram__bytes of the committed --set full capture of this kernel on
+    this workload (profiles/ncu_k_query_kmers.json, written by tools/ncu_summary.py); traffic / algorithmic = wasted
+    DRAM traffic. A_min / A_ref (the sectors the REFERENCE layout's walk would dereference) are context:
+    the arena does not move them, so they are not the roofline."""
+    nodes_pk, depth_pk, found_pk = ws["nodes"] / n, ws["search_depth"] / n, ws["found"] / n
+    cc_pk = ws["cc_probed"] / n
+    bucket_pk = ws["bucket_searches"] / n
+    reject_pk = ws["filter_rejects"] / n
+    a_min = 8 * W + (1 + 4 * RW) + 32.0 * (6 * nodes_pk + depth_pk + found_pk)
+    a_ref = 8 * W + (1 + 4 * RW) + 32.0 * (5 * nodes_pk + 2 * cc_pk + depth_pk + found_pk)
+    a_arena = 8 * W + (1 + 4 * RW) + 32.0 * W * bucket_pk
+    achieved = a_arena * n / (k_ms / 1e3) / 1e9
+    peak, peak_src = peaks()
+    cap = ncu_capture() if traffic_ok else None
+    traffic = cap.get("dram_bytes_per_kmer") if cap else None
+    probe = None
+    if not args.no_probe:
+        probe = eng.random_gather_probe(4 << 30, 1 << 28)
+    st = eng.stats()
+    return {"bound": "hbm", "kernel": kernel or ("k_query_kmers_rows" if RW in (1, 2, 4) else "k_query_kmers+k_expand_rows"),
+            "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+            "traffic": (traffic * n if traffic else None), "peak_source": peak_src, "kernel_ms": k_ms,
+            "kmers_per_sec_kernel": n / (k_ms / 1e3),
+            "algorithmic_bytes_per_kmer": a_arena,
+            "algorithmic_bytes_formula": "8*W in + (1 + 4*RW) out + 32*W * P(walk reaches a bucket)",
+            "bucket_accesses_per_kmer": bucket_pk, "filter_rejects_per_kmer": reject_pk, "found_frac": found_pk,
+            "l2_bytes_per_kmer": 8 + (32 if st.get("filter_bytes") else 0) + 4 * RW * found_pk,
+            "filter_mb": st.get("filter_bytes", 0) / 1e6,
+            "dram_bytes_per_kmer_ncu": traffic,
+            "wasted_traffic_ratio": (traffic / a_arena) if traffic else None,
+            "dram_gbps_physical": (traffic * n / (k_ms / 1e3) / 1e9) if traffic else None,
+            "dram_frac_physical": (traffic * n / (k_ms / 1e3) / 1e9 / peak) if traffic else None,
+            "ncu_capture": ({"file": cap.get("source"), "kernel": cap.get("kernel"), "filter_mb": cap.get("filter_mb")} if cap else None),
+            "random_gather_probe_loads_per_s": probe,
+            "random_access_frac": (bucket_pk * n / (k_ms / 1e3) / probe) if probe else None,
+            "context_reference_layout": {"a_min_bytes_per_kmer": a_min, "a_ref_bytes_per_kmer": a_ref, "nodes_per_kmer": nodes_pk,
+                                         "search_depth_per_kmer": depth_pk,
+                                         "cc_probed_per_node": cc_pk / max(nodes_pk, 1e-9),
+                                         "mean_suffix_block_lines": ws["block_lines"] / max(1, n),
+                                         "note": "sectors the REFERENCE layout's walk dereferences (SURVEY.md 8d); the arena replaces them by one "
+                                                 "L2-resident directory load + one bucket, so they are context, not the roofline"},
+            "note": "frac = algorithmic HBM bytes of the arena walk / measured copy bandwidth; the kernel is bound by the RATE of random "
+                    "64-byte HBM accesses (random_access_frac: bucket accesses/s over the measured rate of independent random loads), "
+                    "not by bytes"}
 
 
 def write_query_file(path, q_np, k):
@@ -245,31 +298,31 @@ def engine_arm(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    pending = []
-
+    # The hit count of every step ("Nb k-mers present" of the reference driver) is the one number the sharded path
+    # reduces. It is accumulated by the query kernels themselves: one uint64 slot per step in rank 0's HBM, mapped into
+    # every rank through CUDA IPC, and each CTA adds its share with one system-scope atomic (over NVLink from the other
+    # ranks) — compute + reduction in one kernel, no NCCL call and no extra launch in the steady state.
     counted = RW in (1, 2, 4)
-    d_hits = torch.zeros(1, dtype=torch.int64, device=dev)
+    n_slots = args.warmup + args.steps + args.warmup + args.steps + 8
+    ctr_local = eng.device_alloc(8 * n_slots) if rank == 0 else 0   # zero-filled by the call
+    ctr_base = ctr_local
+    if world > 1:
+        box = [eng.peer_export(ctr_local) if rank == 0 else None]
+        dist.broadcast_object_list(box, src=0)
+        if rank != 0:
+            ctr_base = eng.peer_import(box[0])
+    slot_i = [0]
 
     def step():
-        if counted:  # the kernel accumulates the batch's hit count itself
-            eng.query_kmers_device_counted(q, n, d_present, d_rows, d_hits)
+        if counted:
+            eng.query_kmers_device_accumulate(q, n, d_present, d_rows, ctr_base + 8 * slot_i[0])
+            slot_i[0] += 1
         else:
             eng.query_kmers_device(q, n, d_present, d_rows, None)
-        if world > 1:  # the only exchange the path has: a summary of each rank's results (no data-path collective);
-            with torch.cuda.stream(es):  # enqueued asynchronously so ranks do not lock-step on it, awaited before the clock stops
-                s = d_hits.clone() if counted else d_present.sum(dtype=torch.int64).reshape(1)
-                pending.append((s, dist.all_reduce(s, async_op=True)))
-
-    def drain():
-        with torch.cuda.stream(es):
-            for _, w in pending:
-                w.wait()
-        pending.clear()
 
     # ---- timed region: K steps, inputs resident in HBM (batch of n*8*W bytes >> 126 MB L2, so no L2 flush needed)
     for _ in range(args.warmup):
         step()
-    drain()
     barrier()
     sampler = ClockSampler(local)
     if rank == 0:
@@ -282,7 +335,6 @@ def engine_arm(args):
     ev0.record(es)
     for _ in range(args.steps):
         step()
-    drain()
     ev1.record(es)
     barrier()
     tw1 = time.time()
@@ -294,17 +346,25 @@ def engine_arm(args):
     ms_step = float(t.item()) / args.steps
     value = n * world / (ms_step / 1e3)
     n_present = int(d_present.sum().item())
-    if counted:
-        assert int(d_hits.item()) == n_present, "kernel hit counter disagrees with the presence bytes"
+    if counted:  # every step's slot must hold the sum of all ranks' hits (checked outside the timed region)
+        tot = torch.tensor([n_present], dtype=torch.int64, device=dev)
+        if world > 1:
+            dist.all_reduce(tot)
+        if rank == 0:
+            slots = eng.copy_from_device(ctr_local, np.zeros(n_slots, dtype=np.uint64))
+            used = slots[:slot_i[0]]
+            assert (used == np.uint64(int(tot.item()))).all(), f"in-kernel hit counters {used.tolist()} != {int(tot.item())}"
     # size-independent property at full size: every window sampled from an inserted genome must be found, and a
     # found k-mer must carry at least one colour
     assert bool(d_present[q_kind == 0].all()), "a k-mer window of an inserted genome was reported absent"
     assert bool((d_rows[d_present.bool()] != 0).any(dim=1).all()), "a present k-mer came back without colours"
     assert not bool((d_rows[~d_present.bool()] != 0).any()), "an absent k-mer came back with colours"
 
+    d_hits = torch.zeros(1, dtype=torch.int64, device=dev)
+
     def step_kernel():
         if counted:
-            eng.query_kmers_device_counted(q, n, d_present, d_rows, d_hits)
+            eng.query_kmers_device_accumulate(q, n, d_present, d_rows, d_hits)
         else:
             eng.query_kmers_device(q, n, d_present, d_rows, None)
 
@@ -323,36 +383,7 @@ def engine_arm(args):
     clocks = sampler.stop(tw0, time.time()) if rank == 0 else None
     ws = eng.kmer_walk_stats_device(q, n)
     nodes_pk, depth_pk, found_pk = ws["nodes"] / n, ws["search_depth"] / n, ws["found"] / n
-    # A_min per k-mer: key words in + (presence byte + colour row) out + 32-byte sectors the walk must
-    # touch: 6 per Node probed, ceil(log2(lines+1)) per suffix search, 1 for the annotation of a found k-mer
-    a_min = 8 * W + (1 + 4 * RW) + 32.0 * (6 * nodes_pk + depth_pk + found_pk)
-    # A_ref: same, with the Bloom-chain term of the REFERENCE layout (2 bytes probed in each of the c CCs walked
-    # before one fires) instead of the single first-CC-table sector — context only
-    cc_pk = ws["cc_probed"] / n
-    a_ref = 8 * W + (1 + 4 * RW) + 32.0 * (5 * nodes_pk + 2 * cc_pk + depth_pk + found_pk)
-    achieved = a_min * n / (k_ms / 1e3) / 1e9
-    peak, peak_src = peaks()
-    # the committed ncu capture is of the default workload (100 genomes x 5 Mbp, k = 27); it says nothing about others
-    traffic = ncu_traffic() if (cfg["name"] == wl.C3["name"] and L == 5_000_000 and K == 27) else None
-    probe = None
-    if not args.no_probe:
-        probe = eng.random_gather_probe(4 << 30, 1 << 28)
-    roofline = {"bound": "hbm", "kernel": "k_query_kmers_rows" if RW in (1, 2, 4) else "k_query_kmers+k_expand_rows",
-                "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": (traffic * n if traffic else None), "peak_source": peak_src, "kernel_ms": k_ms,
-                "kmers_per_sec_kernel": n / (k_ms / 1e3), "a_min_bytes_per_kmer": a_min,
-                "nodes_per_kmer": nodes_pk, "search_depth_per_kmer": depth_pk, "found_frac": found_pk,
-                "a_ref_bytes_per_kmer": a_ref, "cc_probed_per_node_reference_layout": cc_pk / max(nodes_pk, 1e-9),
-                "mean_suffix_block_lines": ws["block_lines"] / max(1, n),
-                "dram_bytes_per_kmer_ncu": traffic,
-                "dram_gbps_physical": (traffic * n / (k_ms / 1e3) / 1e9) if traffic else None,
-                "dram_frac_physical": (traffic * n / (k_ms / 1e3) / 1e9 / peak) if traffic else None,
-                "random_gather_probe_loads_per_s": probe,
-                "random_access_frac": (n / (k_ms / 1e3) / probe) if probe else None,
-                "note": "A_min counts the sectors of the REFERENCE layout's walk; the flattened arena serves the root probe from "
-                        "an L2-resident directory, so achieved can exceed the DRAM peak; dram_bytes_per_kmer_ncu / dram_gbps_physical are the "
-                        "physical traffic (ncu), and random_access_frac compares the kernel with the measured rate of independent "
-                        "random HBM accesses, which is what bounds it"}
+    roofline = kmer_roofline(eng, ws, n, k_ms, W, RW, args, traffic_ok=(cfg["name"] == wl.C3["name"] and L == 5_000_000 and K == 27))
 
     # ---- e2e: host C-ABI call with pinned host buffers, copies inside the timed region
     e2e = None

@@ -22,6 +22,8 @@ DATA = os.path.join(ROOT, "data")
 REF_BFT = os.path.join(ROOT, "oracle", "_ref", "bft")
 REF_HARNESS = os.path.join(ROOT, "oracle", "_ref", "ref_harness")
 
+# config[0]: 4 genomes x 5 Mbp (founder + 3 strains at 1 % SNPs), the reference's own CPU-runnable case
+C1 = dict(name="c1_g4", n_genomes=4, snp=0.01, indel=0.0, seed=12345, tree=False)
 # config[2] of BASELINE.json: 100-genome synthetic bacterial pan-genome, tree-structured SNP/indel strains
 C3 = dict(name="c3_g100", n_genomes=100, snp=0.002, indel=0.0002, seed=12345, tree=True)
 # config[4]: 1000-colour pan-genome (annotation-compression heavy: mode-3 annotations + delta-coded colour pools)

@@ -34,6 +34,12 @@
  *              collapsed into one 8-byte load.
  *   colour classes: distinct annotation byte strings (cls_off/cls_bytes) + the comp_set_colors pools; decoded on
  *              the device once per arena into class rows (bft_kernels.cu: k_decode_classes).
+ *   kfilter[]  (device only, built by k_kf_insert from the arena's own enumeration) a blocked Bloom filter over the
+ *              STORED K-MERS — not one of the reference's Bloom filters, which cover 9-nt prefixes: 32-byte blocks,
+ *              4 bits per k-mer (one in each 64-bit word of the block), ~8 bits per stored k-mer, sized to stay in
+ *              L2. A k-mer the filter rejects is in no Node, so the walk (and its one random HBM access) is
+ *              skipped; a k-mer it accepts is looked up as before, so answers never change. The reference spends
+ *              its Bloom filters on choosing a CC; an absent k-mer still costs it the full descent.
  *
  * The walk functions below are plain C, compiled for the device by nvcc (the product path) and for the host by
  * the flattener (to fill rootdir) and by tests/tools (to debug the arena without a GPU). The shipped library
@@ -147,6 +153,11 @@ typedef struct {
      * traversals (bft_graph.cuh) key their vertex table and marks on it, the way the reference keeps its marks inside
      * the UC a k-mer is stored in (src/marking.c). */
     uint32_t loc_ovf, loc_uc, loc_leaf;
+    /* stored-k-mer filter (see above); kf_blocks == 0: none. kf_quirk_safe != 0: no Node sits at the leaf level, so a
+     * successor lookup with the reference's leaf-level quirk (bft_node_probe_ex) is plain set membership too. */
+    const uint64_t* kfilter;
+    uint32_t kf_blocks;
+    uint32_t kf_quirk_safe;
 } bft_view_t;
 
 /* ---- prefix bit manipulation --------------------------------------------------------------------------------
@@ -183,16 +194,43 @@ BFT_HD bft_entry_t bft_mk_entry(uint32_t kind, uint32_t a, uint32_t n) {
 /* a bucket's 4*W words. On the device each 32-byte half is ONE 256-bit load (LDG.E.256, new on sm_100): measured on
  * B200 (tools/gather_probe.cu) a random 256-bit load sustains the same 37.9 G accesses/s as a random 8-byte load,
  * while two 128-bit loads of the same sector reach only 31-35 G/s. The L2::64B qualifier caps the sector promotion
- * on a miss (128 B of HBM traffic per random access by default, 64 B with it). */
+ * on a miss (128 B of HBM traffic per random access by default, 64 B with it). A bucket is read once per lookup and
+ * 771 MB of them never fit L2: evict-first / no L1 allocation keeps them from displacing the L2-resident tables. */
 BFT_HD void bft_ld_bucket(const uint64_t* p, uint64_t* out, const int W) {
 #ifdef __CUDA_ARCH__
     for (int i = 0; i < W; i++)
-        asm volatile("ld.global.nc.L2::64B.v4.u64 {%0,%1,%2,%3}, [%4];"
+        asm volatile("ld.global.nc.L1::no_allocate.L2::evict_first.L2::64B.v4.u64 {%0,%1,%2,%3}, [%4];"
                      : "=l"(out[4 * i]), "=l"(out[4 * i + 1]), "=l"(out[4 * i + 2]), "=l"(out[4 * i + 3])
                      : "l"(p + 4 * i));
 #else
     for (int i = 0; i < BFT_BUCKET_KEYS * W; i++) out[i] = p[i];
 #endif
+}
+
+/* ---- stored-k-mer filter ---------------------------------------------------------------------------------------
+ * h = 64-bit mix of the k-mer words; block = high 32 bits range-reduced to kf_blocks; bit j of word j = 6 bits of h. */
+BFT_HD uint64_t bft_kf_hash(const uint64_t* kmer, const int W) {
+    uint64_t x = kmer[0];
+    for (int w = 1; w < W; w++) x = (x ^ (x >> 29)) * 0x9FB21C651E98DF25ULL + kmer[w];
+    x ^= x >> 33; x *= 0xFF51AFD7ED558CCDULL;
+    x ^= x >> 33; x *= 0xC4CEB9FE1A85EC53ULL;
+    x ^= x >> 33;
+    return x;
+}
+BFT_HD uint32_t bft_kf_block(uint64_t h, uint32_t n_blocks) { return (uint32_t)(((h >> 32) * (uint64_t)n_blocks) >> 32); }
+
+/* 1: the k-mer may be stored; 0: it is certainly not */
+BFT_HD int bft_kf_test(const bft_view_t* v, const uint64_t* kmer, const int W) {
+    const uint64_t h = bft_kf_hash(kmer, W);
+    const uint64_t* p = v->kfilter + (size_t)bft_kf_block(h, v->kf_blocks) * 4;
+    uint64_t w0, w1, w2, w3;
+#ifdef __CUDA_ARCH__
+    /* one 32-byte sector, kept in L2 (evict-last) */
+    asm("ld.global.nc.L2::evict_last.v4.u64 {%0,%1,%2,%3}, [%4];" : "=l"(w0), "=l"(w1), "=l"(w2), "=l"(w3) : "l"(p));
+#else
+    w0 = p[0]; w1 = p[1]; w2 = p[2]; w3 = p[3];
+#endif
+    return (int)(((w0 >> (h & 63)) & (w1 >> ((h >> 6) & 63)) & (w2 >> ((h >> 12) & 63)) & (w3 >> ((h >> 18) & 63))) & 1ULL);
 }
 
 /* One Node probe: the reference's presenceKmer (src/presenceNode.c:1284-1576) on the flattened layout.
@@ -351,7 +389,8 @@ BFT_HD void bft_shift18(uint64_t* cur, int W) {
 /* st (optional, NULL on the product path): walk statistics for the roofline accounting of SURVEY.md §8(d) —
  * st[0] += Nodes probed, st[1] += sum of ceil(log2(lines+1)) over the line searches, st[2] += 1 if found,
  * st[3] += CCs whose Bloom filter the REFERENCE would probe in those Nodes (index of the first CC that fires + 1, or
- * all of them), st[4] += lines in the searched blocks. */
+ * all of them), st[4] += lines in the searched blocks; and for the arena's own walk: st[5] += bucket / UC searches the
+ * product path performs (those the stored-k-mer filter does not cut short), st[6] += k-mers the filter rejects. */
 BFT_HD uint32_t bft_cc_probed(const bft_view_t* v, uint32_t node_id, uint32_t low18) {
     const bft_node_t* nd = v->nodes + node_id;
     if (!nd->n_cc) return 0;
@@ -375,6 +414,15 @@ BFT_HD uint32_t bft_lookup_loc(const bft_view_t* v, const uint64_t* kmer, const 
     /* a 9-mer trie keeps its k-mers as leaf prefixes of the root: rootdir holds the entry but not its index */
     if (loc && sz == BFT_NB_CHAR_SUF_PREF) e = bft_node_probe_ex(v, 0, (uint32_t)cur[0] & (BFT_ROOTDIR_SIZE - 1u), 0, &pref_idx);
     else e = bft_ld_entry(v->rootdir + ((uint32_t)cur[0] & (BFT_ROOTDIR_SIZE - 1u)));
+    /* the filter block is fetched right behind the root entry (two independent L2 loads in flight) */
+    int rejected = 0; /* statistics mode only: the product path stops at a rejection */
+    if (v->kf_blocks && (!succ_leaf_quirk || v->kf_quirk_safe)) {
+        if (!bft_kf_test(v, kmer, W)) {
+            if (!st) return BFT_CLS_NONE;
+            rejected = 1;
+            st[6]++;
+        }
+    }
     if (st) { st[0]++; st[3] += bft_cc_probed(v, 0, (uint32_t)cur[0] & (BFT_ROOTDIR_SIZE - 1u)); }
     for (;;) {
         const uint32_t kind = e.b >> BFT_KIND_SHIFT;
@@ -387,7 +435,7 @@ BFT_HD uint32_t bft_lookup_loc(const bft_view_t* v, const uint64_t* kmer, const 
         }
         if (kind == BFT_KIND_UC) {
             if (n == 0) return BFT_CLS_NONE;
-            if (st) { st[1] += bft_ceil_log2p1(n); st[4] += n; }
+            if (st) { st[1] += bft_ceil_log2p1(n); st[4] += n; st[5] += !rejected; }
             const uint32_t ln = bft_search_uc(v, e.a, n, cur, W);
             if (st && ln != 0xffffffffu) st[2]++;
             if (loc && ln != 0xffffffffu) *loc = v->loc_uc + ln;
@@ -396,7 +444,7 @@ BFT_HD uint32_t bft_lookup_loc(const bft_view_t* v, const uint64_t* kmer, const 
         bft_shift18(cur, W);
         sz -= BFT_NB_CHAR_SUF_PREF;
         if (kind == BFT_KIND_INLINE) {
-            if (st) { st[1] += bft_ceil_log2p1(n); st[4] += n; }
+            if (st) { st[1] += bft_ceil_log2p1(n); st[4] += n; st[5] += !rejected; }
             const uint32_t cls = bft_search_block_ex(v, e.a, (e.b >> BFT_LB_SHIFT) & BFT_LB_MASK, cur, W, loc);
             if (st && cls != BFT_CLS_NONE) st[2]++;
             return cls;

@@ -70,8 +70,10 @@ struct bft_b200_ctx {
     bft_view_t dview;
     bft_pools_t dpools;
     void* d_pool[4];
-    void* d_hot;              /* one allocation: rootdir | class_rows — the tables every lookup touches, pinned in L2 */
+    void* d_hot;              /* one allocation: rootdir | class_rows | kfilter — the tables every lookup touches, kept in L2 */
     size_t hot_bytes;
+    uint64_t n_loc;           /* storage locations (bft_view_t), counted in 64 bits */
+    cudaMemPool_t pool;       /* private pool of the traversal scratch (the device's default pool is left alone) */
     uint32_t* d_class_rows;   /* inside d_hot */
     uint32_t* d_class_counts;
     uint32_t* h_class_rows;
@@ -151,6 +153,7 @@ extern "C" void bft_b200_close(bft_b200_ctx* c) {
     if (c->d_counter) cudaFree(c->d_counter);
     if (c->d_nbr) cudaFree(c->d_nbr);
     bft_b200_graph_release(c);
+    if (c->pool) cudaMemPoolDestroy(c->pool);
     for (int s = 0; s < BFT_N_SLOTS; s++) {
         slot_t* sl = &c->slot[s];
         if (sl->d_in) cudaFree(sl->d_in);
@@ -171,6 +174,34 @@ extern "C" void bft_b200_close(bft_b200_ctx* c) {
     free(c->h_class_rows);
     free(c->h_class_counts);
     free(c);
+}
+
+static int enqueue_extract(bft_b200_ctx* c, uint64_t* d_kmers, uint32_t* d_cls, uint32_t* d_loc2vid);
+
+/* the stored-k-mer filter (bft_arena.h): enumerate the arena's k-mers on the device, set their bits, then publish it */
+static int build_kfilter(bft_b200_ctx* c, size_t n_kmers, unsigned long long* d_filter, uint32_t n_blocks, int quirk_safe) {
+    uint64_t* d_k = NULL;
+    if (cudaMalloc((void**)&d_k, (n_kmers + 1) * (size_t)c->W * 8) != cudaSuccess) {
+        (void)cudaGetLastError();
+        return 0; /* no room for the scratch: run without a filter */
+    }
+    c->stats.n_kmers = n_kmers; /* enqueue_extract sizes nothing by it, but keep the context coherent */
+    int rc = enqueue_extract(c, d_k, NULL, NULL);
+    if (!rc) {
+#define BFT_L(W_) k_kf_insert<W_><<<grid_for(c, n_kmers, BFT_TPB), BFT_TPB, 0, c->streams[0]>>>(d_k, n_kmers, d_filter, n_blocks)
+        BFT_BY_W(c->W, BFT_L);
+#undef BFT_L
+        c->launches++;
+        cudaError_t e = cudaStreamSynchronize(c->streams[0]);
+        if (e != cudaSuccess) rc = set_err(BFT_B200_ERR_CUDA, "stored-k-mer filter build failed: %s", cudaGetErrorString(e));
+    }
+    cudaFree(d_k);
+    if (!rc) {
+        c->dview.kfilter = (const uint64_t*)d_filter;
+        c->dview.kf_blocks = n_blocks;
+        c->dview.kf_quirk_safe = (uint32_t)(quirk_safe != 0);
+    }
+    return rc;
 }
 
 extern "C" int bft_b200_open(const char* path, int device, bft_b200_ctx** out) {
@@ -254,6 +285,9 @@ extern "C" int bft_b200_open(const char* path, int device, bft_b200_ctx** out) {
         c->dview.cls_mask = a->cls_mask;
         c->dview.k = a->k;
         c->dview.W = a->W;
+        /* storage locations are 32-bit in the kernels; counted here in 64 bits so a BFT with 2^32 or more of them is
+         * caught (bft_b200_graph_prepare refuses it; queries do not use locations) instead of wrapping silently */
+        c->n_loc = (uint64_t)a->n_buckets * BFT_BUCKET_KEYS + a->n_ovf + a->n_uc_lines + a->n_pref;
         c->dview.loc_ovf = (uint32_t)(a->n_buckets * BFT_BUCKET_KEYS);
         c->dview.loc_uc = c->dview.loc_ovf + (uint32_t)a->n_ovf;
         c->dview.loc_leaf = c->dview.loc_uc + (uint32_t)a->n_uc_lines;
@@ -267,11 +301,32 @@ extern "C" int bft_b200_open(const char* path, int device, bft_b200_ctx** out) {
     int* d_bad = NULL;
     int h_bad = 0;
     const size_t row_bytes = (a->n_classes + 1) * (size_t)c->rw * sizeof(uint32_t);
-    /* hot block: rootdir followed by the class rows */
+    /* hot block: rootdir, the class rows, the stored-k-mer filter */
     const size_t rootdir_bytes = BFT_ROOTDIR_SIZE * sizeof(bft_entry_t);
-    c->hot_bytes = rootdir_bytes + row_bytes;
+    const size_t rows_padded = (row_bytes + 31) & ~(size_t)31;
+    /* filter size: BFT_B200_KF_BITS bits per stored k-mer (default 8, 0 = no filter), shrunk to at least 4 bits per
+     * k-mer to stay within BFT_B200_KF_MAX_MB (default 48 MB, a share of the 126 MB L2 that leaves room for the class
+     * rows and the streaming traffic); a BFT too large for that gets no filter — out of L2 it would cost a second HBM
+     * access per present k-mer instead of saving one per absent k-mer */
+    size_t kf_blocks = 0;
+    {
+        const char* eb = getenv("BFT_B200_KF_BITS");
+        const char* em = getenv("BFT_B200_KF_MAX_MB");
+        double bits = eb ? atof(eb) : 8.0;
+        const double max_bytes = (em ? atof(em) : 48.0) * 1048576.0;
+        if (bits > 0 && a->n_kmers > 0) {
+            if (bits * (double)a->n_kmers / 8.0 > max_bytes) bits = max_bytes * 8.0 / (double)a->n_kmers;
+            if (bits >= 4.0) {
+                kf_blocks = (size_t)(bits * (double)a->n_kmers / 256.0) + 1;
+                if (kf_blocks > 0xffffffffu) kf_blocks = 0;
+            }
+        }
+    }
+    const size_t kf_bytes = kf_blocks * 32;
+    c->hot_bytes = rootdir_bytes + rows_padded + kf_bytes;
     if (!rc && cudaMalloc(&c->d_hot, c->hot_bytes + 32) != cudaSuccess) rc = set_err(BFT_B200_ERR_NOMEM, "cudaMalloc(hot tables, %zu) failed", c->hot_bytes);
     if (!rc && cudaMemcpy(c->d_hot, a->rootdir, rootdir_bytes, cudaMemcpyHostToDevice) != cudaSuccess) rc = set_err(BFT_B200_ERR_CUDA, "rootdir upload failed");
+    if (!rc && kf_bytes && cudaMemset((char*)c->d_hot + rootdir_bytes + rows_padded, 0, kf_bytes) != cudaSuccess) rc = set_err(BFT_B200_ERR_CUDA, "filter clear failed");
     if (!rc) {
         c->d_class_rows = (uint32_t*)((char*)c->d_hot + rootdir_bytes);
         c->dview.rootdir = (const bft_entry_t*)c->d_hot;
@@ -287,7 +342,9 @@ extern "C" int bft_b200_open(const char* path, int device, bft_b200_ctx** out) {
         if (win > (size_t)prop.accessPolicyMaxWindowSize) win = (size_t)prop.accessPolicyMaxWindowSize;
         size_t persist = win; /* measured on B200: a set-aside larger than the window buys nothing, 64 MB costs 5 % */
         if (persist > (size_t)prop.persistingL2CacheMaxSize) persist = (size_t)prop.persistingL2CacheMaxSize;
-        if (win && persist && cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, persist) == cudaSuccess) {
+        size_t have = 0; /* the limit is device-wide: raise it if ours is larger, never shrink what another context set */
+        if (cudaDeviceGetLimit(&have, cudaLimitPersistingL2CacheSize) != cudaSuccess) have = 0;
+        if (win && persist && (have >= persist || cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, persist) == cudaSuccess)) {
             cudaStreamAttrValue attr;
             memset(&attr, 0, sizeof attr);
             attr.accessPolicyWindow.base_ptr = c->d_hot;
@@ -309,6 +366,8 @@ extern "C" int bft_b200_open(const char* path, int device, bft_b200_ctx** out) {
         if (e != cudaSuccess) rc = set_err(BFT_B200_ERR_CUDA, "k_decode_classes failed: %s", cudaGetErrorString(e));
         else if (h_bad) rc = set_err(BFT_B200_ERR_FILE, "%d colour annotations are malformed (mode 3 pointing outside the colour pools)", h_bad);
     }
+    if (!rc && kf_blocks) rc = build_kfilter(c, a->n_kmers, (unsigned long long*)((char*)c->d_hot + rootdir_bytes + rows_padded), (uint32_t)kf_blocks,
+                                             a->max_depth < a->k / BFT_NB_CHAR_SUF_PREF || a->k == BFT_NB_CHAR_SUF_PREF);
     double t3 = now_s();
     if (d_bad) cudaFree(d_bad);
     if (d_cls_off) cudaFree(d_cls_off);
@@ -318,6 +377,7 @@ extern "C" int bft_b200_open(const char* path, int device, bft_b200_ctx** out) {
     c->stats.n_prefixes = a->n_pref; c->stats.n_classes = a->n_classes; c->stats.arena_bytes = bft_arena_bytes(a);
     c->stats.class_row_bytes = row_bytes; c->stats.max_cc_per_node = a->max_cc_per_node; c->stats.max_depth = a->max_depth;
     c->stats.n_pools = a->n_pools;
+    c->stats.filter_bytes = rc ? 0 : kf_bytes;
     c->stats.flatten_seconds = t1 - t0; c->stats.upload_seconds = t2 - t1; c->stats.decode_seconds = t3 - t2;
     bft_arena_free(a);
 
@@ -415,6 +475,15 @@ extern "C" int bft_b200_query_kmers_device_counted(bft_b200_ctx* c, const uint64
     CK(cudaSetDevice(c->device));
     CK(cudaMemsetAsync(d_n_present, 0, sizeof(uint64_t), c->streams[0]));
     return enqueue_kmers(c, c->streams[0], d_kmers, n, d_present, d_rows, NULL, (unsigned long long*)d_n_present);
+}
+
+extern "C" int bft_b200_query_kmers_device_accumulate(bft_b200_ctx* c, const uint64_t* d_kmers, size_t n, uint8_t* d_present, uint32_t* d_rows,
+                                                      uint64_t* d_counter) {
+    if (!c || (!d_kmers && n) || !d_rows || !d_counter) return set_err(BFT_B200_ERR_ARG, "bft_b200_query_kmers_device_accumulate: NULL argument");
+    if (!((c->rw == 1 || c->rw == 2 || c->rw == 4) && ((uintptr_t)d_rows & 15) == 0))
+        return set_err(BFT_B200_ERR_ARG, "bft_b200_query_kmers_device_accumulate: needs colour rows of 1, 2 or 4 words (<= 128 genomes) and a 16-byte aligned row buffer");
+    CK(cudaSetDevice(c->device));
+    return enqueue_kmers(c, c->streams[0], d_kmers, n, d_present, d_rows, NULL, (unsigned long long*)d_counter);
 }
 
 static int query_kmers_host(bft_b200_ctx* c, const uint64_t* kmers, const char* ascii, size_t n, uint8_t* valid, uint8_t* present,
@@ -807,12 +876,12 @@ extern "C" int bft_b200_query_neighbors(bft_b200_ctx* c, const uint64_t* kmers, 
     return 0;
 }
 
-extern "C" int bft_b200_kmer_walk_stats_device(bft_b200_ctx* c, const uint64_t* d_kmers, size_t n, uint64_t out[5]) {
+extern "C" int bft_b200_kmer_walk_stats_device(bft_b200_ctx* c, const uint64_t* d_kmers, size_t n, uint64_t out[8]) {
     if (!c || !out || (!d_kmers && n)) return set_err(BFT_B200_ERR_ARG, "bft_b200_kmer_walk_stats_device: NULL argument");
     CK(cudaSetDevice(c->device));
     unsigned long long* d_acc = NULL;
-    CK(cudaMalloc((void**)&d_acc, 5 * sizeof(unsigned long long)));
-    cudaMemsetAsync(d_acc, 0, 5 * sizeof(unsigned long long), c->streams[0]);
+    CK(cudaMalloc((void**)&d_acc, BFT_N_WALK_STATS * sizeof(unsigned long long)));
+    cudaMemsetAsync(d_acc, 0, BFT_N_WALK_STATS * sizeof(unsigned long long), c->streams[0]);
     if (n) {
         const int grid = grid_for(c, n, BFT_TPB);
 #define BFT_L(W_) k_kmer_walk_stats<W_><<<grid, BFT_TPB, 0, c->streams[0]>>>(c->dview, d_kmers, n, d_acc)
@@ -820,12 +889,12 @@ extern "C" int bft_b200_kmer_walk_stats_device(bft_b200_ctx* c, const uint64_t* 
 #undef BFT_L
         c->launches++;
     }
-    unsigned long long h[5] = {0, 0, 0, 0, 0};
+    unsigned long long h[BFT_N_WALK_STATS] = {0, 0, 0, 0, 0, 0, 0, 0};
     cudaError_t e = cudaMemcpyAsync(h, d_acc, sizeof h, cudaMemcpyDeviceToHost, c->streams[0]);
     if (e == cudaSuccess) e = cudaStreamSynchronize(c->streams[0]);
     cudaFree(d_acc);
     if (e != cudaSuccess) return set_err(BFT_B200_ERR_CUDA, "k_kmer_walk_stats failed: %s", cudaGetErrorString(e));
-    for (int j = 0; j < 5; j++) out[j] = h[j];
+    for (int j = 0; j < BFT_N_WALK_STATS; j++) out[j] = h[j];
     return 0;
 }
 
@@ -1068,27 +1137,45 @@ extern "C" int bft_b200_graph_release(bft_b200_ctx* c) {
     if (c->graph.d_adj) cudaFree(c->graph.d_adj);
     if (c->graph.d_loc2vid) cudaFree(c->graph.d_loc2vid);
     memset(&c->graph, 0, sizeof c->graph);
-    cudaMemPool_t pool;
-    if (cudaDeviceGetDefaultMemPool(&pool, c->device) == cudaSuccess) { /* hand the traversal scratch back to the device */
+    if (c->pool) { /* hand the traversal scratch back to the device */
         cudaStreamSynchronize(c->streams[0]);
-        cudaMemPoolTrimTo(pool, 0);
+        cudaMemPoolTrimTo(c->pool, 0);
     }
     return 0;
 }
 
-/* scratch device arrays of one traversal call, freed together. Stream-ordered allocations: after the first call the
- * blocks come back from the device's memory pool without a driver round trip (bft_b200_graph_release trims the pool). */
+/* scratch device arrays of one traversal call, freed together. Stream-ordered allocations from the context's OWN
+ * memory pool (release threshold unlimited, so after the first call the blocks come back without a driver round trip;
+ * bft_b200_graph_release trims it). The device's default pool — which the host application may share — is not touched. */
+static int ensure_pool(bft_b200_ctx* c) {
+    if (c->pool) return 0;
+    cudaMemPoolProps props;
+    memset(&props, 0, sizeof props);
+    props.allocType = cudaMemAllocationTypePinned;
+    props.handleTypes = cudaMemHandleTypeNone;
+    props.location.type = cudaMemLocationTypeDevice;
+    props.location.id = c->device;
+    if (cudaMemPoolCreate(&c->pool, &props) != cudaSuccess) {
+        c->pool = NULL;
+        return set_err(BFT_B200_ERR_CUDA, "graph traversal: cudaMemPoolCreate failed: %s", cudaGetErrorString(cudaGetLastError()));
+    }
+    uint64_t keep = ~0ULL;
+    cudaMemPoolSetAttribute(c->pool, cudaMemPoolAttrReleaseThreshold, &keep);
+    return 0;
+}
+
 struct dev_scratch {
     void* p[24];
     int n;
     cudaStream_t st;
-    explicit dev_scratch(cudaStream_t s) : n(0), st(s) {}
+    cudaMemPool_t pool;
+    explicit dev_scratch(bft_b200_ctx* c) : n(0), st(c->streams[0]), pool(c->pool) {}
     ~dev_scratch() { for (int i = 0; i < n; i++) cudaFreeAsync(p[i], st); }
     template <typename T>
     int get(T** out, size_t count) {
         void* q = NULL;
         const size_t bytes = (count ? count : 1) * sizeof(T) + 32;
-        if (n >= 24 || cudaMallocAsync(&q, bytes, st) != cudaSuccess) {
+        if (n >= 24 || !pool || cudaMallocFromPoolAsync(&q, bytes, pool, st) != cudaSuccess) {
             (void)cudaGetLastError();
             return set_err(BFT_B200_ERR_NOMEM, "graph traversal: cudaMallocAsync(%zu) failed", bytes);
         }
@@ -1103,8 +1190,9 @@ extern "C" int bft_b200_graph_prepare(bft_b200_ctx* c) {
     if (c->graph.ready) return 0;
     CK(cudaSetDevice(c->device));
     const size_t n = (size_t)c->stats.n_kmers, W = (size_t)c->W;
-    const uint64_t n_loc = (uint64_t)c->dview.loc_leaf + c->n_pref;
-    if (n >= BFT_V_NONE || n_loc >= BFT_V_NONE) return set_err(BFT_B200_ERR_ARG, "graph traversal: %zu k-mers exceed the 32-bit vertex ids", n);
+    const uint64_t n_loc = c->n_loc; /* 64-bit count of the untruncated parts (bft_b200_open) */
+    if (n >= BFT_V_NONE || n_loc >= BFT_V_NONE)
+        return set_err(BFT_B200_ERR_ARG, "graph traversal: %zu k-mers / %llu storage locations exceed the 32-bit vertex ids", n, (unsigned long long)n_loc);
     cudaStream_t st = c->streams[0];
     CK(cudaStreamSynchronize(st));
     bft_b200_graph_release(c);
@@ -1129,12 +1217,7 @@ extern "C" int bft_b200_graph_prepare(bft_b200_ctx* c) {
     if (!rc && e != cudaSuccess) rc = set_err(BFT_B200_ERR_CUDA, "graph construction failed: %s", cudaGetErrorString(e));
     if (rc) { bft_b200_graph_release(c); return rc; }
     c->graph.ready = 1;
-    cudaMemPool_t pool;
-    if (cudaDeviceGetDefaultMemPool(&pool, c->device) == cudaSuccess) { /* keep traversal scratch cached between calls */
-        uint64_t keep = ~0ULL;
-        cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
-    }
-    return 0;
+    return ensure_pool(c);
 }
 
 extern "C" int bft_b200_query_vertex_ids(bft_b200_ctx* c, const uint64_t* kmers, size_t n, uint32_t* vertex_ids) {
@@ -1184,7 +1267,7 @@ extern "C" int bft_b200_connected_components(bft_b200_ctx* c, const uint32_t* ge
         if (labels) memset(labels, 0xff, n * sizeof(uint32_t));
         return 0;
     }
-    dev_scratch tmp(st);
+    dev_scratch tmp(c);
     uint32_t *d_parent = NULL, *d_labels = NULL, *d_want = NULL;
     uint8_t* d_in = NULL;
     unsigned long long* d_cnt = NULL;
@@ -1230,7 +1313,7 @@ extern "C" int bft_b200_simple_paths(bft_b200_ctx* c, double core_ratio, char** 
     const size_t n = c->graph.n;
     const uint32_t core = (uint32_t)(int)(core_ratio * c->G); /* nb_genomes_core, src/snippets.c:366 */
     cudaStream_t st = c->streams[0];
-    dev_scratch tmp(st);
+    dev_scratch tmp(c);
     uint8_t* d_chain = NULL;
     uint32_t *d_usucc = NULL, *d_next = NULL, *d_prev = NULL, *d_to[2] = {NULL, NULL}, *d_dist[2] = {NULL, NULL}, *d_low[2] = {NULL, NULL};
     unsigned long long *d_size = NULL, *d_offs = NULL, *d_stats = NULL;

@@ -565,6 +565,7 @@ static uint32_t parse_node(ctx_t* c, int sz, int* cluster_flag) {
 }
 
 void bft_arena_view(const bft_arena_t* a, bft_view_t* v) {
+    memset(v, 0, sizeof *v); /* no stored-k-mer filter on the host: it is built on the device */
     v->rootdir = a->rootdir;
     v->nodes = a->nodes;
     v->ccs = a->ccs;

@@ -15,6 +15,7 @@
 #include "bft_colour.h"
 
 #define BFT_TPB 256
+#define BFT_N_WALK_STATS 8 /* counters of k_kmer_walk_stats (bft_lookup_loc documents them) */
 
 /* ---- multi-word helpers (W = 1, 2 or 4 words, compile-time; loops unroll and runtime word indices become selects,
  * so nothing lands in local memory) */
@@ -82,6 +83,23 @@ __device__ __forceinline__ bool bft_ge(const uint64_t* a, const uint64_t* b) {
     return ge;
 }
 
+/* The batch's hit count (the number `Nb k-mers present` of the reference driver, src/file_io.c:813): warp shuffle, one
+ * shared-memory word per warp, ONE atomic per CTA. The atomic is system-scope because the counter may live in another
+ * GPU's HBM (a CUDA-IPC mapping, bft_b200_peer_import): every rank's kernel then adds its share straight into the
+ * owner's counter over NVLink — the only "collective" the sharded k-mer path has, fused into the query kernel. */
+__device__ __forceinline__ void bft_block_count(unsigned int hits, unsigned long long* counter) {
+    __shared__ unsigned int bft_warp_hits[BFT_TPB / 32];
+    for (int o = 16; o > 0; o >>= 1) hits += __shfl_down_sync(0xffffffffu, hits, o);
+    if ((threadIdx.x & 31) == 0) bft_warp_hits[threadIdx.x >> 5] = hits;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        unsigned long long total = 0;
+#pragma unroll
+        for (int w = 0; w < BFT_TPB / 32; w++) total += bft_warp_hits[w];
+        if (total) atomicAdd_system(counter, total);
+    }
+}
+
 /* ---- a4/a5/a7/a8: k-mer lookup ---------------------------------------------------------------------------- */
 template <int W>
 __global__ void __launch_bounds__(BFT_TPB) k_query_kmers(const bft_view_t v, const uint64_t* __restrict__ kmers, size_t n,
@@ -127,10 +145,7 @@ __global__ void __launch_bounds__(BFT_TPB) k_query_kmers_rows(const bft_view_t v
             __stcs(rows + i, r);
         }
     }
-    if (n_present) { /* the batch's hit count (the number `Nb k-mers present` of the reference driver): one atomic per warp */
-        for (int o = 16; o > 0; o >>= 1) hits += __shfl_down_sync(0xffffffffu, hits, o);
-        if ((threadIdx.x & 31) == 0 && hits) atomicAdd(n_present, (unsigned long long)hits);
-    }
+    if (n_present) bft_block_count(hits, n_present);
 }
 
 /* The same look-up on the reference's own record format: k-mers as ceil(2k/8)-byte records (a kmers_comp file,
@@ -272,10 +287,7 @@ __global__ void __launch_bounds__(BFT_TPB) k_query_records(const bft_view_t v, c
 #undef BFT_IN_BUF
 #undef BFT_OUT_BUF
     if (lead) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); /* shared memory must outlive the copies reading it */
-    if (n_present) {
-        for (int o = 16; o > 0; o >>= 1) hits += __shfl_down_sync(0xffffffffu, hits, o);
-        if ((threadIdx.x & 31) == 0 && hits) atomicAdd(n_present, (unsigned long long)hits);
-    }
+    if (n_present) bft_block_count(hits, n_present);
 }
 
 /* exclusive prefix sum of the per-tile hit counts of one chunk (at most a few thousand tiles): one block */
@@ -358,18 +370,18 @@ template <int W>
 __global__ void __launch_bounds__(BFT_TPB) k_kmer_walk_stats(const bft_view_t v, const uint64_t* __restrict__ kmers, size_t n,
                                                              unsigned long long* __restrict__ acc) {
     const size_t stride = (size_t)gridDim.x * blockDim.x;
-    unsigned long long a[5] = {0, 0, 0, 0, 0};
+    unsigned long long a[BFT_N_WALK_STATS] = {0, 0, 0, 0, 0, 0, 0, 0};
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
         uint64_t km[W];
 #pragma unroll
         for (int w = 0; w < W; w++) km[w] = kmers[i * W + w];
-        uint32_t st[5] = {0, 0, 0, 0, 0};
+        uint32_t st[BFT_N_WALK_STATS] = {0, 0, 0, 0, 0, 0, 0, 0};
         bft_lookup_ex(&v, km, W, 0, st);
 #pragma unroll
-        for (int j = 0; j < 5; j++) a[j] += st[j];
+        for (int j = 0; j < BFT_N_WALK_STATS; j++) a[j] += st[j];
     }
 #pragma unroll
-    for (int j = 0; j < 5; j++) {
+    for (int j = 0; j < BFT_N_WALK_STATS; j++) {
         for (int o = 16; o > 0; o >>= 1) a[j] += __shfl_down_sync(0xffffffffu, a[j], o);
         if ((threadIdx.x & 31) == 0) atomicAdd(acc + j, a[j]);
     }
@@ -462,6 +474,24 @@ __global__ void __launch_bounds__(BFT_TPB) k_blank_invalid(const uint8_t* __rest
         if (cls) cls[i] = BFT_CLS_NONE;
         if (rows)
             for (int w = 0; w < rw; w++) rows[i * (size_t)rw + w] = 0;
+    }
+}
+
+/* Build of the stored-k-mer filter (bft_arena.h): every stored k-mer, as enumerated by k_extract_*, sets its four bits. */
+template <int W>
+__global__ void __launch_bounds__(BFT_TPB) k_kf_insert(const uint64_t* __restrict__ kmers, size_t n, unsigned long long* __restrict__ filter,
+                                                       uint32_t n_blocks) {
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        uint64_t km[W];
+#pragma unroll
+        for (int w = 0; w < W; w++) km[w] = kmers[i * W + w];
+        const uint64_t h = bft_kf_hash(km, W);
+        unsigned long long* p = filter + (size_t)bft_kf_block(h, n_blocks) * 4;
+        atomicOr(p + 0, 1ULL << (h & 63));
+        atomicOr(p + 1, 1ULL << ((h >> 6) & 63));
+        atomicOr(p + 2, 1ULL << ((h >> 12) & 63));
+        atomicOr(p + 3, 1ULL << ((h >> 18) & 63));
     }
 }
 

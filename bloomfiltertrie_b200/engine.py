@@ -23,7 +23,7 @@ ABI_SYMBOLS = [
     "bft_b200_last_error", "bft_b200_open", "bft_b200_close", "bft_b200_k", "bft_b200_n_genomes",
     "bft_b200_genome_name", "bft_b200_kmer_words", "bft_b200_row_words", "bft_b200_device", "bft_b200_stream",
     "bft_b200_get_stats", "bft_b200_host_alloc", "bft_b200_host_free", "bft_b200_query_kmers",
-    "bft_b200_query_kmers_device", "bft_b200_query_kmers_device_counted", "bft_b200_query_kmers_ascii", "bft_b200_class_rows", "bft_b200_class_counts",
+    "bft_b200_query_kmers_device", "bft_b200_query_kmers_device_counted", "bft_b200_query_kmers_device_accumulate", "bft_b200_query_kmers_ascii", "bft_b200_class_rows", "bft_b200_class_counts",
     "bft_b200_query_sequences", "bft_b200_query_sequences_device", "bft_b200_query_branching",
     "bft_b200_query_branching_device", "bft_b200_query_neighbors", "bft_b200_set_reference_exact_branching",
     "bft_b200_query_kmers_file", "bft_b200_query_branching_file",
@@ -41,7 +41,8 @@ class Stats(C.Structure):
     _fields_ = [(n, C.c_uint64) for n in ("n_kmers", "n_nodes", "n_ccs", "n_lines", "n_prefixes", "n_classes",
                                            "arena_bytes", "class_row_bytes")] + \
                [(n, C.c_int) for n in ("max_cc_per_node", "max_depth", "n_pools")] + \
-               [(n, C.c_double) for n in ("flatten_seconds", "upload_seconds", "decode_seconds")]
+               [(n, C.c_double) for n in ("flatten_seconds", "upload_seconds", "decode_seconds")] + \
+               [("filter_bytes", C.c_uint64)]
 
 
 class BFTError(RuntimeError):
@@ -79,6 +80,7 @@ def load_library() -> C.CDLL:
     lib.bft_b200_query_kmers.argtypes = [vp, u64p, sz, u8p, u32p, u32p]
     lib.bft_b200_query_kmers_device.argtypes = [vp, u64p, sz, u8p, u32p, u32p]
     lib.bft_b200_query_kmers_device_counted.argtypes = [vp, u64p, sz, u8p, u32p, u64p]
+    lib.bft_b200_query_kmers_device_accumulate.argtypes = [vp, u64p, sz, u8p, u32p, u64p]
     lib.bft_b200_query_kmers_ascii.argtypes = [vp, C.c_void_p, sz, u8p, u8p, u32p, u32p]
     lib.bft_b200_class_rows.argtypes = [vp, C.POINTER(vp), C.POINTER(C.c_uint64)]
     lib.bft_b200_class_counts.argtypes = [vp, C.POINTER(vp), C.POINTER(C.c_uint64)]
@@ -91,7 +93,7 @@ def load_library() -> C.CDLL:
     lib.bft_b200_query_kmers_file.argtypes = [vp, C.c_char_p, C.c_int, C.c_char_p, C.POINTER(C.c_uint64)]
     lib.bft_b200_query_branching_file.argtypes = [vp, C.c_char_p, C.c_int, C.POINTER(C.c_uint64)]
     lib.bft_b200_query_sequences_file.argtypes = [vp, C.c_char_p, C.c_char_p, C.c_double, C.c_int]
-    lib.bft_b200_kmer_walk_stats_device.argtypes = [vp, u64p, sz, C.POINTER(C.c_uint64 * 5)]
+    lib.bft_b200_kmer_walk_stats_device.argtypes = [vp, u64p, sz, C.POINTER(C.c_uint64 * 8)]
     lib.bft_b200_random_gather_probe.argtypes = [vp, sz, sz, C.POINTER(C.c_double)]
     lib.bft_b200_extract_kmers.argtypes = [vp, u64p, u32p, u32p, sz, C.POINTER(C.c_uint64)]
     lib.bft_b200_extract_kmers_device.argtypes = [vp, u64p, u32p, sz]
@@ -270,6 +272,12 @@ class BFTEngine:
         self._ck(self.lib.bft_b200_query_kmers_device_counted(self.h, _ptr(d_kmers), n, _ptr(d_present), _ptr(d_rows),
                                                               _ptr(d_n_present)), "bft_b200_query_kmers_device_counted")
 
+    def query_kmers_device_accumulate(self, d_kmers, n: int, d_present, d_rows, d_counter):
+        """As query_kmers_device_counted, but ADDS the hit count to d_counter (not zeroed; may be a peer mapping of a
+        counter on another GPU — the sharded path's reduction fused into the query kernel)."""
+        self._ck(self.lib.bft_b200_query_kmers_device_accumulate(self.h, _ptr(d_kmers), n, _ptr(d_present), _ptr(d_rows),
+                                                                 _ptr(d_counter)), "bft_b200_query_kmers_device_accumulate")
+
     def class_rows(self) -> np.ndarray:
         p = C.c_void_p()
         n = C.c_uint64()
@@ -285,11 +293,11 @@ class BFTEngine:
         return np.frombuffer(buf, dtype=np.uint32).copy()
 
     def kmer_walk_stats_device(self, d_kmers, n: int) -> dict:
-        out = (C.c_uint64 * 5)()
+        out = (C.c_uint64 * 8)()
         self._ck(self.lib.bft_b200_kmer_walk_stats_device(self.h, _ptr(d_kmers), n, C.byref(out)),
                  "bft_b200_kmer_walk_stats_device")
         return dict(nodes=int(out[0]), search_depth=int(out[1]), found=int(out[2]), cc_probed=int(out[3]),
-                    block_lines=int(out[4]), n=n)
+                    block_lines=int(out[4]), bucket_searches=int(out[5]), filter_rejects=int(out[6]), n=n)
 
     def random_gather_probe(self, table_bytes: int, n_loads: int) -> float:
         out = C.c_double()

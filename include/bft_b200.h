@@ -20,8 +20,11 @@
  *     and only enqueue work on bft_b200_stream().
  *   - there is no CPU fallback: without a usable CUDA device every call fails with BFT_B200_ERR_CUDA.
  *   - a context serves one caller at a time (the reference's query API is not re-entrant either); use one
- *     context per thread / per GPU. bft_b200_open reserves part of the device's L2 as persisting cache for the tables
- *     every lookup touches (cudaLimitPersistingL2CacheSize, a device-wide setting; BFT_B200_NO_L2_PERSIST=1 disables it).
+ *     context per thread / per GPU. bft_b200_open asks for part of the device's L2 as persisting cache for the tables
+ *     every lookup touches (cudaLimitPersistingL2CacheSize is device-wide: the limit is only ever raised, never shrunk
+ *     below what the host application or another context set; BFT_B200_NO_L2_PERSIST=1 leaves it alone altogether).
+ *     Environment knobs read by bft_b200_open: BFT_B200_KF_BITS (bits per stored k-mer of the L2-resident negative
+ *     filter, default 8, 0 = off), BFT_B200_KF_MAX_MB (its size cap, default 48).
  */
 #ifndef BFT_B200_H
 #define BFT_B200_H
@@ -69,6 +72,7 @@ typedef struct {
     uint64_t n_kmers, n_nodes, n_ccs, n_lines, n_prefixes, n_classes, arena_bytes, class_row_bytes;
     int max_cc_per_node, max_depth, n_pools;
     double flatten_seconds, upload_seconds, decode_seconds;
+    uint64_t filter_bytes; /* stored-k-mer filter in L2 (0: none) */
 } bft_b200_stats;
 int bft_b200_get_stats(const bft_b200_ctx* ctx, bft_b200_stats* out);
 
@@ -90,6 +94,12 @@ int bft_b200_query_kmers_device(bft_b200_ctx* ctx, const uint64_t* d_kmers, size
  * second pass over the presence bytes. Narrow rows only (RW in {1,2,4}, i.e. <= 128 genomes). */
 int bft_b200_query_kmers_device_counted(bft_b200_ctx* ctx, const uint64_t* d_kmers, size_t n, uint8_t* d_present,
                                         uint32_t* d_rows, uint64_t* d_n_present);
+/* Same, without zeroing: the kernel ADDS the batch's hit count to *d_counter with one system-scope atomic per thread
+ * block. d_counter may be a peer mapping of a counter in another GPU's memory (bft_b200_peer_import): every rank of a
+ * sharded query then accumulates into the owner's counter over NVLink from inside its query kernel — the reduction of
+ * the reference driver's `Nb k-mers present` (src/file_io.c:813) fused into the kernel, no NCCL call on the path. */
+int bft_b200_query_kmers_device_accumulate(bft_b200_ctx* ctx, const uint64_t* d_kmers, size_t n, uint8_t* d_present,
+                                           uint32_t* d_rows, uint64_t* d_counter);
 /* ASCII input, n k-mers of exactly k characters each, back to back: parseKmerCount (src/fasta.c:3-53) on the GPU.
  * valid[i] = 0 for a k-mer with a non-ACGTU character (the reference drops such lines, src/file_io.c:786-862);
  * its present/rows are zero. */
@@ -170,8 +180,10 @@ int bft_b200_query_sequences_file(bft_b200_ctx* ctx, const char* query_path, con
 
 /* Roofline accounting helper: over a device-resident batch, sums of out[0] Nodes probed, out[1]
  * binary-search depths ceil(log2(lines+1)), out[2] found k-mers, out[3] CC Bloom filters the reference layout would
- * probe, out[4] lines in the searched suffix blocks. Diagnostic; synchronous. */
-int bft_b200_kmer_walk_stats_device(bft_b200_ctx* ctx, const uint64_t* d_kmers, size_t n, uint64_t out[5]);
+ * probe, out[4] lines in the searched suffix blocks; and of the arena's own walk: out[5] bucket / Node-UC searches the
+ * product path performs (one random HBM access each), out[6] k-mers the stored-k-mer filter rejects; out[7] spare.
+ * Diagnostic; synchronous. */
+int bft_b200_kmer_walk_stats_device(bft_b200_ctx* ctx, const uint64_t* d_kmers, size_t n, uint64_t out[8]);
 
 /* Random-access roofline probe: rate (loads/s) of independent 8-byte loads at random offsets of a table_bytes table
  * (choose it far larger than the 126 MB L2). Diagnostic; synchronous. */
