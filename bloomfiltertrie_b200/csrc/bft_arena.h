@@ -139,11 +139,13 @@ typedef struct {
     const uint32_t* ovfcls;   /* n_ovf, only when cls_shift == 0 */
     const uint64_t* uckeys;   /* n_uc_lines * W words (Node-UC lines) */
     const uint32_t* uccls;    /* n_uc_lines */
+    const uint8_t* uc_rank;   /* n_uc_lines: index of the line inside its UC in the reference's stored order */
     /* enumeration side tables (iterate_over_kmers / -extract_kmers): where each stored prefix sits in the trie */
     const uint32_t* pref_low18;  /* per stored prefix: its 9 nucleotides as they appear in the packed k-mer */
     const uint32_t* pref_node;   /* per stored prefix: the Node whose CC holds it */
     const bft_path_t* node_path; /* per Node: the k-mer bits fixed by the path from the root, and the depth */
-    const uint64_t* pref_out;    /* per stored prefix: index of its first k-mer in the enumeration order */
+    const uint64_t* pref_out;    /* per stored prefix: index of its first k-mer in the enumeration order (the reference's
+                                  * iterate_over_kmers order, depth first; NODE prefixes: first k-mer of the subtree) */
     int k;
     int W;             /* 64-bit words per key: 1 for k <= 27, 2 for k <= 63, 4 for k <= 126 */
     int cls_shift;     /* != 0: class id of an inline line = (top word >> cls_shift) & cls_mask, suffix = the bits below */

@@ -65,7 +65,7 @@ struct bft_b200_ctx {
     char** names;
     bft_b200_stats stats;
     /* device arena */
-    void* d_arena[17];
+    void* d_arena[18];
     size_t n_pref, n_nodes;
     bft_view_t dview;
     bft_pools_t dpools;
@@ -146,7 +146,7 @@ extern "C" void bft_b200_close(bft_b200_ctx* c) {
     if (!c) return;
     cudaSetDevice(c->device);
     cudaDeviceSynchronize();
-    for (int i = 0; i < 17; i++) if (c->d_arena[i]) cudaFree(c->d_arena[i]);
+    for (int i = 0; i < 18; i++) if (c->d_arena[i]) cudaFree(c->d_arena[i]);
     for (int i = 0; i < 4; i++) if (c->d_pool[i]) cudaFree(c->d_pool[i]);
     if (c->d_hot) cudaFree(c->d_hot);
     if (c->d_class_counts) cudaFree(c->d_class_counts);
@@ -253,6 +253,7 @@ extern "C" int bft_b200_open(const char* path, int device, bft_b200_ctx** out) {
     UP(14, pref_node, a->n_pref * sizeof(uint32_t));
     UP(15, node_path, a->n_nodes * sizeof(bft_path_t));
     UP(16, pref_out, (a->n_pref + 1) * sizeof(uint64_t));
+    UP(17, uc_rank, a->n_uc_lines);
     c->n_pref = a->n_pref;
     c->n_nodes = a->n_nodes;
 #undef UP
@@ -281,6 +282,7 @@ extern "C" int bft_b200_open(const char* path, int device, bft_b200_ctx** out) {
         c->dview.pref_node = (const uint32_t*)c->d_arena[14];
         c->dview.node_path = (const bft_path_t*)c->d_arena[15];
         c->dview.pref_out = (const uint64_t*)c->d_arena[16];
+        c->dview.uc_rank = (const uint8_t*)c->d_arena[17];
         c->dview.cls_shift = a->cls_shift;
         c->dview.cls_mask = a->cls_mask;
         c->dview.k = a->k;
@@ -979,8 +981,10 @@ extern "C" int bft_b200_peer_close(bft_b200_ctx* c, void* d_ptr) {
 static int enqueue_extract(bft_b200_ctx* c, uint64_t* d_kmers, uint32_t* d_cls, uint32_t* d_loc2vid) {
     cudaStream_t st = c->streams[0];
     if (c->n_pref) {
-        const int grid = grid_for(c, c->n_pref * 32, BFT_TPB);
-#define BFT_L(W_) k_extract_prefix_kmers<W_><<<grid, BFT_TPB, 0, st>>>(c->dview, c->n_pref, d_kmers, d_cls, d_loc2vid)
+        const int tpb = 32 * BFT_EXTRACT_WARPS;
+        const int grid = grid_for(c, c->n_pref * 32, tpb);
+        const size_t smem = bft_extract_smem(c->W);
+#define BFT_L(W_) k_extract_prefix_kmers<W_><<<grid, tpb, smem, st>>>(c->dview, c->n_pref, d_kmers, d_cls, d_loc2vid)
         BFT_BY_W(c->W, BFT_L);
 #undef BFT_L
         c->launches++;
@@ -1071,24 +1075,43 @@ extern "C" int bft_b200_extract_kmers_file(bft_b200_ctx* c, const char* path, in
 extern "C" int bft_b200_query_kmers_file(bft_b200_ctx* c, const char* query_path, int binary_file, const char* csv_path, uint64_t* n_present) {
     if (!c || !query_path || !csv_path) return set_err(BFT_B200_ERR_ARG, "bft_b200_query_kmers_file: NULL argument");
     uint64_t* q = NULL;
+    char* ascii = NULL;
     size_t n = 0;
-    if (bft_read_kmer_file(query_path, binary_file, c->k, c->W, &q, &n)) return set_err(BFT_B200_ERR_FILE, "cannot read k-mer file %s", query_path);
+    /* "kmers_comp": packed records. "kmers": the text lines go to the GPU as they are — parseKmerCount (src/fasta.c:3-53)
+     * runs there (k_encode_ascii) and flags the lines the reference would drop */
+    if (binary_file ? bft_read_kmer_file(query_path, 1, c->k, c->W, &q, &n) : bft_read_kmer_text_file(query_path, c->k, &ascii, &n))
+        return set_err(BFT_B200_ERR_FILE, "cannot read k-mer file %s", query_path);
     uint8_t* present = (uint8_t*)malloc(n + 1);
+    uint8_t* valid = binary_file ? NULL : (uint8_t*)malloc(n + 1);
     uint32_t* rows = (uint32_t*)malloc((n + 1) * (size_t)c->rw * sizeof(uint32_t));
-    int rc = (!present || !rows) ? set_err(BFT_B200_ERR_NOMEM, "out of host memory") : bft_b200_query_kmers(c, q, n, present, rows, NULL);
+    int rc = (!present || !rows || (!binary_file && !valid)) ? set_err(BFT_B200_ERR_NOMEM, "out of host memory")
+             : binary_file ? bft_b200_query_kmers(c, q, n, present, rows, NULL)
+                           : bft_b200_query_kmers_ascii(c, ascii, n, valid, present, rows, NULL);
     if (!rc) {
+        size_t m = n;
+        if (valid) { /* rejected lines produce no CSV row (src/file_io.c:786-862) */
+            m = 0;
+            for (size_t i = 0; i < n; i++) {
+                if (!valid[i]) continue;
+                if (m != i) {
+                    memcpy(rows + m * (size_t)c->rw, rows + i * (size_t)c->rw, (size_t)c->rw * sizeof(uint32_t));
+                    present[m] = present[i];
+                }
+                m++;
+            }
+        }
         FILE* f = fopen(csv_path, "w");
         if (!f) rc = set_err(BFT_B200_ERR_FILE, "cannot write %s", csv_path);
         else {
-            if (bft_csv_write_header(f, c->names, c->G) || bft_csv_write_rows(f, rows, n, c->G, c->rw) || bft_csv_finish(f))
+            if (bft_csv_write_header(f, c->names, c->G) || bft_csv_write_rows(f, rows, m, c->G, c->rw) || bft_csv_finish(f))
                 rc = set_err(BFT_B200_ERR_FILE, "could not write output to CSV file %s", csv_path);
             fclose(f);
         }
         uint64_t np = 0;
-        for (size_t i = 0; i < n; i++) np += present[i];
+        for (size_t i = 0; i < m; i++) np += present[i];
         if (n_present) *n_present = np;
     }
-    free(q); free(present); free(rows);
+    free(q); free(ascii); free(present); free(valid); free(rows);
     return rc;
 }
 

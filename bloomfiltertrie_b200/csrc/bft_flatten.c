@@ -23,7 +23,7 @@ typedef struct {
     int nb_bits_skip2, nb_bits_skip3, nb_ucs_skp, nb_kmers_uc, level_min, modulo_hash, tresh_suf_pref;
 } lvl_info_t;
 
-typedef struct { uint64_t k[BFT_MAX_WORDS]; uint32_t cls; } line_tmp_t;
+typedef struct { uint64_t k[BFT_MAX_WORDS]; uint32_t cls; uint32_t idx; /* line index in the UC, i.e. the reference's stored order */ } line_tmp_t;
 
 typedef struct {
     const uint8_t* buf;
@@ -249,6 +249,7 @@ static void load_block(ctx_t* c, const uc_body_t* u, int first, int cnt, int key
     for (int i = 0; i < cnt; i++) {
         line_key(c, u, first + i, key_bits, strip_bit7, c->tmp[i].k);
         c->tmp[i].cls = uc_line_class(c, u, first + i);
+        c->tmp[i].idx = (uint32_t)i;
         for (int w = W; w < BFT_MAX_WORDS; w++)
             if (c->tmp[i].k[w]) fail(c, "bft_flatten: key wider than W words");
     }
@@ -274,12 +275,14 @@ static uint32_t append_uc_lines(ctx_t* c, const uc_body_t* u, int cnt, int key_b
         while (ncap < need) ncap += ncap / 2 + 4096;
         a->uckeys = (uint64_t*)xrealloc(c, a->uckeys, ncap * (size_t)W * sizeof(uint64_t));
         a->uccls = (uint32_t*)xrealloc(c, a->uccls, ncap * sizeof(uint32_t));
+        a->uc_rank = (uint8_t*)xrealloc(c, a->uc_rank, ncap);
         c->cap_uc_lines = ncap;
     }
     const uint32_t start = (uint32_t)a->n_uc_lines;
     for (int i = 0; i < cnt; i++) {
         for (int w = 0; w < W; w++) a->uckeys[(a->n_uc_lines + (size_t)i) * W + w] = c->tmp[i].k[w];
         a->uccls[a->n_uc_lines + (size_t)i] = c->tmp[i].cls;
+        a->uc_rank[a->n_uc_lines + (size_t)i] = (uint8_t)c->tmp[i].idx; /* a UC holds at most 255 lines */
     }
     a->n_uc_lines += (size_t)cnt;
     a->n_kmers += (size_t)cnt;
@@ -291,6 +294,7 @@ static uint32_t append_uc_lines(ctx_t* c, const uc_body_t* u, int cnt, int key_b
 static bft_entry_t append_inline_block(ctx_t* c, const uc_body_t* u, int first, int cnt, int key_bits, int strip_bit7) {
     bft_arena_t* a = c->a;
     const int W = a->W, S = BFT_BUCKET_KEYS;
+    if (cnt > 255) fail(c, "bft_flatten: a prefix with %d inline suffixes (children_type counts are bytes: at most 255)", cnt);
     load_block(c, u, first, cnt, key_bits, strip_bit7);
     uint32_t lb = 0;
     while (lb < BFT_MAX_LB && ((size_t)1 << lb) * (S / 2) < (size_t)cnt) lb++;
@@ -579,6 +583,7 @@ void bft_arena_view(const bft_arena_t* a, bft_view_t* v) {
     v->ovfcls = a->ovfcls;
     v->uckeys = a->uckeys;
     v->uccls = a->uccls;
+    v->uc_rank = a->uc_rank;
     v->pref_low18 = a->pref_low18;
     v->pref_node = a->pref_node;
     v->node_path = a->node_path;
@@ -600,7 +605,7 @@ void bft_arena_free(bft_arena_t* a) {
     }
     free(a->rootdir); free(a->nodes); free(a->ccs); free(a->firstcc); free(a->csr); free(a->filter3);
     free(a->pref_low18); free(a->pref_node); free(a->node_path); free(a->pref_out);
-    free(a->pref); free(a->buckets); free(a->slotcls); free(a->ovf); free(a->ovfcls); free(a->uckeys); free(a->uccls); free(a->cls_off); free(a->cls_bytes);
+    free(a->pref); free(a->buckets); free(a->slotcls); free(a->ovf); free(a->ovfcls); free(a->uckeys); free(a->uccls); free(a->uc_rank); free(a->cls_off); free(a->cls_bytes);
     free(a->pool_last_index); free(a->pool_size_annot); free(a->pool_off); free(a->pool_bytes);
     free(a);
 }
@@ -723,6 +728,7 @@ bft_arena_t* bft_arena_from_memory(const uint8_t* buf, size_t len, char* err, si
     if (!a->uckeys) {
         a->uckeys = (uint64_t*)xrealloc(c, NULL, 8 * BFT_MAX_WORDS);
         a->uccls = (uint32_t*)xrealloc(c, NULL, 8);
+        a->uc_rank = (uint8_t*)xrealloc(c, NULL, 8);
     }
 
     /* colour class ids into the spare top bits of the inline keys when they fit between the widest suffix and the
@@ -794,19 +800,44 @@ bft_arena_t* bft_arena_from_memory(const uint8_t* buf, size_t len, char* err, si
         }
     }
     {
+        /* Enumeration order = the reference's iterate_over_kmers_from_node (src/extract_kmers.c:3-597): depth first —
+         * the CCs of a Node in order, the stored prefixes of a CC in order, under a prefix either its inline suffix
+         * lines (in the order the UC stores them) or the whole subtree of its child Node, and after the CCs the
+         * Node's own UC lines. pref_out[j] / node_path[].uc_out = index of the first k-mer of prefix j / of the
+         * Node's UC in that order; an explicit stack replaces the recursion (depth <= k/9 <= 14). */
         uint64_t run = 0;
-        for (size_t pj = 0; pj < a->n_pref; pj++) {
-            a->pref_out[pj] = run;
-            const uint32_t kind = a->pref[pj].b >> BFT_KIND_SHIFT;
-            if (kind == BFT_KIND_INLINE) run += a->pref[pj].b & BFT_CNT_MASK;
-            else if (kind == BFT_KIND_LEAF) run += 1;
+        struct { uint32_t node, cc, j; } stk[16];
+        int sp = 0;
+        stk[0].node = 0; stk[0].cc = 0; stk[0].j = 0;
+        memset(a->pref_out, 0, (a->n_pref + 1) * sizeof(uint64_t));
+        while (sp >= 0) {
+            const bft_node_t* nd = &a->nodes[stk[sp].node];
+            int descended = 0;
+            while (stk[sp].cc < nd->n_cc && !descended) {
+                const bft_cc_t* cc = &a->ccs[nd->cc_begin + stk[sp].cc];
+                while (stk[sp].j < cc->nb_elem) {
+                    const size_t pj = (size_t)cc->pref_off + stk[sp].j++;
+                    const uint32_t kind = a->pref[pj].b >> BFT_KIND_SHIFT;
+                    a->pref_out[pj] = run;
+                    if (kind == BFT_KIND_INLINE) run += a->pref[pj].b & BFT_CNT_MASK;
+                    else if (kind == BFT_KIND_LEAF) run += 1;
+                    else if (kind == BFT_KIND_NODE) {
+                        if (sp + 1 >= 16) fail(c, "bft_flatten: trie deeper than 16 levels");
+                        sp++;
+                        stk[sp].node = a->pref[pj].a; stk[sp].cc = 0; stk[sp].j = 0;
+                        descended = 1;
+                        break;
+                    }
+                }
+                if (!descended) { stk[sp].cc++; stk[sp].j = 0; }
+            }
+            if (descended) continue;
+            a->node_path[stk[sp].node].uc_out_lo = (uint32_t)run;
+            a->node_path[stk[sp].node].uc_out_hi = (uint32_t)(run >> 32);
+            run += nd->uc_n;
+            sp--;
         }
         a->pref_out[a->n_pref] = run;
-        for (size_t nid = 0; nid < a->n_nodes; nid++) {
-            a->node_path[nid].uc_out_lo = (uint32_t)run;
-            a->node_path[nid].uc_out_hi = (uint32_t)(run >> 32);
-            run += a->nodes[nid].uc_n;
-        }
         if (run != a->n_kmers) fail(c, "bft_flatten: enumeration order counts %llu k-mers, the arena %zu", (unsigned long long)run, a->n_kmers);
     }
 

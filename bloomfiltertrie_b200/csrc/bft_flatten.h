@@ -28,6 +28,7 @@ typedef struct bft_arena {
     size_t n_lines;      /* inline suffix lines stored (in buckets + ovf) */
     uint64_t* uckeys;    /* n_uc_lines * W: Node-UC lines */
     uint32_t* uccls;     size_t n_uc_lines;
+    uint8_t* uc_rank;    /* n_uc_lines: position of the line inside its UC as the reference stores it (enumeration order) */
     int cls_shift;
     uint32_t cls_mask;
     /* enumeration side tables (see bft_arena.h) */

@@ -45,6 +45,7 @@ int bft_read_kmer_file(const char* path, int binary, int k, int W, uint64_t** wo
             uint8_t b[32];
             memset(b, 0, sizeof(b));
             memcpy(b, rec, nb);
+            if ((2 * k) & 7) b[nb - 1] &= (uint8_t)((1u << ((2 * k) & 7)) - 1u); /* pad bits of the last byte carry no nucleotide */
             memcpy(out + cnt * (size_t)W, b, (size_t)W * 8);
             cnt++;
         }
@@ -71,44 +72,114 @@ int bft_read_kmer_file(const char* path, int binary, int k, int W, uint64_t** wo
     return 0;
 }
 
+/* whole file into memory (+1 NUL) */
+static char* slurp(const char* path, size_t* len) {
+    FILE* f = fopen(path, "rb");
+    if (!f) return NULL;
+    size_t cap = 1 << 20, n = 0;
+    char* b = (char*)malloc(cap + 1);
+    while (b) {
+        const size_t got = fread(b + n, 1, cap - n, f);
+        n += got;
+        if (got == 0) break;
+        if (n == cap) {
+            cap *= 2;
+            char* t = (char*)realloc(b, cap + 1);
+            if (!t) { free(b); b = NULL; }
+            else b = t;
+        }
+    }
+    fclose(f);
+    if (!b) return NULL;
+    b[n] = 0;
+    *len = n;
+    return b;
+}
+
 int bft_read_sequence_file(const char* path, char** chars, uint64_t** offs, size_t* n) {
     *chars = NULL;
     *offs = NULL;
     *n = 0;
-    FILE* f = fopen(path, "r");
-    if (!f) return -1;
-    size_t ccap = 1 << 20, clen = 0, ocap = 1 << 12, cnt = 0;
-    char* cb = (char*)malloc(ccap);
+    size_t len = 0;
+    char* buf = slurp(path, &len);
+    if (!buf) return -1;
+    /* format: FASTA if the first line starts with '>' (or ';'), FASTQ if it starts with '@', else one sequence per line */
+    const int fasta = len && (buf[0] == '>' || buf[0] == ';');
+    const int fastq = len && buf[0] == '@';
+    size_t ocap = 1 << 12, cnt = 0, w = 0; /* the sequences are compacted in place: w <= read position always */
     uint64_t* ob = (uint64_t*)malloc(ocap * sizeof(uint64_t));
-    if (!cb || !ob) { free(cb); free(ob); fclose(f); return -1; }
+    if (!ob) { free(buf); return -1; }
     ob[0] = 0;
-    char* line = NULL;
-    size_t lcap = 0;
-    ssize_t len;
-    while ((len = getline(&line, &lcap, f)) != -1) {
-        line[strcspn(line, "\r\n")] = '\0';
-        size_t l = strlen(line);
-        if (clen + l + 1 > ccap) {
-            while (clen + l + 1 > ccap) ccap *= 2;
-            char* t = (char*)realloc(cb, ccap);
-            if (!t) { free(cb); free(ob); free(line); fclose(f); return -1; }
-            cb = t;
+    int open_record = 0;   /* FASTA: a header was seen and its sequence is being collected */
+    size_t line_no = 0;    /* FASTQ: position inside the 4-line record */
+    for (size_t pos = 0; pos < len;) {
+        const char* nl = (const char*)memchr(buf + pos, '\n', len - pos);
+        const size_t end = nl ? (size_t)(nl - buf) : len;
+        size_t l = end - pos;
+        { /* the reference cuts a line at the first CR or LF (strcspn, src/file_io.c:1519-1521) */
+            const char* cr = (const char*)memchr(buf + pos, '\r', l);
+            if (cr) l = (size_t)(cr - (buf + pos));
+        }
+        int close_record = 0, take = 0;
+        if (fasta) {
+            if (l && (buf[pos] == '>' || buf[pos] == ';')) {
+                if (buf[pos] == '>') { close_record = open_record; open_record = 1; }
+            } else take = open_record;
+        } else if (fastq) {
+            take = (line_no & 3) == 1;
+            close_record = (line_no & 3) == 3;
+            line_no++;
+        } else {
+            take = 1;
+            close_record = 1;
+        }
+        if (close_record && !take) { /* FASTA header closing the previous record / FASTQ quality line */
+            cnt++;
+            ob[cnt] = w;
+        }
+        if (take) {
+            memmove(buf + w, buf + pos, l);
+            w += l;
+            if (close_record) { cnt++; ob[cnt] = w; }
         }
         if (cnt + 2 > ocap) {
             ocap *= 2;
             uint64_t* t = (uint64_t*)realloc(ob, ocap * sizeof(uint64_t));
-            if (!t) { free(cb); free(ob); free(line); fclose(f); return -1; }
+            if (!t) { free(buf); free(ob); return -1; }
             ob = t;
         }
-        memcpy(cb + clen, line, l);
-        clen += l;
-        cnt++;
-        ob[cnt] = clen;
+        pos = end + 1;
     }
-    free(line);
-    fclose(f);
-    *chars = cb;
+    if (fasta && open_record) { cnt++; ob[cnt] = w; }
+    *chars = buf;
     *offs = ob;
+    *n = cnt;
+    return 0;
+}
+
+int bft_read_kmer_text_file(const char* path, int k, char** ascii, size_t* n) {
+    *ascii = NULL;
+    *n = 0;
+    size_t len = 0;
+    char* buf = slurp(path, &len);
+    if (!buf) return -1;
+    size_t w = 0, cnt = 0;
+    for (size_t pos = 0; pos < len;) {
+        const char* nl = (const char*)memchr(buf + pos, '\n', len - pos);
+        const size_t end = nl ? (size_t)(nl - buf) : len;
+        size_t l = end - pos;
+        const char* cr = (const char*)memchr(buf + pos, '\r', l);
+        if (cr) l = (size_t)(cr - (buf + pos));
+        const char* z = (const char*)memchr(buf + pos, 0, l); /* parseKmerCount stops at a NUL */
+        if (z) l = (size_t)(z - (buf + pos));
+        if (l >= (size_t)k) { /* a shorter line fails parseKmerCount and is dropped (src/file_io.c:786-862) */
+            memmove(buf + w, buf + pos, (size_t)k);
+            w += (size_t)k;
+            cnt++;
+        }
+        pos = end + 1;
+    }
+    *ascii = buf;
     *n = cnt;
     return 0;
 }

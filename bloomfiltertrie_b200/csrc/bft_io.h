@@ -21,9 +21,20 @@ int bft_parse_kmer(const char* s, int k, uint64_t* words, int W);
  * (src/file_io.c:786-862). Returns 0 on success. */
 int bft_read_kmer_file(const char* path, int binary, int k, int W, uint64_t** words, size_t* n);
 
-/* Read a sequence file, one sequence per line, CR/LF stripped (src/file_io.c:1519-1521).
- * Output: concatenated characters + offsets (n+1 entries). Returns 0 on success. */
+/* Read a sequence file into concatenated characters + offsets (n+1 entries). Three layouts, told apart by the first
+ * character of the file:
+ *   - anything but '>' ';' '@': one sequence per line, CR/LF stripped — the only layout the reference reads
+ *     (src/file_io.c:1519-1521);
+ *   - '>' (or a ';' comment): FASTA — header lines dropped, the lines of a record joined into one sequence, so a FASTA
+ *     file is answered exactly like its line-per-sequence flattening (one CSV row per record, empty records included);
+ *   - '@': FASTQ — second line of every 4-line record.
+ * A valid line-per-sequence file never starts with one of these (the reference exit(1)s on such a line). Returns 0 on success. */
 int bft_read_sequence_file(const char* path, char** chars, uint64_t** offs, size_t* n);
+
+/* Text k-mer file ("kmers", one ASCII k-mer per line): the first k characters of every line that has at least k before
+ * its CR/LF/NUL, back to back (n * k chars, malloc'd) — the input of bft_b200_query_kmers_ascii, which does
+ * parseKmerCount on the GPU and flags the k-mers it rejects. Returns 0 on success. */
+int bft_read_kmer_text_file(const char* path, int k, char** ascii, size_t* n);
 
 /* CSV output shared by -query_kmers and -query_sequences: header = genome names joined by ',' + '\n'
  * (src/file_io.c:706-719); one row per query of "0,1,...\n" (2*G bytes); finish() overwrites the last byte

@@ -508,10 +508,28 @@ __device__ __forceinline__ void bft_emit_kmer(const uint64_t* base, const uint64
     for (int w = 0; w < W; w++) out[w] = base[w] | sh[w];
 }
 
+/* byte-swapped word: memcmp over the reference's suffix bytes (byte 0 first, src/UC.c:81-124) orders the lines of a UC
+ * like the words bswap(key[0]), bswap(key[1]), ... compared lexicographically */
+__device__ __forceinline__ uint64_t bft_bswap64(uint64_t x) {
+    return ((uint64_t)__byte_perm((uint32_t)x, 0, 0x0123) << 32) | (uint64_t)__byte_perm((uint32_t)(x >> 32), 0, 0x0123);
+}
+
+#define BFT_EXTRACT_WARPS 4
+#define BFT_EXTRACT_MAX_LINES 256 /* a prefix owns at most 255 inline lines (children_type counts are bytes, include/CC.h:358-366) */
+__host__ __device__ inline size_t bft_extract_smem(int W) { return (size_t)BFT_EXTRACT_WARPS * BFT_EXTRACT_MAX_LINES * ((size_t)W * 8 + 8); }
+
+/* One warp per stored prefix: the lines of its hashed buckets (and overflow runs) are gathered into shared memory, each
+ * line's rank in the reference's stored order (ascending memcmp of the suffix bytes) is counted, and the line is written
+ * at pref_out[prefix] + rank — the very order iterate_over_kmers_from_node visits them (src/extract_kmers.c:3-597). */
 template <int W>
-__global__ void __launch_bounds__(BFT_TPB) k_extract_prefix_kmers(const bft_view_t v, size_t n_pref, uint64_t* __restrict__ kmers,
-                                                                  uint32_t* __restrict__ cls_out, uint32_t* __restrict__ loc2vid) {
-    const int lane = threadIdx.x & 31;
+__global__ void __launch_bounds__(32 * BFT_EXTRACT_WARPS) k_extract_prefix_kmers(const bft_view_t v, size_t n_pref, uint64_t* __restrict__ kmers,
+                                                                                 uint32_t* __restrict__ cls_out, uint32_t* __restrict__ loc2vid) {
+    extern __shared__ __align__(16) unsigned char bft_extract_smem_raw[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    uint64_t* const skey = (uint64_t*)bft_extract_smem_raw + (size_t)warp * BFT_EXTRACT_MAX_LINES * W;
+    uint32_t* const scls = (uint32_t*)((uint64_t*)bft_extract_smem_raw + (size_t)BFT_EXTRACT_WARPS * BFT_EXTRACT_MAX_LINES * W) +
+                           (size_t)warp * 2 * BFT_EXTRACT_MAX_LINES;
+    uint32_t* const sloc = scls + BFT_EXTRACT_MAX_LINES;
     const size_t warp_stride = ((size_t)gridDim.x * blockDim.x) >> 5;
     const int shift = v.cls_shift;
     const uint64_t top_mask = shift ? ((1ULL << shift) - 1ULL) : ~BFT_SLOT_SPECIAL;
@@ -530,7 +548,7 @@ __global__ void __launch_bounds__(BFT_TPB) k_extract_prefix_kmers(const bft_view
 #pragma unroll
             for (int w = 0; w < W; w++) base[w] = path.acc[w] | sh[w];
         }
-        uint64_t out = v.pref_out[j];
+        const uint64_t out = v.pref_out[j];
         if (kind == BFT_KIND_LEAF) {
             if (lane == 0) {
                 for (int w = 0; w < W; w++) kmers[out * W + w] = base[w];
@@ -541,6 +559,8 @@ __global__ void __launch_bounds__(BFT_TPB) k_extract_prefix_kmers(const bft_view
         }
         const int shift_bits = BFT_PREFIX_BITS * (int)(path.depth + 1);
         const uint32_t n_slots = BFT_BUCKET_KEYS << ((e.b >> BFT_LB_SHIFT) & BFT_LB_MASK);
+        /* gather: every line of the block -> (byte-swapped key, class, storage location), in any order */
+        uint32_t n_got = 0;
         for (uint32_t s0 = 0; s0 < n_slots; s0 += 32) {
             const uint32_t slot = s0 + lane;
             uint64_t key[W];
@@ -553,40 +573,63 @@ __global__ void __launch_bounds__(BFT_TPB) k_extract_prefix_kmers(const bft_view
                 if (!(top & BFT_SLOT_SPECIAL)) n_emit = 1;
                 else if (top != BFT_SLOT_EMPTY) { n_emit = (uint32_t)(top >> 32) & 0x7fffffffu; ovf_start = (uint32_t)top; }
             }
-            /* exclusive scan of n_emit over the warp */
             uint32_t incl = n_emit;
             for (int o = 1; o < 32; o <<= 1) {
                 const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
                 if (lane >= o) incl += t;
             }
-            const uint64_t my = out + incl - n_emit;
-            out += __shfl_sync(0xffffffffu, incl, 31);
+            const uint32_t my = n_got + incl - n_emit;
+            n_got += __shfl_sync(0xffffffffu, incl, 31);
             if (n_emit == 1 && !(key[W - 1] & BFT_SLOT_SPECIAL)) {
-                const uint32_t c = shift ? ((uint32_t)(key[W - 1] >> shift) & v.cls_mask) : v.slotcls[gslot];
-                key[W - 1] &= top_mask;
-                uint64_t km[W];
-                bft_emit_kmer<W>(base, key, shift_bits, km);
-                for (int w = 0; w < W; w++) kmers[my * W + w] = km[w];
-                if (cls_out) cls_out[my] = c;
-                if (loc2vid) loc2vid[gslot] = (uint32_t)my;
+                if (my < BFT_EXTRACT_MAX_LINES) {
+                    scls[my] = shift ? ((uint32_t)(key[W - 1] >> shift) & v.cls_mask) : v.slotcls[gslot];
+                    sloc[my] = (uint32_t)gslot;
+                    key[W - 1] &= top_mask;
+                    for (int w = 0; w < W; w++) skey[(size_t)my * W + w] = bft_bswap64(key[w]);
+                }
             } else if (n_emit) { /* overflow run of this bucket */
-                for (uint32_t i = 0; i < n_emit; i++) {
+                for (uint32_t i = 0; i < n_emit && my + i < BFT_EXTRACT_MAX_LINES; i++) {
                     uint64_t ok[W];
                     for (int w = 0; w < W; w++) ok[w] = v.ovf[((size_t)ovf_start + i) * W + w];
-                    const uint32_t c = shift ? ((uint32_t)(ok[W - 1] >> shift) & v.cls_mask) : v.ovfcls[ovf_start + i];
+                    scls[my + i] = shift ? ((uint32_t)(ok[W - 1] >> shift) & v.cls_mask) : v.ovfcls[ovf_start + i];
+                    sloc[my + i] = v.loc_ovf + ovf_start + i;
                     ok[W - 1] &= top_mask;
-                    uint64_t km[W];
-                    bft_emit_kmer<W>(base, ok, shift_bits, km);
-                    for (int w = 0; w < W; w++) kmers[(my + i) * W + w] = km[w];
-                    if (cls_out) cls_out[my + i] = c;
-                    if (loc2vid) loc2vid[v.loc_ovf + ovf_start + i] = (uint32_t)(my + i);
+                    for (int w = 0; w < W; w++) skey[(size_t)(my + i) * W + w] = bft_bswap64(ok[w]);
                 }
             }
         }
+        __syncwarp();
+        if (n_got > BFT_EXTRACT_MAX_LINES) n_got = BFT_EXTRACT_MAX_LINES; /* cannot happen: the serializer refuses such blocks */
+        /* rank by counting, then emit */
+        for (uint32_t i = lane; i < n_got; i += 32) {
+            uint64_t mine[W];
+#pragma unroll
+            for (int w = 0; w < W; w++) mine[w] = skey[(size_t)i * W + w];
+            uint32_t rank = 0;
+            for (uint32_t m = 0; m < n_got; m++) {
+                bool less = false, decided = false; /* lexicographic, word 0 first */
+#pragma unroll
+                for (int w = 0; w < W; w++) {
+                    const uint64_t x = skey[(size_t)m * W + w];
+                    if (!decided && x != mine[w]) { less = x < mine[w]; decided = true; }
+                }
+                rank += less;
+            }
+            uint64_t key[W], km[W];
+#pragma unroll
+            for (int w = 0; w < W; w++) key[w] = bft_bswap64(mine[w]);
+            bft_emit_kmer<W>(base, key, shift_bits, km);
+            const uint64_t dst = out + rank;
+            for (int w = 0; w < W; w++) kmers[dst * W + w] = km[w];
+            if (cls_out) cls_out[dst] = scls[i];
+            if (loc2vid) loc2vid[sloc[i]] = (uint32_t)dst;
+        }
+        __syncwarp();
     }
 }
 
-/* the Nodes' own UC lines: whole remainders below the Node's path (one thread per Node, <= 255 lines each) */
+/* the Nodes' own UC lines: whole remainders below the Node's path (one thread per Node, <= 255 lines each), written in
+ * the order the reference's UC stores them (uc_rank) */
 template <int W>
 __global__ void __launch_bounds__(BFT_TPB) k_extract_uc_kmers(const bft_view_t v, size_t n_nodes, uint64_t* __restrict__ kmers,
                                                               uint32_t* __restrict__ cls_out, uint32_t* __restrict__ loc2vid) {
@@ -604,9 +647,10 @@ __global__ void __launch_bounds__(BFT_TPB) k_extract_uc_kmers(const bft_view_t v
             for (int w = 0; w < W; w++) key[w] = v.uckeys[((size_t)nd.uc_begin + i) * W + w];
             if (path.depth == 0) { for (int w = 0; w < W; w++) km[w] = key[w]; }
             else bft_emit_kmer<W>(base, key, BFT_PREFIX_BITS * (int)path.depth, km);
-            for (int w = 0; w < W; w++) kmers[(out + i) * W + w] = km[w];
-            if (cls_out) cls_out[out + i] = v.uccls[nd.uc_begin + i];
-            if (loc2vid) loc2vid[v.loc_uc + nd.uc_begin + i] = (uint32_t)(out + i);
+            const uint64_t dst = out + v.uc_rank[nd.uc_begin + i]; /* the line's place in the UC as the reference stores it */
+            for (int w = 0; w < W; w++) kmers[dst * W + w] = km[w];
+            if (cls_out) cls_out[dst] = v.uccls[nd.uc_begin + i];
+            if (loc2vid) loc2vid[v.loc_uc + nd.uc_begin + i] = (uint32_t)dst;
         }
     }
 }

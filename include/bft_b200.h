@@ -171,7 +171,10 @@ int bft_b200_peer_close(bft_b200_ctx* ctx, void* d_ptr);
 /* ---- file-level drivers (the CLI-visible bytes) ---------------------------------------------------------------
  * queryBFT_kmerPresences_from_KmerFiles (src/file_io.c:651-895): CSV of colour rows; returns #present via out.
  * queryBFT_kmerBranching_from_KmerFiles (src/file_io.c:897-1020): count of branching k-mers.
- * query_sequences_outputCSV (src/file_io.c:1464-1574). */
+ * query_sequences_outputCSV (src/file_io.c:1464-1574); besides the reference's one-sequence-per-line layout the
+ * sequence file may be FASTA (first character '>' or ';': headers dropped, the lines of a record joined) or FASTQ
+ * (first character '@'): one CSV row per record, byte-identical to what the reference writes for the same records
+ * flattened to one per line. A text k-mer file ("kmers") is parsed on the GPU (parseKmerCount, src/fasta.c:3-53). */
 int bft_b200_query_kmers_file(bft_b200_ctx* ctx, const char* query_path, int binary_file, const char* csv_path,
                               uint64_t* n_present);
 int bft_b200_query_branching_file(bft_b200_ctx* ctx, const char* query_path, int binary_file, uint64_t* n_branching);

@@ -165,6 +165,46 @@ def test_file_drivers_match_reference_cli(built, workdir):
         assert refutil.parse_count(out, "Nb branching k-mers") == n_branching
 
 
+def test_fasta_and_fastq_input_equal_the_flattened_file(built, workdir):
+    """north_star (2): sequences from FASTA. The reference reads one sequence per line (src/file_io.c:1519-1524), so
+    parity = the CSV of a FASTA (multi-line records, CRLF, comments, an empty record) or FASTQ file must be byte-identical
+    to what the REFERENCE CLI writes for the line-per-sequence flattening of the same records."""
+    c, path, eng = built
+    d = os.path.join(workdir, c["name"], "fasta")
+    os.makedirs(d, exist_ok=True)
+    seqs = [s for s in c["seqs"] if b">" not in s and b"@" not in s][:60]
+    seqs.insert(3, b"")                                   # a record without sequence lines
+    flat = os.path.join(d, "flat.txt")
+    with open(flat, "wb") as f:
+        f.write(b"\n".join(seqs) + b"\n")
+    with open(os.path.join(d, "ls"), "w") as f:
+        f.write(flat + "\n")
+    mode = "canonical" if c["canonical"] else "non_canonical"
+    refutil.ref_cli(path, ["-query_sequences", "0.8", mode, os.path.join(d, "ls")], cwd=d)
+    want = open(os.path.join(d, "flat.csv"), "rb").read()
+    rng = np.random.default_rng(3)
+    fa = os.path.join(d, "reads.fa")
+    with open(fa, "wb") as f:
+        f.write(b"; a comment line\n")
+        for i, s in enumerate(seqs):
+            f.write(b">read_%d some description\r\n" % i if i % 2 else b">read_%d\n" % i)
+            pos = 0
+            while pos < len(s):                           # ragged line lengths, some CRLF, a blank line now and then
+                w = int(rng.integers(1, 71))
+                f.write(s[pos:pos + w] + (b"\r\n" if rng.random() < 0.3 else b"\n"))
+                if rng.random() < 0.1:
+                    f.write(b"\n")
+                pos += w
+    eng.query_sequences_file(fa, os.path.join(d, "fa.csv"), 0.8, c["canonical"])
+    assert open(os.path.join(d, "fa.csv"), "rb").read() == want
+    fq = os.path.join(d, "reads.fq")
+    with open(fq, "wb") as f:
+        for i, s in enumerate(seqs):
+            f.write(b"@read_%d\n" % i + s + b"\n+\n" + b"I" * len(s) + b"\n")
+    eng.query_sequences_file(fq, os.path.join(d, "fq.csv"), 0.8, c["canonical"])
+    assert open(os.path.join(d, "fq.csv"), "rb").read() == want
+
+
 def _sort_rows(words):
     order = np.lexsort([words[:, w] for w in range(words.shape[1])])
     return order
@@ -172,8 +212,8 @@ def _sort_rows(words):
 
 def test_enumeration_matches_inserted_sets_and_reference_extract(built, workdir):
     """iterate_over_kmers / -extract_kmers on the device: the set of (k-mer, colour set) pairs must equal what was
-    inserted, and the k-mer records must equal the reference's own -extract_kmers output (as a set: the engine
-    enumerates in arena order, the reference in trie order)."""
+    inserted, and the files the engine writes must be BYTE-IDENTICAL to the reference's own -extract_kmers output
+    (same k-mers in the same iterate_over_kmers order, src/extract_kmers.c:3-597), binary and text form."""
     c, path, eng = built
     k, G = c["k"], c["n_genomes"]
     kmers, cls, rows = eng.extract_kmers(want_classes=True, want_rows=True)
@@ -202,14 +242,18 @@ def test_enumeration_matches_inserted_sets_and_reference_extract(built, workdir)
         l1 = raw.index(b"\n")
         l2 = raw.index(b"\n", l1 + 1)
         assert int(raw[:l1]) == k and int(raw[l1 + 1:l2]) == len(uniq)
-        rec = np.frombuffer(raw[l2 + 1:], dtype=np.uint8).reshape(-1, nb)
-        return rec[np.lexsort(rec.T[::-1])]
+        return np.frombuffer(raw[l2 + 1:], dtype=np.uint8).reshape(-1, nb)
 
-    np.testing.assert_array_equal(records(os.path.join(d, "mine.kc")), records(os.path.join(d, "ref.kc")))
+    mine, ref = records(os.path.join(d, "mine.kc")), records(os.path.join(d, "ref.kc"))
+    if not np.array_equal(mine, ref):
+        bad = np.nonzero((mine != ref).any(axis=1))[0]
+        raise AssertionError(f"{c['name']}: -extract_kmers order differs from the reference at {len(bad)} of {len(ref)} records, first {bad[:5]}")
+    assert open(os.path.join(d, "mine.kc"), "rb").read() == open(os.path.join(d, "ref.kc"), "rb").read()
+    refutil.ref_cli(path, ["-extract_kmers", "kmers", os.path.join(d, "ref.txt")], cwd=d)
     eng.extract_kmers_file(os.path.join(d, "mine.txt"), False)
-    lines = open(os.path.join(d, "mine.txt"), "rb").read().split(b"\n")[:-1]
-    assert len(lines) == len(uniq) and all(len(x) == k for x in lines[:50])
-    np.testing.assert_array_equal(synth.words_to_ascii(kmers[:50], k), np.array([list(x) for x in lines[:50]], dtype=np.uint8))
+    assert open(os.path.join(d, "mine.txt"), "rb").read() == open(os.path.join(d, "ref.txt"), "rb").read()
+    # the in-memory enumeration is that same order
+    np.testing.assert_array_equal(np.ascontiguousarray(kmers).view(np.uint8).reshape(len(kmers), -1)[:, :nb], ref)
 
 
 def test_duplicate_kmers_are_refused(workdir, engine_mod):

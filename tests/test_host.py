@@ -127,6 +127,54 @@ def test_storage_locations_are_unique_per_stored_kmer(name, tmp_path):
     assert f["max_loc"] < f["n_loc"] and f["answer_mismatch"] == 0
 
 
+@pytest.mark.parametrize("name", NAMES)
+def test_arena_enumeration_order_is_the_reference_order(name, tmp_path):
+    """The serializer's enumeration tables (depth-first pref_out, uc_rank, memcmp rank inside a prefix's lines) walked on
+    the host exactly as the extraction kernels walk them: the k-mers must come out in the reference's
+    iterate_over_kmers order — SHA-256 of the reference's own `-extract_kmers` output (tests/golden/extract_sha256.json)."""
+    import hashlib
+    import json
+    exe = str(tmp_path / "arena_enum_check")
+    _gcc(["-O2", "-std=c11", "-I", CSRC, os.path.join(ROOT, "tests", "tools", "arena_enum_check.c"),
+          os.path.join(CSRC, "bft_flatten.c"), "-o", exe])
+    out = str(tmp_path / "enum.txt")
+    msg = subprocess.run([exe, os.path.join(refutil.GOLDEN, name + ".bft"), out], stdout=subprocess.PIPE, check=True).stdout.decode()
+    want = json.load(open(os.path.join(refutil.GOLDEN, "extract_sha256.json")))[name]
+    assert f"kmers={want['n_kmers']} duplicates=0 missing=0" in msg
+    assert hashlib.sha256(open(out, "rb").read()).hexdigest() == want["sha256"]
+
+
+def test_sequence_file_reader_fasta_fastq_and_lines(tmp_path):
+    """bft_read_sequence_file: FASTA (multi-line records, CRLF, ';' comments, empty records, no trailing newline), FASTQ
+    and the reference's own line-per-sequence layout all yield the same list of sequences; bft_read_kmer_text_file keeps
+    the first k characters of every line long enough."""
+    exe = str(tmp_path / "seqfile_dump")
+    _gcc(["-O2", "-std=c11", "-I", CSRC, os.path.join(ROOT, "tests", "tools", "seqfile_dump.c"), os.path.join(CSRC, "bft_io.c"), "-o", exe])
+    seqs = [b"ACGTACGTAC", b"", b"GGGTTTNNNACGT", b"acgu", b"T" * 200]
+
+    def dump(*a):
+        out = subprocess.run([exe, *a], stdout=subprocess.PIPE, check=True).stdout.split(b"\n")
+        return int(out[0]), out[1:-1]
+
+    flat = tmp_path / "flat.txt"
+    flat.write_bytes(b"\n".join(seqs) + b"\n")
+    assert dump("seq", str(flat)) == (len(seqs), seqs)
+    flat.write_bytes(b"\r\n".join(seqs))                       # CRLF, no newline at the end
+    assert dump("seq", str(flat)) == (len(seqs), seqs)
+    fa = tmp_path / "x.fa"
+    fa.write_bytes(b";comment\n>r0 desc\nACGTA\nCGTAC\n>r1\n>r2\r\nGGGTTT\r\n\r\nNNNACGT\n>r3\nacgu\n>r4\n" + b"T" * 120 + b"\n" + b"T" * 80)
+    assert dump("seq", str(fa)) == (len(seqs), seqs)
+    fq = tmp_path / "x.fq"
+    fq.write_bytes(b"".join(b"@r%d\n" % i + s + b"\n+\n" + b"#" * len(s) + b"\n" for i, s in enumerate(seqs)))
+    assert dump("seq", str(fq)) == (len(seqs), seqs)
+    empty = tmp_path / "empty.txt"
+    empty.write_bytes(b"")
+    assert dump("seq", str(empty)) == (0, [])
+    km = tmp_path / "k.txt"
+    km.write_bytes(b"ACGTACGTA\nACG\nACGTACGTACGT\r\n\nNNNNNNNNN")
+    assert dump("kmers", "9", str(km)) == (3, [b"ACGTACGTA", b"ACGTACGTA", b"NNNNNNNNN"])
+
+
 def test_flattener_rejects_garbage(host_tool, tmp_path):
     bad = tmp_path / "bad.bft"
     bad.write_bytes(b"\x01\x02\x03")
