@@ -1,13 +1,15 @@
 #!/usr/bin/env python
 """bench.py — k-mers queried/sec on the 100-genome synthetic pan-genome BFT (BASELINE.json metric, config[2];
-k=27 stands in for "k=31": the reference only accepts k divisible by 9).
+k=27 stands in for "k=31": the reference only accepts k divisible by 9), with the other four BASELINE
+configs measured in the same run as sub-records (`configs`: c1, c2, c4, c5).
 
   python bench.py [--gpus N] [--steps K] [--warmup W]          engine arm (one process per GPU; torchrun for N>1)
   python bench.py --impl reference [...]                       reference arm: the unmodified reference's CPU query
                                                                path (oracle/_ref) on the box's host cores
-A step = one pass of the hot path (k-mer membership + colour rows) over one batch of synthetic queries per GPU.
-`value` is measured with the batch already resident in HBM; `e2e` goes through the host C-ABI call with pinned host
-buffers, host<->device copies inside the timed region. Prints ONE JSON line on rank 0.
+  python bench.py --config c4 --sub ""                         one config as the main line (profiling)
+A step = one pass of the hot path over one batch of synthetic queries per GPU. `value` is measured with the batch
+already resident in HBM; `e2e` goes through the host C-ABI call with pinned host buffers, host<->device copies inside the
+timed region. Prints ONE JSON line on rank 0.
 """
 import argparse
 import json
@@ -23,9 +25,6 @@ sys.path.insert(0, ROOT)
 
 METRIC = "kmers_queried_per_sec"
 UNIT = "k-mers/s"
-K = 27
-DEFAULT_LEN = 5_000_000
-FALLBACK_LEN = 200_000  # built on the fly with the reference when no prebuilt BFT travelled with the repo
 MIX = (0.5, 0.25, 0.25)
 
 
@@ -56,7 +55,7 @@ def emit(line: dict):
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md clocks line)."""
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed regions (B200_PROFILING.md clocks line)."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
@@ -78,14 +77,10 @@ class ClockSampler:
         for line in self.proc.stdout:
             self.rows.append((time.time(), line.strip()))
 
-    def stop(self, t0, t1):
-        if not self.proc:
-            return None
-        time.sleep(0.15)
-        self.proc.terminate()
+    def window(self, t0, t1):
         sm, mx, reasons = [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for t, line in self.rows:
+        for t, line in list(self.rows):
             if t < t0 or t > t1 + 0.2:
                 continue
             f = [x.strip() for x in line.split(",")]
@@ -98,7 +93,7 @@ class ClockSampler:
                 if v.lower().startswith("active"):
                     reasons.add(nme)
         if not sm:
-            for t, line in self.rows[-3:]:
+            for t, line in list(self.rows)[-3:]:
                 f = [x.strip() for x in line.split(",")]
                 try:
                     sm.append(float(f[1]))
@@ -110,18 +105,10 @@ class ClockSampler:
         sm.sort()
         return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": max(mx), "reasons": sorted(reasons), "samples": len(sm)}
 
-
-def pick_workload(args):
-    import bench_workloads as wl
-    if getattr(args, "pangenome", "c3") == "c5":  # informational: 1000 colours, wide rows (RW = 32)
-        return wl.C5, (args.genome_len or 100_000)
-    cfg = wl.C3
-    if args.genome_len:
-        L = args.genome_len
-    else:
-        have = wl.available_lengths(cfg, K)
-        L = DEFAULT_LEN if DEFAULT_LEN in have else (max(have) if have else FALLBACK_LEN)
-    return cfg, L
+    def stop(self):
+        if self.proc:
+            self.proc.terminate()
+            self.proc = None
 
 
 def peaks():
@@ -134,68 +121,16 @@ def peaks():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
-def ncu_capture():
-    """Summary of the committed ncu --set full capture of the dominant kernel (tools/ncu_summary.py writes it), if any."""
-    p = os.path.join(ROOT, "profiles", "ncu_k_query_kmers.json")
+def ncu_capture(tag):
+    """Summary of the committed ncu --set full capture of a config's dominant kernel (tools/ncu_summary.py writes
+    profiles/ncu_summary.json from the .ncu-rep files), if any."""
+    p = os.path.join(ROOT, "profiles", "ncu_summary.json")
     if os.path.exists(p):
         try:
-            return json.load(open(p))
+            return json.load(open(p)).get(tag)
         except Exception:
             return None
     return None
-
-
-def kmer_roofline(eng, ws, n, k_ms, W, RW, args, traffic_ok, kernel=None):
-    """Roofline record of the k-mer query kernel (HBM-bound, random access).
-
-    achieved = ALGORITHMIC bytes of the ARENA's walk per launch / CUDA-event time: per k-mer the key words in (8*W), the
-    presence byte + colour row out (1 + 4*RW) and one 32*W-byte bucket for every k-mer whose walk reaches a bucket
-    (measured on the timed batch by k_kmer_walk_stats; k-mers cut short by the root directory or by the L2-resident
-    stored-k-mer filter touch no HBM). The root directory entry, the filter sector and the class row come from L2 and
-    are listed as l2_bytes_per_kmer. traffic = ncu dram__bytes of the committed --set full capture of this kernel on
-    this workload (profiles/ncu_k_query_kmers.json, written by tools/ncu_summary.py); traffic / algorithmic = wasted
-    DRAM traffic. A_min / A_ref (the sectors the REFERENCE layout's walk would dereference) are context:
-    the arena does not move them, so they are not the roofline."""
-    nodes_pk, depth_pk, found_pk = ws["nodes"] / n, ws["search_depth"] / n, ws["found"] / n
-    cc_pk = ws["cc_probed"] / n
-    bucket_pk = ws["bucket_searches"] / n
-    reject_pk = ws["filter_rejects"] / n
-    a_min = 8 * W + (1 + 4 * RW) + 32.0 * (6 * nodes_pk + depth_pk + found_pk)
-    a_ref = 8 * W + (1 + 4 * RW) + 32.0 * (5 * nodes_pk + 2 * cc_pk + depth_pk + found_pk)
-    a_arena = 8 * W + (1 + 4 * RW) + 32.0 * W * bucket_pk
-    achieved = a_arena * n / (k_ms / 1e3) / 1e9
-    peak, peak_src = peaks()
-    cap = ncu_capture() if traffic_ok else None
-    traffic = cap.get("dram_bytes_per_kmer") if cap else None
-    probe = None
-    if not args.no_probe:
-        probe = eng.random_gather_probe(4 << 30, 1 << 28)
-    st = eng.stats()
-    return {"bound": "hbm", "kernel": kernel or ("k_query_kmers_rows" if RW in (1, 2, 4) else "k_query_kmers+k_expand_rows"),
-            "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-            "traffic": (traffic * n if traffic else None), "peak_source": peak_src, "kernel_ms": k_ms,
-            "kmers_per_sec_kernel": n / (k_ms / 1e3),
-            "algorithmic_bytes_per_kmer": a_arena,
-            "algorithmic_bytes_formula": "8*W in + (1 + 4*RW) out + 32*W * P(walk reaches a bucket)",
-            "bucket_accesses_per_kmer": bucket_pk, "filter_rejects_per_kmer": reject_pk, "found_frac": found_pk,
-            "l2_bytes_per_kmer": 8 + (32 if st.get("filter_bytes") else 0) + 4 * RW * found_pk,
-            "filter_mb": st.get("filter_bytes", 0) / 1e6,
-            "dram_bytes_per_kmer_ncu": traffic,
-            "wasted_traffic_ratio": (traffic / a_arena) if traffic else None,
-            "dram_gbps_physical": (traffic * n / (k_ms / 1e3) / 1e9) if traffic else None,
-            "dram_frac_physical": (traffic * n / (k_ms / 1e3) / 1e9 / peak) if traffic else None,
-            "ncu_capture": ({"file": cap.get("source"), "kernel": cap.get("kernel"), "filter_mb": cap.get("filter_mb")} if cap else None),
-            "random_gather_probe_loads_per_s": probe,
-            "random_access_frac": (bucket_pk * n / (k_ms / 1e3) / probe) if probe else None,
-            "context_reference_layout": {"a_min_bytes_per_kmer": a_min, "a_ref_bytes_per_kmer": a_ref, "nodes_per_kmer": nodes_pk,
-                                         "search_depth_per_kmer": depth_pk,
-                                         "cc_probed_per_node": cc_pk / max(nodes_pk, 1e-9),
-                                         "mean_suffix_block_lines": ws["block_lines"] / max(1, n),
-                                         "note": "sectors the REFERENCE layout's walk dereferences (SURVEY.md 8d); the arena replaces them by one "
-                                                 "L2-resident directory load + one bucket, so they are context, not the roofline"},
-            "note": "frac = algorithmic HBM bytes of the arena walk / measured copy bandwidth; the kernel is bound by the RATE of random "
-                    "64-byte HBM accesses (random_access_frac: bucket accesses/s over the measured rate of independent random loads), "
-                    "not by bytes"}
 
 
 def write_query_file(path, q_np, k):
@@ -204,112 +139,236 @@ def write_query_file(path, q_np, k):
     synth.write_kmers_comp(path, q_np.view(np.uint64), k)
 
 
-def run_reference_harness(bft, qfile, threads, passes):
+def run_ref(argv):
     import bench_workloads as wl
-    out = qfile + ".out"
-    p = subprocess.run([wl.REF_HARNESS, "kmers", bft, qfile, out, str(threads), str(passes)], stdout=subprocess.PIPE,
-                       stderr=subprocess.STDOUT, text=True)
-    if os.path.exists(out):
-        os.remove(out)
+    p = subprocess.run([wl.REF_HARNESS, *argv], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
     if p.returncode != 0:
         raise RuntimeError("ref_harness failed: " + p.stdout[-1000:])
     return [float(x) for x in re.findall(r"REF_PASS \d+ seconds=([0-9.]+)", p.stdout)]
 
 
-def reference_arm(args):
-    """The reference's own CPU implementation of the path (isKmerPresent + get_annotation + get_list_id_genomes under
-    OpenMP, one copy_BFT_Root per thread) on all host cores, each step a bounded sample of the workload."""
-    rank = int(os.environ.get("RANK", "0"))
-    if rank != 0:
-        return
-    import torch
+# ---------------------------------------------------------------------------------------------------------------------
+# the BASELINE configs. queries = per GPU per step. fallback_L: a smaller BFT of the same pan-genome that
+# is used — and flagged `degraded` in the record — when the full-size file did not travel with the repo snapshot.
+def specs():
     import bench_workloads as wl
-    cfg, L = pick_workload(args)
-    genomes = wl.pangenome(cfg, L)
-    bft = wl.ensure_bft(cfg, K, L, genomes)
-    cores = os.cpu_count() or 1
-    n = args.ref_sample
-    cat, starts, lens = wl.genomes_to_torch(genomes, torch.device("cpu"))
-    q = wl.gen_kmer_queries(cat, starts, lens, K, n, seed=777, mix=MIX)[0].numpy()
-    qfile = os.path.join("/tmp", f"bft_bench_ref_{os.getpid()}.kc")
-    write_query_file(qfile, q, K)
-    secs = run_reference_harness(bft, qfile, cores, args.warmup + args.steps)
-    os.remove(qfile)
-    timed = secs[args.warmup:]
-    ms = 1e3 * sum(timed) / len(timed)
-    value = n / (ms / 1e3)
-    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "u64", "data": "synthetic",
-            "config": {"workload": f"{cfg['name']}_k{K}: -query_kmers on a {cfg['n_genomes']}-genome synthetic pan-genome BFT",
-                       "k": K, "n_genomes": cfg["n_genomes"], "genome_len": L, "query_mix_present_mismatch_random": MIX},
-            "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "reference",
-                             "sample": f"{n} k-mers per step (same generator and mix as the GPU batch), all {cores} host threads"},
-            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    emit(line)
+    return {
+        "c3": dict(kind="kmers", cfg=wl.C3, k=27, L=5_000_000, queries=125_000_000,
+                   workload="c3: -query_kmers (presence + colour rows) on the 100-genome synthetic pan-genome BFT built by the reference; "
+                            "1 B k-mers per step over 8 GPUs (125 M per GPU)"),
+        "c1": dict(kind="kmers", cfg=wl.C1, k=27, L=5_000_000, queries=10_000_000,
+                   workload="c1: -query_kmers, 10 M random+present k-mers on the BFT of 4 synthetic 5 Mbp genomes"),
+        "c2": dict(kind="sequences", cfg=wl.C2, k=27, L=5_000_000, reads=1_000_000,
+                   workload="c2: -query_sequences threshold 0.8 canonical, 1 M synthetic 150 bp reads vs the 16-genome pan-genome BFT "
+                            "(value counts k-mer windows)"),
+        "c4": dict(kind="branching", cfg=wl.C3, k=63, L=5_000_000, fallback_L=1_000_000, queries=100_000_000,
+                   workload="c4: -query_branching at k=63 on the 100-genome BFT (value counts query k-mers; 8 neighbour look-ups each)"),
+        "c5": dict(kind="kmers", cfg=wl.C5, k=27, L=500_000, fallback_L=100_000, queries=100_000_000,
+                   workload="c5: colour-set retrieval for 100 M k-mers on the 1000-colour pan-genome BFT (compressed annotations)"),
+    }
 
 
-def engine_arm(args):
+class Run:
+    """torch.distributed plumbing shared by every record: barrier, max over ranks, device."""
+
+    def __init__(self, args):
+        import torch
+        self.torch = torch
+        self.rank = int(os.environ.get("RANK", "0"))
+        self.world = int(os.environ.get("WORLD_SIZE", "1"))
+        self.local = int(os.environ.get("LOCAL_RANK", "0"))
+        if not torch.cuda.is_available():
+            raise SystemExit("bench.py: no CUDA device; the engine has no CPU fallback (use --impl reference for the CPU reference)")
+        torch.cuda.set_device(self.local)
+        self.dev = torch.device("cuda", self.local)
+        self.dist = None
+        if self.world > 1:
+            import torch.distributed as dist
+            claim_stdout()  # NCCL writes its banner to stdout when NCCL_DEBUG is set on the box
+            dist.init_process_group("nccl", device_id=self.dev)
+            self.dist = dist
+        self.args = args
+        self.sampler = ClockSampler(self.local)
+        if self.rank == 0:
+            self.sampler.start()
+        self.cores = os.cpu_count() or 1
+
+    def barrier(self):
+        if self.dist:
+            self.dist.barrier()
+        self.torch.cuda.synchronize()
+
+    def allmax(self, x: float) -> float:
+        if not self.dist:
+            return float(x)
+        t = self.torch.tensor([x], dtype=self.torch.float64, device=self.dev)
+        self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def allsum(self, x: int) -> int:
+        if not self.dist:
+            return int(x)
+        t = self.torch.tensor([x], dtype=self.torch.int64, device=self.dev)
+        self.dist.all_reduce(t)
+        return int(t.item())
+
+    def open(self, spec, headline):
+        """The BFT of a config: rank 0 makes sure the .bft is there (decompressing the shipped .xz); everyone opens it.
+        Returns (engine, stats, path, genome length used, degraded note or None)."""
+        import bench_workloads as wl
+        from bloomfiltertrie_b200 import engine as E
+        cfg, k = spec["cfg"], spec["k"]
+
+        def have(L):
+            p = wl.bft_path(cfg, k, L)
+            return os.path.exists(p) or os.path.exists(p + ".xz")
+
+        L, note, err = spec["L"], None, None
+        if self.rank == 0:
+            if not have(L):
+                fb = spec.get("fallback_L")
+                if self.args.allow_build:
+                    pass
+                elif fb and not headline and have(fb):
+                    note = (f"genome length {fb} instead of {L}: {os.path.basename(wl.bft_path(cfg, k, L))}[.xz] did not travel with the "
+                            f"repo snapshot (see DESIGN.md, data shipping); same pan-genome generator, smaller BFT")
+                    L = fb
+                else:
+                    err = (f"{os.path.relpath(wl.bft_path(cfg, k, L), ROOT)}[.xz] is absent: the BFT of this config is built by the reference "
+                           f"(tools/build_bench_data.py, tens of minutes) and shipped under data/; refusing to substitute another one "
+                           f"(--allow-build builds it here)")
+            if not err:
+                try:
+                    wl.ensure_bft(cfg, k, L, None)
+                except Exception as e:  # noqa: BLE001
+                    err = repr(e)
+        if self.dist:
+            box = [L, note, err]
+            self.dist.broadcast_object_list(box, src=0)
+            L, note, err = box
+        if err:
+            raise FileNotFoundError(err)
+        path = wl.bft_path(cfg, k, L)
+        t0 = time.time()
+        eng = E.BFTEngine(path, device=self.local)
+        st = eng.stats()
+        if self.rank == 0:
+            log(f"{os.path.basename(path)}: {st['n_kmers']} k-mers, {st['n_nodes']} nodes, {st['n_ccs']} CCs, {st['n_classes']} colour classes, "
+                f"arena {st['arena_bytes'] / 1e6:.0f} MB + class rows {st['class_row_bytes'] / 1e6:.0f} MB + filter {st['filter_bytes'] / 1e6:.0f} MB; "
+                f"flatten {st['flatten_seconds']:.1f}s upload {st['upload_seconds']:.1f}s decode+filter {st['decode_seconds']:.3f}s; open {time.time() - t0:.1f}s")
+        return eng, st, path, L, note
+
+    def timed(self, eng, step, steps, warmup, flush_l2=False):
+        """W untimed steps, then K steps between barrier + synchronize on both sides, CUDA events on the engine's stream,
+        max over ranks. flush_l2: the batch is not larger than L2, so a 256 MB buffer is overwritten between steps and
+        every step gets its own event pair (the flushes are outside the pairs)."""
+        torch = self.torch
+        es = torch.cuda.ExternalStream(eng.stream, device=self.dev)
+        flush = torch.empty(256 << 20, dtype=torch.uint8, device=self.dev) if flush_l2 else None
+
+        def do_flush():
+            with torch.cuda.stream(es):
+                flush.fill_(1)
+
+        for _ in range(warmup):
+            step()
+        self.barrier()
+        l0 = eng.launch_count()
+        tw0 = time.time()
+        if flush_l2:
+            pairs = []
+            for _ in range(steps):
+                do_flush()
+                a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                a.record(es)
+                step()
+                b.record(es)
+                pairs.append((a, b))
+            self.barrier()
+            ms_total = sum(a.elapsed_time(b) for a, b in pairs)
+        else:
+            ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            ev0.record(es)
+            for _ in range(steps):
+                step()
+            ev1.record(es)
+            self.barrier()
+            ms_total = ev0.elapsed_time(ev1)
+        tw1 = time.time()
+        launches = eng.launch_count() - l0
+        ms_step = self.allmax(ms_total) / steps
+        del flush
+        return ms_step, launches, (tw0, tw1)
+
+    def clocks(self, win):
+        if self.rank != 0:
+            return None
+        time.sleep(0.05)
+        return self.sampler.window(*win)
+
+    def host_timed(self, fn, steps, warmup=1):
+        """e2e: the blocking host C-ABI call (copies inside), wall clock, max over ranks."""
+        for _ in range(warmup):
+            fn()
+        self.barrier()
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            fn()
+        self.torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        return self.allmax(dt) / steps * 1e3
+
+
+def base_roofline(kernel, a_bytes, formula, units, k_ms, cap, extra):
+    peak, peak_src = peaks()
+    achieved = a_bytes * units / (k_ms / 1e3) / 1e9
+    traffic_per_unit = (cap["dram_bytes_per_launch"] / cap["units_per_launch"]) if cap else None
+    r = {"bound": "hbm", "kernel": kernel, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+         "traffic": (traffic_per_unit * units if traffic_per_unit else None), "peak_source": peak_src, "kernel_ms": k_ms,
+         "units_per_launch": units, "algorithmic_bytes_per_unit": a_bytes, "algorithmic_bytes_formula": formula,
+         "dram_bytes_per_unit_ncu": traffic_per_unit,
+         "wasted_traffic_ratio": (traffic_per_unit / a_bytes) if traffic_per_unit else None,
+         "dram_frac_physical": (traffic_per_unit * units / (k_ms / 1e3) / 1e9 / peak) if traffic_per_unit else None,
+         "ncu_capture": ({k: cap.get(k) for k in ("source", "kernel", "units_per_launch", "duration_ms_under_ncu", "lts_hit_rate_pct",
+                                                  "dram_pct_of_peak", "sm_pct_of_peak")} if cap else None)}
+    r.update(extra)
+    return r
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+def kmers_record(run: Run, tag: str, spec: dict, headline: bool):
+    """-query_kmers: presence + colour rows of a batch of packed k-mers (k_query_kmers_rows, or k_query_kmers + k_expand_rows
+    for more than 128 genomes)."""
     import numpy as np
-    import torch
-    import torch.distributed as dist
+    torch = run.torch
     from bloomfiltertrie_b200 import engine as E
     import bench_workloads as wl
-
-    rank = int(os.environ.get("RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    if not torch.cuda.is_available():
-        raise SystemExit("bench.py: no CUDA device; the engine has no CPU fallback (use --impl reference for the CPU reference)")
-    torch.cuda.set_device(local)
-    dev = torch.device("cuda", local)
-    if world > 1:
-        # NCCL writes its banner ("NCCL version ...", when NCCL_DEBUG is set on the box) to stdout; stdout carries the
-        # one JSON line only
-        claim_stdout()
-        dist.init_process_group("nccl", device_id=dev)
-
-    cfg, L = pick_workload(args)
-    t0 = time.time()
+    args = run.args
+    cfg, k = spec["cfg"], spec["k"]
+    n = args.queries_per_gpu if (headline and args.queries_per_gpu) else spec["queries"]
+    steps, warmup = (args.steps, args.warmup) if headline else (args.sub_steps, 3)
+    eng, st, bft, L, degraded = run.open(spec, headline)
     genomes = wl.pangenome(cfg, L)
-    if rank == 0:
-        bft = wl.ensure_bft(cfg, K, L, genomes)
-    if world > 1:
-        dist.barrier()
-    bft = wl.bft_path(cfg, K, L)
-    eng = E.BFTEngine(bft, device=local)
-    st = eng.stats()
-    if rank == 0:
-        log(f"arena: {st['n_kmers']} k-mers, {st['n_nodes']} nodes, {st['n_ccs']} CCs, {st['n_classes']} colour classes, "
-            f"{st['arena_bytes'] / 1e6:.0f} MB (+{st['class_row_bytes'] / 1e6:.0f} MB class rows); flatten {st['flatten_seconds']:.1f}s "
-            f"upload {st['upload_seconds']:.1f}s decode {st['decode_seconds']:.3f}s; setup {time.time() - t0:.1f}s")
-    n = args.queries_per_gpu
-    cat, starts, lens = wl.genomes_to_torch(genomes, dev)
-    q, q_kind = wl.gen_kmer_queries(cat, starts, lens, K, n, seed=1000 + rank, mix=MIX)
+    cat, starts, lens = wl.genomes_to_torch(genomes, run.dev)
+    q, q_kind = wl.gen_kmer_queries(cat, starts, lens, k, n, seed=1000 + run.rank, mix=MIX)
     del cat
     torch.cuda.empty_cache()
     RW, W = eng.RW, eng.W
+    dev = run.dev
     d_present = torch.empty(n, dtype=torch.uint8, device=dev)
     d_rows = torch.empty((n, RW), dtype=torch.int32, device=dev)
-    es = torch.cuda.ExternalStream(eng.stream, device=dev)
-
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    # The hit count of every step ("Nb k-mers present" of the reference driver) is the one number the sharded path
-    # reduces. It is accumulated by the query kernels themselves: one uint64 slot per step in rank 0's HBM, mapped into
-    # every rank through CUDA IPC, and each CTA adds its share with one system-scope atomic (over NVLink from the other
-    # ranks) — compute + reduction in one kernel, no NCCL call and no extra launch in the steady state.
     counted = RW in (1, 2, 4)
-    n_slots = args.warmup + args.steps + args.warmup + args.steps + 8
-    ctr_local = eng.device_alloc(8 * n_slots) if rank == 0 else 0   # zero-filled by the call
+    # The hit count of every step ("Nb k-mers present" of the reference driver, src/file_io.c:813) is the one number the
+    # sharded path reduces. The query kernels accumulate it themselves: one uint64 slot per step in rank 0's HBM, mapped
+    # into every rank through CUDA IPC; each CTA adds its share with one system-scope atomic (over NVLink from the other
+    # ranks) — compute + reduction in one kernel, no NCCL call and no extra launch in the steady state.
+    n_slots = 2 * (warmup + steps) + 8
+    ctr_local = eng.device_alloc(8 * n_slots) if run.rank == 0 else 0   # zero-filled by the call
     ctr_base = ctr_local
-    if world > 1:
-        box = [eng.peer_export(ctr_local) if rank == 0 else None]
-        dist.broadcast_object_list(box, src=0)
-        if rank != 0:
+    if run.dist and counted:
+        box = [eng.peer_export(ctr_local) if run.rank == 0 else None]
+        run.dist.broadcast_object_list(box, src=0)
+        if run.rank != 0:
             ctr_base = eng.peer_import(box[0])
     slot_i = [0]
 
@@ -320,46 +379,28 @@ def engine_arm(args):
         else:
             eng.query_kmers_device(q, n, d_present, d_rows, None)
 
-    # ---- timed region: K steps, inputs resident in HBM (batch of n*8*W bytes >> 126 MB L2, so no L2 flush needed)
-    for _ in range(args.warmup):
-        step()
-    barrier()
-    sampler = ClockSampler(local)
-    if rank == 0:
-        sampler.start()
-        time.sleep(0.3)
-    launches0 = eng.launch_count()
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    barrier()
-    tw0 = time.time()
-    ev0.record(es)
-    for _ in range(args.steps):
-        step()
-    ev1.record(es)
-    barrier()
-    tw1 = time.time()
-    ms_total = ev0.elapsed_time(ev1)
-    launches = eng.launch_count() - launches0
-    t = torch.tensor([ms_total], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_step = float(t.item()) / args.steps
-    value = n * world / (ms_step / 1e3)
+    flush = n * 8 * W < (200 << 20)
+    ms_step, launches, win = run.timed(eng, step, steps, warmup, flush_l2=flush)
+    value = n * run.world / (ms_step / 1e3)
     n_present = int(d_present.sum().item())
-    if counted:  # every step's slot must hold the sum of all ranks' hits (checked outside the timed region)
-        tot = torch.tensor([n_present], dtype=torch.int64, device=dev)
-        if world > 1:
-            dist.all_reduce(tot)
-        if rank == 0:
-            slots = eng.copy_from_device(ctr_local, np.zeros(n_slots, dtype=np.uint64))
-            used = slots[:slot_i[0]]
-            assert (used == np.uint64(int(tot.item()))).all(), f"in-kernel hit counters {used.tolist()} != {int(tot.item())}"
-    # size-independent property at full size: every window sampled from an inserted genome must be found, and a
-    # found k-mer must carry at least one colour
+    tot = run.allsum(n_present)
+    if counted and run.rank == 0:  # every step's slot must hold the sum of all ranks' hits
+        slots = eng.copy_from_device(ctr_local, np.zeros(n_slots, dtype=np.uint64))
+        used = slots[:slot_i[0]]
+        assert (used == np.uint64(tot)).all(), f"in-kernel hit counters {used.tolist()} != {tot}"
+    # size-independent properties at full size: every window sampled from an inserted genome is found, a found k-mer
+    # carries at least one colour, an absent one none
     assert bool(d_present[q_kind == 0].all()), "a k-mer window of an inserted genome was reported absent"
-    assert bool((d_rows[d_present.bool()] != 0).any(dim=1).all()), "a present k-mer came back without colours"
-    assert not bool((d_rows[~d_present.bool()] != 0).any()), "an absent k-mer came back with colours"
+    pb = d_present.bool()
+    if RW <= 4:
+        assert bool((d_rows[pb] != 0).any(dim=1).all()), "a present k-mer came back without colours"
+        assert not bool((d_rows[~pb] != 0).any()), "an absent k-mer came back with colours"
+    else:  # wide rows: check a slice (the boolean gathers above would need several GB)
+        m = min(n, 4_000_000)
+        assert bool((d_rows[:m][pb[:m]] != 0).any(dim=1).all()) and not bool((d_rows[:m][~pb[:m]] != 0).any())
+    del pb
 
+    # ---- dominant kernel alone (CUDA events on the stream it is launched on)
     d_hits = torch.zeros(1, dtype=torch.int64, device=dev)
 
     def step_kernel():
@@ -368,249 +409,380 @@ def engine_arm(args):
         else:
             eng.query_kmers_device(q, n, d_present, d_rows, None)
 
-    # ---- dominant kernel alone: the fused walk + colour-row kernel (k_query_kmers_rows for RW in {1,2,4}; for wider
-    # rows k_query_kmers followed by k_expand_rows), CUDA events on the stream it is launched on
-    for _ in range(args.warmup):
-        step_kernel()
-    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    a.record(es)
-    for _ in range(args.steps):
-        step_kernel()
-    b.record(es)
-    b.synchronize()
-    k_ms = a.elapsed_time(b) / args.steps
-    # clocks sampled from the start of the timed region to the end of the per-kernel timing loop (GPU busy throughout)
-    clocks = sampler.stop(tw0, time.time()) if rank == 0 else None
+    k_ms, _, win2 = run.timed(eng, step_kernel, steps, warmup, flush_l2=flush)
+    clocks = run.clocks((win[0], win2[1]))
     ws = eng.kmer_walk_stats_device(q, n)
-    nodes_pk, depth_pk, found_pk = ws["nodes"] / n, ws["search_depth"] / n, ws["found"] / n
-    roofline = kmer_roofline(eng, ws, n, k_ms, W, RW, args, traffic_ok=(cfg["name"] == wl.C3["name"] and L == 5_000_000 and K == 27))
+    found_pk, bucket_pk, reject_pk = ws["found"] / n, ws["bucket_searches"] / n, ws["filter_rejects"] / n
+    nodes_pk, depth_pk, cc_pk = ws["nodes"] / n, ws["search_depth"] / n, ws["cc_probed"] / n
+    a_arena = 8 * W + (1 + 4 * RW) + 32.0 * W * bucket_pk + (0 if counted else 8)
+    cap = ncu_capture(tag) if not degraded else None
+    probe = eng.random_gather_probe(4 << 30, 1 << 28) if (headline and not args.no_probe) else None
+    roofline = base_roofline(
+        "k_query_kmers_rows" if counted else "k_query_kmers+k_expand_rows_v4", a_arena,
+        "8*W in + (1 + 4*RW) out + 32*W * P(walk reaches a bucket)" + ("" if counted else " + 4+4 class id out/in"), n, k_ms, cap,
+        {"kmers_per_sec_kernel": n / (k_ms / 1e3), "bucket_accesses_per_kmer": bucket_pk, "filter_rejects_per_kmer": reject_pk,
+         "found_frac": found_pk, "filter_mb": st["filter_bytes"] / 1e6,
+         "l2_bytes_per_kmer": 8 + (32 if st["filter_bytes"] else 0) + 4 * RW * found_pk,
+         "random_gather_probe_loads_per_s": probe,
+         "random_access_frac": (bucket_pk * n / (k_ms / 1e3) / probe) if probe else None,
+         "context_reference_layout": {
+             "a_min_bytes_per_kmer": 8 * W + (1 + 4 * RW) + 32.0 * (6 * nodes_pk + depth_pk + found_pk),
+             "a_ref_bytes_per_kmer": 8 * W + (1 + 4 * RW) + 32.0 * (5 * nodes_pk + 2 * cc_pk + depth_pk + found_pk),
+             "nodes_per_kmer": nodes_pk, "search_depth_per_kmer": depth_pk, "cc_probed_per_node": cc_pk / max(nodes_pk, 1e-9),
+             "note": "sectors the REFERENCE layout's walk dereferences (SURVEY.md 8d); the arena replaces them by one L2-resident "
+                     "directory load + one bucket, so they are context, not the roofline"},
+         "note": "achieved = algorithmic HBM bytes of the arena's walk / kernel time; the root directory, the stored-k-mer filter and "
+                 "the class rows are served by L2 (l2_bytes_per_kmer). The kernel is bound by the RATE of random 64-byte HBM "
+                 "accesses (random_access_frac) on top of the streamed batch, not by bytes"})
 
-    # ---- e2e: host C-ABI call with pinned host buffers, copies inside the timed region
+    # ---- e2e: host C-ABI calls with pinned host buffers, copies inside the timed region
+    e2e = None
+    if not args.no_e2e:
+        nb, rb = (2 * k + 7) // 8, (cfg["n_genomes"] + 7) // 8
+        ne = n if RW <= 4 else min(n, 10_000_000)   # wide rows: 125 B per present k-mer back — bound the pinned footprint
+        qh = q[:ne].cpu().numpy().view(np.uint64)
+        hrec = E.PinnedBuffer((ne, nb), np.uint8)
+        hrec.array[:] = qh.view(np.uint8).reshape(ne, 8 * W)[:, :nb]
+        hrow = E.PinnedBuffer((ne, rb), np.uint8)
+        hbits = E.PinnedBuffer(((ne + 7) // 8,), np.uint8)
+        _, crows, cnt = eng.query_records_compact(hrec.array, out_bits=hbits.array, out_rows=hrow.array)
+        ne_present = int(d_present[:ne].sum().item())
+        assert cnt == ne_present, "compact and device-resident paths disagree"
+        ns = min(ne, 1 << 20)
+        want = d_rows[:ns].cpu().numpy().view(np.uint8).reshape(ns, 4 * RW)[:, :rb]
+        bits_s = np.unpackbits(hbits.array[: ns // 8], bitorder="little").astype(bool)
+        assert np.array_equal(crows[: int(bits_s.sum())], want[: len(bits_s)][bits_s]), "compact rows differ"
+        es = max(2, steps // 2)
+        c_ms = run.host_timed(lambda: eng.query_records_compact(hrec.array, out_bits=hbits.array, out_rows=hrow.array), es)
+        e2e = {"value": ne * run.world / (c_ms / 1e3), "unit": UNIT, "h2d_bytes_per_step": ne * nb * run.world,
+               "d2h_bytes_per_step": ((ne + 7) // 8 + ne_present * rb + 4 * ((ne + (1 << 22) - 1) >> 22)) * run.world, "ms_per_step": c_ms,
+               "kmers_per_step_per_gpu": ne, "steps": es,
+               "api": "bft_b200_query_records_compact (host pointers, pinned): the reference's ceil(2k/8)-byte k-mer records in; one presence bit "
+                      "per k-mer + the ceil(G/8)-byte colour rows of the present k-mers (query order) + their count out",
+               "present_frac": ne_present / ne}
+        if headline:
+            r_ms = run.host_timed(lambda: eng.query_records(hrec.array, want_present=False, out_rows=hrow.array), es)
+            e2e["fixed_stride_records"] = {"value": ne * run.world / (r_ms / 1e3), "unit": UNIT, "h2d_bytes_per_step": ne * nb * run.world,
+                                           "d2h_bytes_per_step": (ne * rb + 8) * run.world, "ms_per_step": r_ms,
+                                           "api": "bft_b200_query_records: same records in, one colour row per k-mer (fixed stride) out"}
+        hbits.free()
+        hrow.free()
+        hrec.free()
+        if headline or RW > 4:  # class ids instead of rows: what a link-bound deployment (or 1000 colours) asks for
+            hq = E.PinnedBuffer((ne, W), np.uint64)
+            hq.array[:] = qh
+            hp = E.PinnedBuffer((ne,), np.uint8)
+            hc = E.PinnedBuffer((ne,), np.uint32)
+            i_ms = run.host_timed(lambda: eng.query_kmers(hq.array, want_rows=False, out_present=hp.array, out_classes=hc.array), es)
+            assert int(hp.array.sum()) == ne_present
+            e2e["class_id_mode"] = {"value": ne * run.world / (i_ms / 1e3), "unit": UNIT, "ms_per_step": i_ms, "h2d_bytes_per_step": ne * 8 * W * run.world,
+                                    "d2h_bytes_per_step": ne * 5 * run.world,
+                                    "api": "bft_b200_query_kmers with class ids instead of rows (the class -> row table is fetched once per context)"}
+            hq.free()
+            hp.free()
+            hc.free()
+
+    # ---- CPU baseline beside it: the unmodified reference on a bounded sample (rank 0)
+    cpu = None
+    if run.rank == 0 and not args.no_cpu_baseline and os.access(wl.REF_HARNESS, os.X_OK):
+        ns = min(args.ref_sample if headline else (1 << 22), n)
+        qfile = os.path.join("/tmp", f"bft_bench_cpu_{os.getpid()}.kc")
+        write_query_file(qfile, q[:ns].cpu().numpy(), k)
+        secs = run_ref(["kmers", bft, qfile, qfile + ".out", str(run.cores), "2"])
+        raw = np.fromfile(qfile + ".out", dtype=np.uint8)
+        assert np.array_equal(raw[:ns], d_present[:ns].cpu().numpy()), "GPU and reference disagree on the sample (presence)"
+        assert np.array_equal(raw[ns:].view(np.uint32).reshape(ns, RW), d_rows[:ns].cpu().numpy().view(np.uint32)), \
+            "GPU and reference disagree on the sample (rows)"
+        os.remove(qfile)
+        os.remove(qfile + ".out")
+        cpu = {"value": ns / min(secs), "unit": UNIT, "cores": run.cores, "kind": "reference",
+               "sample": f"first {ns} k-mers of rank 0's batch; isKmerPresent+get_annotation+get_list_id_genomes, OpenMP over {run.cores} threads "
+                         f"with one copy_BFT_Root each; best of 2 passes; answers identical to the GPU's"}
+    if run.dist:
+        run.dist.barrier()
+    rec = {"value": value, "unit": UNIT, "ms_per_step": ms_step, "steps": steps, "warmup": warmup, "n_gpus": run.world,
+           "config": {"workload": spec["workload"], "k": k, "k_note": "reference accepts only k % 9 == 0; 27 stands in for 31" if k == 27 else None,
+                      "n_genomes": cfg["n_genomes"], "genome_len": L, "degraded": degraded, "kmers_in_bft": st["n_kmers"], "nodes": st["n_nodes"],
+                      "colour_classes": st["n_classes"], "arena_mb": round(st["arena_bytes"] / 1e6, 1), "filter_mb": round(st["filter_bytes"] / 1e6, 1),
+                      "queries_per_gpu": n, "query_mix_present_mismatch_random": MIX, "present_frac": n_present / n,
+                      "l2": ("256 MB written between steps (batch smaller than L2); one event pair per step" if flush
+                             else "inputs larger than L2 (no flush needed)"),
+                      "sharding": f"arena replicated, queries sharded x{run.world}; hit count reduced inside the kernel (peer-mapped counter)"},
+           "clocks": clocks, "e2e": e2e, "gpu_launches": launches * run.world, "roofline": roofline, "cpu_baseline": cpu}
+    if run.dist and counted and run.rank != 0:
+        eng.peer_close(ctr_base)
+    if run.dist:
+        run.dist.barrier()
+    if run.rank == 0:
+        eng.device_free(ctr_local)
+    eng.close()
+    del q, d_present, d_rows
+    torch.cuda.empty_cache()
+    return rec
+
+
+def sequences_record(run: Run, tag: str, spec: dict, headline: bool):
+    """-query_sequences 0.8 canonical: 150 bp reads, per-read per-genome hit counts and threshold (k_query_sequences)."""
+    import numpy as np
+    torch = run.torch
+    from bloomfiltertrie_b200 import engine as E, synth
+    import bench_workloads as wl
+    args = run.args
+    cfg, k = spec["cfg"], spec["k"]
+    steps, warmup = (args.steps, args.warmup) if headline else (args.sub_steps, 3)
+    eng, st, bft, L, degraded = run.open(spec, headline)
+    genomes = wl.pangenome(cfg, L)
+    cat, starts, lens = wl.genomes_to_torch(genomes, run.dev)
+    n, rl = spec["reads"], 150
+    chars, offs = wl.gen_reads(cat, starts, lens, n, rl, seed=4242 + run.rank)
+    del cat
+    units = n * (rl - k + 1)
+    d_rows = torch.empty((n, eng.RW), dtype=torch.int32, device=run.dev)
+    d_stat = torch.empty(n, dtype=torch.uint8, device=run.dev)
+    step = lambda: eng.query_sequences_device(chars, offs, n, 0.8, True, d_rows, d_stat)  # noqa: E731
+    ms_step, launches, win = run.timed(eng, step, steps, warmup)
+    clocks = run.clocks(win)
+    assert int((d_stat != 0).sum().item()) == 0
+    frac_hit = float((d_rows != 0).any(dim=1).float().mean().item())
+    assert frac_hit > 0.9, "reads sampled from the genomes must reach the 0.8 threshold for some genome"
+    # walk statistics of the canonical windows of a sample of reads (host-side packing, device-side walk)
+    codes = synth._CODE[chars[: 2000 * rl].cpu().numpy()].reshape(2000, rl)
+    wins = np.concatenate([synth.canonical_words(synth.pack_windows(c, k), k) for c in codes])
+    ws = eng.kmer_walk_stats_device(torch.from_numpy(wins.view(np.int64)).to(run.dev), len(wins))
+    bucket_pw = ws["bucket_searches"] / len(wins)
+    W, RW, G = eng.W, eng.RW, cfg["n_genomes"]
+    a_win = 1.0 + 32.0 * W * bucket_pw + (4 * RW + 1 + 8) / (rl - k + 1)
+    roofline = base_roofline("k_query_sequences", a_win,
+                             "per k-mer window: 1 char streamed + 32*W * P(walk reaches a bucket) + (row + status + offset) / windows per read",
+                             units, ms_step, ncu_capture(tag) if not degraded else None,
+                             {"bucket_accesses_per_window": bucket_pw, "filter_rejects_per_window": ws["filter_rejects"] / len(wins),
+                              "found_frac_windows": ws["found"] / len(wins),
+                              "note": "one launch per step, so kernel time = step time. This kernel is instruction-issue bound (encode, canonical "
+                                      "pick, class merge, per-genome counters; see the ncu capture), not HBM-bound"})
+    e2e = None
+    if not args.no_e2e:
+        h_chars = E.PinnedBuffer((n * rl,), np.uint8)
+        h_chars.array[:] = chars.cpu().numpy()
+        h_offs = E.PinnedBuffer((n + 1,), np.uint64)
+        h_offs.array[:] = offs.cpu().numpy().view(np.uint64)
+        h_rows = E.PinnedBuffer((n, RW), np.uint32)
+        h_stat = E.PinnedBuffer((n,), np.uint8)
+        e_ms = run.host_timed(lambda: eng.query_sequences(h_chars.array, h_offs.array, 0.8, True, out_rows=h_rows.array, out_status=h_stat.array),
+                              max(2, steps // 2))
+        assert np.array_equal(h_rows.array, d_rows.cpu().numpy().view(np.uint32))
+        e2e = {"value": units * run.world / (e_ms / 1e3), "unit": UNIT, "h2d_bytes_per_step": (n * rl + 8 * (n + 1)) * run.world,
+               "d2h_bytes_per_step": n * (4 * RW + 1) * run.world, "ms_per_step": e_ms, "reads_per_sec": n * run.world / (e_ms / 1e3),
+               "api": "bft_b200_query_sequences (host pointers, pinned): characters + offsets in, one colour row + status per read out"}
+        for b in (h_chars, h_offs, h_rows, h_stat):
+            b.free()
+    cpu = None
+    if run.rank == 0 and not args.no_cpu_baseline and os.access(wl.REF_HARNESS, os.X_OK):
+        nr = min(n, 200_000)
+        p = f"/tmp/bft_bench_reads_{os.getpid()}.txt"
+        arr = chars[: nr * rl].cpu().numpy().reshape(nr, rl)
+        with open(p, "wb") as f:
+            f.write(np.concatenate([arr, np.full((nr, 1), 10, np.uint8)], axis=1).tobytes())
+        secs = run_ref(["sequences", bft, p, "0.8", "canonical", p + ".out", str(run.cores), "2"])
+        ref_rows = np.fromfile(p + ".out", dtype=np.uint32).reshape(nr, RW)
+        assert np.array_equal(ref_rows, d_rows[:nr].cpu().numpy().view(np.uint32)), "GPU and reference disagree on the sample"
+        os.remove(p)
+        os.remove(p + ".out")
+        cpu = {"value": nr * (rl - k + 1) / min(secs), "unit": UNIT, "cores": run.cores, "kind": "reference",
+               "sample": f"first {nr} reads of rank 0's batch; query_sequence under OpenMP, one copy_BFT_Root per thread; rows identical to the GPU's"}
+    if run.dist:
+        run.dist.barrier()
+    rec = {"value": units * run.world / (ms_step / 1e3), "unit": UNIT, "ms_per_step": ms_step, "steps": steps, "warmup": warmup, "n_gpus": run.world,
+           "config": {"workload": spec["workload"], "k": k, "n_genomes": G, "genome_len": L, "degraded": degraded, "kmers_in_bft": st["n_kmers"],
+                      "reads_per_gpu": n, "read_len": rl, "windows_per_read": rl - k + 1, "reads_per_sec": n * run.world / (ms_step / 1e3),
+                      "reads_reaching_threshold": frac_hit, "l2": "inputs larger than L2 (150 MB of characters per step)",
+                      "sharding": f"arena replicated, reads sharded x{run.world}"},
+           "clocks": clocks, "e2e": e2e, "gpu_launches": launches * run.world, "roofline": roofline, "cpu_baseline": cpu}
+    eng.close()
+    del chars, offs, d_rows, d_stat
+    torch.cuda.empty_cache()
+    return rec
+
+
+def neighbours_np(q, k):
+    """The 8 neighbours of packed k-mers (uint64 [n, W]) as the branching kernel forms them: [n*8, W]."""
+    import numpy as np
+    n, W = q.shape
+    out = np.zeros((n, 8, W), dtype=np.uint64)
+    mask = [np.uint64((1 << min(64, max(0, 2 * k - 64 * w))) - 1) for w in range(W)]
+    for c in range(4):
+        s = np.zeros((n, W), dtype=np.uint64)   # successor: (x >> 2) | c << 2(k-1)
+        p = np.zeros((n, W), dtype=np.uint64)   # predecessor: (x << 2 | c) masked
+        for w in range(W):
+            s[:, w] = q[:, w] >> np.uint64(2)
+            p[:, w] = (q[:, w] << np.uint64(2)) & mask[w]
+            if w + 1 < W:
+                s[:, w] |= (q[:, w + 1] & np.uint64(3)) << np.uint64(62)
+            if w > 0:
+                p[:, w] |= q[:, w - 1] >> np.uint64(62)
+                p[:, w] &= mask[w]
+        top = 2 * (k - 1)
+        s[:, top // 64] |= np.uint64(c) << np.uint64(top % 64)
+        p[:, 0] |= np.uint64(c)
+        out[:, c] = s
+        out[:, 4 + c] = p
+    return out.reshape(n * 8, W)
+
+
+def branching_record(run: Run, tag: str, spec: dict, headline: bool):
+    """-query_branching: successors / predecessors present in the graph for every k-mer (k_query_branching, 8 look-ups each)."""
+    import numpy as np
+    torch = run.torch
+    from bloomfiltertrie_b200 import engine as E
+    import bench_workloads as wl
+    args = run.args
+    cfg, k = spec["cfg"], spec["k"]
+    steps, warmup = (args.steps, args.warmup) if headline else (args.sub_steps, 3)
+    eng, st, bft, L, degraded = run.open(spec, headline)
+    genomes = wl.pangenome(cfg, L)
+    cat, starts, lens = wl.genomes_to_torch(genomes, run.dev)
+    n = args.queries_per_gpu if (headline and args.queries_per_gpu) else spec["queries"]
+    q, _ = wl.gen_kmer_queries(cat, starts, lens, k, n, seed=99 + run.rank, mix=MIX)
+    del cat
+    W = eng.W
+    d_succ = torch.empty(n, dtype=torch.uint8, device=run.dev)
+    d_pred = torch.empty(n, dtype=torch.uint8, device=run.dev)
+    d_cnt = torch.zeros(1, dtype=torch.int64, device=run.dev)
+    step = lambda: eng.query_branching_device(q, n, d_succ, d_pred, d_cnt)  # noqa: E731
+    ms_step, launches, win = run.timed(eng, step, steps, warmup)
+    clocks = run.clocks(win)
+    n_br = int(d_cnt.item())
+    assert n_br == int(((d_succ > 1) | (d_pred > 1)).sum().item()), "in-kernel branching counter disagrees with the per-k-mer counts"
+    ns = 500_000
+    nb8 = neighbours_np(q[:ns].cpu().numpy().view(np.uint64), k)
+    ws = eng.kmer_walk_stats_device(torch.from_numpy(nb8.view(np.int64)).to(run.dev), len(nb8))
+    bucket_pl = ws["bucket_searches"] / len(nb8)
+    # the walk statistics should count exactly the neighbours the kernel found (same k-mers, same look-up)
+    stats_consistent = ws["found"] == int(d_succ[:ns].sum().item()) + int(d_pred[:ns].sum().item())
+    a_q = 8.0 * W + 2 + 8 * 32.0 * W * bucket_pl
+    roofline = base_roofline("k_query_branching", a_q, "per query k-mer: 8*W in + 2 out + 8 look-ups * 32*W * P(walk reaches a bucket)", n, ms_step,
+                             ncu_capture(tag) if not degraded else None,
+                             {"lookups_per_sec": 8 * n / (ms_step / 1e3), "bucket_accesses_per_lookup": bucket_pl,
+                              "filter_rejects_per_lookup": ws["filter_rejects"] / len(nb8), "neighbours_present_frac": ws["found"] / len(nb8),
+                              "filter_mb": st["filter_bytes"] / 1e6, "walk_stats_match_kernel_counts": bool(stats_consistent),
+                              "note": "one launch per step, so kernel time = step time; most of the 8 neighbours of a k-mer are absent and are "
+                                      "answered by the L2-resident stored-k-mer filter"})
     e2e = None
     if not args.no_e2e:
         hq = E.PinnedBuffer((n, W), np.uint64)
-        hp = E.PinnedBuffer((n,), np.uint8)
-        hr = E.PinnedBuffer((n, RW), np.uint32)
         hq.array[:] = q.cpu().numpy().view(np.uint64)
-        for _ in range(max(1, args.warmup - 1)):
-            eng.query_kmers(hq.array, out_present=hp.array, out_rows=hr.array)
-        barrier()
-        t0 = time.perf_counter()
-        for _ in range(args.steps):
-            eng.query_kmers(hq.array, out_present=hp.array, out_rows=hr.array)
-        torch.cuda.synchronize()
-        dt = time.perf_counter() - t0
-        tt = torch.tensor([dt], dtype=torch.float64, device=dev)
-        if world > 1:
-            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-        e2e_ms = float(tt.item()) / args.steps * 1e3
-        assert int(hp.array.sum()) == n_present, "e2e and device-resident paths disagree"
-        word_api = {"value": n * world / (e2e_ms / 1e3), "unit": UNIT, "h2d_bytes_per_step": n * W * 8 * world,
-                    "d2h_bytes_per_step": n * (1 + 4 * RW) * world, "ms_per_step": e2e_ms,
-                    "api": "bft_b200_query_kmers (host pointers, pinned): 8*W-byte words in, presence byte + 4*RW-byte colour row out"}
-        # the same call asking for colour-class ids instead of rows (4 B instead of 4*RW B back per k-mer; the class ->
-        # row table is downloaded once per context): information for link-bound deployments, not the headline
-        hc = E.PinnedBuffer((n,), np.uint32)
-        eng.query_kmers(hq.array, want_rows=False, out_present=hp.array, out_classes=hc.array)
-        barrier()
-        t0 = time.perf_counter()
-        for _ in range(args.steps):
-            eng.query_kmers(hq.array, want_rows=False, out_present=hp.array, out_classes=hc.array)
-        torch.cuda.synchronize()
-        tt = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
-        if world > 1:
-            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-        c_ms = float(tt.item()) / args.steps * 1e3
-        class_id_mode = {"value": n * world / (c_ms / 1e3), "unit": UNIT, "ms_per_step": c_ms,
-                                "d2h_bytes_per_step": n * 5 * world}
-        # the headline e2e: the same batch in the reference's own record format (ceil(2k/8)-byte kmers_comp records in,
-        # ceil(G/8)-byte colour rows + the present count out) — fewer bytes over the link that bounds this call
-        nb, rb = (2 * K + 7) // 8, (cfg["n_genomes"] + 7) // 8
-        hrec = E.PinnedBuffer((n, nb), np.uint8)
-        hrec.array[:] = hq.array.view(np.uint8).reshape(n, 8 * W)[:, :nb]
-        ns = min(n, 1 << 20)
-        want_sample = hr.array[:ns].view(np.uint8).reshape(ns, 4 * RW)[:, :rb].copy()
-        hq.free(); hp.free(); hr.free(); hc.free()          # keep the pinned footprint per rank small
-        hrow = E.PinnedBuffer((n, rb), np.uint8)
-        _, _, cnt = eng.query_records(hrec.array, want_present=False, out_rows=hrow.array)
-        assert cnt == n_present, "record-format and device-resident paths disagree"
-        assert np.array_equal(hrow.array[:ns], want_sample), "record-format rows differ"
-        barrier()
-        t0 = time.perf_counter()
-        for _ in range(args.steps):
-            eng.query_records(hrec.array, want_present=False, out_rows=hrow.array)
-        torch.cuda.synchronize()
-        tt = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
-        if world > 1:
-            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-        r_ms = float(tt.item()) / args.steps * 1e3
-        fixed = {"value": n * world / (r_ms / 1e3), "unit": UNIT, "h2d_bytes_per_step": n * nb * world,
-                 "d2h_bytes_per_step": (n * rb + 8) * world, "ms_per_step": r_ms,
-                 "api": "bft_b200_query_records (host pointers, pinned): the reference's ceil(2k/8)-byte k-mer records in, "
-                        "ceil(G/8)-byte colour row per k-mer (fixed stride) + the number of k-mers present out"}
-        # the same answers without the zeros: one presence bit per k-mer + the rows of the present k-mers only, in query
-        # order (the row of k-mer i is found with one running index, the way a CSV writer walks the batch)
-        hbits = E.PinnedBuffer(((n + 7) // 8,), np.uint8)
-        _, crows, cnt = eng.query_records_compact(hrec.array, out_bits=hbits.array, out_rows=hrow.array)
-        assert cnt == n_present, "compact and device-resident paths disagree"
-        bits_s = np.unpackbits(hbits.array[: ns // 8], bitorder="little").astype(bool)
-        assert np.array_equal(crows[: int(bits_s.sum())], want_sample[: len(bits_s)][bits_s]), "compact rows differ"
-        barrier()
-        t0 = time.perf_counter()
-        for _ in range(args.steps):
-            eng.query_records_compact(hrec.array, out_bits=hbits.array, out_rows=hrow.array)
-        torch.cuda.synchronize()
-        tt = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
-        if world > 1:
-            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-        k_ms2 = float(tt.item()) / args.steps * 1e3
-        e2e = {"value": n * world / (k_ms2 / 1e3), "unit": UNIT, "h2d_bytes_per_step": n * nb * world,
-               "d2h_bytes_per_step": ((n + 7) // 8 + n_present * rb + 4 * ((n + (1 << 22) - 1) >> 22)) * world, "ms_per_step": k_ms2,
-               "api": "bft_b200_query_records_compact (host pointers, pinned): the reference's ceil(2k/8)-byte k-mer records in; "
-                      "one presence bit per k-mer + the ceil(G/8)-byte colour rows of the present k-mers (query order) + their count out — "
-                      "every answer of the fixed-stride call, without the all-zero rows of absent k-mers",
-               "present_frac": n_present / n,
-               "fixed_stride_records": fixed, "word_api": word_api, "class_id_mode": class_id_mode}
-        hbits.free()
-        hrec.free(); hrow.free()
-
-    # ---- CPU baseline beside it: the unmodified reference on a bounded sample (rank 0, N=1 only)
+        hs = E.PinnedBuffer((n,), np.uint8)
+        hp = E.PinnedBuffer((n,), np.uint8)
+        e_ms = run.host_timed(lambda: eng.query_branching(hq.array, out_succ=hs.array, out_pred=hp.array), max(2, steps // 2))
+        assert np.array_equal(hs.array, d_succ.cpu().numpy()) and np.array_equal(hp.array, d_pred.cpu().numpy())
+        e2e = {"value": n * run.world / (e_ms / 1e3), "unit": UNIT, "h2d_bytes_per_step": n * 8 * W * run.world, "d2h_bytes_per_step": (2 * n + 8) * run.world,
+               "ms_per_step": e_ms, "api": "bft_b200_query_branching (host pointers, pinned): packed k-mers in, successor / predecessor counts + branching total out"}
+        hq.free()
+        hs.free()
+        hp.free()
     cpu = None
-    if rank == 0 and world == 1 and not args.no_cpu_baseline and os.access(wl.REF_HARNESS, os.X_OK):
-        cores = os.cpu_count() or 1
-        ns = min(args.ref_sample, n)
-        qfile = os.path.join("/tmp", f"bft_bench_cpu_{os.getpid()}.kc")
-        write_query_file(qfile, q[:ns].cpu().numpy(), K)
-        secs = run_reference_harness(bft, qfile, cores, 2)
-        os.remove(qfile)
-        cpu = {"value": ns / min(secs), "unit": UNIT, "cores": cores, "kind": "reference",
-               "sample": f"first {ns} k-mers of the GPU batch; isKmerPresent+get_annotation+get_list_id_genomes, OpenMP over "
-                         f"{cores} threads with one copy_BFT_Root each; best of 2 passes"}
-
-    if rank == 0:
-        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-                "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u64",
-                "data": "synthetic",
-                "config": {"workload": f"{cfg['name']}_k{K}: -query_kmers (presence + colour rows) on a {cfg['n_genomes']}-genome "
-                                       f"synthetic pan-genome BFT built by the reference",
-                           "k": K, "k_note": "reference accepts only k % 9 == 0; 27 stands in for 31", "n_genomes": cfg["n_genomes"],
-                           "genome_len": L, "kmers_in_bft": st["n_kmers"], "colour_classes": st["n_classes"],
-                           "arena_mb": round(st["arena_bytes"] / 1e6, 1), "queries_per_gpu": n,
-                           "query_mix_present_mismatch_random": MIX, "present_frac": n_present / n,
-                           "l2": "inputs larger than L2 (no flush needed)", "sharding": f"arena replicated, queries sharded x{world}"},
-                "clocks": clocks, "e2e": e2e, "gpu_launches": launches * world, "roofline": roofline, "cpu_baseline": cpu}
-        emit(line)
+    if run.rank == 0 and not args.no_cpu_baseline and os.access(wl.REF_HARNESS, os.X_OK):
+        nsr = min(n, 1 << 22)
+        p = f"/tmp/bft_bench_br_{os.getpid()}.kc"
+        write_query_file(p, q[:nsr].cpu().numpy(), k)
+        secs = run_ref(["branching", bft, p, p + ".out", str(run.cores), "2"])
+        raw = np.fromfile(p + ".out", dtype=np.uint8)
+        assert np.array_equal(raw[:nsr], d_succ[:nsr].cpu().numpy()) and np.array_equal(raw[nsr:2 * nsr], d_pred[:nsr].cpu().numpy()), \
+            "GPU and reference disagree on the sample"
+        os.remove(p)
+        os.remove(p + ".out")
+        cpu = {"value": nsr / min(secs), "unit": UNIT, "cores": run.cores, "kind": "reference",
+               "sample": f"first {nsr} k-mers of rank 0's batch; isBranchingRight + isBranchingLeft under OpenMP; counts identical to the GPU's"}
+    if run.dist:
+        run.dist.barrier()
+    rec = {"value": n * run.world / (ms_step / 1e3), "unit": UNIT, "ms_per_step": ms_step, "steps": steps, "warmup": warmup, "n_gpus": run.world,
+           "config": {"workload": spec["workload"], "k": k, "n_genomes": cfg["n_genomes"], "genome_len": L, "degraded": degraded,
+                      "kmers_in_bft": st["n_kmers"], "nodes": st["n_nodes"], "arena_mb": round(st["arena_bytes"] / 1e6, 1),
+                      "filter_mb": round(st["filter_bytes"] / 1e6, 1), "queries_per_gpu": n, "branching_frac": n_br / n,
+                      "query_mix_present_mismatch_random": MIX, "l2": "inputs larger than L2 (no flush needed)",
+                      "sharding": f"arena replicated, queries sharded x{run.world}"},
+           "clocks": clocks, "e2e": e2e, "gpu_launches": launches * run.world, "roofline": roofline, "cpu_baseline": cpu}
     eng.close()
-    if world > 1:
-        dist.destroy_process_group()
+    del q, d_succ, d_pred
+    torch.cuda.empty_cache()
+    return rec
 
 
-def side_workload(args):
-    """Informational single-GPU lines for the other two query kinds (not the headline metric): BASELINE config[1]
-    (-query_sequences 0.8 canonical, 150 bp reads vs the 16-genome canonical BFT) and config[3] (-query_branching at
-    k=63 on the 100-genome BFT). Same JSON keys; `metric` stays k-mers (windows / k-mers) per second."""
-    import numpy as np
+RECORD = {"kmers": kmers_record, "sequences": sequences_record, "branching": branching_record}
+
+
+def engine_arm(args):
+    run = Run(args)
+    sp = specs()
+    main_tag = args.config
+    if args.genome_len:  # explicit override (development only): named in the config, never silent
+        sp[main_tag] = dict(sp[main_tag], L=args.genome_len,
+                            workload=sp[main_tag]["workload"] + f" [genome length overridden to {args.genome_len}]")
+    t0 = time.time()
+    main = RECORD[sp[main_tag]["kind"]](run, main_tag, sp[main_tag], True)
+    subs = {}
+    for tag in [t for t in args.sub.split(",") if t]:
+        if tag == main_tag or tag not in sp:
+            continue
+        t1 = time.time()
+        try:
+            subs[tag] = RECORD[sp[tag]["kind"]](run, tag, sp[tag], False)
+            subs[tag]["wall_s"] = round(time.time() - t1, 1)
+        except FileNotFoundError as e:  # the BFT of this config did not travel: say so, never substitute silently
+            subs[tag] = {"unavailable": str(e)}
+    if run.rank == 0:
+        line = {"metric": METRIC, "value": main["value"], "unit": UNIT, "n_gpus": run.world, "steps": main["steps"], "warmup": main["warmup"],
+                "ms_per_step": main["ms_per_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": "u64", "data": "synthetic", "config": main["config"], "clocks": main["clocks"], "e2e": main["e2e"],
+                "gpu_launches": main["gpu_launches"], "roofline": main["roofline"], "cpu_baseline": main["cpu_baseline"],
+                "configs": subs, "wall_s": round(time.time() - t0, 1)}
+        emit(line)
+    run.sampler.stop()
+    if run.dist:
+        run.dist.destroy_process_group()
+
+
+def reference_arm(args):
+    """The reference's own CPU implementation of the path (isKmerPresent + get_annotation + get_list_id_genomes under
+    OpenMP, one copy_BFT_Root per thread) on all host cores, each step a bounded sample of the workload."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
     import torch
-    from bloomfiltertrie_b200 import engine as E
     import bench_workloads as wl
-    dev = torch.device("cuda", 0)
-    torch.cuda.set_device(0)
-    seq = args.workload == "sequences"
-    cfg, k, L = (wl.C2, 27, args.genome_len or 5_000_000) if seq else (wl.C3, 63, args.genome_len or 1_000_000)
+    spec = specs()["c3"]
+    cfg, k, L = spec["cfg"], spec["k"], args.genome_len or spec["L"]
+    path = wl.bft_path(cfg, k, L)
+    if not (os.path.exists(path) or os.path.exists(path + ".xz")) and not args.allow_build:
+        raise SystemExit(f"bench.py --impl reference: {path}[.xz] is absent (tools/build_bench_data.py c3)")
     genomes = wl.pangenome(cfg, L)
     bft = wl.ensure_bft(cfg, k, L, genomes)
-    eng = E.BFTEngine(bft, device=0)
-    st = eng.stats()
-    cat, starts, lens = wl.genomes_to_torch(genomes, dev)
-    es = torch.cuda.ExternalStream(eng.stream, device=dev)
     cores = os.cpu_count() or 1
-    if seq:
-        n, rl = args.reads, 150
-        chars, offs = wl.gen_reads(cat, starts, lens, n, rl, seed=4242)
-        units = n * (rl - k + 1)
-        d_rows = torch.empty((n, eng.RW), dtype=torch.int32, device=dev)
-        d_stat = torch.empty(n, dtype=torch.uint8, device=dev)
-        run = lambda: eng.query_sequences_device(chars, offs, n, 0.8, True, d_rows, d_stat)
-        h_chars = E.PinnedBuffer((n * rl,), np.uint8); h_chars.array[:] = chars.cpu().numpy()
-        h_offs = E.PinnedBuffer((n + 1,), np.uint64); h_offs.array[:] = offs.cpu().numpy().view(np.uint64)
-        h_rows = E.PinnedBuffer((n, eng.RW), np.uint32); h_stat = E.PinnedBuffer((n,), np.uint8)
-        run_e2e = lambda: eng.query_sequences(h_chars.array, h_offs.array, 0.8, True, out_rows=h_rows.array, out_status=h_stat.array)
-        h2d, d2h = n * rl + 8 * (n + 1), n * (4 * eng.RW + 1)
-    else:
-        n = args.queries_per_gpu
-        q, _ = wl.gen_kmer_queries(cat, starts, lens, k, n, seed=99, mix=MIX)
-        units = n
-        d_succ = torch.empty(n, dtype=torch.uint8, device=dev)
-        d_pred = torch.empty(n, dtype=torch.uint8, device=dev)
-        d_cnt = torch.zeros(1, dtype=torch.int64, device=dev)
-        run = lambda: eng.query_branching_device(q, n, d_succ, d_pred, d_cnt)
-        hq = E.PinnedBuffer((n, eng.W), np.uint64); hq.array[:] = q.cpu().numpy().view(np.uint64)
-        hs = E.PinnedBuffer((n,), np.uint8); hp = E.PinnedBuffer((n,), np.uint8)
-        run_e2e = lambda: eng.query_branching(hq.array, out_succ=hs.array, out_pred=hp.array)
-        h2d, d2h = n * 8 * eng.W, 2 * n + 8
-    for _ in range(args.warmup):
-        run()
-    torch.cuda.synchronize()
-    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    l0 = eng.launch_count()
-    a.record(es)
-    for _ in range(args.steps):
-        run()
-    b.record(es)
-    b.synchronize()
-    ms = a.elapsed_time(b) / args.steps
-    launches = eng.launch_count() - l0
-    run_e2e()
-    t0 = time.perf_counter()
-    for _ in range(args.steps):
-        run_e2e()
-    e2e_ms = (time.perf_counter() - t0) / args.steps * 1e3
-    cpu = None
-    if not args.no_cpu_baseline and os.access(wl.REF_HARNESS, os.X_OK):
-        if seq:
-            ns = min(n, 200_000)
-            p = f"/tmp/bft_bench_reads_{os.getpid()}.txt"
-            arr = chars[: ns * 150].cpu().numpy().reshape(ns, 150)
-            with open(p, "wb") as f:
-                f.write(np.concatenate([arr, np.full((ns, 1), 10, np.uint8)], axis=1).tobytes())
-            out = subprocess.run([wl.REF_HARNESS, "sequences", bft, p, "0.8", "canonical", p + ".out", str(cores), "2"],
-                                 stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True).stdout
-            secs = [float(x) for x in re.findall(r"REF_PASS \d+ seconds=([0-9.]+)", out)]
-            ref_rows = np.fromfile(p + ".out", dtype=np.uint32).reshape(ns, eng.RW)
-            assert np.array_equal(ref_rows, d_rows[:ns].cpu().numpy().view(np.uint32)), "GPU and reference disagree on the sample"
-            os.remove(p); os.remove(p + ".out")
-            cpu = {"value": ns * (150 - k + 1) / min(secs), "unit": UNIT, "cores": cores, "kind": "reference",
-                   "sample": f"first {ns} reads; query_sequence under OpenMP, one copy_BFT_Root per thread; rows identical to the GPU's"}
-        else:
-            ns = min(n, 1 << 22)
-            p = f"/tmp/bft_bench_br_{os.getpid()}.kc"
-            write_query_file(p, q[:ns].cpu().numpy(), k)
-            out = subprocess.run([wl.REF_HARNESS, "branching", bft, p, p + ".out", str(cores), "2"], stdout=subprocess.PIPE,
-                                 stderr=subprocess.STDOUT, text=True).stdout
-            secs = [float(x) for x in re.findall(r"REF_PASS \d+ seconds=([0-9.]+)", out)]
-            raw = np.fromfile(p + ".out", dtype=np.uint8)
-            assert np.array_equal(raw[:ns], d_succ[:ns].cpu().numpy()) and np.array_equal(raw[ns:2 * ns], d_pred[:ns].cpu().numpy()), \
-                "GPU and reference disagree on the sample"
-            os.remove(p); os.remove(p + ".out")
-            cpu = {"value": ns / min(secs), "unit": UNIT, "cores": cores, "kind": "reference",
-                   "sample": f"first {ns} k-mers; isBranchingRight + isBranchingLeft under OpenMP; counts identical to the GPU's"}
-    line = {"metric": METRIC, "value": units / (ms / 1e3), "unit": UNIT, "n_gpus": 1, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u64", "data": "synthetic",
-            "config": {"workload": ("c2: -query_sequences 0.8 canonical, 150 bp reads vs 16-genome canonical BFT (value counts k-mer windows)"
-                                    if seq else "c4: -query_branching at k=63 on the 100-genome BFT (value counts query k-mers; 8 neighbour lookups each)"),
-                       "k": k, "n_genomes": cfg["n_genomes"], "genome_len": L, "kmers_in_bft": st["n_kmers"], "items_per_step": n,
-                       "reads_per_sec": (n / (ms / 1e3)) if seq else None},
-            "e2e": {"value": units / (e2e_ms / 1e3), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms},
-            "gpu_launches": launches, "cpu_baseline": cpu}
+    n = args.ref_sample
+    cat, starts, lens = wl.genomes_to_torch(genomes, torch.device("cpu"))
+    q = wl.gen_kmer_queries(cat, starts, lens, k, n, seed=777, mix=MIX)[0].numpy()
+    qfile = os.path.join("/tmp", f"bft_bench_ref_{os.getpid()}.kc")
+    write_query_file(qfile, q, k)
+    secs = run_ref(["kmers", bft, qfile, qfile + ".out", str(cores), str(args.warmup + args.steps)])
+    os.remove(qfile)
+    os.remove(qfile + ".out")
+    timed = secs[args.warmup:]
+    ms = 1e3 * sum(timed) / len(timed)
+    value = n / (ms / 1e3)
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "u64", "data": "synthetic",
+            "config": {"workload": spec["workload"], "k": k, "n_genomes": cfg["n_genomes"], "genome_len": L, "query_mix_present_mismatch_random": MIX,
+                       "sample": f"{n} k-mers per step (same generator and mix as the GPU batch)"},
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "reference",
+                             "sample": f"{n} k-mers per step (same generator and mix as the GPU batch), all {cores} host threads"},
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     emit(line)
-    eng.close()
 
 
 def graph_workload(args):
     """Informational single-GPU line for the traversal snippets: build the device graph of the
     100-genome BFT, count its connected components, extract its simple paths; beside it the reference's own
     get_nb_connected_component(BFS) / extract_simple_core_paths_to_disk on one host core (they cannot thread)."""
-    import numpy as np
     import torch
     from bloomfiltertrie_b200 import engine as E
     import bench_workloads as wl
@@ -637,7 +809,9 @@ def graph_workload(args):
         t2 = time.perf_counter()
         _, n_paths, longest, path_bytes = eng.simple_paths_raw(0.0, copy=False)   # the C call: kernels + copy to a host buffer
         t3 = time.perf_counter()
-        t["build"].append(t1 - t0); t["components"].append(t2 - t1); t["paths"].append(t3 - t2)
+        t["build"].append(t1 - t0)
+        t["components"].append(t2 - t1)
+        t["paths"].append(t3 - t2)
     launches = eng.launch_count() - l0
     ms = {kk: 1e3 * sum(v) / len(v) for kk, v in t.items()}
     step_ms = ms["build"] + ms["components"]
@@ -646,7 +820,7 @@ def graph_workload(args):
     if not args.no_cpu_baseline and os.access(ref_graph, os.X_OK):
         t0 = time.perf_counter()
         out = subprocess.run([ref_graph, "components", bft, "bfs"], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True).stdout
-        dt = time.perf_counter() - t0 - st["flatten_seconds"] * 0  # includes the reference's own load of the file
+        dt = time.perf_counter() - t0
         m = re.search(r"REF_COMPONENTS (\d+)", out)
         assert m and int(m.group(1)) == n_comp, f"GPU and reference disagree: {n_comp} vs {out[-200:]}"
         cpu = {"value": n / dt, "unit": "k-mers/s", "cores": 1, "kind": "reference",
@@ -672,26 +846,25 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="engine", choices=["engine", "reference"])
-    ap.add_argument("--genome-len", type=int, default=0, help="override the genome length of the 100-genome pan-genome")
-    ap.add_argument("--queries-per-gpu", type=int, default=125_000_000)
+    ap.add_argument("--config", default="c3", choices=["c1", "c2", "c3", "c4", "c5"],
+                    help="the config reported as the main line (default c3 = BASELINE config[2], the headline metric)")
+    ap.add_argument("--sub", default=None, help="comma-separated configs measured as sub-records (default: c1,c2,c4,c5 when --config c3)")
+    ap.add_argument("--sub-steps", type=int, default=5, help="timed steps of every sub-record")
+    ap.add_argument("--genome-len", type=int, default=0, help="development only: override the genome length of the main config")
+    ap.add_argument("--queries-per-gpu", type=int, default=0, help="override the k-mers per GPU per step of the main config")
     ap.add_argument("--ref-sample", type=int, default=1 << 24, help="k-mers per step of the CPU reference legs")
+    ap.add_argument("--allow-build", action="store_true", help="build a missing BFT with the reference instead of failing")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-probe", action="store_true")
-    ap.add_argument("--workload", default="kmers", choices=["kmers", "sequences", "branching", "graph"],
-                    help="kmers = the headline metric (default); the other two print informational single-GPU lines")
-    ap.add_argument("--reads", type=int, default=1_000_000)
-    ap.add_argument("--pangenome", default="c3", choices=["c3", "c5"],
-                    help="c3 = 100 genomes (headline); c5 = 1000 colours, 100 kbp genomes (informational)")
+    ap.add_argument("--workload", default="kmers", choices=["kmers", "graph"], help="graph = informational traversal line")
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3
+    if args.sub is None:
+        args.sub = "c1,c2,c4,c5" if args.config == "c3" else ""
     if args.workload == "graph":
         graph_workload(args)
-    elif args.workload != "kmers":
-        if args.queries_per_gpu == 125_000_000:
-            args.queries_per_gpu = 20_000_000
-        side_workload(args)
     elif args.impl == "reference":
         reference_arm(args)
     else:

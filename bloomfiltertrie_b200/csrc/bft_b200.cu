@@ -306,19 +306,20 @@ extern "C" int bft_b200_open(const char* path, int device, bft_b200_ctx** out) {
     /* hot block: rootdir, the class rows, the stored-k-mer filter */
     const size_t rootdir_bytes = BFT_ROOTDIR_SIZE * sizeof(bft_entry_t);
     const size_t rows_padded = (row_bytes + 31) & ~(size_t)31;
-    /* filter size: BFT_B200_KF_BITS bits per stored k-mer (default 8, 0 = no filter), shrunk to at least 4 bits per
-     * k-mer to stay within BFT_B200_KF_MAX_MB (default 48 MB, a share of the 126 MB L2 that leaves room for the class
-     * rows and the streaming traffic); a BFT too large for that gets no filter — out of L2 it would cost a second HBM
-     * access per present k-mer instead of saving one per absent k-mer */
+    /* filter size: BFT_B200_KF_BITS bits per stored k-mer (default 6: 5.6 % false positives; 0 = no filter), shrunk down
+     * to 3 bits per k-mer (29 %) to stay within BFT_B200_KF_MAX_MB (default 36 MB). Measured on C3 (33 M k-mers, B200):
+     * 25 MB -> 45.2 G k-mers/s, 33 MB -> 44.4, 45 MB -> 41.4, 58 MB -> 33.2 (no better than without a filter): the filter
+     * shares the 126 MB L2 with the class rows, the root directory and the streamed batch. A BFT too large for that
+     * gets no filter — out of L2 it would cost a second HBM access per present k-mer instead of saving one per absent one */
     size_t kf_blocks = 0;
     {
         const char* eb = getenv("BFT_B200_KF_BITS");
         const char* em = getenv("BFT_B200_KF_MAX_MB");
-        double bits = eb ? atof(eb) : 8.0;
-        const double max_bytes = (em ? atof(em) : 48.0) * 1048576.0;
+        double bits = eb ? atof(eb) : 6.0;
+        const double max_bytes = (em ? atof(em) : 36.0) * 1048576.0;
         if (bits > 0 && a->n_kmers > 0) {
             if (bits * (double)a->n_kmers / 8.0 > max_bytes) bits = max_bytes * 8.0 / (double)a->n_kmers;
-            if (bits >= 4.0) {
+            if (bits >= 3.0) {
                 kf_blocks = (size_t)(bits * (double)a->n_kmers / 256.0) + 1;
                 if (kf_blocks > 0xffffffffu) kf_blocks = 0;
             }
@@ -338,6 +339,11 @@ extern "C" int bft_b200_open(const char* path, int device, bft_b200_ctx** out) {
     if (!rc && cudaMalloc((void**)&c->d_counter, sizeof(unsigned long long)) != cudaSuccess) rc = set_err(BFT_B200_ERR_NOMEM, "cudaMalloc failed");
     for (int s = 0; s < BFT_N_SLOTS && !rc; s++)
         if (cudaStreamCreateWithFlags(&c->streams[s], cudaStreamNonBlocking) != cudaSuccess) rc = set_err(BFT_B200_ERR_CUDA, "cudaStreamCreate failed");
+    if (!rc && getenv("BFT_B200_L2_FETCH")) { /* experiment knob (device-wide hint): DRAM -> L2 fetch granularity in bytes (32, 64 or 128) */
+        const int gran = atoi(getenv("BFT_B200_L2_FETCH"));
+        if (gran == 32 || gran == 64 || gran == 128) cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, (size_t)gran);
+        cudaGetLastError();
+    }
     if (!rc && !(getenv("BFT_B200_NO_L2_PERSIST") && getenv("BFT_B200_NO_L2_PERSIST")[0] == '1')) {
         /* keep the hot block resident in L2 (persisting access-policy window on both streams); best effort */
         size_t win = c->hot_bytes;

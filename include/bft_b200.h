@@ -24,7 +24,7 @@
  *     every lookup touches (cudaLimitPersistingL2CacheSize is device-wide: the limit is only ever raised, never shrunk
  *     below what the host application or another context set; BFT_B200_NO_L2_PERSIST=1 leaves it alone altogether).
  *     Environment knobs read by bft_b200_open: BFT_B200_KF_BITS (bits per stored k-mer of the L2-resident negative
- *     filter, default 8, 0 = off), BFT_B200_KF_MAX_MB (its size cap, default 48).
+ *     filter, default 6, 0 = off), BFT_B200_KF_MAX_MB (its size cap, default 36).
  */
 #ifndef BFT_B200_H
 #define BFT_B200_H
