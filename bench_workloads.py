@@ -32,11 +32,22 @@ C5 = dict(name="c5_g1000", n_genomes=1000, snp=0.002, indel=0.0002, seed=54321, 
 C2 = dict(name="c2_g16_canon", n_genomes=16, snp=0.005, indel=0.0005, seed=2345, tree=False, canonical=True)
 
 
+# forced-deep trie (not a BASELINE config): genomes spelled from a vocabulary of 24 random 9-mers, so a few
+# thousand 9-nt prefixes carry hundreds of suffixes each and burst into child Nodes, several levels deep, while consecutive
+# windows are still true de Bruijn neighbours. 8 genomes (founder + 7 strains at 0.3 % SNPs), k = 63.
+DEEP = dict(name="deep_g8_v24", n_genomes=8, snp=0.003, indel=0.0, seed=77, tree=False, vocab=24)
+
+
 def log(*a):
     print("[workloads]", *a, file=sys.stderr, flush=True)
 
 
 def pangenome(cfg: dict, genome_len: int) -> List[np.ndarray]:
+    if cfg.get("vocab"):
+        rng = np.random.default_rng(cfg["seed"])
+        words9 = rng.integers(0, 4, size=(cfg["vocab"], 9), dtype=np.uint8)
+        founder = words9[rng.integers(0, cfg["vocab"], size=genome_len // 9)].reshape(-1)
+        return [founder] + [synth.mutate(rng, founder, cfg["snp"]) for _ in range(cfg["n_genomes"] - 1)]
     return synth.make_pangenome(cfg["n_genomes"], genome_len, cfg["snp"], cfg["indel"], seed=cfg["seed"], tree=cfg["tree"])
 
 

@@ -6,11 +6,16 @@
  * into HBM. Everything in the arena is derived exactly from the reference's own bytes — no result changes:
  *
  *   nodes[]    one descriptor per trie Node.
- *   firstcc[]  per Node with CCs: 16384 bytes, entry idx14 -> index of the FIRST CC of the node whose Bloom filter
+ *   firstcc[]  per Node with more than BFT_BF_DIRECT_MAX CCs: 16384 bytes, entry idx14 -> index of the FIRST CC of the node whose Bloom filter
  *              fires for the 14-bit hash index idx14 (0xff: none fires). The reference probes the CC chain in order
  *              and lets the first hit decide (src/presenceNode.c:1354-1550); the probe depends only on idx14
  *              (src/presenceNode.c:1341-1343), so this table is that chain, precomputed (the reference builds the
  *              same table for its root in get_bf_presence_per_cc, src/presenceNode.c:1213-1270).
+ *              A Node with at most BFT_BF_DIRECT_MAX CCs (every Node below the root of a deep trie has exactly one)
+ *              keeps the regenerated Bloom filters themselves instead (bf_mode = 1: n_cc filters of bf_stride bytes,
+ *              188 bytes each at the reference's 1504-bit filters) and is probed the way the reference probes it: the
+ *              two bit positions of idx14 (hpos[], 64 KB per trie level, L2-resident) tested in each filter in turn.
+ *              16 KB per Node would put the tables of a 10^4-Node trie (160 MB) out of L2; 188 bytes keeps them in.
  *   ccs[]      one descriptor per CC.
  *   csr[]      per CC: 2^p + 1 uint16, csr[pu] = number of stored prefixes whose p_u is < pu. Replaces the
  *              filter2 bit test + rank (SkipFilter2) + select in the cluster-start bits (SkipFilter3 /
@@ -75,6 +80,7 @@
 #define BFT_N_IDX14 16384
 #define BFT_ROOTDIR_SIZE (1u << BFT_PREFIX_BITS)
 #define BFT_FIRSTCC_NONE 0xffu
+#define BFT_BF_DIRECT_MAX 4            /* Nodes with at most this many CCs keep their Bloom filters instead of a first-CC table */
 #define BFT_MAX_WORDS 4                /* k <= 126 (252 bits), the reference's KMER_LENGTH_MAX */
 #define BFT_BUCKET_KEYS 4              /* slots per bucket */
 #define BFT_MAX_LB 8                   /* at most 256 buckets per prefix */
@@ -105,7 +111,9 @@ typedef struct {
     uint32_t fc_off;   /* byte offset of this node's firstcc table (valid when n_cc > 0) */
     uint32_t uc_begin; /* first line of the Node's own UC */
     uint32_t uc_n;     /* number of lines in the Node's own UC */
-    uint32_t pad[3];
+    uint32_t bf_mode;  /* 0: fc_off is a 16384-byte first-CC table; 1: fc_off is n_cc Bloom filters of bf_stride bytes */
+    uint32_t hp_off;   /* bf_mode 1: offset (uint32 units) of this level's bit-position table in hpos[] */
+    uint32_t bf_stride;
 } bft_node_t;
 
 typedef struct {
@@ -130,6 +138,7 @@ typedef struct {
     const bft_node_t* nodes;
     const bft_cc_t* ccs;
     const uint8_t* firstcc;
+    const uint32_t* hpos;     /* per trie level in use: 16384 entries h1 | h2 << 16, the two Bloom-filter bit positions of idx14 */
     const uint16_t* csr;
     const uint8_t* filter3;
     const bft_entry_t* pref;
@@ -235,6 +244,17 @@ BFT_HD int bft_kf_test(const bft_view_t* v, const uint64_t* kmer, const int W) {
     return (int)(((w0 >> (h & 63)) & (w1 >> ((h >> 6) & 63)) & (w2 >> ((h >> 12) & 63)) & (w3 >> ((h >> 18) & 63))) & 1ULL);
 }
 
+/* index of the first CC of a Node whose Bloom filter fires for idx14, or BFT_FIRSTCC_NONE (src/presenceNode.c:1354-1362) */
+BFT_HD uint32_t bft_first_cc(const bft_view_t* v, const bft_node_t* nd, uint32_t idx14) {
+    if (!nd->bf_mode) return BFT_LD8(v->firstcc + nd->fc_off + idx14);
+    const uint32_t hp = BFT_LD32(v->hpos + nd->hp_off + idx14);
+    const uint32_t h1 = hp & 0xffffu, h2 = hp >> 16;
+    const uint8_t* bf = v->firstcc + nd->fc_off;
+    for (uint32_t i = 0; i < nd->n_cc; i++, bf += nd->bf_stride)
+        if ((BFT_LD8(bf + (h1 >> 3)) >> (h1 & 7u)) & (BFT_LD8(bf + (h2 >> 3)) >> (h2 & 7u)) & 1u) return i;
+    return BFT_FIRSTCC_NONE;
+}
+
 /* One Node probe: the reference's presenceKmer (src/presenceNode.c:1284-1576) on the flattened layout.
  * succ_leaf_quirk != 0 reproduces presenceNeighborsRight at the leaf level (size_kmer == 9,
  * src/presenceNode.c:719-723): the reference clears nucleotide 7 of the prefix (`& 0xfc` on the second byte) before
@@ -245,8 +265,9 @@ BFT_HD bft_entry_t bft_node_probe_ex(const bft_view_t* v, uint32_t node_id, uint
 #ifdef __CUDA_ARCH__
     {
         const uint4 t = __ldg((const uint4*)(v->nodes + node_id));
+        const uint4 u = __ldg((const uint4*)(v->nodes + node_id) + 1);
         nd.cc_begin = t.x; nd.n_cc = t.y; nd.fc_off = t.z; nd.uc_begin = t.w;
-        nd.uc_n = BFT_LD32(&v->nodes[node_id].uc_n);
+        nd.uc_n = u.x; nd.bf_mode = u.y; nd.hp_off = u.z; nd.bf_stride = u.w;
     }
 #else
     nd = v->nodes[node_id];
@@ -254,7 +275,7 @@ BFT_HD bft_entry_t bft_node_probe_ex(const bft_view_t* v, uint32_t node_id, uint
     uint32_t r18 = bft_msb_first18(low18);
     if (succ_leaf_quirk) r18 &= ~0xcu; /* nuc 7 sits at bits 2-3 of the MSB-first prefix */
     if (nd.n_cc) {
-        const uint32_t c = BFT_LD8(v->firstcc + nd.fc_off + bft_idx14(r18));
+        const uint32_t c = bft_first_cc(v, &nd, bft_idx14(r18));
         if (c != BFT_FIRSTCC_NONE) {
             bft_cc_t cc;
 #ifdef __CUDA_ARCH__
@@ -396,7 +417,7 @@ BFT_HD void bft_shift18(uint64_t* cur, int W) {
 BFT_HD uint32_t bft_cc_probed(const bft_view_t* v, uint32_t node_id, uint32_t low18) {
     const bft_node_t* nd = v->nodes + node_id;
     if (!nd->n_cc) return 0;
-    const uint32_t c = v->firstcc[nd->fc_off + bft_idx14(bft_msb_first18(low18))];
+    const uint32_t c = bft_first_cc(v, nd, bft_idx14(bft_msb_first18(low18)));
     return c == BFT_FIRSTCC_NONE ? nd->n_cc : c + 1;
 }
 

@@ -65,7 +65,7 @@ struct bft_b200_ctx {
     char** names;
     bft_b200_stats stats;
     /* device arena */
-    void* d_arena[18];
+    void* d_arena[19];
     size_t n_pref, n_nodes;
     bft_view_t dview;
     bft_pools_t dpools;
@@ -99,6 +99,16 @@ struct bft_b200_ctx {
 
 extern "C" const char* bft_b200_last_error(void) { return g_err; }
 
+static int drain_ret(bft_b200_ctx* c, int rc) {
+    char keep[sizeof g_err];
+    memcpy(keep, g_err, sizeof keep); /* the message of the failure that brought us here */
+    for (int s = 0; s < BFT_N_SLOTS; s++)
+        if (c->streams[s]) cudaStreamSynchronize(c->streams[s]);
+    (void)cudaGetLastError();
+    memcpy(g_err, keep, sizeof keep);
+    return rc;
+}
+
 /* instantiate a launch for the arena's key width (W = 1, 2 or 4 words) */
 #define BFT_BY_W(w_, LAUNCH)                 \
     do {                                     \
@@ -124,6 +134,22 @@ static int ensure(void** p, size_t* cap, size_t need) {
         if (r_) return r_;                                             \
     } while (0)
 
+/* Error exits of the chunked host pipelines: copies of earlier chunks may still be reading the caller's input or writing
+ * its output buffers, so every stream is drained before the error is returned (the caller is free to release its buffers
+ * the moment the call comes back). CKP / ENSUREP are CK / ENSURE with that drain. */
+static int drain_ret(bft_b200_ctx* c, int rc);
+#define CKP(call)                                                                                                         \
+    do {                                                                                                                 \
+        cudaError_t e_ = (call);                                                                                         \
+        if (e_ != cudaSuccess)                                                                                           \
+            return drain_ret(c, set_err(BFT_B200_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__)); \
+    } while (0)
+#define ENSUREP(ptr, cap, need)                                        \
+    do {                                                               \
+        int r_ = ensure((void**)&(ptr), &(cap), (need));               \
+        if (r_) return drain_ret(c, r_);                               \
+    } while (0)
+
 static int upload(void** dst, const void* src, size_t bytes) {
     size_t n = bytes ? bytes : 16;
     cudaError_t e = cudaMalloc(dst, n + 32); /* slack for vector loads at the tail */
@@ -146,7 +172,7 @@ extern "C" void bft_b200_close(bft_b200_ctx* c) {
     if (!c) return;
     cudaSetDevice(c->device);
     cudaDeviceSynchronize();
-    for (int i = 0; i < 18; i++) if (c->d_arena[i]) cudaFree(c->d_arena[i]);
+    for (int i = 0; i < 19; i++) if (c->d_arena[i]) cudaFree(c->d_arena[i]);
     for (int i = 0; i < 4; i++) if (c->d_pool[i]) cudaFree(c->d_pool[i]);
     if (c->d_hot) cudaFree(c->d_hot);
     if (c->d_class_counts) cudaFree(c->d_class_counts);
@@ -254,6 +280,7 @@ extern "C" int bft_b200_open(const char* path, int device, bft_b200_ctx** out) {
     UP(15, node_path, a->n_nodes * sizeof(bft_path_t));
     UP(16, pref_out, (a->n_pref + 1) * sizeof(uint64_t));
     UP(17, uc_rank, a->n_uc_lines);
+    UP(18, hpos, a->n_hpos * sizeof(uint32_t));
     c->n_pref = a->n_pref;
     c->n_nodes = a->n_nodes;
 #undef UP
@@ -283,6 +310,7 @@ extern "C" int bft_b200_open(const char* path, int device, bft_b200_ctx** out) {
         c->dview.node_path = (const bft_path_t*)c->d_arena[15];
         c->dview.pref_out = (const uint64_t*)c->d_arena[16];
         c->dview.uc_rank = (const uint8_t*)c->d_arena[17];
+        c->dview.hpos = (const uint32_t*)c->d_arena[18];
         c->dview.cls_shift = a->cls_shift;
         c->dview.cls_mask = a->cls_mask;
         c->dview.k = a->k;
@@ -505,44 +533,44 @@ static int query_kmers_host(bft_b200_ctx* c, const uint64_t* kmers, const char* 
         const int s = it & 1;
         slot_t* sl = &c->slot[s];
         cudaStream_t st = c->streams[s];
-        CK(cudaStreamSynchronize(st)); /* slot buffers free again */
+        CKP(cudaStreamSynchronize(st)); /* slot buffers free again */
         const uint64_t* d_k;
         if (ascii) {
-            ENSURE(sl->d_in, sl->cap_in, m * k);
-            ENSURE(sl->d_kmers, sl->cap_kmers, m * W * 8);
-            ENSURE(sl->d_u8b, sl->cap_u8b, m);
-            CK(cudaMemcpyAsync(sl->d_in, ascii + done * k, m * k, cudaMemcpyHostToDevice, st));
+            ENSUREP(sl->d_in, sl->cap_in, m * k);
+            ENSUREP(sl->d_kmers, sl->cap_kmers, m * W * 8);
+            ENSUREP(sl->d_u8b, sl->cap_u8b, m);
+            CKP(cudaMemcpyAsync(sl->d_in, ascii + done * k, m * k, cudaMemcpyHostToDevice, st));
 #define BFT_L(W_) k_encode_ascii<W_><<<grid_for(c, m, BFT_TPB), BFT_TPB, 0, st>>>((const char*)sl->d_in, m, c->k, sl->d_kmers, sl->d_u8b)
             BFT_BY_W(c->W, BFT_L);
 #undef BFT_L
             c->launches++;
             d_k = sl->d_kmers;
         } else {
-            ENSURE(sl->d_in, sl->cap_in, m * W * 8);
-            CK(cudaMemcpyAsync(sl->d_in, kmers + done * W, m * W * 8, cudaMemcpyHostToDevice, st));
+            ENSUREP(sl->d_in, sl->cap_in, m * W * 8);
+            CKP(cudaMemcpyAsync(sl->d_in, kmers + done * W, m * W * 8, cudaMemcpyHostToDevice, st));
             d_k = (const uint64_t*)sl->d_in;
         }
-        ENSURE(sl->d_u8a, sl->cap_u8a, m);
-        ENSURE(sl->d_cls, sl->cap_cls, m * sizeof(uint32_t));
-        if (rows) ENSURE(sl->d_rows, sl->cap_rows, m * rw * sizeof(uint32_t));
+        ENSUREP(sl->d_u8a, sl->cap_u8a, m);
+        ENSUREP(sl->d_cls, sl->cap_cls, m * sizeof(uint32_t));
+        if (rows) ENSUREP(sl->d_rows, sl->cap_rows, m * rw * sizeof(uint32_t));
         /* class ids are materialised only when asked for, or as the intermediate of the wide-row path */
         const int fused = rows && (c->rw == 1 || c->rw == 2 || c->rw == 4);
         uint32_t* d_cls = (class_ids || (rows && !fused) || !rows) ? sl->d_cls : NULL;
         int rc = enqueue_kmers(c, st, d_k, m, sl->d_u8a, rows ? sl->d_rows : NULL, d_cls);
-        if (rc) return rc;
+        if (rc) return drain_ret(c, rc);
         if (ascii) {
             k_blank_invalid<<<grid_for(c, m, BFT_TPB), BFT_TPB, 0, st>>>(sl->d_u8b, m, c->rw, sl->d_u8a, d_cls, rows ? sl->d_rows : NULL);
             c->launches++;
         }
-        if (present) CK(cudaMemcpyAsync(present + done, sl->d_u8a, m, cudaMemcpyDeviceToHost, st));
-        if (valid) CK(cudaMemcpyAsync(valid + done, sl->d_u8b, m, cudaMemcpyDeviceToHost, st));
-        if (class_ids) CK(cudaMemcpyAsync(class_ids + done, sl->d_cls, m * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
-        if (rows) CK(cudaMemcpyAsync(rows + done * rw, sl->d_rows, m * rw * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+        if (present) CKP(cudaMemcpyAsync(present + done, sl->d_u8a, m, cudaMemcpyDeviceToHost, st));
+        if (valid) CKP(cudaMemcpyAsync(valid + done, sl->d_u8b, m, cudaMemcpyDeviceToHost, st));
+        if (class_ids) CKP(cudaMemcpyAsync(class_ids + done, sl->d_cls, m * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+        if (rows) CKP(cudaMemcpyAsync(rows + done * rw, sl->d_rows, m * rw * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
         done += m;
         it++;
     }
-    CK(cudaStreamSynchronize(c->streams[0]));
-    CK(cudaStreamSynchronize(c->streams[1]));
+    CKP(cudaStreamSynchronize(c->streams[0]));
+    CKP(cudaStreamSynchronize(c->streams[1]));
     return 0;
 }
 
@@ -615,10 +643,10 @@ extern "C" int bft_b200_query_records(bft_b200_ctx* c, const uint8_t* records, s
     if (!c || (!records && n) || !rows) return set_err(BFT_B200_ERR_ARG, "bft_b200_query_records: NULL argument");
     CK(cudaSetDevice(c->device));
     const size_t nb = (size_t)bft_b200_record_bytes(c), rb = (size_t)bft_b200_row_bytes(c);
-    CK(cudaStreamSynchronize(c->streams[0]));
-    CK(cudaStreamSynchronize(c->streams[1]));
-    CK(cudaMemsetAsync(c->d_counter, 0, sizeof(unsigned long long), c->streams[0]));
-    CK(cudaStreamSynchronize(c->streams[0]));
+    CKP(cudaStreamSynchronize(c->streams[0]));
+    CKP(cudaStreamSynchronize(c->streams[1]));
+    CKP(cudaMemsetAsync(c->d_counter, 0, sizeof(unsigned long long), c->streams[0]));
+    CKP(cudaStreamSynchronize(c->streams[0]));
     size_t done = 0;
     int it = 0;
     while (done < n) {
@@ -626,23 +654,23 @@ extern "C" int bft_b200_query_records(bft_b200_ctx* c, const uint8_t* records, s
         const int s = it & 1;
         slot_t* sl = &c->slot[s];
         cudaStream_t st = c->streams[s];
-        CK(cudaStreamSynchronize(st)); /* slot buffers free again */
-        ENSURE(sl->d_in, sl->cap_in, m * nb);
-        ENSURE(sl->d_u8a, sl->cap_u8a, m);
-        ENSURE(sl->d_rows, sl->cap_rows, m * rb);
-        CK(cudaMemcpyAsync(sl->d_in, records + done * nb, m * nb, cudaMemcpyHostToDevice, st));
+        CKP(cudaStreamSynchronize(st)); /* slot buffers free again */
+        ENSUREP(sl->d_in, sl->cap_in, m * nb);
+        ENSUREP(sl->d_u8a, sl->cap_u8a, m);
+        ENSUREP(sl->d_rows, sl->cap_rows, m * rb);
+        CKP(cudaMemcpyAsync(sl->d_in, records + done * nb, m * nb, cudaMemcpyHostToDevice, st));
         int rc = enqueue_records(c, st, (const uint8_t*)sl->d_in, m, present ? sl->d_u8a : NULL, (uint8_t*)sl->d_rows, n_present ? c->d_counter : NULL);
-        if (rc) return rc;
-        if (present) CK(cudaMemcpyAsync(present + done, sl->d_u8a, m, cudaMemcpyDeviceToHost, st));
-        CK(cudaMemcpyAsync(rows + done * rb, sl->d_rows, m * rb, cudaMemcpyDeviceToHost, st));
+        if (rc) return drain_ret(c, rc);
+        if (present) CKP(cudaMemcpyAsync(present + done, sl->d_u8a, m, cudaMemcpyDeviceToHost, st));
+        CKP(cudaMemcpyAsync(rows + done * rb, sl->d_rows, m * rb, cudaMemcpyDeviceToHost, st));
         done += m;
         it++;
     }
-    CK(cudaStreamSynchronize(c->streams[0]));
-    CK(cudaStreamSynchronize(c->streams[1]));
+    CKP(cudaStreamSynchronize(c->streams[0]));
+    CKP(cudaStreamSynchronize(c->streams[1]));
     if (n_present) {
         unsigned long long h = 0;
-        CK(cudaMemcpy(&h, c->d_counter, sizeof h, cudaMemcpyDeviceToHost));
+        CKP(cudaMemcpy(&h, c->d_counter, sizeof h, cudaMemcpyDeviceToHost));
         *n_present = h;
     }
     return 0;
@@ -668,26 +696,26 @@ extern "C" int bft_b200_query_records_compact(bft_b200_ctx* c, const uint8_t* re
             const size_t first = i * BFT_CHUNK_KMERS;
             const size_t m = n - first < BFT_CHUNK_KMERS ? n - first : BFT_CHUNK_KMERS;
             const size_t n_tiles = (m + BFT_TPB - 1) / BFT_TPB;
-            CK(cudaStreamSynchronize(st)); /* the slot's rows of four chunks ago reached the host long ago */
-            ENSURE(sl->d_in, sl->cap_in, m * nb);
-            ENSURE(sl->d_cls, sl->cap_cls, m * sizeof(uint32_t));
-            ENSURE(sl->d_u8a, sl->cap_u8a, (m + 31) / 32 * 4);
-            ENSURE(sl->d_rows, sl->cap_rows, m * rb);
-            ENSURE(sl->d_tile, sl->cap_tile, (2 * n_tiles + 1) * sizeof(uint32_t));
-            if (!sl->h_total) CK(cudaMallocHost((void**)&sl->h_total, 16));
-            CK(cudaMemcpyAsync(sl->d_in, records + first * nb, m * nb, cudaMemcpyHostToDevice, st));
+            CKP(cudaStreamSynchronize(st)); /* the slot's rows of four chunks ago reached the host long ago */
+            ENSUREP(sl->d_in, sl->cap_in, m * nb);
+            ENSUREP(sl->d_cls, sl->cap_cls, m * sizeof(uint32_t));
+            ENSUREP(sl->d_u8a, sl->cap_u8a, (m + 31) / 32 * 4);
+            ENSUREP(sl->d_rows, sl->cap_rows, m * rb);
+            ENSUREP(sl->d_tile, sl->cap_tile, (2 * n_tiles + 1) * sizeof(uint32_t));
+            if (!sl->h_total) CKP(cudaMallocHost((void**)&sl->h_total, 16));
+            CKP(cudaMemcpyAsync(sl->d_in, records + first * nb, m * nb, cudaMemcpyHostToDevice, st));
             int rc = enqueue_records_compact(c, st, sl, m);
-            if (rc) return rc;
-            CK(cudaMemcpyAsync(present_bits + first / 8, sl->d_u8a, (m + 7) / 8, cudaMemcpyDeviceToHost, st)); /* chunks are multiples of 8 */
-            CK(cudaMemcpyAsync(sl->h_total, sl->d_tile + 2 * n_tiles, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+            if (rc) return drain_ret(c, rc);
+            CKP(cudaMemcpyAsync(present_bits + first / 8, sl->d_u8a, (m + 7) / 8, cudaMemcpyDeviceToHost, st)); /* chunks are multiples of 8 */
+            CKP(cudaMemcpyAsync(sl->h_total, sl->d_tile + 2 * n_tiles, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
         }
         if (i >= lag) { /* back half of chunk i - lag: its rows, now that their number is known */
             const size_t j = i - lag;
             slot_t* pl = &c->slot[j % BFT_N_SLOTS];
             cudaStream_t pst = c->streams[j % BFT_N_SLOTS];
-            CK(cudaStreamSynchronize(pst));
+            CKP(cudaStreamSynchronize(pst));
             const size_t hits = pl->h_total[0];
-            if (hits) CK(cudaMemcpyAsync(rows + rows_done * rb, pl->d_rows, hits * rb, cudaMemcpyDeviceToHost, pst));
+            if (hits) CKP(cudaMemcpyAsync(rows + rows_done * rb, pl->d_rows, hits * rb, cudaMemcpyDeviceToHost, pst));
             rows_done += hits;
         }
     }
@@ -766,7 +794,7 @@ extern "C" int bft_b200_query_sequences(bft_b200_ctx* c, const char* chars, cons
                                         uint32_t* rows, uint8_t* status) {
     if (!c || !offs || !rows) return set_err(BFT_B200_ERR_ARG, "bft_b200_query_sequences: NULL argument");
     int rc = check_threshold(thr);
-    if (rc) return rc;
+    if (rc) return drain_ret(c, rc);
     CK(cudaSetDevice(c->device));
     const size_t rw = (size_t)c->rw;
     size_t done = 0;
@@ -778,23 +806,23 @@ extern "C" int bft_b200_query_sequences(bft_b200_ctx* c, const char* chars, cons
         const int s = it & 1;
         slot_t* sl = &c->slot[s];
         cudaStream_t st = c->streams[s];
-        CK(cudaStreamSynchronize(st));
-        ENSURE(sl->d_in, sl->cap_in, (size_t)(c1 - c0) + 64);
-        ENSURE(sl->d_offs, sl->cap_offs, (m + 1) * sizeof(uint64_t));
-        ENSURE(sl->d_rows, sl->cap_rows, m * rw * sizeof(uint32_t));
-        ENSURE(sl->d_u8a, sl->cap_u8a, m);
-        if (c1 > c0) CK(cudaMemcpyAsync(sl->d_in, chars + c0, (size_t)(c1 - c0), cudaMemcpyHostToDevice, st));
-        CK(cudaMemcpyAsync(sl->d_offs, offs + done, (m + 1) * sizeof(uint64_t), cudaMemcpyHostToDevice, st));
+        CKP(cudaStreamSynchronize(st));
+        ENSUREP(sl->d_in, sl->cap_in, (size_t)(c1 - c0) + 64);
+        ENSUREP(sl->d_offs, sl->cap_offs, (m + 1) * sizeof(uint64_t));
+        ENSUREP(sl->d_rows, sl->cap_rows, m * rw * sizeof(uint32_t));
+        ENSUREP(sl->d_u8a, sl->cap_u8a, m);
+        if (c1 > c0) CKP(cudaMemcpyAsync(sl->d_in, chars + c0, (size_t)(c1 - c0), cudaMemcpyHostToDevice, st));
+        CKP(cudaMemcpyAsync(sl->d_offs, offs + done, (m + 1) * sizeof(uint64_t), cudaMemcpyHostToDevice, st));
         /* offsets stay absolute: hand the kernel a base pointer shifted back by the chunk's first offset */
         rc = enqueue_sequences(c, st, (const char*)sl->d_in - c0, sl->d_offs, m, thr, canonical, sl->d_rows, sl->d_u8a);
-        if (rc) return rc;
-        CK(cudaMemcpyAsync(rows + done * rw, sl->d_rows, m * rw * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
-        if (status) CK(cudaMemcpyAsync(status + done, sl->d_u8a, m, cudaMemcpyDeviceToHost, st));
+        if (rc) return drain_ret(c, rc);
+        CKP(cudaMemcpyAsync(rows + done * rw, sl->d_rows, m * rw * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+        if (status) CKP(cudaMemcpyAsync(status + done, sl->d_u8a, m, cudaMemcpyDeviceToHost, st));
         done += m;
         it++;
     }
-    CK(cudaStreamSynchronize(c->streams[0]));
-    CK(cudaStreamSynchronize(c->streams[1]));
+    CKP(cudaStreamSynchronize(c->streams[0]));
+    CKP(cudaStreamSynchronize(c->streams[1]));
     return 0;
 }
 
@@ -823,10 +851,10 @@ extern "C" int bft_b200_query_branching(bft_b200_ctx* c, const uint64_t* kmers, 
     if (!c || (!kmers && n)) return set_err(BFT_B200_ERR_ARG, "bft_b200_query_branching: NULL argument");
     CK(cudaSetDevice(c->device));
     const size_t W = (size_t)c->W;
-    CK(cudaStreamSynchronize(c->streams[0]));
-    CK(cudaStreamSynchronize(c->streams[1]));
-    CK(cudaMemsetAsync(c->d_counter, 0, sizeof(unsigned long long), c->streams[0]));
-    CK(cudaStreamSynchronize(c->streams[0]));
+    CKP(cudaStreamSynchronize(c->streams[0]));
+    CKP(cudaStreamSynchronize(c->streams[1]));
+    CKP(cudaMemsetAsync(c->d_counter, 0, sizeof(unsigned long long), c->streams[0]));
+    CKP(cudaStreamSynchronize(c->streams[0]));
     size_t done = 0;
     int it = 0;
     while (done < n) {
@@ -834,23 +862,23 @@ extern "C" int bft_b200_query_branching(bft_b200_ctx* c, const uint64_t* kmers, 
         const int s = it & 1;
         slot_t* sl = &c->slot[s];
         cudaStream_t st = c->streams[s];
-        CK(cudaStreamSynchronize(st));
-        ENSURE(sl->d_in, sl->cap_in, m * W * 8);
-        ENSURE(sl->d_u8a, sl->cap_u8a, m);
-        ENSURE(sl->d_u8b, sl->cap_u8b, m);
-        CK(cudaMemcpyAsync(sl->d_in, kmers + done * W, m * W * 8, cudaMemcpyHostToDevice, st));
+        CKP(cudaStreamSynchronize(st));
+        ENSUREP(sl->d_in, sl->cap_in, m * W * 8);
+        ENSUREP(sl->d_u8a, sl->cap_u8a, m);
+        ENSUREP(sl->d_u8b, sl->cap_u8b, m);
+        CKP(cudaMemcpyAsync(sl->d_in, kmers + done * W, m * W * 8, cudaMemcpyHostToDevice, st));
         int rc = enqueue_branching(c, st, (const uint64_t*)sl->d_in, m, sl->d_u8a, sl->d_u8b, c->d_counter, NULL);
-        if (rc) return rc;
-        if (succ) CK(cudaMemcpyAsync(succ + done, sl->d_u8a, m, cudaMemcpyDeviceToHost, st));
-        if (pred) CK(cudaMemcpyAsync(pred + done, sl->d_u8b, m, cudaMemcpyDeviceToHost, st));
+        if (rc) return drain_ret(c, rc);
+        if (succ) CKP(cudaMemcpyAsync(succ + done, sl->d_u8a, m, cudaMemcpyDeviceToHost, st));
+        if (pred) CKP(cudaMemcpyAsync(pred + done, sl->d_u8b, m, cudaMemcpyDeviceToHost, st));
         done += m;
         it++;
     }
-    CK(cudaStreamSynchronize(c->streams[0]));
-    CK(cudaStreamSynchronize(c->streams[1]));
+    CKP(cudaStreamSynchronize(c->streams[0]));
+    CKP(cudaStreamSynchronize(c->streams[1]));
     if (n_branching) {
         unsigned long long h = 0;
-        CK(cudaMemcpy(&h, c->d_counter, sizeof h, cudaMemcpyDeviceToHost));
+        CKP(cudaMemcpy(&h, c->d_counter, sizeof h, cudaMemcpyDeviceToHost));
         *n_branching = h;
     }
     return 0;
@@ -866,19 +894,19 @@ extern "C" int bft_b200_query_neighbors(bft_b200_ctx* c, const uint64_t* kmers, 
     if (!c || !nbr || (!kmers && n)) return set_err(BFT_B200_ERR_ARG, "bft_b200_query_neighbors: NULL argument");
     CK(cudaSetDevice(c->device));
     const size_t W = (size_t)c->W;
-    CK(cudaStreamSynchronize(c->streams[0]));
+    CKP(cudaStreamSynchronize(c->streams[0]));
     size_t done = 0;
     while (done < n) {
         const size_t m = n - done < BFT_CHUNK_KMERS ? n - done : BFT_CHUNK_KMERS;
         slot_t* sl = &c->slot[0];
         cudaStream_t st = c->streams[0];
-        ENSURE(sl->d_in, sl->cap_in, m * W * 8);
-        ENSURE(c->d_nbr, c->cap_nbr, m * 8 * sizeof(uint32_t));
-        CK(cudaMemcpyAsync(sl->d_in, kmers + done * W, m * W * 8, cudaMemcpyHostToDevice, st));
+        ENSUREP(sl->d_in, sl->cap_in, m * W * 8);
+        ENSUREP(c->d_nbr, c->cap_nbr, m * 8 * sizeof(uint32_t));
+        CKP(cudaMemcpyAsync(sl->d_in, kmers + done * W, m * W * 8, cudaMemcpyHostToDevice, st));
         int rc = enqueue_branching(c, st, (const uint64_t*)sl->d_in, m, NULL, NULL, NULL, c->d_nbr);
-        if (rc) return rc;
-        CK(cudaMemcpyAsync(nbr + done * 8, c->d_nbr, m * 8 * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
-        CK(cudaStreamSynchronize(st));
+        if (rc) return drain_ret(c, rc);
+        CKP(cudaMemcpyAsync(nbr + done * 8, c->d_nbr, m * 8 * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+        CKP(cudaStreamSynchronize(st));
         done += m;
     }
     return 0;
@@ -1252,22 +1280,22 @@ extern "C" int bft_b200_graph_prepare(bft_b200_ctx* c) {
 extern "C" int bft_b200_query_vertex_ids(bft_b200_ctx* c, const uint64_t* kmers, size_t n, uint32_t* vertex_ids) {
     if (!c || !vertex_ids || (!kmers && n)) return set_err(BFT_B200_ERR_ARG, "bft_b200_query_vertex_ids: NULL argument");
     int rc = bft_b200_graph_prepare(c);
-    if (rc) return rc;
+    if (rc) return drain_ret(c, rc);
     const size_t W = (size_t)c->W;
     cudaStream_t st = c->streams[0];
-    CK(cudaStreamSynchronize(st));
+    CKP(cudaStreamSynchronize(st));
     slot_t* sl = &c->slot[0];
     for (size_t done = 0; done < n;) {
         const size_t m = n - done < BFT_CHUNK_KMERS ? n - done : BFT_CHUNK_KMERS;
-        ENSURE(sl->d_in, sl->cap_in, m * W * 8);
-        ENSURE(sl->d_cls, sl->cap_cls, m * sizeof(uint32_t));
-        CK(cudaMemcpyAsync(sl->d_in, kmers + done * W, m * W * 8, cudaMemcpyHostToDevice, st));
+        ENSUREP(sl->d_in, sl->cap_in, m * W * 8);
+        ENSUREP(sl->d_cls, sl->cap_cls, m * sizeof(uint32_t));
+        CKP(cudaMemcpyAsync(sl->d_in, kmers + done * W, m * W * 8, cudaMemcpyHostToDevice, st));
 #define BFT_L(W_) k_query_vertex_ids<W_><<<grid_for(c, m, BFT_TPB), BFT_TPB, 0, st>>>(c->dview, (const uint64_t*)sl->d_in, m, c->graph.d_loc2vid, (uint32_t*)sl->d_cls)
         BFT_BY_W(c->W, BFT_L);
 #undef BFT_L
         c->launches++;
-        CK(cudaMemcpyAsync(vertex_ids + done, sl->d_cls, m * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
-        CK(cudaStreamSynchronize(st));
+        CKP(cudaMemcpyAsync(vertex_ids + done, sl->d_cls, m * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+        CKP(cudaStreamSynchronize(st));
         done += m;
     }
     return 0;

@@ -33,6 +33,8 @@ typedef struct {
     uint64_t* hv1; /* raw XXH64 per idx14 */
     uint64_t* hv2;
     /* capacities */
+    int64_t hp_off[16]; /* per level: offset of its bit-position table in hpos[], or -1 */
+    size_t cap_hpos;
     size_t cap_nodes, cap_ccs, cap_firstcc, cap_csr, cap_filter3, cap_pref, cap_buckets, cap_ovf, cap_uc_lines, cap_cls_off, cap_cls_bytes;
     /* class hash map */
     /* colour-class dedup: open addressing; a slot carries the hash and (for annotations up to 16 bytes — nearly all
@@ -535,11 +537,33 @@ static uint32_t parse_node(ctx_t* c, int sz, int* cluster_flag) {
     a->n_ccs += n_cc;
     if ((int)n_cc > a->max_cc_per_node) a->max_cc_per_node = (int)n_cc;
 
-    uint32_t fc_off = 0;
+    uint32_t fc_off = 0, bf_mode = 0, bf_stride = 0;
     if (n_cc) {
         const int nbf = CEILDIV(li->modulo_hash, 8);
         uint8_t* bfs = (uint8_t*)tmp_alloc(c, (size_t)n_cc * (size_t)nbf);
         for (uint32_t i = 0; i < n_cc; i++) parse_cc(c, sz, cc_begin + i, bfs + (size_t)i * nbf);
+        if (n_cc <= BFT_BF_DIRECT_MAX) {
+            /* few CCs: keep the Bloom filters themselves (bf_mode 1, see bft_arena.h) */
+            if (c->hp_off[lvl] < 0) { /* this level's bit positions per idx14 (src/presenceNode.c:1341-1350) */
+                GROW(c, a->hpos, c->cap_hpos, a->n_hpos + BFT_N_IDX14, uint32_t);
+                for (uint32_t idx = 0; idx < BFT_N_IDX14; idx++) {
+                    const uint32_t h1 = (uint32_t)(c->hv1[idx] % (uint64_t)li->modulo_hash);
+                    const uint32_t h2 = (uint32_t)(c->hv2[idx] % (uint64_t)li->modulo_hash);
+                    a->hpos[a->n_hpos + idx] = h1 | (h2 << 16);
+                }
+                c->hp_off[lvl] = (int64_t)a->n_hpos;
+                a->n_hpos += BFT_N_IDX14;
+            }
+            const size_t stride = ((size_t)nbf + 3) & ~(size_t)3;
+            if (a->firstcc_bytes + n_cc * stride > 0xfffffff0u) fail(c, "bft_flatten: Bloom filters exceed 4 GiB");
+            GROW(c, a->firstcc, c->cap_firstcc, a->firstcc_bytes + n_cc * stride, uint8_t);
+            fc_off = (uint32_t)a->firstcc_bytes;
+            memset(a->firstcc + fc_off, 0, n_cc * stride);
+            for (uint32_t i = 0; i < n_cc; i++) memcpy(a->firstcc + fc_off + i * stride, bfs + (size_t)i * nbf, (size_t)nbf);
+            a->firstcc_bytes += n_cc * stride;
+            bf_mode = 1;
+            bf_stride = (uint32_t)stride;
+        } else {
         /* first CC whose Bloom filter fires, per 14-bit hash index (src/presenceNode.c:1354-1362) */
         if (a->firstcc_bytes + BFT_N_IDX14 > 0xfffffff0u) fail(c, "bft_flatten: first-CC tables exceed 4 GiB");
         GROW(c, a->firstcc, c->cap_firstcc, a->firstcc_bytes + BFT_N_IDX14, uint8_t);
@@ -556,6 +580,7 @@ static uint32_t parse_node(ctx_t* c, int sz, int* cluster_flag) {
             fc[idx] = hit;
         }
         a->firstcc_bytes += BFT_N_IDX14;
+        }
         tmp_free(c, bfs);
     }
     bft_node_t* nd = &a->nodes[id];
@@ -564,6 +589,9 @@ static uint32_t parse_node(ctx_t* c, int sz, int* cluster_flag) {
     nd->fc_off = fc_off;
     nd->uc_begin = uc_begin;
     nd->uc_n = (uint32_t)n_uc;
+    nd->bf_mode = bf_mode;
+    nd->hp_off = bf_mode ? (uint32_t)c->hp_off[lvl] : 0;
+    nd->bf_stride = bf_stride;
     c->depth--;
     return id;
 }
@@ -574,6 +602,7 @@ void bft_arena_view(const bft_arena_t* a, bft_view_t* v) {
     v->nodes = a->nodes;
     v->ccs = a->ccs;
     v->firstcc = a->firstcc;
+    v->hpos = a->hpos;
     v->csr = a->csr;
     v->filter3 = a->filter3;
     v->pref = a->pref;
@@ -603,7 +632,7 @@ void bft_arena_free(bft_arena_t* a) {
         for (int i = 0; i < a->n_genomes; i++) free(a->filenames[i]);
         free(a->filenames);
     }
-    free(a->rootdir); free(a->nodes); free(a->ccs); free(a->firstcc); free(a->csr); free(a->filter3);
+    free(a->rootdir); free(a->nodes); free(a->ccs); free(a->firstcc); free(a->hpos); free(a->csr); free(a->filter3);
     free(a->pref_low18); free(a->pref_node); free(a->node_path); free(a->pref_out);
     free(a->pref); free(a->buckets); free(a->slotcls); free(a->ovf); free(a->ovfcls); free(a->uckeys); free(a->uccls); free(a->uc_rank); free(a->cls_off); free(a->cls_bytes);
     free(a->pool_last_index); free(a->pool_size_annot); free(a->pool_off); free(a->pool_bytes);
@@ -612,7 +641,7 @@ void bft_arena_free(bft_arena_t* a) {
 
 size_t bft_arena_bytes(const bft_arena_t* a) {
     return BFT_ROOTDIR_SIZE * sizeof(bft_entry_t) + a->n_nodes * sizeof(bft_node_t) + a->n_ccs * sizeof(bft_cc_t) +
-           a->firstcc_bytes + a->n_csr * 2 + a->filter3_bytes + a->n_pref * sizeof(bft_entry_t) +
+           a->firstcc_bytes + a->n_hpos * 4 + a->n_csr * 2 + a->filter3_bytes + a->n_pref * sizeof(bft_entry_t) +
            (a->n_buckets * BFT_BUCKET_KEYS + a->n_ovf) * ((size_t)a->W * 8 + (a->cls_shift ? 0 : 4)) +
            a->n_uc_lines * ((size_t)a->W * 8 + 4) + (a->n_classes + 1) * 4 + a->cls_bytes_len + a->pool_bytes_len +
            a->n_pref * 16 + a->n_nodes * sizeof(bft_path_t);
@@ -624,6 +653,7 @@ bft_arena_t* bft_arena_from_memory(const uint8_t* buf, size_t len, char* err, si
     bft_arena_t* a = (bft_arena_t*)calloc(1, sizeof(bft_arena_t));
     if (!c || !a) { free(c); free(a); if (err) snprintf(err, errlen, "bft_flatten: out of memory"); return NULL; }
     c->buf = buf; c->len = len; c->a = a; c->err = err; c->errlen = errlen;
+    for (int i = 0; i < 16; i++) c->hp_off[i] = -1;
     if (err && errlen) err[0] = 0;
     if (setjmp(c->jb)) {
         for (size_t i = 0; i < c->n_live; i++) free(c->live[i]);
@@ -717,6 +747,7 @@ bft_arena_t* bft_arena_from_memory(const uint8_t* buf, size_t len, char* err, si
     GROW(c, a->pref, c->cap_pref, a->n_pref + 1, bft_entry_t);
     GROW(c, a->ccs, c->cap_ccs, a->n_ccs + 1, bft_cc_t);
     GROW(c, a->firstcc, c->cap_firstcc, a->firstcc_bytes + 1, uint8_t);
+    GROW(c, a->hpos, c->cap_hpos, a->n_hpos + 1, uint32_t);
     if (!a->buckets) {
         a->buckets = (uint64_t*)xrealloc(c, NULL, 8 * BFT_MAX_WORDS * BFT_BUCKET_KEYS);
         a->slotcls = (uint32_t*)xrealloc(c, NULL, 4 * BFT_BUCKET_KEYS);

@@ -17,7 +17,8 @@ typedef struct bft_arena {
     bft_entry_t* rootdir; /* BFT_ROOTDIR_SIZE */
     bft_node_t* nodes;   size_t n_nodes;
     bft_cc_t* ccs;       size_t n_ccs;
-    uint8_t* firstcc;    size_t firstcc_bytes;
+    uint8_t* firstcc;    size_t firstcc_bytes; /* first-CC tables and, for Nodes with few CCs, their Bloom filters */
+    uint32_t* hpos;      size_t n_hpos;        /* Bloom-filter bit positions per idx14, one table per trie level in use */
     uint16_t* csr;       size_t n_csr;
     uint8_t* filter3;    size_t filter3_bytes;
     bft_entry_t* pref;   size_t n_pref;

@@ -2,7 +2,7 @@
 """Build (with the UNMODIFIED reference, oracle/_ref/bft) and cache under data/ the BFTs of the BASELINE configs.
 Bench/test infrastructure; run in this container only (the GPU box receives the cached files).
 
-  python tools/build_bench_data.py c1 c2 c3 c4 c5      # any subset
+  python tools/build_bench_data.py c1 c2 c3 c4 c5 deep      # any subset
 """
 import os
 import sys
@@ -17,6 +17,7 @@ SPECS = {
     "c3": (wl.C3, 27, 5_000_000),
     "c4": (wl.C3, 63, 5_000_000),
     "c5": (wl.C5, 27, 500_000),
+    "deep": (wl.DEEP, 63, 4_500_000),
 }
 
 if __name__ == "__main__":
