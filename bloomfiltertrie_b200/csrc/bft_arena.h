@@ -219,21 +219,43 @@ BFT_HD void bft_ld_bucket(const uint64_t* p, uint64_t* out, const int W) {
 }
 
 /* ---- stored-k-mer filter ---------------------------------------------------------------------------------------
- * h = 64-bit mix of the k-mer words; block = high 32 bits range-reduced to kf_blocks; bit j of word j = 6 bits of h. */
-BFT_HD uint64_t bft_kf_hash(const uint64_t* kmer, const int W) {
-    uint64_t x = kmer[0];
-    for (int w = 1; w < W; w++) x = (x ^ (x >> 29)) * 0x9FB21C651E98DF25ULL + kmer[w];
+ * The BLOCK of a k-mer is chosen by a hash of its middle k-2 nucleotides (first and last dropped); the four bit
+ * positions inside the block by a hash of that plus the two end nucleotides. The four successors of a k-mer differ
+ * only in their last nucleotide and its four predecessors only in their first, so the eight neighbour look-ups of a
+ * branching query (k_query_branching, k_graph_adjacency) read TWO filter blocks — two L2 sectors — instead of eight. */
+typedef struct { uint32_t block; uint32_t b0, b1, b2, b3; } bft_kf_pos_t;
+
+BFT_HD bft_kf_pos_t bft_kf_pos(const uint64_t* kmer, const int W, const int k, const uint32_t n_blocks) {
+    /* middle = (kmer >> 2) without its top nucleotide */
+    uint64_t x = 0;
+    const int mid_bits = 2 * (k - 2);
+    for (int w = 0; w < W; w++) {
+        uint64_t m = kmer[w] >> 2;
+        if (w + 1 < W) m |= kmer[w + 1] << 62;
+        const int b = mid_bits - 64 * w;
+        if (b < 64) m &= b <= 0 ? 0ULL : ((1ULL << b) - 1ULL);
+        x = w == 0 ? m : (x ^ (x >> 29)) * 0x9FB21C651E98DF25ULL + m;
+    }
     x ^= x >> 33; x *= 0xFF51AFD7ED558CCDULL;
     x ^= x >> 33; x *= 0xC4CEB9FE1A85EC53ULL;
     x ^= x >> 33;
-    return x;
+    const int top = 2 * (k - 1);
+    const uint64_t ends = (kmer[0] & 3ULL) | (((kmer[top >> 6] >> (top & 63)) & 3ULL) << 2);
+    uint64_t y = (x ^ ((ends + 1ULL) * 0xD6E8FEB86659FD93ULL)) * 0x9E3779B97F4A7C15ULL;
+    y ^= y >> 29;
+    bft_kf_pos_t p;
+    p.block = (uint32_t)(((x >> 32) * (uint64_t)n_blocks) >> 32);
+    p.b0 = (uint32_t)(y >> 58);
+    p.b1 = (uint32_t)(y >> 52) & 63u;
+    p.b2 = (uint32_t)(y >> 46) & 63u;
+    p.b3 = (uint32_t)(y >> 40) & 63u;
+    return p;
 }
-BFT_HD uint32_t bft_kf_block(uint64_t h, uint32_t n_blocks) { return (uint32_t)(((h >> 32) * (uint64_t)n_blocks) >> 32); }
 
 /* 1: the k-mer may be stored; 0: it is certainly not */
 BFT_HD int bft_kf_test(const bft_view_t* v, const uint64_t* kmer, const int W) {
-    const uint64_t h = bft_kf_hash(kmer, W);
-    const uint64_t* p = v->kfilter + (size_t)bft_kf_block(h, v->kf_blocks) * 4;
+    const bft_kf_pos_t q = bft_kf_pos(kmer, W, v->k, v->kf_blocks);
+    const uint64_t* p = v->kfilter + (size_t)q.block * 4;
     uint64_t w0, w1, w2, w3;
 #ifdef __CUDA_ARCH__
     /* one 32-byte sector, kept in L2 (evict-last) */
@@ -241,7 +263,7 @@ BFT_HD int bft_kf_test(const bft_view_t* v, const uint64_t* kmer, const int W) {
 #else
     w0 = p[0]; w1 = p[1]; w2 = p[2]; w3 = p[3];
 #endif
-    return (int)(((w0 >> (h & 63)) & (w1 >> ((h >> 6) & 63)) & (w2 >> ((h >> 12) & 63)) & (w3 >> ((h >> 18) & 63))) & 1ULL);
+    return (int)(((w0 >> q.b0) & (w1 >> q.b1) & (w2 >> q.b2) & (w3 >> q.b3)) & 1ULL);
 }
 
 /* index of the first CC of a Node whose Bloom filter fires for idx14, or BFT_FIRSTCC_NONE (src/presenceNode.c:1354-1362) */
@@ -427,19 +449,35 @@ BFT_HD uint32_t bft_ceil_log2p1(uint32_t n) { /* ceil(log2(n + 1)) */
     return b;
 }
 
+/* flags of bft_lookup_loc */
+#define BFT_LK_SUCC_QUIRK 1   /* reproduce presenceNeighborsRight at the leaf level (see bft_node_probe_ex) */
+#define BFT_LK_FILTER_FIRST 2 /* test the stored-k-mer filter BEFORE fetching the root directory entry: for look-ups that mostly
+                               * miss (the 8 neighbours of a branching query); otherwise both loads are issued back to back */
+
+#define BFT_LK_NO_FILTER 4    /* skip the stored-k-mer filter: for look-ups known to mostly hit (see k_query_sequences) */
+
 /* loc (optional): receives the storage location of the k-mer when it is found (see bft_view_t). */
-BFT_HD uint32_t bft_lookup_loc(const bft_view_t* v, const uint64_t* kmer, const int W, const int succ_leaf_quirk, uint32_t* st, uint32_t* loc) {
+BFT_HD uint32_t bft_lookup_loc(const bft_view_t* v, const uint64_t* kmer, const int W, const int flags, uint32_t* st, uint32_t* loc) {
+    const int succ_leaf_quirk = flags & BFT_LK_SUCC_QUIRK;
     uint64_t cur[BFT_MAX_WORDS];
     for (int w = 0; w < BFT_MAX_WORDS; w++) cur[w] = w < W ? kmer[w] : 0;
     int sz = v->k;
     uint32_t pref_idx = 0;
     bft_entry_t e;
+    const int filtered = v->kf_blocks && !(flags & BFT_LK_NO_FILTER) && (!succ_leaf_quirk || v->kf_quirk_safe);
+    int rejected = 0; /* statistics mode only: the product path stops at a rejection */
+    if (filtered && (flags & BFT_LK_FILTER_FIRST)) {
+        if (!bft_kf_test(v, kmer, W)) {
+            if (!st) return BFT_CLS_NONE;
+            rejected = 1;
+            st[6]++;
+        }
+    }
     /* a 9-mer trie keeps its k-mers as leaf prefixes of the root: rootdir holds the entry but not its index */
     if (loc && sz == BFT_NB_CHAR_SUF_PREF) e = bft_node_probe_ex(v, 0, (uint32_t)cur[0] & (BFT_ROOTDIR_SIZE - 1u), 0, &pref_idx);
     else e = bft_ld_entry(v->rootdir + ((uint32_t)cur[0] & (BFT_ROOTDIR_SIZE - 1u)));
     /* the filter block is fetched right behind the root entry (two independent L2 loads in flight) */
-    int rejected = 0; /* statistics mode only: the product path stops at a rejection */
-    if (v->kf_blocks && (!succ_leaf_quirk || v->kf_quirk_safe)) {
+    if (filtered && !(flags & BFT_LK_FILTER_FIRST)) {
         if (!bft_kf_test(v, kmer, W)) {
             if (!st) return BFT_CLS_NONE;
             rejected = 1;
@@ -479,8 +517,8 @@ BFT_HD uint32_t bft_lookup_loc(const bft_view_t* v, const uint64_t* kmer, const 
     }
 }
 
-BFT_HD uint32_t bft_lookup_ex(const bft_view_t* v, const uint64_t* kmer, const int W, const int succ_leaf_quirk, uint32_t* st) {
-    return bft_lookup_loc(v, kmer, W, succ_leaf_quirk, st, (uint32_t*)0);
+BFT_HD uint32_t bft_lookup_ex(const bft_view_t* v, const uint64_t* kmer, const int W, const int flags, uint32_t* st) {
+    return bft_lookup_loc(v, kmer, W, flags, st, (uint32_t*)0);
 }
 
 BFT_HD uint32_t bft_lookup_w(const bft_view_t* v, const uint64_t* kmer, const int W) { return bft_lookup_ex(v, kmer, W, 0, (uint32_t*)0); }

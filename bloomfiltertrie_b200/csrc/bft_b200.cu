@@ -214,7 +214,7 @@ static int build_kfilter(bft_b200_ctx* c, size_t n_kmers, unsigned long long* d_
     c->stats.n_kmers = n_kmers; /* enqueue_extract sizes nothing by it, but keep the context coherent */
     int rc = enqueue_extract(c, d_k, NULL, NULL);
     if (!rc) {
-#define BFT_L(W_) k_kf_insert<W_><<<grid_for(c, n_kmers, BFT_TPB), BFT_TPB, 0, c->streams[0]>>>(d_k, n_kmers, d_filter, n_blocks)
+#define BFT_L(W_) k_kf_insert<W_><<<grid_for(c, n_kmers, BFT_TPB), BFT_TPB, 0, c->streams[0]>>>(d_k, n_kmers, c->k, d_filter, n_blocks)
         BFT_BY_W(c->W, BFT_L);
 #undef BFT_L
         c->launches++;
@@ -755,6 +755,61 @@ extern "C" int bft_b200_class_counts(bft_b200_ctx* c, const uint32_t** counts, u
     }
     *counts = c->h_class_counts;
     if (n_classes) *n_classes = c->n_classes;
+    return 0;
+}
+
+/* ---- annotation set algebra ----------------------------------------------------------------------------------------- */
+extern "C" int bft_b200_annotation_setop_device(bft_b200_ctx* c, int op, const uint32_t* d_class_ids, const uint64_t* d_group_offs, size_t n_groups,
+                                                uint32_t* d_rows, uint32_t* d_counts) {
+    if (!c || (n_groups && (!d_class_ids || !d_group_offs)) || (!d_rows && !d_counts)) return set_err(BFT_B200_ERR_ARG, "bft_b200_annotation_setop_device: NULL argument");
+    if (op < 0 || op > 2) return set_err(BFT_B200_ERR_ARG, "bft_b200_annotation_setop: op %d is not BFT_B200_SET_INTERSECTION / _UNION / _SYM_DIFFERENCE", op);
+    CK(cudaSetDevice(c->device));
+    if (!n_groups) return 0;
+    cudaStream_t st = c->streams[0];
+    if (d_counts && c->rw > 1) CK(cudaMemsetAsync(d_counts, 0, n_groups * sizeof(uint32_t), st));
+    k_annotation_setop<<<grid_for(c, n_groups * (size_t)c->rw, BFT_TPB), BFT_TPB, 0, st>>>(c->d_class_rows, c->rw, d_class_ids, d_group_offs, n_groups, op, d_rows, d_counts);
+    c->launches++;
+    CK(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int bft_b200_annotation_setop(bft_b200_ctx* c, int op, const uint32_t* class_ids, const uint64_t* group_offs, size_t n_groups, uint32_t* rows,
+                                         uint32_t* counts) {
+    if (!c || (n_groups && (!class_ids || !group_offs)) || (!rows && !counts)) return set_err(BFT_B200_ERR_ARG, "bft_b200_annotation_setop: NULL argument");
+    if (op < 0 || op > 2) return set_err(BFT_B200_ERR_ARG, "bft_b200_annotation_setop: op %d is not BFT_B200_SET_INTERSECTION / _UNION / _SYM_DIFFERENCE", op);
+    if (!n_groups) return 0;
+    for (size_t g = 0; g < n_groups; g++)
+        if (group_offs[g + 1] < group_offs[g]) return set_err(BFT_B200_ERR_ARG, "bft_b200_annotation_setop: group offsets must be non-decreasing");
+    const size_t n_ids = (size_t)(group_offs[n_groups] - group_offs[0]);
+    for (size_t i = 0; i < n_ids; i++) {
+        const uint32_t id = class_ids[group_offs[0] + i];
+        if (id != BFT_CLS_NONE && id >= c->n_classes) return set_err(BFT_B200_ERR_ARG, "bft_b200_annotation_setop: class id %u out of range (%zu classes)", id, c->n_classes);
+    }
+    CK(cudaSetDevice(c->device));
+    cudaStream_t st = c->streams[0];
+    CK(cudaStreamSynchronize(st));
+    slot_t* sl = &c->slot[0];
+    const size_t rw = (size_t)c->rw;
+    /* groups in chunks bounded by ids and by groups, so the device buffers stay small */
+    size_t g0 = 0;
+    while (g0 < n_groups) {
+        size_t g1 = g0;
+        while (g1 < n_groups && g1 - g0 < BFT_CHUNK_KMERS && (g1 == g0 || group_offs[g1 + 1] - group_offs[g0] <= 4 * BFT_CHUNK_KMERS)) g1++;
+        const size_t m = g1 - g0, ids = (size_t)(group_offs[g1] - group_offs[g0]);
+        ENSUREP(sl->d_cls, sl->cap_cls, (ids + 1) * sizeof(uint32_t));
+        ENSUREP(sl->d_offs, sl->cap_offs, (m + 1) * sizeof(uint64_t));
+        ENSUREP(sl->d_rows, sl->cap_rows, m * rw * sizeof(uint32_t));
+        ENSUREP(sl->d_tile, sl->cap_tile, m * sizeof(uint32_t));
+        if (ids) CKP(cudaMemcpyAsync(sl->d_cls, class_ids + group_offs[g0], ids * sizeof(uint32_t), cudaMemcpyHostToDevice, st));
+        CKP(cudaMemcpyAsync(sl->d_offs, group_offs + g0, (m + 1) * sizeof(uint64_t), cudaMemcpyHostToDevice, st));
+        /* offsets stay absolute: hand the kernel the id array shifted back by the chunk's first offset */
+        int rc = bft_b200_annotation_setop_device(c, op, sl->d_cls - group_offs[g0], sl->d_offs, m, rows ? sl->d_rows : NULL, counts ? sl->d_tile : NULL);
+        if (rc) return drain_ret(c, rc);
+        if (rows) CKP(cudaMemcpyAsync(rows + g0 * rw, sl->d_rows, m * rw * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+        if (counts) CKP(cudaMemcpyAsync(counts + g0, sl->d_tile, m * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+        CKP(cudaStreamSynchronize(st));
+        g0 = g1;
+    }
     return 0;
 }
 

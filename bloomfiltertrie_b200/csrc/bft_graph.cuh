@@ -57,7 +57,7 @@ __global__ void __launch_bounds__(BFT_TPB) k_graph_adjacency(const bft_view_t v,
         for (int w = 0; w < W; w++) x[w] = vk[q * W + w];
         bft_neighbor_kmer<W>(x, v.k, sub, y);
         uint32_t loc = 0;
-        const uint32_t cls = bft_lookup_loc(&v, y, W, 0, (uint32_t*)0, &loc);
+        const uint32_t cls = bft_lookup_loc(&v, y, W, BFT_LK_FILTER_FIRST, (uint32_t*)0, &loc);
         adj[q * 8 + (sub < 4 ? 4 + sub : sub - 4)] = cls != BFT_CLS_NONE ? __ldg(loc2vid + loc) : BFT_V_NONE;
     }
 }

@@ -416,6 +416,36 @@ __global__ void __launch_bounds__(BFT_TPB) k_expand_rows_v4(const uint32_t* __re
     }
 }
 
+/* Annotation set algebra, batched (intersection_/union_/sym_difference_annotations, src/bft.c:421-613, which fold cmp_annots,
+ * src/annotation.c:2358-2552, over their arguments from left to right): group g combines the colour rows of the classes
+ * cls[offs[g] .. offs[g+1]) word by word. One thread per (group, row word); the per-group genome count (get_count_id_genomes
+ * of the result) is accumulated with one atomic per word. A class id of BFT_CLS_NONE (an absent k-mer) is the empty set. */
+__global__ void __launch_bounds__(BFT_TPB) k_annotation_setop(const uint32_t* __restrict__ class_rows, int rw, const uint32_t* __restrict__ cls,
+                                                              const uint64_t* __restrict__ offs, size_t n_groups, int op,
+                                                              uint32_t* __restrict__ rows, uint32_t* __restrict__ counts) {
+    const size_t total = n_groups * (size_t)rw;
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += stride) {
+        const size_t g = t / (size_t)rw;
+        const int w = (int)(t - g * (size_t)rw);
+        const uint64_t b = offs[g], e = offs[g + 1];
+        uint32_t acc = 0;
+        for (uint64_t i = b; i < e; i++) {
+            const uint32_t c = __ldg(cls + i);
+            const uint32_t x = c == BFT_CLS_NONE ? 0u : __ldg(class_rows + (size_t)c * rw + w);
+            if (i == b) acc = x;
+            else if (op == 0) acc &= x;
+            else if (op == 1) acc |= x;
+            else acc ^= x;
+        }
+        if (rows) rows[t] = acc;
+        if (counts) {
+            if (rw == 1) counts[g] = (uint32_t)__popc(acc);
+            else if (acc) atomicAdd(counts + g, (uint32_t)__popc(acc));
+        }
+    }
+}
+
 /* a9/a10: decode every distinct annotation once (get_id_genomes_from_annot, src/annotation.c:2086-2250) */
 __global__ void __launch_bounds__(BFT_TPB) k_decode_classes(const uint32_t* __restrict__ cls_off, const uint8_t* __restrict__ cls_bytes,
                                                             size_t n_classes, const bft_pools_t pools, uint32_t* __restrict__ rows,
@@ -479,19 +509,19 @@ __global__ void __launch_bounds__(BFT_TPB) k_blank_invalid(const uint8_t* __rest
 
 /* Build of the stored-k-mer filter (bft_arena.h): every stored k-mer, as enumerated by k_extract_*, sets its four bits. */
 template <int W>
-__global__ void __launch_bounds__(BFT_TPB) k_kf_insert(const uint64_t* __restrict__ kmers, size_t n, unsigned long long* __restrict__ filter,
+__global__ void __launch_bounds__(BFT_TPB) k_kf_insert(const uint64_t* __restrict__ kmers, size_t n, int k, unsigned long long* __restrict__ filter,
                                                        uint32_t n_blocks) {
     const size_t stride = (size_t)gridDim.x * blockDim.x;
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
         uint64_t km[W];
 #pragma unroll
         for (int w = 0; w < W; w++) km[w] = kmers[i * W + w];
-        const uint64_t h = bft_kf_hash(km, W);
-        unsigned long long* p = filter + (size_t)bft_kf_block(h, n_blocks) * 4;
-        atomicOr(p + 0, 1ULL << (h & 63));
-        atomicOr(p + 1, 1ULL << ((h >> 6) & 63));
-        atomicOr(p + 2, 1ULL << ((h >> 12) & 63));
-        atomicOr(p + 3, 1ULL << ((h >> 18) & 63));
+        const bft_kf_pos_t q = bft_kf_pos(km, W, k, n_blocks);
+        unsigned long long* p = filter + (size_t)q.block * 4;
+        atomicOr(p + 0, 1ULL << q.b0);
+        atomicOr(p + 1, 1ULL << q.b1);
+        atomicOr(p + 2, 1ULL << q.b2);
+        atomicOr(p + 3, 1ULL << q.b3);
     }
 }
 
@@ -691,7 +721,7 @@ __global__ void __launch_bounds__(BFT_TPB) k_query_branching(const bft_view_t v,
                 for (int w = 0; w < W; w++) y[w] &= bft_word_mask(2 * k, w);
             }
             /* the reference's successor search deviates from set membership at the leaf level; see bft_node_probe */
-            const uint32_t cls = bft_lookup_ex(&v, y, W, ref_quirks && sub < 4, (uint32_t*)0);
+            const uint32_t cls = bft_lookup_ex(&v, y, W, ((ref_quirks && sub < 4) ? BFT_LK_SUCC_QUIRK : 0) | BFT_LK_FILTER_FIRST, (uint32_t*)0);
             hit = cls != BFT_CLS_NONE;
             if (nbr_cls) nbr_cls[q * 8 + (sub < 4 ? 4 + sub : sub - 4)] = cls; /* get_neighbors order: 0-3 pred, 4-7 succ */
         }
@@ -824,6 +854,10 @@ __global__ void __launch_bounds__(32 * BFT_SEQ_WARPS) k_query_sequences(const bf
         const long long n_win = len - k + 1;
         for (int g = lane; g < n_counts; g += 32) counts[g] = 0;
         int bad = 0;
+        /* The stored-k-mer filter pays for look-ups that miss. A read of an organism in the graph hits on nearly every
+         * window, and this kernel is issue-bound, so the filter's hash and L2 load would be pure overhead there: the first
+         * 32 windows of a sequence are looked up without it, and it is switched on for the rest only if most of them missed. */
+        int lk_flags = BFT_LK_NO_FILTER;
         __syncwarp();
         for (long long t0 = 0; t0 < n_win; t0 += BFT_SEQ_TILE) {
             const int n_here = (int)(n_win - t0 < BFT_SEQ_TILE ? n_win - t0 : BFT_SEQ_TILE); /* windows in this tile */
@@ -913,8 +947,13 @@ __global__ void __launch_bounds__(32 * BFT_SEQ_WARPS) k_query_sequences(const bf
                                 for (int w = 0; w < W; w++) x[w] = ~rx[w] & bft_word_mask(2 * k, w);
                             }
                         }
-                        cls = bft_lookup_w(&v, x, W);
+                        cls = bft_lookup_ex(&v, x, W, lk_flags, (uint32_t*)0);
                     }
+                }
+                if (t0 == 0 && j0 == 0) {
+                    const uint32_t looked = __ballot_sync(0xffffffffu, j < n_here);
+                    const uint32_t found = __ballot_sync(0xffffffffu, cls != BFT_CLS_NONE);
+                    if (2 * __popc(found) < __popc(looked)) lk_flags = 0;
                 }
                 /* merge windows with the same colour class, then bump the per-genome counters warp-wide */
                 const uint32_t active = __ballot_sync(0xffffffffu, cls != BFT_CLS_NONE);

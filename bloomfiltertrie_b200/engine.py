@@ -33,7 +33,7 @@ ABI_SYMBOLS = [
     "bft_b200_graph_prepare", "bft_b200_graph_release", "bft_b200_graph_adjacency", "bft_b200_connected_components",
     "bft_b200_simple_paths", "bft_b200_simple_paths_file", "bft_b200_free", "bft_b200_query_vertex_ids",
     "bft_b200_record_bytes", "bft_b200_row_bytes", "bft_b200_query_records", "bft_b200_query_records_device",
-    "bft_b200_query_records_compact",
+    "bft_b200_query_records_compact", "bft_b200_annotation_setop", "bft_b200_annotation_setop_device",
 ]
 
 
@@ -108,6 +108,8 @@ def load_library() -> C.CDLL:
     lib.bft_b200_query_records.argtypes = [vp, u8p, sz, u8p, u8p, C.POINTER(C.c_uint64)]
     lib.bft_b200_query_records_device.argtypes = [vp, u8p, sz, u8p, u8p, u64p]
     lib.bft_b200_query_records_compact.argtypes = [vp, u8p, sz, u8p, u8p, C.POINTER(C.c_uint64)]
+    lib.bft_b200_annotation_setop.argtypes = [vp, C.c_int, u32p, u64p, sz, u32p, u32p]
+    lib.bft_b200_annotation_setop_device.argtypes = [vp, C.c_int, u32p, u64p, sz, u32p, u32p]
     lib.bft_b200_graph_prepare.argtypes = [vp]
     lib.bft_b200_graph_release.argtypes = [vp]
     lib.bft_b200_graph_adjacency.argtypes = [vp, u32p, sz]
@@ -291,6 +293,24 @@ class BFTEngine:
         self._ck(self.lib.bft_b200_class_counts(self.h, C.byref(p), C.byref(n)), "bft_b200_class_counts")
         buf = (C.c_uint32 * n.value).from_address(p.value)
         return np.frombuffer(buf, dtype=np.uint32).copy()
+
+    SET_INTERSECTION, SET_UNION, SET_SYM_DIFFERENCE = 0, 1, 2
+
+    def annotation_setop(self, op: int, class_ids: np.ndarray, group_offs: np.ndarray):
+        """intersection / union / symmetric difference of the colour sets of groups of classes (host arrays):
+        (rows uint32 [n_groups, RW], genome counts uint32 [n_groups])."""
+        class_ids = np.ascontiguousarray(class_ids, dtype=np.uint32)
+        group_offs = np.ascontiguousarray(group_offs, dtype=np.uint64)
+        n = len(group_offs) - 1
+        rows = np.empty((n, self.RW), dtype=np.uint32)
+        counts = np.empty(n, dtype=np.uint32)
+        self._ck(self.lib.bft_b200_annotation_setop(self.h, int(op), _ptr(class_ids), _ptr(group_offs), n, _ptr(rows), _ptr(counts)),
+                 "bft_b200_annotation_setop")
+        return rows, counts
+
+    def annotation_setop_device(self, op: int, d_class_ids, d_group_offs, n_groups: int, d_rows=None, d_counts=None):
+        self._ck(self.lib.bft_b200_annotation_setop_device(self.h, int(op), _ptr(d_class_ids), _ptr(d_group_offs), n_groups, _ptr(d_rows),
+                                                           _ptr(d_counts)), "bft_b200_annotation_setop_device")
 
     def kmer_walk_stats_device(self, d_kmers, n: int) -> dict:
         out = (C.c_uint64 * 8)()

@@ -110,6 +110,21 @@ int bft_b200_class_rows(bft_b200_ctx* ctx, const uint32_t** rows, uint64_t* n_cl
 /* get_count_id_genomes (include/bft.h:116): number of genomes per class (host copy owned by ctx) */
 int bft_b200_class_counts(bft_b200_ctx* ctx, const uint32_t** counts, uint64_t* n_classes);
 
+/* ---- annotation set algebra -------------------------------------------------------------------------------------
+ * Batch form of intersection_annotations / union_annotations / sym_difference_annotations (include/bft.h:99-113,
+ * src/bft.c:421-613, which fold cmp_annots, src/annotation.c:2358-2552, over their arguments from left to right):
+ * group g combines the colour sets of the classes class_ids[group_offs[g] .. group_offs[g+1]) (ids as returned by the
+ * query calls; 0xffffffff = the empty set of an absent k-mer). rows: n_groups*RW bitmap words, counts: n_groups genome
+ * counts (get_count_id_genomes of the result); either may be NULL. An empty group yields the empty set (the reference
+ * exit(1)s on "no annotations given"). */
+#define BFT_B200_SET_INTERSECTION 0
+#define BFT_B200_SET_UNION 1
+#define BFT_B200_SET_SYM_DIFFERENCE 2
+int bft_b200_annotation_setop(bft_b200_ctx* ctx, int op, const uint32_t* class_ids, const uint64_t* group_offs,
+                              size_t n_groups, uint32_t* rows, uint32_t* counts);
+int bft_b200_annotation_setop_device(bft_b200_ctx* ctx, int op, const uint32_t* d_class_ids, const uint64_t* d_group_offs,
+                                     size_t n_groups, uint32_t* d_rows, uint32_t* d_counts);
+
 /* ---- sequences ------------------------------------------------------------------------------------------------
  * Batch form of query_sequence (include/bft.h:127, src/bft.c:1241-1351) / query_sequences_outputCSV
  * (src/file_io.c:1464-1574): sequence i = chars[offs[i] .. offs[i+1]). For every window: optional canonical pick
