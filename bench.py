@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """bench.py — k-mers queried/sec on the 100-genome synthetic pan-genome BFT (BASELINE.json metric, config[2];
 k=27 stands in for "k=31": the reference only accepts k divisible by 9), with the other four BASELINE
-configs measured in the same run as sub-records (`configs`: c1, c2, c4, c5).
+configs measured in the same run as sub-records (`configs`: c1, c2, c4, c5) plus one forced-deep trie (`deep`).
 
   python bench.py [--gpus N] [--steps K] [--warmup W]          engine arm (one process per GPU; torchrun for N>1)
   python bench.py --impl reference [...]                       reference arm: the unmodified reference's CPU query
@@ -165,6 +165,10 @@ def specs():
                    workload="c4: -query_branching at k=63 on the 100-genome BFT (value counts query k-mers; 8 neighbour look-ups each)"),
         "c5": dict(kind="kmers", cfg=wl.C5, k=27, L=500_000, fallback_L=100_000, queries=100_000_000,
                    workload="c5: colour-set retrieval for 100 M k-mers on the 1000-colour pan-genome BFT (compressed annotations)"),
+        # not a BASELINE config: the per-level path of the walk, 3-4 Nodes per look-up
+        "deep": dict(kind="kmers", cfg=wl.DEEP, k=63, L=0, queries=30_000_000,
+                     workload="deep: -query_kmers on a forced-deep trie (6 M random 63-mers with pooled 9-nt blocks, 16 921 Nodes, 4 levels); "
+                              "queries 1/3 members, 1/3 one-mismatch, 1/3 random"),
     }
 
 
@@ -348,10 +352,15 @@ def kmers_record(run: Run, tag: str, spec: dict, headline: bool):
     n = args.queries_per_gpu if (headline and args.queries_per_gpu) else spec["queries"]
     steps, warmup = (args.steps, args.warmup) if headline else (args.sub_steps, 3)
     eng, st, bft, L, degraded = run.open(spec, headline)
-    genomes = wl.pangenome(cfg, L)
-    cat, starts, lens = wl.genomes_to_torch(genomes, run.dev)
-    q, q_kind = wl.gen_kmer_queries(cat, starts, lens, k, n, seed=1000 + run.rank, mix=MIX)
-    del cat
+    if cfg.get("pools"):
+        words, _ = wl.kmer_sets(cfg, k)
+        q, q_kind = wl.gen_set_queries(words, k, n, 1000 + run.rank, run.dev)
+        del words
+    else:
+        genomes = wl.pangenome(cfg, L)
+        cat, starts, lens = wl.genomes_to_torch(genomes, run.dev)
+        q, q_kind = wl.gen_kmer_queries(cat, starts, lens, k, n, seed=1000 + run.rank, mix=MIX)
+        del cat
     torch.cuda.empty_cache()
     RW, W = eng.RW, eng.W
     dev = run.dev
@@ -504,7 +513,9 @@ def kmers_record(run: Run, tag: str, spec: dict, headline: bool):
            "config": {"workload": spec["workload"], "k": k, "k_note": "reference accepts only k % 9 == 0; 27 stands in for 31" if k == 27 else None,
                       "n_genomes": cfg["n_genomes"], "genome_len": L, "degraded": degraded, "kmers_in_bft": st["n_kmers"], "nodes": st["n_nodes"],
                       "colour_classes": st["n_classes"], "arena_mb": round(st["arena_bytes"] / 1e6, 1), "filter_mb": round(st["filter_bytes"] / 1e6, 1),
-                      "queries_per_gpu": n, "query_mix_present_mismatch_random": MIX, "present_frac": n_present / n,
+                      "arena_bytes_per_kmer": round(st["arena_bytes"] / max(1, st["n_kmers"]), 1), "nodes_per_lookup": nodes_pk,
+                      "queries_per_gpu": n, "query_mix_present_mismatch_random": (1 / 3, 1 / 3, 1 / 3) if cfg.get("pools") else MIX,
+                      "present_frac": n_present / n,
                       "l2": ("256 MB written between steps (batch smaller than L2); one event pair per step" if flush
                              else "inputs larger than L2 (no flush needed)"),
                       "sharding": f"arena replicated, queries sharded x{run.world}; hit count reduced inside the kernel (peer-mapped counter)"},
@@ -848,9 +859,9 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="engine", choices=["engine", "reference"])
-    ap.add_argument("--config", default="c3", choices=["c1", "c2", "c3", "c4", "c5"],
+    ap.add_argument("--config", default="c3", choices=["c1", "c2", "c3", "c4", "c5", "deep"],
                     help="the config reported as the main line (default c3 = BASELINE config[2], the headline metric)")
-    ap.add_argument("--sub", default=None, help="comma-separated configs measured as sub-records (default: c1,c2,c4,c5 when --config c3)")
+    ap.add_argument("--sub", default=None, help="comma-separated configs measured as sub-records (default: c1,c2,c4,c5,deep when --config c3)")
     ap.add_argument("--sub-steps", type=int, default=5, help="timed steps of every sub-record")
     ap.add_argument("--genome-len", type=int, default=0, help="development only: override the genome length of the main config")
     ap.add_argument("--queries-per-gpu", type=int, default=0, help="override the k-mers per GPU per step of the main config")
@@ -864,7 +875,7 @@ def main():
     if args.warmup < 3:
         args.warmup = 3
     if args.sub is None:
-        args.sub = "c1,c2,c4,c5" if args.config == "c3" else ""
+        args.sub = "c1,c2,c4,c5,deep" if args.config == "c3" else ""
     if args.workload == "graph":
         graph_workload(args)
     elif args.impl == "reference":

@@ -32,22 +32,23 @@ C5 = dict(name="c5_g1000", n_genomes=1000, snp=0.002, indel=0.0002, seed=54321, 
 C2 = dict(name="c2_g16_canon", n_genomes=16, snp=0.005, indel=0.0005, seed=2345, tree=False, canonical=True)
 
 
-# forced-deep trie (not a BASELINE config): genomes spelled from a vocabulary of 24 random 9-mers, so a few
-# thousand 9-nt prefixes carry hundreds of suffixes each and burst into child Nodes, several levels deep, while consecutive
-# windows are still true de Bruijn neighbours. 8 genomes (founder + 7 strains at 0.3 % SNPs), k = 63.
-DEEP = dict(name="deep_g8_v24", n_genomes=8, snp=0.003, indel=0.0, seed=77, tree=False, vocab=24)
+# forced-deep trie (not a BASELINE config): random 63-mers whose first three 9-nt blocks are drawn from pools of
+# 120, 20 and 6 blocks, so every 9-nt prefix carries far more than 255 suffixes and the reference bursts it into child Nodes, four
+# levels deep: 6 M k-mers, 16 921 Nodes. (Repeat-rich GENOMES of the same size make the reference's own insertion lose 1-3 % of the
+# k-mers it stores — it then cannot find them itself — and the serializer refuses such files; this set is one it builds consistently.)
+DEEP = dict(name="deep_g8_p120-20-6", n_genomes=8, seed=93, pools=(120, 20, 6), n_kmers=6_000_000)
 
 
 def log(*a):
     print("[workloads]", *a, file=sys.stderr, flush=True)
 
 
+def kmer_sets(cfg: dict, k: int):
+    """Pool-based k-mer sets of a forced-deep config: (all distinct k-mers [n, W], per-genome subsets)."""
+    return synth.deep_kmer_sets(k, cfg["n_kmers"], cfg["n_genomes"], cfg["seed"], pool_sizes=cfg["pools"], membership=0.5)
+
+
 def pangenome(cfg: dict, genome_len: int) -> List[np.ndarray]:
-    if cfg.get("vocab"):
-        rng = np.random.default_rng(cfg["seed"])
-        words9 = rng.integers(0, 4, size=(cfg["vocab"], 9), dtype=np.uint8)
-        founder = words9[rng.integers(0, cfg["vocab"], size=genome_len // 9)].reshape(-1)
-        return [founder] + [synth.mutate(rng, founder, cfg["snp"]) for _ in range(cfg["n_genomes"] - 1)]
     return synth.make_pangenome(cfg["n_genomes"], genome_len, cfg["snp"], cfg["indel"], seed=cfg["seed"], tree=cfg["tree"])
 
 
@@ -97,9 +98,19 @@ def ensure_bft(cfg: dict, k: int, genome_len: int, genomes=None) -> str:
     tmp = os.path.join(os.environ.get("TMPDIR", "/tmp"), f"bft_build_{cfg['name']}_k{k}_L{genome_len}_{os.getpid()}")
     os.makedirs(tmp, exist_ok=True)
     t0 = time.time()
-    if genomes is None:
-        genomes = pangenome(cfg, genome_len)
-    lst = synth.write_genome_kmer_files(tmp, genomes, k, canonical=bool(cfg.get("canonical")))
+    if cfg.get("pools"):  # k-mer sets, not genomes: one kmers_comp file per genome
+        _, per = kmer_sets(cfg, k)
+        paths = []
+        for g, w in enumerate(per):
+            paths.append(os.path.join(tmp, f"genome_{g:04d}.kc"))
+            synth.write_kmers_comp(paths[-1], w, k)
+        lst = os.path.join(tmp, "genome_list.txt")
+        with open(lst, "w") as f:
+            f.write("\n".join(paths) + "\n")
+    else:
+        if genomes is None:
+            genomes = pangenome(cfg, genome_len)
+        lst = synth.write_genome_kmer_files(tmp, genomes, k, canonical=bool(cfg.get("canonical")))
     log(f"building {os.path.basename(path)} with the reference ({cfg['n_genomes']} genomes x {genome_len} bp)...")
     out = os.path.join(tmp, "out.bft")
     p = subprocess.run([REF_BFT, "build", str(k), "kmers_comp", lst, out], cwd=tmp, stdout=subprocess.PIPE, stderr=subprocess.STDOUT)
@@ -164,6 +175,31 @@ def gen_kmer_queries(cat, starts, lens, k: int, n: int, seed: int, mix: Tuple[fl
                       torch.full((n_r,), 2, dtype=torch.uint8, device=dev)])
     perm = torch.randperm(n, generator=g, device=dev)
     return out[perm].contiguous(), kind[perm].contiguous()
+
+
+def gen_set_queries(words: np.ndarray, k: int, n: int, seed: int, device):
+    """Query batch around a k-mer SET (forced-deep configs): 1/3 members, 1/3 members with one nucleotide changed, 1/3 uniform random,
+    shuffled. Returns (int64 [n, W] on `device`, uint8 [n] kind: 0 member / 1 mismatch / 2 random)."""
+    import torch
+    rng = np.random.default_rng(seed)
+    nw = words.shape[1]
+    third = n // 3
+    a = words[rng.integers(0, len(words), size=third)]
+    m = words[rng.integers(0, len(words), size=third)].copy()
+    pos = rng.integers(0, k, size=third)
+    delta = rng.integers(1, 4, size=third).astype(np.uint64)
+    for w in range(nw):
+        in_w = (pos // 32) == w
+        sh = (2 * (pos % 32)).astype(np.uint64)
+        cur = (m[:, w] >> sh) & np.uint64(3)
+        m[:, w] = np.where(in_w, (m[:, w] & ~(np.uint64(3) << sh)) | (((cur + delta) & np.uint64(3)) << sh), m[:, w])
+    r = rng.integers(0, 1 << 63, size=(n - 2 * third, nw), dtype=np.uint64) * np.uint64(2) + \
+        rng.integers(0, 2, size=(n - 2 * third, nw), dtype=np.uint64)
+    synth.mask_words(r, k)
+    q = np.concatenate([a, m, r])
+    kind = np.concatenate([np.zeros(third, np.uint8), np.ones(third, np.uint8), np.full(n - 2 * third, 2, np.uint8)])
+    perm = rng.permutation(n)
+    return torch.from_numpy(q[perm].view(np.int64)).to(device), torch.from_numpy(kind[perm]).to(device)
 
 
 def gen_reads(cat, starts, lens, n_reads: int, read_len: int, seed: int, err: float = 0.005, frac_random: float = 0.0):

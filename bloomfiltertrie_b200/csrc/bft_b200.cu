@@ -84,7 +84,6 @@ struct bft_b200_ctx {
     uint64_t launches;
     size_t seq_smem;
     int ref_quirks;
-    uint32_t* d_nbr; size_t cap_nbr;
     /* device graph (bft_graph.cuh), built on first use */
     struct {
         int ready;
@@ -177,7 +176,6 @@ extern "C" void bft_b200_close(bft_b200_ctx* c) {
     if (c->d_hot) cudaFree(c->d_hot);
     if (c->d_class_counts) cudaFree(c->d_class_counts);
     if (c->d_counter) cudaFree(c->d_counter);
-    if (c->d_nbr) cudaFree(c->d_nbr);
     bft_b200_graph_release(c);
     if (c->pool) cudaMemPoolDestroy(c->pool);
     for (int s = 0; s < BFT_N_SLOTS; s++) {
@@ -949,21 +947,25 @@ extern "C" int bft_b200_query_neighbors(bft_b200_ctx* c, const uint64_t* kmers, 
     if (!c || !nbr || (!kmers && n)) return set_err(BFT_B200_ERR_ARG, "bft_b200_query_neighbors: NULL argument");
     CK(cudaSetDevice(c->device));
     const size_t W = (size_t)c->W;
-    CKP(cudaStreamSynchronize(c->streams[0]));
     size_t done = 0;
-    while (done < n) {
+    int it = 0;
+    while (done < n) { /* two slots on two streams: the copies of one chunk overlap the look-ups of the other */
         const size_t m = n - done < BFT_CHUNK_KMERS ? n - done : BFT_CHUNK_KMERS;
-        slot_t* sl = &c->slot[0];
-        cudaStream_t st = c->streams[0];
+        const int s = it & 1;
+        slot_t* sl = &c->slot[s];
+        cudaStream_t st = c->streams[s];
+        CKP(cudaStreamSynchronize(st)); /* slot buffers free again */
         ENSUREP(sl->d_in, sl->cap_in, m * W * 8);
-        ENSUREP(c->d_nbr, c->cap_nbr, m * 8 * sizeof(uint32_t));
+        ENSUREP(sl->d_rows, sl->cap_rows, m * 8 * sizeof(uint32_t));
         CKP(cudaMemcpyAsync(sl->d_in, kmers + done * W, m * W * 8, cudaMemcpyHostToDevice, st));
-        int rc = enqueue_branching(c, st, (const uint64_t*)sl->d_in, m, NULL, NULL, NULL, c->d_nbr);
+        int rc = enqueue_branching(c, st, (const uint64_t*)sl->d_in, m, NULL, NULL, NULL, sl->d_rows);
         if (rc) return drain_ret(c, rc);
-        CKP(cudaMemcpyAsync(nbr + done * 8, c->d_nbr, m * 8 * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
-        CKP(cudaStreamSynchronize(st));
+        CKP(cudaMemcpyAsync(nbr + done * 8, sl->d_rows, m * 8 * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
         done += m;
+        it++;
     }
+    CKP(cudaStreamSynchronize(c->streams[0]));
+    CKP(cudaStreamSynchronize(c->streams[1]));
     return 0;
 }
 
@@ -1335,13 +1337,16 @@ extern "C" int bft_b200_graph_prepare(bft_b200_ctx* c) {
 extern "C" int bft_b200_query_vertex_ids(bft_b200_ctx* c, const uint64_t* kmers, size_t n, uint32_t* vertex_ids) {
     if (!c || !vertex_ids || (!kmers && n)) return set_err(BFT_B200_ERR_ARG, "bft_b200_query_vertex_ids: NULL argument");
     int rc = bft_b200_graph_prepare(c);
-    if (rc) return drain_ret(c, rc);
+    if (rc) return rc;
     const size_t W = (size_t)c->W;
-    cudaStream_t st = c->streams[0];
-    CKP(cudaStreamSynchronize(st));
-    slot_t* sl = &c->slot[0];
-    for (size_t done = 0; done < n;) {
+    size_t done = 0;
+    int it = 0;
+    while (done < n) { /* two slots on two streams, as the other host pipelines */
         const size_t m = n - done < BFT_CHUNK_KMERS ? n - done : BFT_CHUNK_KMERS;
+        const int s = it & 1;
+        slot_t* sl = &c->slot[s];
+        cudaStream_t st = c->streams[s];
+        CKP(cudaStreamSynchronize(st));
         ENSUREP(sl->d_in, sl->cap_in, m * W * 8);
         ENSUREP(sl->d_cls, sl->cap_cls, m * sizeof(uint32_t));
         CKP(cudaMemcpyAsync(sl->d_in, kmers + done * W, m * W * 8, cudaMemcpyHostToDevice, st));
@@ -1350,9 +1355,11 @@ extern "C" int bft_b200_query_vertex_ids(bft_b200_ctx* c, const uint64_t* kmers,
 #undef BFT_L
         c->launches++;
         CKP(cudaMemcpyAsync(vertex_ids + done, sl->d_cls, m * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
-        CKP(cudaStreamSynchronize(st));
         done += m;
+        it++;
     }
+    CKP(cudaStreamSynchronize(c->streams[0]));
+    CKP(cudaStreamSynchronize(c->streams[1]));
     return 0;
 }
 

@@ -475,7 +475,7 @@ static void parse_cc(ctx_t* c, int sz, uint32_t cc_id, uint8_t* bf) {
         if ((f2[pu / 8] >> (pu % 8)) & 1) rank++;
     }
     csr[n_pu] = (uint16_t)(rank < n_starts ? starts[rank] : nb_elem);
-    if (rank != n_starts) fail(c, "bft_flatten: filter2 has %d p_u but %d cluster starts", rank, n_starts);
+    if (rank != n_starts) fail(c, "bft_flatten: filter2 has %d p_u but %d cluster starts (level of %d nt, %d prefixes, s=%d, level_min=%d, %d child nodes, file offset %zu)", rank, n_starts, sz, nb_elem, s, li->level_min, nb_node_children, c->pos);
     if (nb_elem && starts[0] != 0) fail(c, "bft_flatten: first stored prefix does not start a cluster");
     a->n_csr += (size_t)n_pu + 1;
 

@@ -17,7 +17,7 @@ SPECS = {
     "c3": (wl.C3, 27, 5_000_000),
     "c4": (wl.C3, 63, 5_000_000),
     "c5": (wl.C5, 27, 500_000),
-    "deep": (wl.DEEP, 63, 4_500_000),
+    "deep": (wl.DEEP, 63, 0),
 }
 
 if __name__ == "__main__":
