@@ -75,6 +75,15 @@
 #define BFT_LD64(p) (*(const uint64_t*)(p))
 #endif
 
+/* BFT_OPAQUE(x): hides a 64-bit value from the optimiser at this point (no instruction is emitted). Used where a word of a
+ * W-word key is picked by a run-time index through "select by value" loops: LLVM recognises the pattern and turns it back
+ * into an indexed access, which puts the key in local memory (LDL/STL on the lookup path). */
+#ifdef __CUDA_ARCH__
+#define BFT_OPAQUE(x) asm volatile("" : "+l"(x))
+#else
+#define BFT_OPAQUE(x) ((void)0)
+#endif
+
 #define BFT_NB_CHAR_SUF_PREF 9         /* reference include/default_param.h:12 */
 #define BFT_PREFIX_BITS 18
 #define BFT_N_IDX14 16384
@@ -225,23 +234,19 @@ BFT_HD void bft_ld_bucket(const uint64_t* p, uint64_t* out, const int W) {
  * branching query (k_query_branching, k_graph_adjacency) read TWO filter blocks — two L2 sectors — instead of eight. */
 typedef struct { uint32_t block; uint32_t b0, b1, b2, b3; } bft_kf_pos_t;
 
-BFT_HD bft_kf_pos_t bft_kf_pos(const uint64_t* kmer, const int W, const int k, const uint32_t n_blocks) {
-    /* middle = (kmer >> 2) without its top nucleotide */
-    uint64_t x = 0;
-    const int mid_bits = 2 * (k - 2);
-    for (int w = 0; w < W; w++) {
-        uint64_t m = kmer[w] >> 2;
-        if (w + 1 < W) m |= kmer[w + 1] << 62;
-        const int b = mid_bits - 64 * w;
-        if (b < 64) m &= b <= 0 ? 0ULL : ((1ULL << b) - 1ULL);
-        x = w == 0 ? m : (x ^ (x >> 29)) * 0x9FB21C651E98DF25ULL + m;
-    }
+/* stage 1: 64-bit mix of the middle (W words, bits above 2(k-2) zero) */
+BFT_HD uint64_t bft_kf_mix_mid(const uint64_t* mid, const int W) {
+    uint64_t x = mid[0];
+    for (int w = 1; w < W; w++) x = (x ^ (x >> 29)) * 0x9FB21C651E98DF25ULL + mid[w];
     x ^= x >> 33; x *= 0xFF51AFD7ED558CCDULL;
     x ^= x >> 33; x *= 0xC4CEB9FE1A85EC53ULL;
     x ^= x >> 33;
-    const int top = 2 * (k - 1);
-    const uint64_t ends = (kmer[0] & 3ULL) | (((kmer[top >> 6] >> (top & 63)) & 3ULL) << 2);
-    uint64_t y = (x ^ ((ends + 1ULL) * 0xD6E8FEB86659FD93ULL)) * 0x9E3779B97F4A7C15ULL;
+    return x;
+}
+
+/* stage 2: block from the middle's hash, bit positions from that and the two end nucleotides (ends = first | last << 2) */
+BFT_HD bft_kf_pos_t bft_kf_finish(const uint64_t x, const uint32_t ends, const uint32_t n_blocks) {
+    uint64_t y = (x ^ ((uint64_t)(ends + 1u) * 0xD6E8FEB86659FD93ULL)) * 0x9E3779B97F4A7C15ULL;
     y ^= y >> 29;
     bft_kf_pos_t p;
     p.block = (uint32_t)(((x >> 32) * (uint64_t)n_blocks) >> 32);
@@ -252,18 +257,45 @@ BFT_HD bft_kf_pos_t bft_kf_pos(const uint64_t* kmer, const int W, const int k, c
     return p;
 }
 
+BFT_HD bft_kf_pos_t bft_kf_pos(const uint64_t* kmer, const int W, const int k, const uint32_t n_blocks) {
+    /* middle = (kmer >> 2) without its top nucleotide; word indices are compared, never computed, so that W-word arrays
+     * stay in registers on the device */
+    uint64_t mid[BFT_MAX_WORDS];
+    const int mid_bits = 2 * (k - 2), top = 2 * (k - 1);
+    uint64_t last = 0;
+    for (int w = 0; w < W; w++) {
+        uint64_t m = kmer[w] >> 2;
+        if (w + 1 < W) m |= kmer[w + 1] << 62;
+        const int b = mid_bits - 64 * w;
+        if (b < 64) m &= b <= 0 ? 0ULL : ((1ULL << b) - 1ULL);
+        mid[w] = m;
+        uint64_t cand = (kmer[w] >> (top & 63)) & 3ULL;
+        BFT_OPAQUE(cand);
+        last |= ((top >> 6) == w) ? cand : 0ULL;
+    }
+    return bft_kf_finish(bft_kf_mix_mid(mid, W), (uint32_t)(kmer[0] & 3ULL) | ((uint32_t)last << 2), n_blocks);
+}
+
+/* the filter block at position q.block, and the test of one k-mer's four bits in it */
+BFT_HD void bft_kf_load(const bft_view_t* v, uint32_t block, uint64_t* w) {
+    const uint64_t* p = v->kfilter + (size_t)block * 4;
+#ifdef __CUDA_ARCH__
+    /* one 32-byte sector, kept in L2 (evict-last) */
+    asm("ld.global.nc.L2::evict_last.v4.u64 {%0,%1,%2,%3}, [%4];" : "=l"(w[0]), "=l"(w[1]), "=l"(w[2]), "=l"(w[3]) : "l"(p));
+#else
+    w[0] = p[0]; w[1] = p[1]; w[2] = p[2]; w[3] = p[3];
+#endif
+}
+BFT_HD int bft_kf_bits(const uint64_t* w, const bft_kf_pos_t q) {
+    return (int)(((w[0] >> q.b0) & (w[1] >> q.b1) & (w[2] >> q.b2) & (w[3] >> q.b3)) & 1ULL);
+}
+
 /* 1: the k-mer may be stored; 0: it is certainly not */
 BFT_HD int bft_kf_test(const bft_view_t* v, const uint64_t* kmer, const int W) {
     const bft_kf_pos_t q = bft_kf_pos(kmer, W, v->k, v->kf_blocks);
-    const uint64_t* p = v->kfilter + (size_t)q.block * 4;
-    uint64_t w0, w1, w2, w3;
-#ifdef __CUDA_ARCH__
-    /* one 32-byte sector, kept in L2 (evict-last) */
-    asm("ld.global.nc.L2::evict_last.v4.u64 {%0,%1,%2,%3}, [%4];" : "=l"(w0), "=l"(w1), "=l"(w2), "=l"(w3) : "l"(p));
-#else
-    w0 = p[0]; w1 = p[1]; w2 = p[2]; w3 = p[3];
-#endif
-    return (int)(((w0 >> q.b0) & (w1 >> q.b1) & (w2 >> q.b2) & (w3 >> q.b3)) & 1ULL);
+    uint64_t w[4];
+    bft_kf_load(v, q.block, w);
+    return bft_kf_bits(w, q);
 }
 
 /* index of the first CC of a Node whose Bloom filter fires for idx14, or BFT_FIRSTCC_NONE (src/presenceNode.c:1354-1362) */

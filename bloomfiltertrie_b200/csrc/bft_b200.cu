@@ -883,7 +883,7 @@ extern "C" int bft_b200_query_sequences(bft_b200_ctx* c, const char* chars, cons
 static int enqueue_branching(bft_b200_ctx* c, cudaStream_t st, const uint64_t* d_kmers, size_t n, uint8_t* d_succ, uint8_t* d_pred,
                              unsigned long long* d_count, uint32_t* d_nbr) {
     if (n == 0) return 0;
-    const int grid = grid_for(c, n * 8, BFT_TPB);
+    const int grid = grid_for(c, (n + BFT_NBR_Q - 1) / BFT_NBR_Q, BFT_TPB); /* one lane per BFT_NBR_Q queries */
 #define BFT_L(W_) k_query_branching<W_><<<grid, BFT_TPB, 0, st>>>(c->dview, d_kmers, n, d_succ, d_pred, d_count, d_nbr, c->ref_quirks)
     BFT_BY_W(c->W, BFT_L);
 #undef BFT_L
@@ -1321,7 +1321,7 @@ extern "C" int bft_b200_graph_prepare(bft_b200_ctx* c) {
     CK(cudaMemsetAsync(d_loc2vid, 0xff, ((size_t)n_loc + 1) * 4, st));
     int rc = enqueue_extract(c, c->graph.d_vk, c->graph.d_vcls, d_loc2vid);
     if (!rc && n) {
-        const int grid = grid_for(c, n * 8, BFT_TPB);
+        const int grid = grid_for(c, (n + BFT_NBR_Q - 1) / BFT_NBR_Q, BFT_TPB);
 #define BFT_L(W_) k_graph_adjacency<W_><<<grid, BFT_TPB, 0, st>>>(c->dview, c->graph.d_vk, n, d_loc2vid, c->graph.d_adj)
         BFT_BY_W(c->W, BFT_L);
 #undef BFT_L

@@ -26,40 +26,12 @@
 
 #define BFT_V_NONE 0xffffffffu
 
-/* the neighbour of x that lane `sub` of an 8-lane group looks up: sub 0-3 successor (drop nuc 0, append nuc sub),
- * sub 4-7 predecessor (prepend nuc sub-4, drop the last nuc) */
-template <int W>
-__device__ __forceinline__ void bft_neighbor_kmer(const uint64_t* x, int k, int sub, uint64_t* y) {
-    const uint32_t c = sub & 3;
-    if (sub < 4) {
-        bft_shr<W>(x, 2, y);
-        const int top = 2 * (k - 1);
-#pragma unroll
-        for (int w = 0; w < W; w++)
-            if ((top >> 6) == w) y[w] |= (uint64_t)c << (top & 63);
-    } else {
-        bft_shl<W>(x, 2, y);
-        y[0] |= c;
-#pragma unroll
-        for (int w = 0; w < W; w++) y[w] &= bft_word_mask(2 * k, w);
-    }
-}
-
-/* 8 lanes per vertex: neighbour k-mer -> look-up -> storage location -> vertex id */
+/* neighbour k-mers -> look-ups -> storage locations -> vertex ids: the two-phase neighbour engine of bft_kernels.cuh
+ * (filter per query, survivors compacted across the warp, walked 32 at a time) with plain set membership */
 template <int W>
 __global__ void __launch_bounds__(BFT_TPB) k_graph_adjacency(const bft_view_t v, const uint64_t* __restrict__ vk, size_t n,
                                                              const uint32_t* __restrict__ loc2vid, uint32_t* __restrict__ adj) {
-    const size_t stride = ((size_t)gridDim.x * blockDim.x) >> 3;
-    const int sub = threadIdx.x & 7;
-    for (size_t q = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 3; q < n; q += stride) {
-        uint64_t x[W], y[W];
-#pragma unroll
-        for (int w = 0; w < W; w++) x[w] = vk[q * W + w];
-        bft_neighbor_kmer<W>(x, v.k, sub, y);
-        uint32_t loc = 0;
-        const uint32_t cls = bft_lookup_loc(&v, y, W, BFT_LK_FILTER_FIRST, (uint32_t*)0, &loc);
-        adj[q * 8 + (sub < 4 ? 4 + sub : sub - 4)] = cls != BFT_CLS_NONE ? __ldg(loc2vid + loc) : BFT_V_NONE;
-    }
+    bft_neighbors_core<W, 1>(v, vk, n, 0, (uint8_t*)0, (uint8_t*)0, (unsigned long long*)0, adj, loc2vid);
 }
 
 /* vertex id of each queried k-mer (BFT_V_NONE when it is not stored): the handle under which callers keep their own

@@ -45,11 +45,13 @@ __device__ __forceinline__ void bft_shr(const uint64_t* in, int sh, uint64_t* ou
     const int ws = sh >> 6, bs = sh & 63;
 #pragma unroll
     for (int w = 0; w < W; w++) {
-        uint64_t lo = 0, hi = 0;
+        uint64_t lo = 0, hi = 0; /* selected by value (no indexed access: the words must stay in registers, see BFT_OPAQUE) */
 #pragma unroll
         for (int u = 0; u < W; u++) {
-            if (u == w + ws) lo = in[u];
-            if (u == w + ws + 1) hi = in[u];
+            uint64_t t = in[u];
+            if (W > 1) BFT_OPAQUE(t);
+            lo |= (u == w + ws) ? t : 0ULL;
+            hi |= (u == w + ws + 1) ? t : 0ULL;
         }
         out[w] = bs ? (lo >> bs) | (hi << (64 - bs)) : lo;
     }
@@ -64,8 +66,10 @@ __device__ __forceinline__ void bft_shl(const uint64_t* in, int sh, uint64_t* ou
         uint64_t lo = 0, hi = 0; /* hi: the word that lands at w, lo: the one below it */
 #pragma unroll
         for (int u = 0; u < W; u++) {
-            if (u + ws == w) hi = in[u];
-            if (u + ws + 1 == w) lo = in[u];
+            uint64_t t = in[u];
+            if (W > 1) BFT_OPAQUE(t);
+            hi |= (u + ws == w) ? t : 0ULL;
+            lo |= (u + ws + 1 == w) ? t : 0ULL;
         }
         out[w] = bs ? (hi << bs) | (lo >> (64 - bs)) : hi;
     }
@@ -473,16 +477,22 @@ __global__ void __launch_bounds__(BFT_TPB) k_encode_ascii(const char* __restrict
 #pragma unroll
         for (int w = 0; w < W; w++) km[w] = 0;
         int ok = 1;
-        for (int j = 0; j < k; j++) {
-            uint64_t code = 0;
-            switch (s[j]) {
-                case 'A': case 'a': code = 0; break;
-                case 'C': case 'c': code = 1; break;
-                case 'G': case 'g': code = 2; break;
-                case 'T': case 't': case 'U': case 'u': code = 3; break;
-                default: ok = 0; break;
+#pragma unroll
+        for (int w = 0; w < W; w++) { /* word by word, so that km[] is never indexed at run time */
+            uint64_t word = 0;
+            const int j1 = k - 32 * w < 32 ? k - 32 * w : 32;
+            for (int jj = 0; jj < j1; jj++) {
+                uint64_t code = 0;
+                switch (s[32 * w + jj]) {
+                    case 'A': case 'a': code = 0; break;
+                    case 'C': case 'c': code = 1; break;
+                    case 'G': case 'g': code = 2; break;
+                    case 'T': case 't': case 'U': case 'u': code = 3; break;
+                    default: ok = 0; break;
+                }
+                word |= code << (2 * jj);
             }
-            km[j >> 5] |= code << (2 * (j & 31));
+            km[w] = word;
         }
         if (!ok) {
 #pragma unroll
@@ -685,59 +695,189 @@ __global__ void __launch_bounds__(BFT_TPB) k_extract_uc_kmers(const bft_view_t v
     }
 }
 
-/* ---- a13/a14: branching ------------------------------------------------------------------------------------
- * 8 lanes per query: lanes 0-3 look up the four successors (drop nuc 0, append c), lanes 4-7 the four
- * predecessors (prepend c, drop the last nuc) — isBranchingRight / isBranchingLeft (src/branchingNode.c:16-110,
- * 240-413) count exactly the neighbours present in the graph. */
+/* ---- a13/a14: branching / neighbours ---------------------------------------------------------------------------
+ * isBranchingRight / isBranchingLeft (src/branchingNode.c:16-110, 240-413) count the successors (drop nuc 0, append c)
+ * and predecessors (prepend c, drop the last nuc) of a k-mer that are present in the graph; get_neighbors
+ * (src/bft.c:804-886) returns them. Eight look-ups per query, most of which miss. Two phases per warp:
+ *
+ *   filter   one LANE per query (two queries per lane per round). The four successors of a k-mer share the middle k-2
+ *            nucleotides, and so do its four predecessors, hence one block of the stored-k-mer filter each (bft_arena.h):
+ *            two hashes and two 32-byte L2 loads answer all eight "certainly absent?" questions of a query.
+ *   walk     the neighbours that survive (1.5 of 8 on the 100-genome pan-genome) are compacted across the warp into a
+ *            shared-memory queue and walked 32 at a time with every lane busy — in the first version of this kernel each
+ *            of 8 lanes per query walked its own neighbour, and a warp executed the whole walk for the 19 % of its lanes
+ *            that needed it (469 warp instructions per 4 queries, issue-bound).
+ * MODE 0: successor / predecessor counts, branching total, optional neighbour classes (k_query_branching).
+ * MODE 1: vertex ids of the neighbours through loc2vid (k_graph_adjacency, bft_graph.cuh). */
+#define BFT_NBR_Q 2 /* queries per lane per round */
+
+template <int W>
+__device__ __forceinline__ void bft_neighbor_kmer(const uint64_t* x, int k, int sub, uint64_t* y) {
+    /* sub 0-3: successor with last nucleotide sub; sub 4-7: predecessor with first nucleotide sub - 4 */
+    const uint32_t c = sub & 3;
+    if (sub < 4) {
+        bft_shr<W>(x, 2, y);
+        const int top = 2 * (k - 1);
+#pragma unroll
+        for (int w = 0; w < W; w++) {
+            uint64_t add = (uint64_t)c << (top & 63);
+            if (W > 1) BFT_OPAQUE(add);
+            y[w] |= ((top >> 6) == w) ? add : 0ULL;
+        }
+    } else {
+        bft_shl<W>(x, 2, y);
+        y[0] |= c;
+#pragma unroll
+        for (int w = 0; w < W; w++) y[w] &= bft_word_mask(2 * k, w);
+    }
+}
+
+/* the 8-bit survivor mask of one query: bit sub set = neighbour sub may be stored */
+template <int W>
+__device__ __forceinline__ uint32_t bft_neighbor_filter(const bft_view_t& v, const uint64_t* x, bool filter_succ, bool filter_pred) {
+    const int k = v.k;
+    uint32_t mask = 0;
+    uint64_t mid[W], blk[4];
+    /* successors: middle = nucleotides 2..k-1 of x; ends = (nucleotide 1 of x, c) */
+    if (filter_succ) {
+        bft_shr<W>(x, 4, mid);
+        const uint64_t h = bft_kf_mix_mid(mid, W);
+        const uint32_t first = (uint32_t)(x[0] >> 2) & 3u;
+        bft_kf_load(&v, bft_kf_finish(h, first, v.kf_blocks).block, blk);
+#pragma unroll
+        for (uint32_t c = 0; c < 4; c++) mask |= (uint32_t)bft_kf_bits(blk, bft_kf_finish(h, first | (c << 2), v.kf_blocks)) << c;
+    } else mask |= 0x0fu;
+    /* predecessors: middle = nucleotides 0..k-3 of x; ends = (c, nucleotide k-2 of x) */
+    if (filter_pred) {
+        uint32_t last = 0;
+        const int lpos = 2 * (k - 2);
+#pragma unroll
+        for (int w = 0; w < W; w++) {
+            mid[w] = x[w] & bft_word_mask(lpos, w);
+            uint64_t cand = (x[w] >> (lpos & 63)) & 3ULL;
+            if (W > 1) BFT_OPAQUE(cand);
+            last |= ((lpos >> 6) == w) ? (uint32_t)cand : 0u;
+        }
+        const uint64_t h = bft_kf_mix_mid(mid, W);
+        bft_kf_load(&v, bft_kf_finish(h, last << 2, v.kf_blocks).block, blk);
+#pragma unroll
+        for (uint32_t c = 0; c < 4; c++) mask |= (uint32_t)bft_kf_bits(blk, bft_kf_finish(h, c | (last << 2), v.kf_blocks)) << (4 + c);
+    } else mask |= 0xf0u;
+    return mask;
+}
+
+template <int W, int MODE>
+__device__ __forceinline__ void bft_neighbors_core(const bft_view_t& v, const uint64_t* __restrict__ kmers, size_t n, int ref_quirks,
+                                                   uint8_t* __restrict__ succ, uint8_t* __restrict__ pred, unsigned long long* __restrict__ n_branching,
+                                                   uint32_t* __restrict__ nbr_out, const uint32_t* __restrict__ loc2vid) {
+    constexpr int QW = 32 * BFT_NBR_Q; /* queries per warp per round */
+    __shared__ uint64_t s_x[BFT_TPB / 32][QW * W];
+    __shared__ uint16_t s_queue[BFT_TPB / 32][QW * 8];
+    __shared__ uint32_t s_cnt[BFT_TPB / 32][QW]; /* successors found | predecessors found << 16 */
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    uint64_t* const xs = s_x[warp];
+    uint16_t* const queue = s_queue[warp];
+    uint32_t* const cnt = s_cnt[warp];
+    const size_t n_warps = ((size_t)gridDim.x * blockDim.x) >> 5;
+    const size_t n_rounds = (n + QW - 1) / QW;
+    /* the successor look-ups may have to reproduce the reference's leaf-level quirk (bft_node_probe_ex): they can be
+     * pre-filtered only if the quirk cannot trigger in this trie */
+    const bool have_filter = v.kf_blocks != 0;
+    const bool quirk = MODE == 0 && ref_quirks;
+    const bool filter_succ = have_filter && (!quirk || v.kf_quirk_safe), filter_pred = have_filter;
+    unsigned long long local = 0;
+    for (size_t r = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5; r < n_rounds; r += n_warps) {
+        const size_t base = r * QW;
+        uint32_t masks[BFT_NBR_Q], total_mine = 0;
+#pragma unroll
+        for (int j = 0; j < BFT_NBR_Q; j++) {
+            const int slot = j * 32 + lane;
+            const size_t q = base + slot;
+            masks[j] = 0;
+            if (q < n) {
+                uint64_t x[W];
+                bft_load_kmer<W>(kmers, q, x);
+#pragma unroll
+                for (int w = 0; w < W; w++) xs[slot * W + w] = x[w];
+                masks[j] = bft_neighbor_filter<W>(v, x, filter_succ, filter_pred);
+                if (nbr_out) { /* absent unless the walk says otherwise */
+                    uint4* o = (uint4*)(nbr_out + q * 8);
+                    o[0] = make_uint4(0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu);
+                    o[1] = make_uint4(0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu);
+                }
+            }
+            cnt[slot] = 0;
+            total_mine += __popc(masks[j]);
+        }
+        /* queue slots: exclusive scan of the survivor counts over the warp */
+        uint32_t incl = total_mine;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += t;
+        }
+        const uint32_t total = __shfl_sync(0xffffffffu, incl, 31);
+        uint32_t at = incl - total_mine;
+#pragma unroll
+        for (int j = 0; j < BFT_NBR_Q; j++) {
+            uint32_t m = masks[j];
+            while (m) {
+                const int sub = __ffs(m) - 1;
+                m &= m - 1;
+                queue[at++] = (uint16_t)(((j * 32 + lane) << 3) | sub);
+            }
+        }
+        __syncwarp();
+        /* walk: 32 surviving neighbours at a time */
+        for (uint32_t i = lane; i < total; i += 32) {
+            const uint32_t e = queue[i];
+            const int slot = (int)(e >> 3), sub = (int)(e & 7u);
+            uint64_t x[W], y[W];
+#pragma unroll
+            for (int w = 0; w < W; w++) x[w] = xs[slot * W + w];
+            bft_neighbor_kmer<W>(x, v.k, sub, y);
+            uint32_t loc = 0;
+            const uint32_t cls = bft_lookup_loc(&v, y, W, ((quirk && sub < 4) ? BFT_LK_SUCC_QUIRK : 0) | BFT_LK_NO_FILTER, (uint32_t*)0,
+                                                MODE == 1 ? &loc : (uint32_t*)0);
+            if (cls != BFT_CLS_NONE) {
+                const int pos = sub < 4 ? 4 + sub : sub - 4; /* get_neighbors order: 0-3 predecessors, 4-7 successors */
+                if (MODE == 0) {
+                    atomicAdd(&cnt[slot], sub < 4 ? 1u : 0x10000u);
+                    if (nbr_out) nbr_out[(base + slot) * 8 + pos] = cls;
+                } else {
+                    nbr_out[(base + slot) * 8 + pos] = __ldg(loc2vid + loc);
+                }
+            }
+        }
+        __syncwarp();
+        if (MODE == 0) {
+#pragma unroll
+            for (int j = 0; j < BFT_NBR_Q; j++) {
+                const int slot = j * 32 + lane;
+                const size_t q = base + slot;
+                if (q < n) {
+                    const uint32_t c = cnt[slot];
+                    const uint32_t ns = c & 0xffffu, np = c >> 16;
+                    if (succ) succ[q] = (uint8_t)ns;
+                    if (pred) pred[q] = (uint8_t)np;
+                    local += (ns > 1) || (np > 1); /* isBranchingRight > 1, else isBranchingLeft > 1 (src/file_io.c:971-976) */
+                }
+            }
+        }
+        __syncwarp();
+    }
+    if (MODE == 0 && n_branching) {
+        for (int o = 16; o > 0; o >>= 1) local += __shfl_down_sync(0xffffffffu, local, o);
+        if (lane == 0 && local) atomicAdd(n_branching, local);
+    }
+}
+
 template <int W>
 __global__ void __launch_bounds__(BFT_TPB) k_query_branching(const bft_view_t v, const uint64_t* __restrict__ kmers, size_t n,
                                                              uint8_t* __restrict__ succ, uint8_t* __restrict__ pred,
                                                              unsigned long long* __restrict__ n_branching,
                                                              uint32_t* __restrict__ nbr_cls, int ref_quirks) {
-    const int k = v.k;
-    const size_t stride = ((size_t)gridDim.x * blockDim.x) >> 3;
-    const int sub = threadIdx.x & 7;
-    const uint32_t c = sub & 3;
-    unsigned long long local = 0;
-    /* all 32 lanes of a warp iterate the same number of times so the shuffles below are full-warp */
-    const size_t n_rounds = (n + stride - 1) / stride;
-    size_t q = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 3;
-    for (size_t r = 0; r < n_rounds; r++, q += stride) {
-        uint32_t hit = 0;
-        if (q < n) {
-            uint64_t x[W], y[W];
-#pragma unroll
-            for (int w = 0; w < W; w++) x[w] = kmers[q * W + w];
-            if (sub < 4) { /* successor: (x >> 2) | c << 2(k-1) */
-                bft_shr<W>(x, 2, y);
-                const int top = 2 * (k - 1);
-#pragma unroll
-                for (int w = 0; w < W; w++)
-                    if ((top >> 6) == w) y[w] |= (uint64_t)c << (top & 63);
-            } else { /* predecessor: (x << 2 | c) masked to 2k bits */
-                bft_shl<W>(x, 2, y);
-                y[0] |= c;
-#pragma unroll
-                for (int w = 0; w < W; w++) y[w] &= bft_word_mask(2 * k, w);
-            }
-            /* the reference's successor search deviates from set membership at the leaf level; see bft_node_probe */
-            const uint32_t cls = bft_lookup_ex(&v, y, W, ((ref_quirks && sub < 4) ? BFT_LK_SUCC_QUIRK : 0) | BFT_LK_FILTER_FIRST, (uint32_t*)0);
-            hit = cls != BFT_CLS_NONE;
-            if (nbr_cls) nbr_cls[q * 8 + (sub < 4 ? 4 + sub : sub - 4)] = cls; /* get_neighbors order: 0-3 pred, 4-7 succ */
-        }
-        const uint32_t ball = __ballot_sync(0xffffffffu, hit);
-        const uint32_t grp = (ball >> ((threadIdx.x & 31) & ~7)) & 0xffu;
-        const int ns = __popc(grp & 0x0fu), np = __popc(grp >> 4);
-        if (sub == 0 && q < n) {
-            if (succ) succ[q] = (uint8_t)ns;
-            if (pred) pred[q] = (uint8_t)np;
-            local += (ns > 1) || (np > 1); /* isBranchingRight > 1, else isBranchingLeft > 1 (src/file_io.c:971-976) */
-        }
-    }
-    if (n_branching) {
-        for (int o = 16; o > 0; o >>= 1) local += __shfl_down_sync(0xffffffffu, local, o);
-        if ((threadIdx.x & 31) == 0 && local) atomicAdd(n_branching, local);
-    }
+    bft_neighbors_core<W, 0>(v, kmers, n, ref_quirks, succ, pred, n_branching, nbr_cls, (const uint32_t*)0);
 }
 
 /* ---- a1/a2/a12: sequences ----------------------------------------------------------------------------------
