@@ -341,8 +341,8 @@ def base_roofline(kernel, a_bytes, formula, units, k_ms, cap, extra):
 
 # ---------------------------------------------------------------------------------------------------------------------
 def kmers_record(run: Run, tag: str, spec: dict, headline: bool):
-    """-query_kmers: presence + colour rows of a batch of packed k-mers (k_query_kmers_rows, or k_query_kmers + k_expand_rows
-    for more than 128 genomes)."""
+    """-query_kmers: presence + colour rows of a batch of packed k-mers (k_query_kmers_rows, or k_query_kmers_wide for more
+    than 128 genomes)."""
     import numpy as np
     torch = run.torch
     from bloomfiltertrie_b200 import engine as E
@@ -366,7 +366,7 @@ def kmers_record(run: Run, tag: str, spec: dict, headline: bool):
     dev = run.dev
     d_present = torch.empty(n, dtype=torch.uint8, device=dev)
     d_rows = torch.empty((n, RW), dtype=torch.int32, device=dev)
-    counted = RW in (1, 2, 4)
+    counted = True   # every row width accumulates the hit count in the kernel (k_query_kmers_rows / k_query_kmers_wide)
     # The hit count of every step ("Nb k-mers present" of the reference driver, src/file_io.c:813) is the one number the
     # sharded path reduces. The query kernels accumulate it themselves: one uint64 slot per step in rank 0's HBM, mapped
     # into every rank through CUDA IPC; each CTA adds its share with one system-scope atomic (over NVLink from the other
@@ -374,11 +374,28 @@ def kmers_record(run: Run, tag: str, spec: dict, headline: bool):
     n_slots = 2 * (warmup + steps) + 8
     ctr_local = eng.device_alloc(8 * n_slots) if run.rank == 0 else 0   # zero-filled by the call
     ctr_base = ctr_local
+    reduction = "none (one GPU)"
     if run.dist and counted:
         box = [eng.peer_export(ctr_local) if run.rank == 0 else None]
         run.dist.broadcast_object_list(box, src=0)
+        failed = 0
         if run.rank != 0:
-            ctr_base = eng.peer_import(box[0])
+            try:
+                ctr_base = eng.peer_import(box[0])
+            except Exception as e:  # noqa: BLE001 — a box without CUDA IPC between its GPUs
+                log(f"rank {run.rank}: peer mapping of the hit counter failed ({e})")
+                failed = 1
+        if run.allsum(failed):
+            # Fallback, named in the record: every rank counts into its own slots and the slots are summed ONCE after the
+            # timed region (still no collective per step).
+            if run.rank != 0:
+                if not failed:
+                    eng.peer_close(ctr_base)
+                ctr_local = ctr_base = eng.device_alloc(8 * n_slots)
+            reduction = "per-rank counters, one NCCL all_reduce after the timed region (CUDA IPC unavailable on this box)"
+        else:
+            reduction = "inside the kernel: system-scope atomics into rank 0's peer-mapped counter (CUDA IPC over NVLink)"
+    peer_mapped = reduction.startswith("inside")
     slot_i = [0]
 
     def step():
@@ -393,10 +410,16 @@ def kmers_record(run: Run, tag: str, spec: dict, headline: bool):
     value = n * run.world / (ms_step / 1e3)
     n_present = int(d_present.sum().item())
     tot = run.allsum(n_present)
-    if counted and run.rank == 0:  # every step's slot must hold the sum of all ranks' hits
-        slots = eng.copy_from_device(ctr_local, np.zeros(n_slots, dtype=np.uint64))
-        used = slots[:slot_i[0]]
-        assert (used == np.uint64(tot)).all(), f"in-kernel hit counters {used.tolist()} != {tot}"
+    if counted:  # every step's slot must hold the sum of all ranks' hits
+        if run.dist and not peer_mapped:
+            slots_t = torch.from_numpy(eng.copy_from_device(ctr_local, np.zeros(n_slots, dtype=np.uint64)).view(np.int64)).to(dev)
+            run.dist.all_reduce(slots_t)
+            slots = slots_t.cpu().numpy().view(np.uint64)
+        elif run.rank == 0:
+            slots = eng.copy_from_device(ctr_local, np.zeros(n_slots, dtype=np.uint64))
+        if run.rank == 0:
+            used = slots[:slot_i[0]]
+            assert (used == np.uint64(tot)).all(), f"in-kernel hit counters {used.tolist()} != {tot}"
     # size-independent properties at full size: every window sampled from an inserted genome is found, a found k-mer
     # carries at least one colour, an absent one none
     assert bool(d_present[q_kind == 0].all()), "a k-mer window of an inserted genome was reported absent"
@@ -423,12 +446,12 @@ def kmers_record(run: Run, tag: str, spec: dict, headline: bool):
     ws = eng.kmer_walk_stats_device(q, n)
     found_pk, bucket_pk, reject_pk = ws["found"] / n, ws["bucket_searches"] / n, ws["filter_rejects"] / n
     nodes_pk, depth_pk, cc_pk = ws["nodes"] / n, ws["search_depth"] / n, ws["cc_probed"] / n
-    a_arena = 8 * W + (1 + 4 * RW) + 32.0 * W * bucket_pk + (0 if counted else 8)
+    a_arena = 8 * W + (1 + 4 * RW) + 32.0 * W * bucket_pk
     cap = ncu_capture(tag) if not degraded else None
     probe = eng.random_gather_probe(4 << 30, 1 << 28) if (headline and not args.no_probe) else None
     roofline = base_roofline(
-        "k_query_kmers_rows" if counted else "k_query_kmers+k_expand_rows_v4", a_arena,
-        "8*W in + (1 + 4*RW) out + 32*W * P(walk reaches a bucket)" + ("" if counted else " + 4+4 class id out/in"), n, k_ms, cap,
+        "k_query_kmers_rows" if RW <= 4 else "k_query_kmers_wide", a_arena,
+        "8*W in + (1 + 4*RW) out + 32*W * P(walk reaches a bucket)", n, k_ms, cap,
         {"kmers_per_sec_kernel": n / (k_ms / 1e3), "bucket_accesses_per_kmer": bucket_pk, "filter_rejects_per_kmer": reject_pk,
          "found_frac": found_pk, "filter_mb": st["filter_bytes"] / 1e6,
          "l2_bytes_per_kmer": 8 + (32 if st["filter_bytes"] else 0) + 4 * RW * found_pk,
@@ -518,13 +541,13 @@ def kmers_record(run: Run, tag: str, spec: dict, headline: bool):
                       "present_frac": n_present / n,
                       "l2": ("256 MB written between steps (batch smaller than L2); one event pair per step" if flush
                              else "inputs larger than L2 (no flush needed)"),
-                      "sharding": f"arena replicated, queries sharded x{run.world}; hit count reduced inside the kernel (peer-mapped counter)"},
+                      "sharding": f"arena replicated, queries sharded x{run.world}", "hit_count_reduction": reduction},
            "clocks": clocks, "e2e": e2e, "gpu_launches": launches * run.world, "roofline": roofline, "cpu_baseline": cpu}
-    if run.dist and counted and run.rank != 0:
+    if run.dist and counted and run.rank != 0 and peer_mapped:
         eng.peer_close(ctr_base)
     if run.dist:
         run.dist.barrier()
-    if run.rank == 0:
+    if run.rank == 0 or (run.dist and not peer_mapped):
         eng.device_free(ctr_local)
     eng.close()
     del q, d_present, d_rows

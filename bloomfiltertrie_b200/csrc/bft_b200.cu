@@ -474,17 +474,24 @@ static int enqueue_kmers(bft_b200_ctx* c, cudaStream_t st, const uint64_t* d_kme
         CK(cudaGetLastError());
         return 0;
     }
+    if (d_rows) { /* wide rows: walk and row expansion in one kernel, 32 rows per warp written together */
+        if (c->rw % 4 == 0 && ((uintptr_t)d_rows & 15) == 0 && ((uintptr_t)c->d_class_rows & 15) == 0) {
+#define BFT_L(W_) k_query_kmers_wide<W_, uint4><<<grid, BFT_TPB, 0, st>>>(c->dview, d_kmers, n, d_present, d_cls, (const uint4*)c->d_class_rows, c->rw / 4, (uint4*)d_rows, d_n_present)
+            BFT_BY_W(c->W, BFT_L);
+#undef BFT_L
+        } else {
+#define BFT_L(W_) k_query_kmers_wide<W_, uint32_t><<<grid, BFT_TPB, 0, st>>>(c->dview, d_kmers, n, d_present, d_cls, c->d_class_rows, c->rw, d_rows, d_n_present)
+            BFT_BY_W(c->W, BFT_L);
+#undef BFT_L
+        }
+        c->launches++;
+        CK(cudaGetLastError());
+        return 0;
+    }
 #define BFT_L(W_) k_query_kmers<W_><<<grid, BFT_TPB, 0, st>>>(c->dview, d_kmers, n, d_present, d_cls)
     BFT_BY_W(c->W, BFT_L);
 #undef BFT_L
     c->launches++;
-    if (d_rows) {
-        if (c->rw % 4 == 0 && ((uintptr_t)d_rows & 15) == 0 && ((uintptr_t)c->d_class_rows & 15) == 0)
-            k_expand_rows_v4<<<grid_for(c, n * (size_t)(c->rw / 4), BFT_TPB), BFT_TPB, 0, st>>>(d_cls, n, (const uint4*)c->d_class_rows, c->rw / 4, (uint4*)d_rows);
-        else
-            k_expand_rows<<<grid_for(c, n * (size_t)c->rw, BFT_TPB), BFT_TPB, 0, st>>>(d_cls, n, c->d_class_rows, c->rw, d_rows);
-        c->launches++;
-    }
     CK(cudaGetLastError());
     return 0;
 }
@@ -493,19 +500,12 @@ extern "C" int bft_b200_query_kmers_device(bft_b200_ctx* c, const uint64_t* d_km
                                            uint32_t* d_cls) {
     if (!c || (!d_kmers && n)) return set_err(BFT_B200_ERR_ARG, "bft_b200_query_kmers_device: NULL argument");
     CK(cudaSetDevice(c->device));
-    if (d_rows && !d_cls && !((c->rw == 1 || c->rw == 2 || c->rw == 4) && ((uintptr_t)d_rows & 15) == 0)) { /* wide rows need the class ids as an intermediate */
-        slot_t* sl = &c->slot[0];
-        ENSURE(sl->d_cls, sl->cap_cls, n * sizeof(uint32_t));
-        d_cls = sl->d_cls;
-    }
     return enqueue_kmers(c, c->streams[0], d_kmers, n, d_present, d_rows, d_cls);
 }
 
 extern "C" int bft_b200_query_kmers_device_counted(bft_b200_ctx* c, const uint64_t* d_kmers, size_t n, uint8_t* d_present, uint32_t* d_rows,
                                                    uint64_t* d_n_present) {
     if (!c || (!d_kmers && n) || !d_rows || !d_n_present) return set_err(BFT_B200_ERR_ARG, "bft_b200_query_kmers_device_counted: NULL argument");
-    if (!((c->rw == 1 || c->rw == 2 || c->rw == 4) && ((uintptr_t)d_rows & 15) == 0))
-        return set_err(BFT_B200_ERR_ARG, "bft_b200_query_kmers_device_counted: needs colour rows of 1, 2 or 4 words (<= 128 genomes) and a 16-byte aligned row buffer");
     CK(cudaSetDevice(c->device));
     CK(cudaMemsetAsync(d_n_present, 0, sizeof(uint64_t), c->streams[0]));
     return enqueue_kmers(c, c->streams[0], d_kmers, n, d_present, d_rows, NULL, (unsigned long long*)d_n_present);
@@ -514,8 +514,6 @@ extern "C" int bft_b200_query_kmers_device_counted(bft_b200_ctx* c, const uint64
 extern "C" int bft_b200_query_kmers_device_accumulate(bft_b200_ctx* c, const uint64_t* d_kmers, size_t n, uint8_t* d_present, uint32_t* d_rows,
                                                       uint64_t* d_counter) {
     if (!c || (!d_kmers && n) || !d_rows || !d_counter) return set_err(BFT_B200_ERR_ARG, "bft_b200_query_kmers_device_accumulate: NULL argument");
-    if (!((c->rw == 1 || c->rw == 2 || c->rw == 4) && ((uintptr_t)d_rows & 15) == 0))
-        return set_err(BFT_B200_ERR_ARG, "bft_b200_query_kmers_device_accumulate: needs colour rows of 1, 2 or 4 words (<= 128 genomes) and a 16-byte aligned row buffer");
     CK(cudaSetDevice(c->device));
     return enqueue_kmers(c, c->streams[0], d_kmers, n, d_present, d_rows, NULL, (unsigned long long*)d_counter);
 }

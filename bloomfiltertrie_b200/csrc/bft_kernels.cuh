@@ -152,6 +152,48 @@ __global__ void __launch_bounds__(BFT_TPB) k_query_kmers_rows(const bft_view_t v
     if (n_present) bft_block_count(hits, n_present);
 }
 
+/* a4-a10 fused for WIDE colour rows (more than 128 genomes; 1000 colours = 32 words = 128 bytes per k-mer): each lane looks
+ * one k-mer up, then the warp writes the 32 rows of its 32 consecutive k-mers together — lane t of pass p copies vector
+ * (32 p + t) of the 32 * RWV-vector block, whose class id comes from the owning lane by shuffle. The block is contiguous in
+ * the output (32 rows back to back), so every pass is one fully coalesced 512-byte store; the class rows come from the
+ * L2-resident table. Against k_query_kmers + k_expand_rows_v4 this drops the class-id round trip through HBM (8 B per k-mer)
+ * and the second launch, and — the point — lets the latency-bound walks of some warps overlap the bandwidth-bound row
+ * writes of others instead of running one after the other. T = uint4 when the row width and the buffers allow, else uint32_t. */
+template <int W, typename T>
+__global__ void __launch_bounds__(BFT_TPB) k_query_kmers_wide(const bft_view_t v, const uint64_t* __restrict__ kmers, size_t n,
+                                                              uint8_t* __restrict__ present, uint32_t* __restrict__ cls_out,
+                                                              const T* __restrict__ class_rows, int rwv, T* __restrict__ rows,
+                                                              unsigned long long* __restrict__ n_present) {
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    const int lane = threadIdx.x & 31;
+    unsigned int hits = 0;
+    const int per_warp = 32 * rwv;
+    /* warp-uniform trip count: the lanes of a warp own 32 consecutive k-mers, the last warp may run past n */
+    for (size_t base = (size_t)blockIdx.x * blockDim.x + (threadIdx.x & ~31u); base < n; base += stride) {
+        const size_t i = base + lane;
+        uint32_t cls = BFT_CLS_NONE;
+        if (i < n) {
+            uint64_t km[W];
+            bft_load_kmer<W>(kmers, i, km);
+            cls = bft_lookup_w(&v, km, W);
+            hits += cls != BFT_CLS_NONE;
+            if (present) present[i] = cls != BFT_CLS_NONE;
+            if (cls_out) cls_out[i] = cls;
+        }
+        T* const out = rows + base * (size_t)rwv;
+        const size_t live = (n - base < 32 ? n - base : 32) * (size_t)rwv; /* vectors of this block that exist */
+#pragma unroll 2
+        for (int t = lane; t < per_warp; t += 32) {
+            const int kk = t / rwv, w = t - kk * rwv;
+            const uint32_t c = __shfl_sync(0xffffffffu, cls, kk);
+            T r = T();
+            if (c != BFT_CLS_NONE) r = __ldg(class_rows + (size_t)c * rwv + w);
+            if ((size_t)t < live) __stcs(out + t, r);
+        }
+    }
+    if (n_present) bft_block_count(hits, n_present);
+}
+
 /* The same look-up on the reference's own record format: k-mers as ceil(2k/8)-byte records (a kmers_comp file,
  * BFT_kmer.kmer_comp; src/file_io.c:721-774) in, colour rows of ceil(n_genomes/8) bytes out (bit g = genome g; an absent
  * k-mer has an all-zero row). For k = 27 and 100 genomes that is 7 + 13 bytes per k-mer over PCIe instead of 8 + 17,
@@ -401,22 +443,6 @@ __global__ void __launch_bounds__(BFT_TPB) k_expand_rows(const uint32_t* __restr
         const int w = (int)(t - i * (size_t)rw);
         const uint32_t c = cls[i];
         rows[t] = c == BFT_CLS_NONE ? 0u : __ldg(class_rows + (size_t)c * rw + w);
-    }
-}
-
-/* same, for RW a multiple of 4 (wide colour sets, e.g. 1000 genomes = 32 words): one 16-byte vector per thread,
- * class rows read through the read-only path (L2), output rows written with streaming stores */
-__global__ void __launch_bounds__(BFT_TPB) k_expand_rows_v4(const uint32_t* __restrict__ cls, size_t n, const uint4* __restrict__ class_rows,
-                                                            int rw4, uint4* __restrict__ rows) {
-    const size_t total = n * (size_t)rw4;
-    const size_t stride = (size_t)gridDim.x * blockDim.x;
-    for (size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += stride) {
-        const size_t i = t / (size_t)rw4;
-        const int w = (int)(t - i * (size_t)rw4);
-        const uint32_t c = __ldg(cls + i);
-        uint4 r = make_uint4(0, 0, 0, 0);
-        if (c != BFT_CLS_NONE) r = __ldg(class_rows + (size_t)c * rw4 + w);
-        __stcs(rows + t, r);
     }
 }
 

@@ -57,6 +57,22 @@ def test_kmer_presence_and_colours(built):
     np.testing.assert_array_equal(table[cls[hit]], rows[hit])
     pop = np.unpackbits(rows[hit].view(np.uint8), axis=1).sum(axis=1)
     np.testing.assert_array_equal(counts[cls[hit]], pop)
+    # device-resident entry points with the in-kernel hit counter, at batch sizes that are not multiples of a warp (every row
+    # width: k_query_kmers_rows for 1/2/4 words, k_query_kmers_wide — 32 rows written per warp — for the rest)
+    import torch
+    dev = torch.device("cuda", eng.device)
+    dq = torch.from_numpy(np.ascontiguousarray(q).view(np.int64)).to(dev)
+    for n in (len(q), len(q) - 1, 33, 31, 1):
+        dp = torch.full((n + 64,), 7, dtype=torch.uint8, device=dev)
+        dr = torch.full((n + 64, eng.RW), -1, dtype=torch.int32, device=dev)
+        dc = torch.zeros(2, dtype=torch.int64, device=dev)
+        eng.query_kmers_device_accumulate(dq, n, dp, dr, dc)
+        eng.query_kmers_device_accumulate(dq, n, dp, dr, dc)      # accumulates: twice the hits
+        eng.sync()
+        np.testing.assert_array_equal(dp[:n].cpu().numpy(), ref_present[:n])
+        np.testing.assert_array_equal(dr[:n].cpu().numpy().view(np.uint32), ref_rows[:n])
+        assert int(dc[0].item()) == 2 * int(ref_present[:n].sum()) and int(dc[1].item()) == 0
+        assert bool((dp[n:] == 7).all()) and bool((dr[n:] == -1).all()), "stores past the end of the batch"
 
 
 def test_kmer_ascii_input(built):
