@@ -258,7 +258,8 @@ class Run:
         st = eng.stats()
         if self.rank == 0:
             log(f"{os.path.basename(path)}: {st['n_kmers']} k-mers, {st['n_nodes']} nodes, {st['n_ccs']} CCs, {st['n_classes']} colour classes, "
-                f"arena {st['arena_bytes'] / 1e6:.0f} MB + class rows {st['class_row_bytes'] / 1e6:.0f} MB + filter {st['filter_bytes'] / 1e6:.0f} MB; "
+                f"arena {st['arena_bytes'] / 1e6:.0f} MB + class rows {st['class_row_bytes'] / 1e6:.0f} MB + filter {st['filter_bytes'] / 1e6:.0f} MB "
+                f"+ fused root/filter {st['rootkf_bytes'] / 1e6:.0f} MB; "
                 f"flatten {st['flatten_seconds']:.1f}s upload {st['upload_seconds']:.1f}s decode+filter {st['decode_seconds']:.3f}s; open {time.time() - t0:.1f}s")
         return eng, st, path, L, note
 
@@ -453,8 +454,9 @@ def kmers_record(run: Run, tag: str, spec: dict, headline: bool):
         "k_query_kmers_rows" if RW <= 4 else "k_query_kmers_wide", a_arena,
         "8*W in + (1 + 4*RW) out + 32*W * P(walk reaches a bucket)", n, k_ms, cap,
         {"kmers_per_sec_kernel": n / (k_ms / 1e3), "bucket_accesses_per_kmer": bucket_pk, "filter_rejects_per_kmer": reject_pk,
-         "found_frac": found_pk, "filter_mb": st["filter_bytes"] / 1e6,
-         "l2_bytes_per_kmer": 8 + (32 if st["filter_bytes"] else 0) + 4 * RW * found_pk,
+         "found_frac": found_pk, "filter_mb": st["filter_bytes"] / 1e6, "rootkf_mb": st["rootkf_bytes"] / 1e6,
+         "l2_random_requests_per_kmer": (1 if st["rootkf_bytes"] else (2 if st["filter_bytes"] else 1)) + bucket_pk + found_pk,
+         "l2_bytes_per_kmer": (32 if st["rootkf_bytes"] else 8 + (32 if st["filter_bytes"] else 0)) + 4 * RW * found_pk,
          "random_gather_probe_loads_per_s": probe,
          "random_access_frac": (bucket_pk * n / (k_ms / 1e3) / probe) if probe else None,
          "context_reference_layout": {
@@ -463,9 +465,10 @@ def kmers_record(run: Run, tag: str, spec: dict, headline: bool):
              "nodes_per_kmer": nodes_pk, "search_depth_per_kmer": depth_pk, "cc_probed_per_node": cc_pk / max(nodes_pk, 1e-9),
              "note": "sectors the REFERENCE layout's walk dereferences (SURVEY.md 8d); the arena replaces them by one L2-resident "
                      "directory load + one bucket, so they are context, not the roofline"},
-         "note": "achieved = algorithmic HBM bytes of the arena's walk / kernel time; the root directory, the stored-k-mer filter and "
-                 "the class rows are served by L2 (l2_bytes_per_kmer). The kernel is bound by the RATE of random 64-byte HBM "
-                 "accesses (random_access_frac) on top of the streamed batch, not by bytes"})
+         "note": "achieved = algorithmic HBM bytes of the arena's walk / kernel time; the root directory entry + filter bits (one fused "
+                 "sector when rootkf_mb > 0) and the class rows are served by L2 (l2_bytes_per_kmer). The kernel is bound by the RATE of "
+                 "random accesses — 64-byte HBM accesses (random_access_frac) and random L2 sectors (l2_random_requests_per_kmer; "
+                 "about 300 G/s chip-wide, tools/mix_probe.cu) — on top of the streamed batch, not by bytes"})
 
     # ---- e2e: host C-ABI calls with pinned host buffers, copies inside the timed region
     e2e = None
@@ -536,6 +539,7 @@ def kmers_record(run: Run, tag: str, spec: dict, headline: bool):
            "config": {"workload": spec["workload"], "k": k, "k_note": "reference accepts only k % 9 == 0; 27 stands in for 31" if k == 27 else None,
                       "n_genomes": cfg["n_genomes"], "genome_len": L, "degraded": degraded, "kmers_in_bft": st["n_kmers"], "nodes": st["n_nodes"],
                       "colour_classes": st["n_classes"], "arena_mb": round(st["arena_bytes"] / 1e6, 1), "filter_mb": round(st["filter_bytes"] / 1e6, 1),
+                      "rootkf_mb": round(st["rootkf_bytes"] / 1e6, 1),
                       "arena_bytes_per_kmer": round(st["arena_bytes"] / max(1, st["n_kmers"]), 1), "nodes_per_lookup": nodes_pk,
                       "queries_per_gpu": n, "query_mix_present_mismatch_random": (1 / 3, 1 / 3, 1 / 3) if cfg.get("pools") else MIX,
                       "present_frac": n_present / n,

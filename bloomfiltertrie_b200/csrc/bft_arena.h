@@ -45,6 +45,14 @@
  *              L2. A k-mer the filter rejects is in no Node, so the walk (and its one random HBM access) is
  *              skipped; a k-mer it accepts is looked up as before, so answers never change. The reference spends
  *              its Bloom filters on choosing a CC; an absent k-mer still costs it the full descent.
+ *   rootkf[]   (device only, built by k_rkf_insert) the root directory and a stored-k-mer filter FUSED into one table:
+ *              every 9-nt prefix owns S 32-byte sectors, each holding the prefix's rootdir entry (8 bytes, repeated) and 192
+ *              filter bits; a k-mer reads the ONE sector its hash names and gets both the root probe's answer and the
+ *              filter's verdict. Measured on B200 (tools/mix_probe.cu) the walk is bound as much by the number of random
+ *              L2 requests per k-mer as by its one HBM access: a random sector served by L2 costs about 1/300 G s
+ *              chip-wide, so rootdir + kfilter as two requests cost 0.5 ms per 125 M k-mers more than one. Used by the
+ *              plain look-ups (k-mers, records, sequences); the neighbour engine keeps kfilter, whose block is chosen by
+ *              the k-mer's middle so that 8 neighbours share two blocks.
  *
  * The walk functions below are plain C, compiled for the device by nvcc (the product path) and for the host by
  * the flattener (to fill rootdir) and by tests/tools (to debug the arena without a GPU). The shipped library
@@ -178,6 +186,11 @@ typedef struct {
     const uint64_t* kfilter;
     uint32_t kf_blocks;
     uint32_t kf_quirk_safe;
+    /* fused root directory + stored-k-mer filter (see above); rkf_sectors == 0: none. Sector (prefix * rkf_sectors + j):
+     * word 0 = the rootdir entry of the prefix, words 1-3 = 3 x 64 filter bits. */
+    const uint64_t* rootkf;
+    uint32_t rkf_sectors;
+    uint32_t rkf_pad;
 } bft_view_t;
 
 /* ---- prefix bit manipulation --------------------------------------------------------------------------------
@@ -296,6 +309,25 @@ BFT_HD int bft_kf_test(const bft_view_t* v, const uint64_t* kmer, const int W) {
     uint64_t w[4];
     bft_kf_load(v, q.block, w);
     return bft_kf_bits(w, q);
+}
+
+/* ---- fused root directory + filter ------------------------------------------------------------------------------
+ * The sector of a k-mer inside its prefix's group and its three bit positions (one in each filter word), all from one
+ * 64-bit hash of the whole k-mer. */
+typedef struct { uint32_t j; uint32_t b1, b2, b3; } bft_rkf_pos_t;
+
+BFT_HD bft_rkf_pos_t bft_rkf_pos(const uint64_t* kmer, const int W, const uint32_t n_sectors) {
+    uint64_t x = kmer[0];
+    for (int w = 1; w < W; w++) x = (x ^ (x >> 29)) * 0x9FB21C651E98DF25ULL + kmer[w];
+    x *= 0xD6E8FEB86659FD93ULL;
+    x ^= x >> 32;
+    x *= 0x9E3779B97F4A7C15ULL;
+    bft_rkf_pos_t p;
+    p.b1 = (uint32_t)(x >> 58);
+    p.b2 = (uint32_t)(x >> 52) & 63u;
+    p.b3 = (uint32_t)(x >> 46) & 63u;
+    p.j = (uint32_t)((((x >> 14) & 0xffffffffULL) * (uint64_t)n_sectors) >> 32);
+    return p;
 }
 
 /* index of the first CC of a Node whose Bloom filter fires for idx14, or BFT_FIRSTCC_NONE (src/presenceNode.c:1354-1362) */
@@ -496,7 +528,8 @@ BFT_HD uint32_t bft_lookup_loc(const bft_view_t* v, const uint64_t* kmer, const 
     int sz = v->k;
     uint32_t pref_idx = 0;
     bft_entry_t e;
-    const int filtered = v->kf_blocks && !(flags & BFT_LK_NO_FILTER) && (!succ_leaf_quirk || v->kf_quirk_safe);
+    const int may_filter = !(flags & BFT_LK_NO_FILTER) && (!succ_leaf_quirk || v->kf_quirk_safe);
+    const int filtered = v->kf_blocks && may_filter;
     int rejected = 0; /* statistics mode only: the product path stops at a rejection */
     if (filtered && (flags & BFT_LK_FILTER_FIRST)) {
         if (!bft_kf_test(v, kmer, W)) {
@@ -505,15 +538,35 @@ BFT_HD uint32_t bft_lookup_loc(const bft_view_t* v, const uint64_t* kmer, const 
             st[6]++;
         }
     }
-    /* a 9-mer trie keeps its k-mers as leaf prefixes of the root: rootdir holds the entry but not its index */
-    if (loc && sz == BFT_NB_CHAR_SUF_PREF) e = bft_node_probe_ex(v, 0, (uint32_t)cur[0] & (BFT_ROOTDIR_SIZE - 1u), 0, &pref_idx);
-    else e = bft_ld_entry(v->rootdir + ((uint32_t)cur[0] & (BFT_ROOTDIR_SIZE - 1u)));
-    /* the filter block is fetched right behind the root entry (two independent L2 loads in flight) */
-    if (filtered && !(flags & BFT_LK_FILTER_FIRST)) {
-        if (!bft_kf_test(v, kmer, W)) {
+    const int fused = may_filter && v->rkf_sectors && !(flags & BFT_LK_FILTER_FIRST) && !(loc && sz == BFT_NB_CHAR_SUF_PREF);
+    if (fused) {
+        /* ONE L2 sector: the root entry of the prefix and the filter bits of this k-mer */
+        const bft_rkf_pos_t q = bft_rkf_pos(kmer, W, v->rkf_sectors);
+        const uint64_t* p = v->rootkf + ((size_t)((uint32_t)cur[0] & (BFT_ROOTDIR_SIZE - 1u)) * v->rkf_sectors + q.j) * 4;
+        uint64_t w0, w1, w2, w3;
+#ifdef __CUDA_ARCH__
+        asm("ld.global.nc.L2::evict_last.v4.u64 {%0,%1,%2,%3}, [%4];" : "=l"(w0), "=l"(w1), "=l"(w2), "=l"(w3) : "l"(p));
+#else
+        w0 = p[0]; w1 = p[1]; w2 = p[2]; w3 = p[3];
+#endif
+        e.a = (uint32_t)w0;
+        e.b = (uint32_t)(w0 >> 32);
+        if (!(((w1 >> q.b1) & (w2 >> q.b2) & (w3 >> q.b3)) & 1ULL)) {
             if (!st) return BFT_CLS_NONE;
             rejected = 1;
             st[6]++;
+        }
+    } else {
+        /* a 9-mer trie keeps its k-mers as leaf prefixes of the root: rootdir holds the entry but not its index */
+        if (loc && sz == BFT_NB_CHAR_SUF_PREF) e = bft_node_probe_ex(v, 0, (uint32_t)cur[0] & (BFT_ROOTDIR_SIZE - 1u), 0, &pref_idx);
+        else e = bft_ld_entry(v->rootdir + ((uint32_t)cur[0] & (BFT_ROOTDIR_SIZE - 1u)));
+        /* the filter block is fetched right behind the root entry (two independent L2 loads in flight) */
+        if (filtered && !(flags & BFT_LK_FILTER_FIRST)) {
+            if (!bft_kf_test(v, kmer, W)) {
+                if (!st) return BFT_CLS_NONE;
+                rejected = 1;
+                st[6]++;
+            }
         }
     }
     if (st) { st[0]++; st[3] += bft_cc_probed(v, 0, (uint32_t)cur[0] & (BFT_ROOTDIR_SIZE - 1u)); }

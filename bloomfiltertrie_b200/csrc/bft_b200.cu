@@ -71,6 +71,7 @@ struct bft_b200_ctx {
     bft_pools_t dpools;
     void* d_pool[4];
     void* d_hot;              /* one allocation: rootdir | class_rows | kfilter — the tables every lookup touches, kept in L2 */
+    void* d_rootkf;           /* fused root directory + filter (bft_arena.h), the plain look-ups' first stop; NULL: none */
     size_t hot_bytes;
     uint64_t n_loc;           /* storage locations (bft_view_t), counted in 64 bits */
     cudaMemPool_t pool;       /* private pool of the traversal scratch (the device's default pool is left alone) */
@@ -174,6 +175,7 @@ extern "C" void bft_b200_close(bft_b200_ctx* c) {
     for (int i = 0; i < 19; i++) if (c->d_arena[i]) cudaFree(c->d_arena[i]);
     for (int i = 0; i < 4; i++) if (c->d_pool[i]) cudaFree(c->d_pool[i]);
     if (c->d_hot) cudaFree(c->d_hot);
+    if (c->d_rootkf) cudaFree(c->d_rootkf);
     if (c->d_class_counts) cudaFree(c->d_class_counts);
     if (c->d_counter) cudaFree(c->d_counter);
     bft_b200_graph_release(c);
@@ -202,29 +204,94 @@ extern "C" void bft_b200_close(bft_b200_ctx* c) {
 
 static int enqueue_extract(bft_b200_ctx* c, uint64_t* d_kmers, uint32_t* d_cls, uint32_t* d_loc2vid);
 
-/* the stored-k-mer filter (bft_arena.h): enumerate the arena's k-mers on the device, set their bits, then publish it */
-static int build_kfilter(bft_b200_ctx* c, size_t n_kmers, unsigned long long* d_filter, uint32_t n_blocks, int quirk_safe) {
+/* The two stored-k-mer filters (bft_arena.h): enumerate the arena's k-mers on the device ONCE, set their bits in kfilter (when
+ * n_blocks != 0), and build the fused root directory + filter when the k-mers are spread evenly enough over the 9-nt prefixes
+ * for 192 * S bits per prefix to filter anything. Both are optional accelerators: on any shortage of memory the engine runs
+ * without them. rkf_bytes_out receives the size of the fused table (0: not built). */
+static int build_filters(bft_b200_ctx* c, size_t n_kmers, unsigned long long* d_filter, uint32_t n_blocks, int quirk_safe, size_t* rkf_bytes_out) {
+    *rkf_bytes_out = 0;
+    c->dview.kf_quirk_safe = (uint32_t)(quirk_safe != 0);
+    /* sectors per prefix of the fused table: enough for BFT_B200_RKF_BITS (default 5.5) filter bits per stored k-mer, at most 4
+     * (33.5 MB: it must stay in L2 next to the class rows), at least 3.5 bits per k-mer or not at all. BFT_B200_RKF_SECTORS forces S. */
+    uint32_t S = 0;
+    {
+        const char* es = getenv("BFT_B200_RKF_SECTORS");
+        const char* eb = getenv("BFT_B200_RKF_BITS");
+        const double want = (eb ? atof(eb) : 5.5) * (double)n_kmers, per_s = 192.0 * BFT_ROOTDIR_SIZE;
+        if (es) S = (uint32_t)atoi(es);
+        else if (n_kmers) {
+            for (S = 1; S < 4 && per_s * S < want; S++) {}
+            if (per_s * S < 3.5 * (double)n_kmers) S = 0;
+        }
+        if (S > 16) S = 16;
+    }
+    if (!n_blocks && !S) return 0;
     uint64_t* d_k = NULL;
     if (cudaMalloc((void**)&d_k, (n_kmers + 1) * (size_t)c->W * 8) != cudaSuccess) {
         (void)cudaGetLastError();
-        return 0; /* no room for the scratch: run without a filter */
+        return 0; /* no room for the scratch: run without filters */
     }
     c->stats.n_kmers = n_kmers; /* enqueue_extract sizes nothing by it, but keep the context coherent */
+    cudaStream_t st = c->streams[0];
     int rc = enqueue_extract(c, d_k, NULL, NULL);
-    if (!rc) {
-#define BFT_L(W_) k_kf_insert<W_><<<grid_for(c, n_kmers, BFT_TPB), BFT_TPB, 0, c->streams[0]>>>(d_k, n_kmers, c->k, d_filter, n_blocks)
+    if (!rc && n_blocks) {
+#define BFT_L(W_) k_kf_insert<W_><<<grid_for(c, n_kmers, BFT_TPB), BFT_TPB, 0, st>>>(d_k, n_kmers, c->k, d_filter, n_blocks)
         BFT_BY_W(c->W, BFT_L);
 #undef BFT_L
         c->launches++;
-        cudaError_t e = cudaStreamSynchronize(c->streams[0]);
+        cudaError_t e = cudaStreamSynchronize(st);
         if (e != cudaSuccess) rc = set_err(BFT_B200_ERR_CUDA, "stored-k-mer filter build failed: %s", cudaGetErrorString(e));
+        if (!rc) {
+            c->dview.kfilter = (const uint64_t*)d_filter;
+            c->dview.kf_blocks = n_blocks;
+        }
+    }
+    if (!rc && S) {
+        /* how many stored k-mers sit under each prefix: expected false-positive rate of a query distributed like the stored
+         * k-mers, sum_p c_p (1 - exp(-3 c_p / (192 S)))^3 / n. A trie whose k-mers crowd under a few prefixes (a forced-deep
+         * one) would saturate their sectors: it keeps the two-table path, whose filter blocks are shared by all prefixes. */
+        uint32_t* d_cnt = NULL;
+        uint32_t* h_cnt = (uint32_t*)malloc(BFT_ROOTDIR_SIZE * sizeof(uint32_t));
+        bool use = h_cnt && cudaMalloc((void**)&d_cnt, BFT_ROOTDIR_SIZE * sizeof(uint32_t)) == cudaSuccess;
+        if (use) {
+            cudaMemsetAsync(d_cnt, 0, BFT_ROOTDIR_SIZE * sizeof(uint32_t), st);
+#define BFT_L(W_) k_rkf_count<W_><<<grid_for(c, n_kmers, BFT_TPB), BFT_TPB, 0, st>>>(d_k, n_kmers, d_cnt)
+            BFT_BY_W(c->W, BFT_L);
+#undef BFT_L
+            c->launches++;
+            use = cudaMemcpyAsync(h_cnt, d_cnt, BFT_ROOTDIR_SIZE * sizeof(uint32_t), cudaMemcpyDeviceToHost, st) == cudaSuccess &&
+                  cudaStreamSynchronize(st) == cudaSuccess;
+        }
+        if (use && !getenv("BFT_B200_RKF_SECTORS")) {
+            double fp = 0;
+            for (size_t p = 0; p < BFT_ROOTDIR_SIZE; p++) {
+                const double cp = (double)h_cnt[p], t = 1.0 - exp(-3.0 * cp / (192.0 * S));
+                fp += cp * t * t * t;
+            }
+            use = fp / (double)n_kmers <= 0.15;
+        }
+        const size_t bytes = (size_t)BFT_ROOTDIR_SIZE * S * 32;
+        if (use && cudaMalloc(&c->d_rootkf, bytes + 32) != cudaSuccess) { c->d_rootkf = NULL; use = false; }
+        if (use) {
+            cudaMemsetAsync(c->d_rootkf, 0, bytes + 32, st);
+            k_rkf_fill_entries<<<grid_for(c, (size_t)BFT_ROOTDIR_SIZE * S, BFT_TPB), BFT_TPB, 0, st>>>(c->dview.rootdir, (unsigned long long*)c->d_rootkf, S);
+#define BFT_L(W_) k_rkf_insert<W_><<<grid_for(c, n_kmers, BFT_TPB), BFT_TPB, 0, st>>>(d_k, n_kmers, (unsigned long long*)c->d_rootkf, S)
+            BFT_BY_W(c->W, BFT_L);
+#undef BFT_L
+            c->launches += 2;
+            cudaError_t e = cudaStreamSynchronize(st);
+            if (e != cudaSuccess) rc = set_err(BFT_B200_ERR_CUDA, "fused root directory + filter build failed: %s", cudaGetErrorString(e));
+            else {
+                c->dview.rootkf = (const uint64_t*)c->d_rootkf;
+                c->dview.rkf_sectors = S;
+                *rkf_bytes_out = bytes;
+            }
+        }
+        (void)cudaGetLastError();
+        if (d_cnt) cudaFree(d_cnt);
+        free(h_cnt);
     }
     cudaFree(d_k);
-    if (!rc) {
-        c->dview.kfilter = (const uint64_t*)d_filter;
-        c->dview.kf_blocks = n_blocks;
-        c->dview.kf_quirk_safe = (uint32_t)(quirk_safe != 0);
-    }
     return rc;
 }
 
@@ -400,8 +467,9 @@ extern "C" int bft_b200_open(const char* path, int device, bft_b200_ctx** out) {
         if (e != cudaSuccess) rc = set_err(BFT_B200_ERR_CUDA, "k_decode_classes failed: %s", cudaGetErrorString(e));
         else if (h_bad) rc = set_err(BFT_B200_ERR_FILE, "%d colour annotations are malformed (mode 3 pointing outside the colour pools)", h_bad);
     }
-    if (!rc && kf_blocks) rc = build_kfilter(c, a->n_kmers, (unsigned long long*)((char*)c->d_hot + rootdir_bytes + rows_padded), (uint32_t)kf_blocks,
-                                             a->max_depth < a->k / BFT_NB_CHAR_SUF_PREF || a->k == BFT_NB_CHAR_SUF_PREF);
+    size_t rkf_bytes = 0;
+    if (!rc && a->n_kmers) rc = build_filters(c, a->n_kmers, (unsigned long long*)((char*)c->d_hot + rootdir_bytes + rows_padded), (uint32_t)kf_blocks,
+                                              a->max_depth < a->k / BFT_NB_CHAR_SUF_PREF || a->k == BFT_NB_CHAR_SUF_PREF, &rkf_bytes);
     double t3 = now_s();
     if (d_bad) cudaFree(d_bad);
     if (d_cls_off) cudaFree(d_cls_off);
@@ -412,6 +480,7 @@ extern "C" int bft_b200_open(const char* path, int device, bft_b200_ctx** out) {
     c->stats.class_row_bytes = row_bytes; c->stats.max_cc_per_node = a->max_cc_per_node; c->stats.max_depth = a->max_depth;
     c->stats.n_pools = a->n_pools;
     c->stats.filter_bytes = rc ? 0 : kf_bytes;
+    c->stats.rootkf_bytes = rc ? 0 : rkf_bytes;
     c->stats.flatten_seconds = t1 - t0; c->stats.upload_seconds = t2 - t1; c->stats.decode_seconds = t3 - t2;
     bft_arena_free(a);
 

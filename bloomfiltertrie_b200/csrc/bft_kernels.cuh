@@ -561,6 +561,41 @@ __global__ void __launch_bounds__(BFT_TPB) k_kf_insert(const uint64_t* __restric
     }
 }
 
+/* Build of the fused root directory + filter (bft_arena.h, rootkf): every sector gets its prefix's root entry; every stored
+ * k-mer sets its three bits in the sector its hash names, and is counted under its prefix (bft_b200_open sizes the table and
+ * decides from the counts whether the k-mers are spread evenly enough over the prefixes for it to filter at all). */
+__global__ void __launch_bounds__(BFT_TPB) k_rkf_fill_entries(const bft_entry_t* __restrict__ rootdir, unsigned long long* __restrict__ rootkf,
+                                                              uint32_t n_sectors) {
+    const size_t total = (size_t)BFT_ROOTDIR_SIZE * n_sectors, stride = (size_t)gridDim.x * blockDim.x;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
+        const bft_entry_t e = rootdir[i / n_sectors];
+        rootkf[i * 4] = (unsigned long long)e.a | ((unsigned long long)e.b << 32);
+    }
+}
+
+template <int W>
+__global__ void __launch_bounds__(BFT_TPB) k_rkf_count(const uint64_t* __restrict__ kmers, size_t n, uint32_t* __restrict__ per_prefix) {
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
+        atomicAdd(per_prefix + ((uint32_t)kmers[i * W] & (BFT_ROOTDIR_SIZE - 1u)), 1u);
+}
+
+template <int W>
+__global__ void __launch_bounds__(BFT_TPB) k_rkf_insert(const uint64_t* __restrict__ kmers, size_t n, unsigned long long* __restrict__ rootkf,
+                                                        uint32_t n_sectors) {
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        uint64_t km[W];
+#pragma unroll
+        for (int w = 0; w < W; w++) km[w] = kmers[i * W + w];
+        const bft_rkf_pos_t q = bft_rkf_pos(km, W, n_sectors);
+        unsigned long long* p = rootkf + ((size_t)((uint32_t)km[0] & (BFT_ROOTDIR_SIZE - 1u)) * n_sectors + q.j) * 4;
+        atomicOr(p + 1, 1ULL << q.b1);
+        atomicOr(p + 2, 1ULL << q.b2);
+        atomicOr(p + 3, 1ULL << q.b3);
+    }
+}
+
 /* ---- enumeration: iterate_over_kmers / -extract_kmers (include/bft.h:88,164; src/extract_kmers.c:3-597) ------------
  * One warp per stored prefix. The k-mer is re-assembled from the Node's path (the prefixes above it), the prefix's own
  * 9 nucleotides and the suffix found in its buckets; the output slot of every k-mer is fixed by the exclusive counts
@@ -1024,8 +1059,18 @@ __global__ void __launch_bounds__(32 * BFT_SEQ_WARPS) k_query_sequences(const bf
          * window, and this kernel is issue-bound, so the filter's hash and L2 load would be pure overhead there: the first
          * 32 windows of a sequence are looked up without it, and it is switched on for the rest only if most of them missed. */
         int lk_flags = BFT_LK_NO_FILTER;
+        /* threshold: count >= ceil(n_win * threshold) (src/bft.c:1279, 1327-1339). The reference stops scanning a sequence as
+         * soon as no genome can reach it any more — `found + windows left < need` (src/bft.c:1319) — and so does the warp, at
+         * its own granularity of 32 windows: the answer is the all-zero row either way (a genome's count never exceeds the
+         * number of windows found), and the warp stops no earlier than the reference does. */
+        /* found + left < need  <=>  windows missed so far > n_win - need; 32-bit, saturating (a budget that does not fit never trips) */
+        unsigned int miss_budget = 0xffffffffu, missed = 0;
+        if (n_win > 0) {
+            const long long slack = n_win - (long long)ceil((double)n_win * threshold);
+            if (slack < 0xffffffffLL) miss_budget = (unsigned int)slack;
+        }
         __syncwarp();
-        for (long long t0 = 0; t0 < n_win; t0 += BFT_SEQ_TILE) {
+        for (long long t0 = 0; t0 < n_win && missed <= miss_budget; t0 += BFT_SEQ_TILE) {
             const int n_here = (int)(n_win - t0 < BFT_SEQ_TILE ? n_win - t0 : BFT_SEQ_TILE); /* windows in this tile */
             const int n_chars = n_here + k - 1;
             /* stage + encode: 32 characters per step, up to one zeroed 64-base word past the data (the funnel
@@ -1123,6 +1168,11 @@ __global__ void __launch_bounds__(32 * BFT_SEQ_WARPS) k_query_sequences(const bf
                 }
                 /* merge windows with the same colour class, then bump the per-genome counters warp-wide */
                 const uint32_t active = __ballot_sync(0xffffffffu, cls != BFT_CLS_NONE);
+                {
+                    const unsigned int m = (unsigned int)min(32, n_here - j0) - (unsigned int)__popc(active);
+                    missed = missed + m < missed ? 0xffffffffu : missed + m;
+                    if (missed > miss_budget) break;
+                }
                 if (active) {
                     uint32_t grp = 0;
                     if (cls != BFT_CLS_NONE) grp = __match_any_sync(active, cls);
@@ -1142,13 +1192,13 @@ __global__ void __launch_bounds__(32 * BFT_SEQ_WARPS) k_query_sequences(const bf
             }
             __syncwarp();
         }
-        /* threshold: count >= ceil(n_win * threshold) (src/bft.c:1279, 1327-1339) */
         bad = __any_sync(0xffffffffu, bad);
         long long need = 0;
         if (n_win > 0) need = (long long)ceil((double)n_win * threshold);
+        const bool unreachable = missed > miss_budget;
         for (int w = 0; w < rw; w++) {
             const uint32_t cnt = counts[w * 32 + lane];
-            const uint32_t bits = __ballot_sync(0xffffffffu, n_win > 0 && cnt > 0 && (long long)cnt >= need);
+            const uint32_t bits = __ballot_sync(0xffffffffu, !unreachable && n_win > 0 && cnt > 0 && (long long)cnt >= need);
             if (lane == 0) rows[s * (size_t)rw + w] = bits;
         }
         if (lane == 0 && status) status[s] = bad ? 2 : (n_win <= 0 ? 1 : 0);

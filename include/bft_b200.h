@@ -73,6 +73,7 @@ typedef struct {
     int max_cc_per_node, max_depth, n_pools;
     double flatten_seconds, upload_seconds, decode_seconds;
     uint64_t filter_bytes; /* stored-k-mer filter in L2 (0: none) */
+    uint64_t rootkf_bytes; /* fused root directory + stored-k-mer filter of the plain look-ups (0: none) */
 } bft_b200_stats;
 int bft_b200_get_stats(const bft_b200_ctx* ctx, bft_b200_stats* out);
 
@@ -91,7 +92,7 @@ int bft_b200_query_kmers_device(bft_b200_ctx* ctx, const uint64_t* d_kmers, size
                                 uint32_t* d_rows, uint32_t* d_class_ids);
 /* Same as the _device call with rows, plus the batch's hit count accumulated by the kernel itself into *d_n_present (a
  * device uint64, zeroed by the call): the "Nb k-mers present" of the reference driver (src/file_io.c:813) without a
- * second pass over the presence bytes. Narrow rows only (RW in {1,2,4}, i.e. <= 128 genomes). */
+ * second pass over the presence bytes. Any row width. */
 int bft_b200_query_kmers_device_counted(bft_b200_ctx* ctx, const uint64_t* d_kmers, size_t n, uint8_t* d_present,
                                         uint32_t* d_rows, uint64_t* d_n_present);
 /* Same, without zeroing: the kernel ADDS the batch's hit count to *d_counter with one system-scope atomic per thread
@@ -130,7 +131,10 @@ int bft_b200_annotation_setop_device(bft_b200_ctx* ctx, int op, const uint32_t* 
  * (src/file_io.c:1464-1574): sequence i = chars[offs[i] .. offs[i+1]). For every window: optional canonical pick
  * (reverse_complement + strcmp, src/bft.c:1287-1293), IUPAC windows skipped (src/fasta.c:357-363), lookup, colour
  * decode, per-genome hit count; genome g is reported iff count >= ceil(n_windows * threshold) (double arithmetic,
- * src/bft.c:1279). rows: n_seq*RW. status (may be NULL): BFT_B200_SEQ_*. 0 < threshold <= 1 (src/bft.c:1246-1247). */
+ * src/bft.c:1279). rows: n_seq*RW. status (may be NULL): BFT_B200_SEQ_*. 0 < threshold <= 1 (src/bft.c:1246-1247).
+ * Like the reference (src/bft.c:1319) the scan of a sequence stops once no genome can reach the threshold any more (windows
+ * found so far + windows left < need; tested every 32 windows, never earlier than the reference's own test): the row is all
+ * zero, and a bad character past that point is not reported (the reference would not have reached it either). */
 int bft_b200_query_sequences(bft_b200_ctx* ctx, const char* chars, const uint64_t* offs, size_t n_seq,
                              double threshold, int canonical, uint32_t* rows, uint8_t* status);
 int bft_b200_query_sequences_device(bft_b200_ctx* ctx, const char* d_chars, const uint64_t* d_offs, size_t n_seq,

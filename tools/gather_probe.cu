@@ -99,7 +99,7 @@ static void run(const char* name, const uint64_t* table, size_t bytes, size_t n_
 }
 
 int main(int argc, char** argv) {
-    size_t bytes = (size_t)(argc > 1 ? atof(argv[1]) : 4.0) * (1ull << 30);
+    size_t bytes = (size_t)((argc > 1 ? atof(argv[1]) : 4.0) * (double)(1ull << 30)) / 4096 * 4096;
     size_t n_loads = (size_t)1 << 28;
     uint64_t* table; unsigned long long* sink;
     cudaMalloc(&table, bytes); cudaMalloc(&sink, 8);
@@ -107,7 +107,7 @@ int main(int argc, char** argv) {
     int g = argc > 2 ? atoi(argv[2]) : 0;
     if (g) printf("cudaLimitMaxL2FetchGranularity=%d -> %s\n", g, cudaGetErrorString(cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, g)));
     size_t cur = 0; cudaDeviceGetLimit(&cur, cudaLimitMaxL2FetchGranularity);
-    printf("table %.1f GiB, %zu loads, L2 fetch granularity limit %zu\n", bytes / 1073741824.0, n_loads, cur);
+    printf("table %.2f GiB, %zu loads, L2 fetch granularity limit %zu\n", bytes / 1073741824.0, n_loads, cur);
     run<0, 8>("ld.global.nc (__ldg)", table, bytes, n_loads, sink);
     run<1, 8>("ld.global.cs (__ldcs)", table, bytes, n_loads, sink);
     run<2, 8>("ld.global.nc.L2::64B", table, bytes, n_loads, sink);

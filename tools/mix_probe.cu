@@ -38,7 +38,8 @@ struct Tables {
     uint32_t p_thresh, q_thresh; // probabilities scaled to 2^32
 };
 
-// FLAGS: 1 = stream in/out, 2 = L2 tables (rootdir + filter), 4 = random HBM bucket, 8 = class row
+// FLAGS: 1 = stream in/out, 2 = root directory entry (L2), 16 = filter block (L2), 4 = random HBM bucket, 8 = class row (L2),
+//        32 = "filter first": only the items that go on to a bucket fetch their root directory entry
 template <int FLAGS>
 __global__ void __launch_bounds__(256) k_mix(const Tables t, size_t n, unsigned long long* sink) {
     const size_t stride = (size_t)gridDim.x * blockDim.x;
@@ -47,16 +48,24 @@ __global__ void __launch_bounds__(256) k_mix(const Tables t, size_t n, unsigned 
         uint64_t x = (FLAGS & 1) ? __ldcs((const unsigned long long*)t.in + i) : (uint64_t)i;
         const uint64_t h = mix(x);
         uint64_t dep = 0;
-        if (FLAGS & 2) {
+        if ((FLAGS & 2) && !(FLAGS & 32)) {
             const uint2 e = __ldg(t.rootdir + (h & 0x3ffffu));
+            dep ^= (e.x ^ e.y) & 1ULL; // tables are zero-filled: dep == 0, but the compiler cannot know
+        }
+        if (FLAGS & 16) {
             uint64_t a, b, c, d;
             const uint64_t* p = t.filter + (size_t)((uint32_t)(((h >> 32) * (uint64_t)t.n_filter) >> 32)) * 4;
             asm volatile("ld.global.nc.L2::evict_last.v4.u64 {%0,%1,%2,%3}, [%4];" : "=l"(a), "=l"(b), "=l"(c), "=l"(d) : "l"(p));
-            dep = (e.x ^ e.y ^ a ^ b ^ c ^ d) & 1ULL; // tables are zero-filled: dep == 0, but the compiler cannot know
+            dep ^= (a ^ b ^ c ^ d) & 1ULL;
         }
-        const uint64_t h2 = mix(h + dep);
+        uint64_t h2 = mix(h + dep);
+        const bool to_bucket = (uint32_t)h2 < t.p_thresh;
+        if ((FLAGS & 2) && (FLAGS & 32) && to_bucket) {
+            const uint2 e = __ldg(t.rootdir + (h & 0x3ffffu));
+            h2 += (e.x ^ e.y) & 1ULL;
+        }
         uint64_t got = 0;
-        if ((FLAGS & 4) && (uint32_t)h2 < t.p_thresh) {
+        if ((FLAGS & 4) && to_bucket) {
             const uint64_t* p = t.buckets + ((h2 >> 20) % t.n_buckets) * 4;
             uint64_t a, b, c, d;
             asm volatile("ld.global.nc.L1::no_allocate.L2::evict_first.L2::64B.v4.u64 {%0,%1,%2,%3}, [%4];"
@@ -66,11 +75,12 @@ __global__ void __launch_bounds__(256) k_mix(const Tables t, size_t n, unsigned 
         uint4 r = make_uint4(0, 0, 0, 0);
         const bool hit = (uint32_t)(h2 >> 32) < t.q_thresh;
         if ((FLAGS & 8) && hit) r = __ldg(t.rows + (uint32_t)((((h2 + got) & 0xffffffffu) * (uint64_t)t.n_rows) >> 32));
+        r.y ^= (uint32_t)got; // zero tables: the stored value does not change, the loads stay
         if (FLAGS & 1) {
             t.present[i] = hit;
             __stcs(t.out_rows + i, r);
         } else {
-            acc += r.x ^ got;
+            acc += r.x ^ r.y;
         }
     }
     if (acc == 0x1234567ULL) *sink = acc;
@@ -101,7 +111,7 @@ int main(int argc, char** argv) {
     const double P = argc > 4 ? atof(argv[4]) : 0.54, Q = argc > 5 ? atof(argv[5]) : 0.51;
     Tables t;
     uint64_t* in; uint8_t* present; uint4* out_rows; void *rootdir, *filter, *buckets, *rows; unsigned long long* sink;
-    const size_t fb = (size_t)(f_mb * 1e6) / 32 * 32, tb = (size_t)(t_mb * 1e6) / 32 * 32, rb = 20000000 / 16 * 16;
+    const size_t fb = (size_t)((f_mb > 0.001 ? f_mb : 0.001) * 1e6) / 32 * 32, tb = (size_t)(t_mb * 1e6) / 32 * 32, rb = 20000000 / 16 * 16;
     cudaMalloc(&in, n * 8); cudaMalloc(&present, n); cudaMalloc(&out_rows, n * 16);
     cudaMalloc(&rootdir, 2 << 20); cudaMalloc(&filter, fb); cudaMalloc(&buckets, tb); cudaMalloc(&rows, rb); cudaMalloc(&sink, 8);
     if (cudaGetLastError() != cudaSuccess) { printf("allocation failed\n"); return 1; }
@@ -116,15 +126,22 @@ int main(int argc, char** argv) {
     }
     t.in = in; t.rootdir = (const uint2*)rootdir; t.filter = (const uint64_t*)filter; t.buckets = (const uint64_t*)buckets; t.rows = (const uint4*)rows;
     t.present = present; t.out_rows = out_rows;
-    t.n_filter = (uint32_t)(fb / 32); t.n_rows = (uint32_t)(rb / 16); t.n_buckets = tb / 32;
+    t.n_filter = (uint32_t)(fb / 32 ? fb / 32 : 1); t.n_rows = (uint32_t)(rb / 16); t.n_buckets = tb / 32;
     t.p_thresh = (uint32_t)(P * 4294967295.0); t.q_thresh = (uint32_t)(Q * 4294967295.0);
     printf("items %zu, bucket table %.0f MB, filter %.0f MB, P(bucket) %.3f, P(row) %.3f\n", n, t_mb, f_mb, P, Q);
     const float stream = run<1>("stream only (8 B in, 17 B out)", t, n, sink, 25);
     const float rnd = run<4>("random 64-byte HBM accesses only (P per item)", t, n, sink, 32 * P);
-    run<2 | 4>("L2 tables + dependent random HBM access", t, n, sink, 32 * P);
     run<1 | 4>("stream + random HBM access", t, n, sink, 25 + 32 * P);
-    run<1 | 2>("stream + L2 tables", t, n, sink, 25);
-    const float all = run<1 | 2 | 4 | 8>("all: the traffic of k_query_kmers_rows<1,4>", t, n, sink, 25 + 32 * P);
+    run<2>("root directory entry only (1 random L2 sector per item)", t, n, sink, 0);
+    run<16>("filter block only (1 random L2 sector per item)", t, n, sink, 0);
+    run<2 | 16>("root directory + filter (2 random L2 sectors per item)", t, n, sink, 0);
+    run<1 | 2 | 16>("stream + root directory + filter", t, n, sink, 25);
+    run<2 | 16 | 4>("root directory + filter + dependent random HBM access", t, n, sink, 32 * P);
+    const float all = run<1 | 2 | 16 | 4 | 8>("ALL: the traffic of k_query_kmers_rows<1,4>", t, n, sink, 25 + 32 * P);
+    run<1 | 2 | 16 | 4 | 8 | 32>("variant: filter first, root entry only for bucket-bound items", t, n, sink, 25 + 32 * P);
+    run<1 | 16 | 4 | 8>("variant: no root directory (flat hash of the k-mer)", t, n, sink, 25 + 32 * P);
+    run<1 | 16 | 4>("variant: no root directory, no class row", t, n, sink, 25 + 32 * P);
+    run<1 | 4 | 8>("variant: no root directory, no filter (P applies)", t, n, sink, 25 + 32 * P);
     printf("additive (stream + random) %.3f ms, max %.3f ms, measured mix %.3f ms; random accesses in the mix: %.2f G/s\n", stream + rnd,
            stream > rnd ? stream : rnd, all, P * n / all / 1e6);
     return 0;
