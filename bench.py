@@ -448,7 +448,7 @@ def kmers_record(run: Run, tag: str, spec: dict, headline: bool):
     found_pk, bucket_pk, reject_pk = ws["found"] / n, ws["bucket_searches"] / n, ws["filter_rejects"] / n
     nodes_pk, depth_pk, cc_pk = ws["nodes"] / n, ws["search_depth"] / n, ws["cc_probed"] / n
     a_arena = 8 * W + (1 + 4 * RW) + 32.0 * W * bucket_pk
-    cap = ncu_capture(tag) if not degraded else None
+    cap = ncu_capture(tag if not degraded else tag + "_fb")
     probe = eng.random_gather_probe(4 << 30, 1 << 28) if (headline and not args.no_probe) else None
     roofline = base_roofline(
         "k_query_kmers_rows" if RW <= 4 else "k_query_kmers_wide", a_arena,
@@ -594,7 +594,7 @@ def sequences_record(run: Run, tag: str, spec: dict, headline: bool):
     a_win = 1.0 + 32.0 * W * bucket_pw + (4 * RW + 1 + 8) / (rl - k + 1)
     roofline = base_roofline("k_query_sequences", a_win,
                              "per k-mer window: 1 char streamed + 32*W * P(walk reaches a bucket) + (row + status + offset) / windows per read",
-                             units, ms_step, ncu_capture(tag) if not degraded else None,
+                             units, ms_step, ncu_capture(tag if not degraded else tag + "_fb"),
                              {"bucket_accesses_per_window": bucket_pw, "filter_rejects_per_window": ws["filter_rejects"] / len(wins),
                               "found_frac_windows": ws["found"] / len(wins),
                               "note": "one launch per step, so kernel time = step time. This kernel is instruction-issue bound (encode, canonical "
@@ -700,7 +700,7 @@ def branching_record(run: Run, tag: str, spec: dict, headline: bool):
     stats_consistent = ws["found"] == int(d_succ[:ns].sum().item()) + int(d_pred[:ns].sum().item())
     a_q = 8.0 * W + 2 + 8 * 32.0 * W * bucket_pl
     roofline = base_roofline("k_query_branching", a_q, "per query k-mer: 8*W in + 2 out + 8 look-ups * 32*W * P(walk reaches a bucket)", n, ms_step,
-                             ncu_capture(tag) if not degraded else None,
+                             ncu_capture(tag if not degraded else tag + "_fb"),
                              {"lookups_per_sec": 8 * n / (ms_step / 1e3), "bucket_accesses_per_lookup": bucket_pl,
                               "filter_rejects_per_lookup": ws["filter_rejects"] / len(nb8), "neighbours_present_frac": ws["found"] / len(nb8),
                               "filter_mb": st["filter_bytes"] / 1e6, "walk_stats_match_kernel_counts": bool(stats_consistent),
