@@ -437,8 +437,12 @@ extern "C" int bft_b200_open(const char* path, int device, bft_b200_ctx** out) {
         if (gran == 32 || gran == 64 || gran == 128) cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, (size_t)gran);
         cudaGetLastError();
     }
-    if (!rc && !(getenv("BFT_B200_NO_L2_PERSIST") && getenv("BFT_B200_NO_L2_PERSIST")[0] == '1')) {
-        /* keep the hot block resident in L2 (persisting access-policy window on both streams); best effort */
+    if (!rc && getenv("BFT_B200_L2_PERSIST") && getenv("BFT_B200_L2_PERSIST")[0] == '1') {
+        /* Opt-in experiment knob, OFF by default: a persisting access-policy window over the hot block. Measured on B200 it buys
+         * nothing (C3: 46.8 vs 46.7 G k-mers/s — the evict_last / evict_first hints on the loads already keep the hot tables in
+         * L2) and it costs: the set-aside is a DEVICE-wide limit that outlives the context, so every later context in the
+         * process (and the host application) runs with that much less L2 — the 1000-colour config dropped from 28.0 to 18.9 G
+         * k-mers/s, the 4-genome one from 74.6 to 59.2, when opened after the 100-genome BFT (profiles/r02_l2_persist_ab.md). */
         size_t win = c->hot_bytes;
         if (win > (size_t)prop.accessPolicyMaxWindowSize) win = (size_t)prop.accessPolicyMaxWindowSize;
         size_t persist = win; /* measured on B200: a set-aside larger than the window buys nothing, 64 MB costs 5 % */

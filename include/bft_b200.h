@@ -20,11 +20,13 @@
  *     and only enqueue work on bft_b200_stream().
  *   - there is no CPU fallback: without a usable CUDA device every call fails with BFT_B200_ERR_CUDA.
  *   - a context serves one caller at a time (the reference's query API is not re-entrant either); use one
- *     context per thread / per GPU. bft_b200_open asks for part of the device's L2 as persisting cache for the tables
- *     every lookup touches (cudaLimitPersistingL2CacheSize is device-wide: the limit is only ever raised, never shrunk
- *     below what the host application or another context set; BFT_B200_NO_L2_PERSIST=1 leaves it alone altogether).
+ *     context per thread / per GPU. The library changes no device-wide state: the tables every lookup touches are kept in
+ *     L2 by the cache hints on the loads themselves (a persisting-L2 set-aside is an opt-in experiment, BFT_B200_L2_PERSIST=1;
+ *     it is a device-wide limit that would outlive the context and take L2 away from everyone else).
  *     Environment knobs read by bft_b200_open: BFT_B200_KF_BITS (bits per stored k-mer of the L2-resident negative
- *     filter, default 6, 0 = off), BFT_B200_KF_MAX_MB (its size cap, default 36).
+ *     filter, default 6, 0 = off), BFT_B200_KF_MAX_MB (its size cap, default 36), BFT_B200_RKF_BITS / BFT_B200_RKF_SECTORS
+ *     (fused root directory + filter table of the plain look-ups: filter bits per stored k-mer, default 5.5; or the
+ *     number of 32-byte sectors per 9-nt prefix outright, 0 = off).
  */
 #ifndef BFT_B200_H
 #define BFT_B200_H
