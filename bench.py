@@ -259,7 +259,7 @@ class Run:
         if self.rank == 0:
             log(f"{os.path.basename(path)}: {st['n_kmers']} k-mers, {st['n_nodes']} nodes, {st['n_ccs']} CCs, {st['n_classes']} colour classes, "
                 f"arena {st['arena_bytes'] / 1e6:.0f} MB + class rows {st['class_row_bytes'] / 1e6:.0f} MB + filter {st['filter_bytes'] / 1e6:.0f} MB "
-                f"+ fused root/filter {st['rootkf_bytes'] / 1e6:.0f} MB; "
+                f"+ fused root/filter {st['rootkf_bytes'] / 1e6:.0f} MB + collapsed subtrees {st['deep_bytes'] / 1e6:.0f} MB; "
                 f"flatten {st['flatten_seconds']:.1f}s upload {st['upload_seconds']:.1f}s decode+filter {st['decode_seconds']:.3f}s; open {time.time() - t0:.1f}s")
         return eng, st, path, L, note
 
@@ -539,7 +539,7 @@ def kmers_record(run: Run, tag: str, spec: dict, headline: bool):
            "config": {"workload": spec["workload"], "k": k, "k_note": "reference accepts only k % 9 == 0; 27 stands in for 31" if k == 27 else None,
                       "n_genomes": cfg["n_genomes"], "genome_len": L, "degraded": degraded, "kmers_in_bft": st["n_kmers"], "nodes": st["n_nodes"],
                       "colour_classes": st["n_classes"], "arena_mb": round(st["arena_bytes"] / 1e6, 1), "filter_mb": round(st["filter_bytes"] / 1e6, 1),
-                      "rootkf_mb": round(st["rootkf_bytes"] / 1e6, 1),
+                      "rootkf_mb": round(st["rootkf_bytes"] / 1e6, 1), "collapsed_subtrees_mb": round(st["deep_bytes"] / 1e6, 1),
                       "arena_bytes_per_kmer": round(st["arena_bytes"] / max(1, st["n_kmers"]), 1), "nodes_per_lookup": nodes_pk,
                       "queries_per_gpu": n, "query_mix_present_mismatch_random": (1 / 3, 1 / 3, 1 / 3) if cfg.get("pools") else MIX,
                       "present_frac": n_present / n,
@@ -737,7 +737,8 @@ def branching_record(run: Run, tag: str, spec: dict, headline: bool):
     rec = {"value": n * run.world / (ms_step / 1e3), "unit": UNIT, "ms_per_step": ms_step, "steps": steps, "warmup": warmup, "n_gpus": run.world,
            "config": {"workload": spec["workload"], "k": k, "n_genomes": cfg["n_genomes"], "genome_len": L, "degraded": degraded,
                       "kmers_in_bft": st["n_kmers"], "nodes": st["n_nodes"], "arena_mb": round(st["arena_bytes"] / 1e6, 1),
-                      "filter_mb": round(st["filter_bytes"] / 1e6, 1), "queries_per_gpu": n, "branching_frac": n_br / n,
+                      "filter_mb": round(st["filter_bytes"] / 1e6, 1), "collapsed_subtrees_mb": round(st["deep_bytes"] / 1e6, 1),
+                      "queries_per_gpu": n, "branching_frac": n_br / n,
                       "query_mix_present_mismatch_random": MIX, "l2": "inputs larger than L2 (no flush needed)",
                       "sharding": f"arena replicated, queries sharded x{run.world}"},
            "clocks": clocks, "e2e": e2e, "gpu_launches": launches * run.world, "roofline": roofline, "cpu_baseline": cpu}

@@ -72,6 +72,7 @@ struct bft_b200_ctx {
     void* d_pool[4];
     void* d_hot;              /* one allocation: rootdir | class_rows | kfilter — the tables every lookup touches, kept in L2 */
     void* d_rootkf;           /* fused root directory + filter (bft_arena.h), the plain look-ups' first stop; NULL: none */
+    void* d_deep[3];          /* collapsed subtrees (bft_arena.h): rootdir_fast, dbuckets, dslotcls; NULL: none */
     size_t hot_bytes;
     uint64_t n_loc;           /* storage locations (bft_view_t), counted in 64 bits */
     cudaMemPool_t pool;       /* private pool of the traversal scratch (the device's default pool is left alone) */
@@ -176,6 +177,7 @@ extern "C" void bft_b200_close(bft_b200_ctx* c) {
     for (int i = 0; i < 4; i++) if (c->d_pool[i]) cudaFree(c->d_pool[i]);
     if (c->d_hot) cudaFree(c->d_hot);
     if (c->d_rootkf) cudaFree(c->d_rootkf);
+    for (int i = 0; i < 3; i++) if (c->d_deep[i]) cudaFree(c->d_deep[i]);
     if (c->d_class_counts) cudaFree(c->d_class_counts);
     if (c->d_counter) cudaFree(c->d_counter);
     bft_b200_graph_release(c);
@@ -208,8 +210,92 @@ static int enqueue_extract(bft_b200_ctx* c, uint64_t* d_kmers, uint32_t* d_cls, 
  * n_blocks != 0), and build the fused root directory + filter when the k-mers are spread evenly enough over the 9-nt prefixes
  * for 192 * S bits per prefix to filter anything. Both are optional accelerators: on any shortage of memory the engine runs
  * without them. rkf_bytes_out receives the size of the fused table (0: not built). */
-static int build_filters(bft_b200_ctx* c, size_t n_kmers, unsigned long long* d_filter, uint32_t n_blocks, int quirk_safe, size_t* rkf_bytes_out) {
+/* Collapsed subtrees (bft_arena.h, rootdir_fast / dbuckets): every root prefix whose suffixes live in a child Node gets one hashed
+ * block with all the k-mers below it. d_k / d_cls: the enumeration (k-mers and classes). Optional: on a shortage of memory, or when
+ * BFT_B200_NO_DEEP=1, the look-ups keep walking the Nodes. */
+static int build_deep_blocks(bft_b200_ctx* c, const bft_entry_t* h_rootdir, const uint64_t* d_k, const uint32_t* d_cls, size_t n_kmers, size_t* bytes_out) {
+    *bytes_out = 0;
+    if (getenv("BFT_B200_NO_DEEP") && getenv("BFT_B200_NO_DEEP")[0] == '1') return 0;
+    bool any = false;
+    for (size_t p = 0; p < BFT_ROOTDIR_SIZE && !any; p++) any = (h_rootdir[p].b >> BFT_KIND_SHIFT) == BFT_KIND_NODE;
+    if (!any) return 0;
+    cudaStream_t st = c->streams[0];
+    uint32_t* d_cnt = NULL;
+    unsigned int* d_failed = NULL;
+    uint32_t* h_cnt = (uint32_t*)malloc(BFT_ROOTDIR_SIZE * sizeof(uint32_t));
+    bft_entry_t* h_fast = (bft_entry_t*)malloc(BFT_ROOTDIR_SIZE * sizeof(bft_entry_t));
+    int rc = 0;
+    bool ok = h_cnt && h_fast && cudaMalloc((void**)&d_cnt, BFT_ROOTDIR_SIZE * sizeof(uint32_t)) == cudaSuccess &&
+              cudaMalloc((void**)&d_failed, sizeof(unsigned int)) == cudaSuccess;
+    if (ok) {
+        cudaMemsetAsync(d_cnt, 0, BFT_ROOTDIR_SIZE * sizeof(uint32_t), st);
+        cudaMemsetAsync(d_failed, 0, sizeof(unsigned int), st);
+#define BFT_L(W_) k_deep_count<W_><<<grid_for(c, n_kmers, BFT_TPB), BFT_TPB, 0, st>>>(c->dview.rootdir, d_k, n_kmers, d_cnt)
+        BFT_BY_W(c->W, BFT_L);
+#undef BFT_L
+        c->launches++;
+        ok = cudaMemcpyAsync(h_cnt, d_cnt, BFT_ROOTDIR_SIZE * sizeof(uint32_t), cudaMemcpyDeviceToHost, st) == cudaSuccess &&
+             cudaStreamSynchronize(st) == cudaSuccess;
+    }
+    size_t n_db = 0, n_deep = 0;
+    if (ok) {
+        /* block of a prefix: the smallest power of two of buckets that keeps the load at or below 1/2; the entry has four bits
+         * for its log2, so a subtree of more than 2^16 k-mers stays a Node (and is walked) */
+        memcpy(h_fast, h_rootdir, BFT_ROOTDIR_SIZE * sizeof(bft_entry_t));
+        for (size_t p = 0; p < BFT_ROOTDIR_SIZE; p++) {
+            if ((h_rootdir[p].b >> BFT_KIND_SHIFT) != BFT_KIND_NODE || h_cnt[p] == 0) continue;
+            uint32_t lb = 0;
+            while (lb < BFT_LB_MASK && ((size_t)1 << lb) * (BFT_BUCKET_KEYS / 2) < (size_t)h_cnt[p]) lb++;
+            if (((size_t)1 << lb) * (BFT_BUCKET_KEYS / 2) < (size_t)h_cnt[p]) continue;
+            if (n_db + ((size_t)1 << lb) >= 0xfffffff0u) { ok = false; break; }
+            h_fast[p] = bft_mk_entry(BFT_KIND_DEEP, (uint32_t)n_db, h_cnt[p] > BFT_CNT_MASK ? BFT_CNT_MASK : h_cnt[p]);
+            h_fast[p].b = (BFT_KIND_DEEP << BFT_KIND_SHIFT) | (lb << BFT_LB_SHIFT) | (h_fast[p].b & ((1u << BFT_LB_SHIFT) - 1u));
+            n_db += (size_t)1 << lb;
+            n_deep += h_cnt[p];
+        }
+        ok = ok && n_db > 0;
+    }
+    const size_t bk_bytes = n_db * (size_t)(BFT_BUCKET_KEYS * c->W) * 8, sc_bytes = c->dview.cls_shift ? 0 : n_db * BFT_BUCKET_KEYS * 4;
+    if (ok) {
+        ok = cudaMalloc(&c->d_deep[0], BFT_ROOTDIR_SIZE * sizeof(bft_entry_t)) == cudaSuccess && cudaMalloc(&c->d_deep[1], bk_bytes + 64) == cudaSuccess &&
+             (!sc_bytes || cudaMalloc(&c->d_deep[2], sc_bytes + 64) == cudaSuccess);
+    }
+    if (ok) {
+        cudaMemcpyAsync(c->d_deep[0], h_fast, BFT_ROOTDIR_SIZE * sizeof(bft_entry_t), cudaMemcpyHostToDevice, st);
+        cudaMemsetAsync(c->d_deep[1], 0xff, bk_bytes + 64, st);
+        if (sc_bytes) cudaMemsetAsync(c->d_deep[2], 0xff, sc_bytes + 64, st);
+#define BFT_L(W_) k_deep_insert<W_><<<grid_for(c, n_kmers, BFT_TPB), BFT_TPB, 0, st>>>((const bft_entry_t*)c->d_deep[0], d_k, d_cls, n_kmers, \
+            (unsigned long long*)c->d_deep[1], (uint32_t*)c->d_deep[2], c->dview.cls_shift, d_failed)
+        BFT_BY_W(c->W, BFT_L);
+#undef BFT_L
+        c->launches++;
+        unsigned int h_failed = 0;
+        cudaMemcpyAsync(&h_failed, d_failed, sizeof h_failed, cudaMemcpyDeviceToHost, st);
+        cudaError_t e = cudaStreamSynchronize(st);
+        if (e != cudaSuccess) rc = set_err(BFT_B200_ERR_CUDA, "collapsed-subtree build failed: %s", cudaGetErrorString(e));
+        else if (h_failed) rc = set_err(BFT_B200_ERR_CUDA, "collapsed-subtree build: %u k-mers found no slot", h_failed);
+        else {
+            c->dview.rootdir_fast = (const bft_entry_t*)c->d_deep[0];
+            c->dview.dbuckets = (const uint64_t*)c->d_deep[1];
+            c->dview.dslotcls = (const uint32_t*)c->d_deep[2];
+            *bytes_out = bk_bytes + sc_bytes + BFT_ROOTDIR_SIZE * sizeof(bft_entry_t);
+        }
+    }
+    if (!ok || rc) {
+        (void)cudaGetLastError();
+        for (int i = 0; i < 3; i++) { if (c->d_deep[i]) cudaFree(c->d_deep[i]); c->d_deep[i] = NULL; }
+    }
+    if (d_cnt) cudaFree(d_cnt);
+    if (d_failed) cudaFree(d_failed);
+    free(h_cnt);
+    free(h_fast);
+    return rc;
+}
+
+static int build_filters(bft_b200_ctx* c, const bft_entry_t* h_rootdir, size_t n_kmers, unsigned long long* d_filter, uint32_t n_blocks, int quirk_safe,
+                         size_t* rkf_bytes_out, size_t* deep_bytes_out) {
     *rkf_bytes_out = 0;
+    *deep_bytes_out = 0;
     c->dview.kf_quirk_safe = (uint32_t)(quirk_safe != 0);
     /* sectors per prefix of the fused table: enough for BFT_B200_RKF_BITS (default 5.5) filter bits per stored k-mer, at most 4
      * (33.5 MB: it must stay in L2 next to the class rows), at least 3.5 bits per k-mer or not at all. BFT_B200_RKF_SECTORS forces S. */
@@ -225,15 +311,18 @@ static int build_filters(bft_b200_ctx* c, size_t n_kmers, unsigned long long* d_
         }
         if (S > 16) S = 16;
     }
-    if (!n_blocks && !S) return 0;
     uint64_t* d_k = NULL;
-    if (cudaMalloc((void**)&d_k, (n_kmers + 1) * (size_t)c->W * 8) != cudaSuccess) {
+    uint32_t* d_cls = NULL;
+    if (cudaMalloc((void**)&d_k, (n_kmers + 1) * (size_t)c->W * 8) != cudaSuccess || cudaMalloc((void**)&d_cls, (n_kmers + 1) * 4) != cudaSuccess) {
         (void)cudaGetLastError();
-        return 0; /* no room for the scratch: run without filters */
+        if (d_k) cudaFree(d_k);
+        return 0; /* no room for the scratch: run without the accelerators */
     }
     c->stats.n_kmers = n_kmers; /* enqueue_extract sizes nothing by it, but keep the context coherent */
     cudaStream_t st = c->streams[0];
-    int rc = enqueue_extract(c, d_k, NULL, NULL);
+    int rc = enqueue_extract(c, d_k, d_cls, NULL);
+    if (!rc) rc = build_deep_blocks(c, h_rootdir, d_k, d_cls, n_kmers, deep_bytes_out);
+    cudaFree(d_cls);
     if (!rc && n_blocks) {
 #define BFT_L(W_) k_kf_insert<W_><<<grid_for(c, n_kmers, BFT_TPB), BFT_TPB, 0, st>>>(d_k, n_kmers, c->k, d_filter, n_blocks)
         BFT_BY_W(c->W, BFT_L);
@@ -274,7 +363,8 @@ static int build_filters(bft_b200_ctx* c, size_t n_kmers, unsigned long long* d_
         if (use && cudaMalloc(&c->d_rootkf, bytes + 32) != cudaSuccess) { c->d_rootkf = NULL; use = false; }
         if (use) {
             cudaMemsetAsync(c->d_rootkf, 0, bytes + 32, st);
-            k_rkf_fill_entries<<<grid_for(c, (size_t)BFT_ROOTDIR_SIZE * S, BFT_TPB), BFT_TPB, 0, st>>>(c->dview.rootdir, (unsigned long long*)c->d_rootkf, S);
+            k_rkf_fill_entries<<<grid_for(c, (size_t)BFT_ROOTDIR_SIZE * S, BFT_TPB), BFT_TPB, 0, st>>>(
+                c->dview.rootdir_fast ? c->dview.rootdir_fast : c->dview.rootdir, (unsigned long long*)c->d_rootkf, S);
 #define BFT_L(W_) k_rkf_insert<W_><<<grid_for(c, n_kmers, BFT_TPB), BFT_TPB, 0, st>>>(d_k, n_kmers, (unsigned long long*)c->d_rootkf, S)
             BFT_BY_W(c->W, BFT_L);
 #undef BFT_L
@@ -471,9 +561,9 @@ extern "C" int bft_b200_open(const char* path, int device, bft_b200_ctx** out) {
         if (e != cudaSuccess) rc = set_err(BFT_B200_ERR_CUDA, "k_decode_classes failed: %s", cudaGetErrorString(e));
         else if (h_bad) rc = set_err(BFT_B200_ERR_FILE, "%d colour annotations are malformed (mode 3 pointing outside the colour pools)", h_bad);
     }
-    size_t rkf_bytes = 0;
-    if (!rc && a->n_kmers) rc = build_filters(c, a->n_kmers, (unsigned long long*)((char*)c->d_hot + rootdir_bytes + rows_padded), (uint32_t)kf_blocks,
-                                              a->max_depth < a->k / BFT_NB_CHAR_SUF_PREF || a->k == BFT_NB_CHAR_SUF_PREF, &rkf_bytes);
+    size_t rkf_bytes = 0, deep_bytes = 0;
+    if (!rc && a->n_kmers) rc = build_filters(c, a->rootdir, a->n_kmers, (unsigned long long*)((char*)c->d_hot + rootdir_bytes + rows_padded), (uint32_t)kf_blocks,
+                                              a->max_depth < a->k / BFT_NB_CHAR_SUF_PREF || a->k == BFT_NB_CHAR_SUF_PREF, &rkf_bytes, &deep_bytes);
     double t3 = now_s();
     if (d_bad) cudaFree(d_bad);
     if (d_cls_off) cudaFree(d_cls_off);
@@ -485,6 +575,7 @@ extern "C" int bft_b200_open(const char* path, int device, bft_b200_ctx** out) {
     c->stats.n_pools = a->n_pools;
     c->stats.filter_bytes = rc ? 0 : kf_bytes;
     c->stats.rootkf_bytes = rc ? 0 : rkf_bytes;
+    c->stats.deep_bytes = rc ? 0 : deep_bytes;
     c->stats.flatten_seconds = t1 - t0; c->stats.upload_seconds = t2 - t1; c->stats.decode_seconds = t3 - t2;
     bft_arena_free(a);
 

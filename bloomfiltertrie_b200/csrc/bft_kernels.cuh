@@ -596,6 +596,52 @@ __global__ void __launch_bounds__(BFT_TPB) k_rkf_insert(const uint64_t* __restri
     }
 }
 
+/* Build of the collapsed subtrees (bft_arena.h, rootdir_fast / dbuckets). k_deep_count: how many stored k-mers sit below each
+ * root prefix whose suffixes live in a child Node. k_deep_insert: every such k-mer, minus its first 9 nucleotides, claims a slot
+ * of its block — the bucket its hash names, or the next one with room — with one compare-and-swap on the slot's top word; the
+ * words below and the class are written once the slot is owned (nothing reads the blocks before the build has completed). */
+template <int W>
+__global__ void __launch_bounds__(BFT_TPB) k_deep_count(const bft_entry_t* __restrict__ rootdir, const uint64_t* __restrict__ kmers, size_t n,
+                                                         uint32_t* __restrict__ per_prefix) {
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        const uint32_t p = (uint32_t)kmers[i * W] & (BFT_ROOTDIR_SIZE - 1u);
+        if ((rootdir[p].b >> BFT_KIND_SHIFT) == BFT_KIND_NODE) atomicAdd(per_prefix + p, 1u);
+    }
+}
+
+template <int W>
+__global__ void __launch_bounds__(BFT_TPB) k_deep_insert(const bft_entry_t* __restrict__ fastdir, const uint64_t* __restrict__ kmers,
+                                                          const uint32_t* __restrict__ cls, size_t n, unsigned long long* __restrict__ dbuckets,
+                                                          uint32_t* __restrict__ dslotcls, int cls_shift, unsigned int* __restrict__ failed) {
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        uint64_t key[W];
+#pragma unroll
+        for (int w = 0; w < W; w++) key[w] = kmers[i * W + w];
+        const bft_entry_t e = fastdir[(uint32_t)key[0] & (BFT_ROOTDIR_SIZE - 1u)];
+        if ((e.b >> BFT_KIND_SHIFT) != BFT_KIND_DEEP) continue;
+        bft_shift18(key, W);
+        const uint32_t lb = (e.b >> BFT_LB_SHIFT) & BFT_LB_MASK, mask = (1u << lb) - 1u;
+        const unsigned long long top = key[W - 1] | (cls_shift ? (unsigned long long)cls[i] << cls_shift : 0ULL);
+        uint32_t b = bft_bucket_of(key, W, lb);
+        bool placed = false;
+        for (uint32_t probe = 0; probe <= mask && !placed; probe++, b = (b + 1u) & mask) {
+            const size_t bucket = (size_t)e.a + b;
+            for (int j = 0; j < BFT_BUCKET_KEYS && !placed; j++) {
+                unsigned long long* slot = dbuckets + (bucket * BFT_BUCKET_KEYS + j) * W;
+                if (atomicCAS(slot + (W - 1), (unsigned long long)BFT_SLOT_EMPTY, top) == (unsigned long long)BFT_SLOT_EMPTY) {
+#pragma unroll
+                    for (int w = 0; w < W - 1; w++) slot[w] = key[w];
+                    if (!cls_shift) dslotcls[bucket * BFT_BUCKET_KEYS + j] = cls[i];
+                    placed = true;
+                }
+            }
+        }
+        if (!placed) atomicAdd(failed, 1u); /* cannot happen at load <= 1/2; checked by the host */
+    }
+}
+
 /* ---- enumeration: iterate_over_kmers / -extract_kmers (include/bft.h:88,164; src/extract_kmers.c:3-597) ------------
  * One warp per stored prefix. The k-mer is re-assembled from the Node's path (the prefixes above it), the prefix's own
  * 9 nucleotides and the suffix found in its buckets; the output slot of every k-mer is fixed by the exclusive counts
@@ -898,8 +944,8 @@ __device__ __forceinline__ void bft_neighbors_core(const bft_view_t& v, const ui
             for (int w = 0; w < W; w++) x[w] = xs[slot * W + w];
             bft_neighbor_kmer<W>(x, v.k, sub, y);
             uint32_t loc = 0;
-            const uint32_t cls = bft_lookup_loc(&v, y, W, ((quirk && sub < 4) ? BFT_LK_SUCC_QUIRK : 0) | BFT_LK_NO_FILTER, (uint32_t*)0,
-                                                MODE == 1 ? &loc : (uint32_t*)0);
+            const uint32_t cls = bft_lookup_loc(&v, y, W, ((quirk && sub < 4) ? BFT_LK_SUCC_QUIRK : 0) | BFT_LK_NO_FILTER |
+                                                ((MODE == 0 && !nbr_out) ? BFT_LK_PRESENCE : 0), (uint32_t*)0, MODE == 1 ? &loc : (uint32_t*)0);
             if (cls != BFT_CLS_NONE) {
                 const int pos = sub < 4 ? 4 + sub : sub - 4; /* get_neighbors order: 0-3 predecessors, 4-7 successors */
                 if (MODE == 0) {

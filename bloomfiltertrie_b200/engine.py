@@ -42,7 +42,7 @@ class Stats(C.Structure):
                                            "arena_bytes", "class_row_bytes")] + \
                [(n, C.c_int) for n in ("max_cc_per_node", "max_depth", "n_pools")] + \
                [(n, C.c_double) for n in ("flatten_seconds", "upload_seconds", "decode_seconds")] + \
-               [("filter_bytes", C.c_uint64), ("rootkf_bytes", C.c_uint64)]
+               [("filter_bytes", C.c_uint64), ("rootkf_bytes", C.c_uint64), ("deep_bytes", C.c_uint64)]
 
 
 class BFTError(RuntimeError):

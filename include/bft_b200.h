@@ -26,7 +26,8 @@
  *     Environment knobs read by bft_b200_open: BFT_B200_KF_BITS (bits per stored k-mer of the L2-resident negative
  *     filter, default 6, 0 = off), BFT_B200_KF_MAX_MB (its size cap, default 36), BFT_B200_RKF_BITS / BFT_B200_RKF_SECTORS
  *     (fused root directory + filter table of the plain look-ups: filter bits per stored k-mer, default 5.5; or the
- *     number of 32-byte sectors per 9-nt prefix outright, 0 = off).
+ *     number of 32-byte sectors per 9-nt prefix outright, 0 = off), BFT_B200_NO_DEEP=1 (no collapsed subtrees: look-ups
+ *     walk the Nodes below the root).
  */
 #ifndef BFT_B200_H
 #define BFT_B200_H
@@ -76,6 +77,7 @@ typedef struct {
     double flatten_seconds, upload_seconds, decode_seconds;
     uint64_t filter_bytes; /* stored-k-mer filter in L2 (0: none) */
     uint64_t rootkf_bytes; /* fused root directory + stored-k-mer filter of the plain look-ups (0: none) */
+    uint64_t deep_bytes;   /* collapsed subtrees: one hashed block per root prefix that leads to child Nodes (0: none) */
 } bft_b200_stats;
 int bft_b200_get_stats(const bft_b200_ctx* ctx, bft_b200_stats* out);
 
