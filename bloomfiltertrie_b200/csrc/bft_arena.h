@@ -223,9 +223,11 @@ BFT_HD uint32_t bft_rot18(uint32_t r18) { return ((r18 << 2) & 0x3ffffu) | (r18 
 BFT_HD bft_entry_t bft_ld_entry(const bft_entry_t* p) {
     bft_entry_t e;
 #ifdef __CUDA_ARCH__
-    const uint2 t = __ldg((const uint2*)p);
-    e.a = t.x;
-    e.b = t.y;
+    /* the 2 MB root directory is every look-up's first stop: kept in L2 (evict-last policy) against the streamed batch. Loads
+     * narrower than 256 bits take the priority through a cache-policy operand (createpolicy), not a qualifier. */
+    uint64_t pol;
+    asm("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
+    asm("ld.global.nc.L2::cache_hint.v2.u32 {%0,%1}, [%2], %3;" : "=r"(e.a), "=r"(e.b) : "l"(p), "l"(pol));
 #else
     e = *p;
 #endif

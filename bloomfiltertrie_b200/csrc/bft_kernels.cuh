@@ -104,6 +104,29 @@ __device__ __forceinline__ void bft_block_count(unsigned int hits, unsigned long
     }
 }
 
+/* class rows (decoded colour sets, read by every found k-mer): L2-resident table, loaded evict-last so that the streamed batch and
+ * the one-touch buckets (evict-first) do not push it out */
+__device__ __forceinline__ uint64_t bft_policy_evict_last() {
+    uint64_t pol;
+    asm("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
+    return pol;
+}
+__device__ __forceinline__ uint32_t bft_ld_row(const uint32_t* p) {
+    uint32_t r;
+    asm("ld.global.nc.L2::cache_hint.u32 %0, [%1], %2;" : "=r"(r) : "l"(p), "l"(bft_policy_evict_last()));
+    return r;
+}
+__device__ __forceinline__ uint2 bft_ld_row(const uint2* p) {
+    uint2 r;
+    asm("ld.global.nc.L2::cache_hint.v2.u32 {%0,%1}, [%2], %3;" : "=r"(r.x), "=r"(r.y) : "l"(p), "l"(bft_policy_evict_last()));
+    return r;
+}
+__device__ __forceinline__ uint4 bft_ld_row(const uint4* p) {
+    uint4 r;
+    asm("ld.global.nc.L2::cache_hint.v4.u32 {%0,%1,%2,%3}, [%4], %5;" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p), "l"(bft_policy_evict_last()));
+    return r;
+}
+
 /* ---- a4/a5/a7/a8: k-mer lookup ---------------------------------------------------------------------------- */
 template <int W>
 __global__ void __launch_bounds__(BFT_TPB) k_query_kmers(const bft_view_t v, const uint64_t* __restrict__ kmers, size_t n,
@@ -137,15 +160,15 @@ __global__ void __launch_bounds__(BFT_TPB) k_query_kmers_rows(const bft_view_t v
         if (cls_out) cls_out[i] = cls;
         if (RW == 4) {
             uint4 r = make_uint4(0, 0, 0, 0);
-            if (cls != BFT_CLS_NONE) r = __ldg((const uint4*)class_rows + cls);
+            if (cls != BFT_CLS_NONE) r = bft_ld_row((const uint4*)class_rows + cls);
             __stcs((uint4*)rows + i, r);
         } else if (RW == 2) {
             uint2 r = make_uint2(0, 0);
-            if (cls != BFT_CLS_NONE) r = __ldg((const uint2*)class_rows + cls);
+            if (cls != BFT_CLS_NONE) r = bft_ld_row((const uint2*)class_rows + cls);
             __stcs((uint2*)rows + i, r);
         } else {
             uint32_t r = 0;
-            if (cls != BFT_CLS_NONE) r = __ldg(class_rows + cls);
+            if (cls != BFT_CLS_NONE) r = bft_ld_row(class_rows + cls);
             __stcs(rows + i, r);
         }
     }
@@ -187,7 +210,7 @@ __global__ void __launch_bounds__(BFT_TPB) k_query_kmers_wide(const bft_view_t v
             const int kk = t / rwv, w = t - kk * rwv;
             const uint32_t c = __shfl_sync(0xffffffffu, cls, kk);
             T r = T();
-            if (c != BFT_CLS_NONE) r = __ldg(class_rows + (size_t)c * rwv + w);
+            if (c != BFT_CLS_NONE) r = bft_ld_row(class_rows + (size_t)c * rwv + w);
             if ((size_t)t < live) __stcs(out + t, r);
         }
     }
@@ -318,7 +341,7 @@ __global__ void __launch_bounds__(BFT_TPB) k_query_records(const bft_view_t v, c
             if (present) present[base + threadIdx.x] = hit;
             uint8_t* o = BFT_OUT_BUF(b) + (size_t)threadIdx.x * rb;
             for (int j = 0; j < rb; j += 4) {
-                const uint32_t word = hit ? __ldg(class_rows + (size_t)cls * rw + (j >> 2)) : 0u;
+                const uint32_t word = hit ? bft_ld_row(class_rows + (size_t)cls * rw + (j >> 2)) : 0u;
                 for (int q = 0; q < 4 && j + q < rb; q++) o[j + q] = (uint8_t)(word >> (8 * q));
             }
         }
@@ -384,7 +407,7 @@ __global__ void __launch_bounds__(BFT_TPB) k_compact_rows(const uint32_t* __rest
         if (hit) {
             uint8_t* o = sm + (size_t)(before + (uint32_t)__popc(ball & ((1u << lane) - 1u))) * rb;
             for (int j = 0; j < rb; j += 4) {
-                const uint32_t word = __ldg(class_rows + (size_t)c * rw + (j >> 2));
+                const uint32_t word = bft_ld_row(class_rows + (size_t)c * rw + (j >> 2));
                 for (int q = 0; q < 4 && j + q < rb; q++) o[j + q] = (uint8_t)(word >> (8 * q));
             }
         }
@@ -1230,7 +1253,7 @@ __global__ void __launch_bounds__(32 * BFT_SEQ_WARPS) k_query_sequences(const bf
                         const uint32_t add = __popc(__shfl_sync(0xffffffffu, grp, src));
                         const uint32_t* row = class_rows + (size_t)c * rw;
                         for (int w = 0; w < rw; w++) {
-                            const uint32_t bits = __ldg(row + w);
+                            const uint32_t bits = bft_ld_row(row + w);
                             if ((bits >> lane) & 1u) counts[w * 32 + lane] += add;
                         }
                     }
