@@ -241,12 +241,15 @@ static int build_deep_blocks(bft_b200_ctx* c, const bft_entry_t* h_rootdir, cons
     if (ok) {
         /* block of a prefix: the smallest power of two of buckets that keeps the load at or below 1/2; the entry has four bits
          * for its log2, so a subtree of more than 2^16 k-mers stays a Node (and is walked) */
+        /* test knob: BFT_B200_DEEP_TIGHT=1 sizes the blocks for a load of up to 1 (every slot may be taken), which makes the
+         * linear probing — and its termination in a block without an empty slot — the common case instead of the rare one */
+        const size_t per_bucket = (getenv("BFT_B200_DEEP_TIGHT") && getenv("BFT_B200_DEEP_TIGHT")[0] == '1') ? BFT_BUCKET_KEYS : BFT_BUCKET_KEYS / 2;
         memcpy(h_fast, h_rootdir, BFT_ROOTDIR_SIZE * sizeof(bft_entry_t));
         for (size_t p = 0; p < BFT_ROOTDIR_SIZE; p++) {
             if ((h_rootdir[p].b >> BFT_KIND_SHIFT) != BFT_KIND_NODE || h_cnt[p] == 0) continue;
             uint32_t lb = 0;
-            while (lb < BFT_LB_MASK && ((size_t)1 << lb) * (BFT_BUCKET_KEYS / 2) < (size_t)h_cnt[p]) lb++;
-            if (((size_t)1 << lb) * (BFT_BUCKET_KEYS / 2) < (size_t)h_cnt[p]) continue;
+            while (lb < BFT_LB_MASK && ((size_t)1 << lb) * per_bucket < (size_t)h_cnt[p]) lb++;
+            if (((size_t)1 << lb) * per_bucket < (size_t)h_cnt[p]) continue;
             if (n_db + ((size_t)1 << lb) >= 0xfffffff0u) { ok = false; break; }
             h_fast[p] = bft_mk_entry(BFT_KIND_DEEP, (uint32_t)n_db, h_cnt[p] > BFT_CNT_MASK ? BFT_CNT_MASK : h_cnt[p]);
             h_fast[p].b = (BFT_KIND_DEEP << BFT_KIND_SHIFT) | (lb << BFT_LB_SHIFT) | (h_fast[p].b & ((1u << BFT_LB_SHIFT) - 1u));
