@@ -588,9 +588,9 @@ extern "C" int bft_b200_open(const char* path, int device, bft_b200_ctx** out) {
         if (c->seq_smem > (size_t)prop.sharedMemPerBlockOptin)
             c->seq_smem = 0; /* too many genomes for the shared-memory counters: sequence queries will refuse */
         else {
-            cudaFuncSetAttribute(k_query_sequences<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->seq_smem);
-            cudaFuncSetAttribute(k_query_sequences<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->seq_smem);
-            cudaFuncSetAttribute(k_query_sequences<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->seq_smem);
+            cudaFuncSetAttribute(k_query_sequences<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->seq_smem);
+            cudaFuncSetAttribute(k_query_sequences<2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->seq_smem);
+            cudaFuncSetAttribute(k_query_sequences<4, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->seq_smem);
         }
     }
     if (rc) { bft_b200_close(c); return rc; }
@@ -984,10 +984,12 @@ static int enqueue_sequences(bft_b200_ctx* c, cudaStream_t st, const char* d_cha
     size_t blocks = (n_seq + BFT_SEQ_WARPS - 1) / BFT_SEQ_WARPS;
     const size_t cap = (size_t)c->sm_count * 16;
     if (blocks > cap) blocks = cap;
-#define BFT_L(W_) k_query_sequences<W_><<<(int)blocks, 32 * BFT_SEQ_WARPS, c->seq_smem, st>>>(c->dview, d_chars, d_offs, n_seq, thr, canonical, \
-                                                                                               c->d_class_rows, c->rw, c->G, d_rows, d_status)
+#define BFT_L2(W_, G32_) k_query_sequences<W_, G32_><<<(int)blocks, 32 * BFT_SEQ_WARPS, c->seq_smem, st>>>(c->dview, d_chars, d_offs, n_seq, thr, canonical, \
+                                                                                                      c->d_class_rows, c->rw, c->G, d_rows, d_status)
+#define BFT_L(W_) do { if (c->rw == 1) BFT_L2(W_, true); else BFT_L2(W_, false); } while (0)
     BFT_BY_W(c->W, BFT_L);
 #undef BFT_L
+#undef BFT_L2
     c->launches++;
     CK(cudaGetLastError());
     return 0;

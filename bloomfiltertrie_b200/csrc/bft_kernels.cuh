@@ -1021,10 +1021,10 @@ __global__ void __launch_bounds__(BFT_TPB) k_query_branching(const bft_view_t v,
 #define BFT_SEQ_SPAN (BFT_SEQ_TILE + 128)      /* characters held per tile (k <= 126 overlap, rounded to 64) */
 #define BFT_SEQ_WARPS 4
 
-/* shared memory one warp of k_query_sequences needs (codes + 4 masks + characters + per-genome counters) */
+/* shared memory one warp of k_query_sequences needs (codes + 4 masks + per-genome counters; up to 32 genomes are counted in registers) */
 __host__ __device__ inline size_t bft_seq_smem_per_warp(int n_genomes) {
     const size_t n_code_words = BFT_SEQ_SPAN / 32 + 2, n_mask_words = BFT_SEQ_SPAN / 64 + 2;
-    const size_t b = n_code_words * 8 + 4 * n_mask_words * 8 + BFT_SEQ_SPAN + (size_t)((n_genomes + 31) & ~31) * 4;
+    const size_t b = n_code_words * 8 + 4 * n_mask_words * 8 + (n_genomes > 32 ? (size_t)((n_genomes + 31) & ~31) * 4 : 0);
     return (b + 15) & ~(size_t)15;
 }
 
@@ -1095,7 +1095,25 @@ __device__ __forceinline__ char bft_rc_char(char c) { /* reverse_complement on A
     }
 }
 
-template <int W>
+/* 32 x 32 bit-matrix transpose across a warp: lane r holds row r, afterwards lane c holds column c (bit r of the result = bit c of
+ * lane r's input). Five butterfly steps, one shuffle each. */
+__device__ __forceinline__ uint32_t bft_warp_transpose32(uint32_t x, const int lane) {
+#define BFT_TR_STEP(J_, M_)                                                                  \
+    {                                                                                        \
+        const uint32_t y = __shfl_xor_sync(0xffffffffu, x, J_);                              \
+        x = (lane & J_) ? ((x & ~M_) | ((y & ~M_) >> J_)) : ((x & M_) | ((y & M_) << J_));   \
+    }
+    BFT_TR_STEP(16, 0x0000ffffu)
+    BFT_TR_STEP(8, 0x00ff00ffu)
+    BFT_TR_STEP(4, 0x0f0f0f0fu)
+    BFT_TR_STEP(2, 0x33333333u)
+    BFT_TR_STEP(1, 0x55555555u)
+#undef BFT_TR_STEP
+    return x;
+}
+
+/* G32: at most 32 genomes (one row word), counted in registers; otherwise the class-merge + shared-memory counters */
+template <int W, bool G32>
 __global__ void __launch_bounds__(32 * BFT_SEQ_WARPS) k_query_sequences(const bft_view_t v, const char* __restrict__ chars,
                                                                         const uint64_t* __restrict__ offs, size_t n_seq, double threshold,
                                                                         int canonical, const uint32_t* __restrict__ class_rows, int rw,
@@ -1113,9 +1131,8 @@ __global__ void __launch_bounds__(32 * BFT_SEQ_WARPS) k_query_sequences(const bf
     uint64_t* m_rcbad = m_iupac + n_mask_words; /* class DOTDASH or OTHER */
     uint64_t* m_other = m_rcbad + n_mask_words; /* class OTHER */
     uint64_t* m_nonpl = m_other + n_mask_words; /* lowercase acgt / U / u */
-    char* tile_chars = (char*)(m_nonpl + n_mask_words);
-    uint32_t* counts = (uint32_t*)(tile_chars + BFT_SEQ_SPAN);
-    const int n_counts = (n_genomes + 31) & ~31;
+    uint32_t* counts = (uint32_t*)(m_nonpl + n_mask_words); /* !G32 only */
+    const int n_counts = G32 ? 0 : ((n_genomes + 31) & ~31);
 
     const size_t warp_stride = (size_t)gridDim.x * BFT_SEQ_WARPS;
     for (size_t s = (size_t)blockIdx.x * BFT_SEQ_WARPS + warp; s < n_seq; s += warp_stride) {
@@ -1123,6 +1140,7 @@ __global__ void __launch_bounds__(32 * BFT_SEQ_WARPS) k_query_sequences(const bf
         const long long len = (long long)(o1 - o0);
         const long long n_win = len - k + 1;
         for (int g = lane; g < n_counts; g += 32) counts[g] = 0;
+        uint32_t cnt_reg = 0; /* G32: lane g counts genome g in a register */
         int bad = 0;
         /* The stored-k-mer filter pays for look-ups that miss. A read of an organism in the graph hits on nearly every
          * window, and this kernel is issue-bound, so the filter's hash and L2 load would be pure overhead there: the first
@@ -1142,42 +1160,47 @@ __global__ void __launch_bounds__(32 * BFT_SEQ_WARPS) k_query_sequences(const bf
         for (long long t0 = 0; t0 < n_win && missed <= miss_budget; t0 += BFT_SEQ_TILE) {
             const int n_here = (int)(n_win - t0 < BFT_SEQ_TILE ? n_win - t0 : BFT_SEQ_TILE); /* windows in this tile */
             const int n_chars = n_here + k - 1;
-            /* stage + encode: 32 characters per step, up to one zeroed 64-base word past the data (the funnel
-             * shifts below may read one word beyond the last window). Upper-case A/C/G/T — all there is in ordinary
-             * reads — take a branch-free path: code = ((ch >> 1) ^ (ch >> 2)) & 3; anything else is classified in
-             * full, and a tile without such characters skips every mask test below (tile_special == 0). */
-            const int stage_end = min(BFT_SEQ_SPAN + 64, ((n_chars + 63) & ~63) + 64);
+            /* stage + encode: 32 characters per step. Upper-case A/C/G/T — all there is in ordinary reads — take a branch-free
+             * path: code = ((ch >> 1) ^ (ch >> 2)) & 3; the 2-bit codes of the 32 lanes become one 64-bit word of the plane with
+             * two warp-wide OR reductions (REDUX; lanes 0-15 fill the low half, 16-31 the high half). Anything else is classified
+             * in full: the first such character of a tile clears the four mask planes, blocks with such characters write their
+             * bits, and a tile without any skips every mask test below (tile_special == 0). */
+            const char* const cp = chars + o0 + (uint64_t)t0;
+            const int n_blocks = (n_chars + 31) >> 5;
             uint32_t tile_special = 0;
-            for (int c0 = 0; c0 < stage_end; c0 += 32) {
-                const int ci = c0 + lane;
+            for (int blk = 0; blk < n_blocks; blk++) {
+                const int ci = (blk << 5) + lane;
                 uint32_t code = 0, cls = BFT_CH_ACGT, nonplain = 0;
                 if (ci < n_chars) {
-                    const unsigned char ch = (unsigned char)chars[o0 + (uint64_t)t0 + (uint64_t)ci];
-                    tile_chars[ci] = (char)ch;
+                    const unsigned char ch = (unsigned char)cp[ci];
                     const uint32_t d = (uint32_t)ch - 'A';
                     if (d < 26u && ((0x00080045u >> d) & 1u)) code = ((ch >> 1) ^ (ch >> 2)) & 3u; /* A, C, G, T */
                     else bft_classify_char(ch, code, cls, nonplain);
                 }
-                const uint32_t b0 = __ballot_sync(0xffffffffu, code & 1u);
-                const uint32_t b1 = __ballot_sync(0xffffffffu, code >> 1);
+                const uint32_t sh = (uint32_t)(lane & 15) << 1;
+                const uint32_t lo = __reduce_or_sync(0xffffffffu, lane < 16 ? code << sh : 0u);
+                const uint32_t hi = __reduce_or_sync(0xffffffffu, lane < 16 ? 0u : code << sh);
                 const uint32_t special = __ballot_sync(0xffffffffu, cls != BFT_CH_ACGT || nonplain);
-                uint32_t bi = 0, br = 0, bo = 0, bn = 0;
                 if (special) {
-                    bi = __ballot_sync(0xffffffffu, cls == BFT_CH_IUPAC || cls == BFT_CH_DOTDASH);
-                    br = __ballot_sync(0xffffffffu, cls == BFT_CH_DOTDASH || cls == BFT_CH_OTHER);
-                    bo = __ballot_sync(0xffffffffu, cls == BFT_CH_OTHER);
-                    bn = __ballot_sync(0xffffffffu, nonplain);
-                    tile_special = 1;
+                    if (!tile_special) { /* the four planes are contiguous */
+                        for (int i = lane; i < 8 * n_mask_words; i += 32) ((uint32_t*)m_iupac)[i] = 0u;
+                        tile_special = 1;
+                        __syncwarp();
+                    }
+                    const uint32_t bi = __ballot_sync(0xffffffffu, cls == BFT_CH_IUPAC || cls == BFT_CH_DOTDASH);
+                    const uint32_t br = __ballot_sync(0xffffffffu, cls == BFT_CH_DOTDASH || cls == BFT_CH_OTHER);
+                    const uint32_t bo = __ballot_sync(0xffffffffu, cls == BFT_CH_OTHER);
+                    const uint32_t bn = __ballot_sync(0xffffffffu, nonplain);
+                    if (lane == 1) {
+                        ((uint32_t*)m_iupac)[blk] = bi;
+                        ((uint32_t*)m_rcbad)[blk] = br;
+                        ((uint32_t*)m_other)[blk] = bo;
+                        ((uint32_t*)m_nonpl)[blk] = bn;
+                    }
                 }
-                if (lane == 0 && (c0 >> 5) < n_code_words) codes[c0 >> 5] = bft_spread32(b0) | (bft_spread32(b1) << 1);
-                if (lane == 1 && (c0 >> 6) < n_mask_words) {
-                    uint32_t* p;
-                    p = (uint32_t*)m_iupac; p[c0 >> 5] = bi;
-                    p = (uint32_t*)m_rcbad; p[c0 >> 5] = br;
-                    p = (uint32_t*)m_other; p[c0 >> 5] = bo;
-                    p = (uint32_t*)m_nonpl; p[c0 >> 5] = bn;
-                }
+                if (lane == 0) codes[blk] = (uint64_t)lo | ((uint64_t)hi << 32);
             }
+            if (lane < 2 && n_blocks + lane < n_code_words) codes[n_blocks + lane] = 0; /* nothing reads past the data; kept defined */
             __syncwarp();
             /* windows: lane handles j = lane, lane+32, ... (whole warp iterates together for the collectives) */
             for (int j0 = 0; j0 < n_here; j0 += 32) {
@@ -1218,7 +1241,7 @@ __global__ void __launch_bounds__(32 * BFT_SEQ_WARPS) k_query_sequences(const bf
                             if (tile_special && bft_any_bits(m_nonpl, j, k)) { /* mixed case / U: ASCII order decides */
                                 use_rc = 1;
                                 for (int i = 0; i < k; i++) {
-                                    const char a = tile_chars[j + i], b = bft_rc_char(tile_chars[j + k - 1 - i]);
+                                    const char a = cp[j + i], b = bft_rc_char(cp[j + k - 1 - i]);
                                     if (a != b) { use_rc = (unsigned char)a > (unsigned char)b; break; }
                                 }
                             }
@@ -1235,13 +1258,24 @@ __global__ void __launch_bounds__(32 * BFT_SEQ_WARPS) k_query_sequences(const bf
                     const uint32_t found = __ballot_sync(0xffffffffu, cls != BFT_CLS_NONE);
                     if (2 * __popc(found) < __popc(looked)) lk_flags = 0;
                 }
-                /* merge windows with the same colour class, then bump the per-genome counters warp-wide */
                 const uint32_t active = __ballot_sync(0xffffffffu, cls != BFT_CLS_NONE);
                 {
                     const unsigned int m = (unsigned int)min(32, n_here - j0) - (unsigned int)__popc(active);
                     missed = missed + m < missed ? 0xffffffffu : missed + m;
                     if (missed > miss_budget) break;
                 }
+                if (G32) {
+                    /* up to 32 genomes: every lane fetches the row of its own window (a table this small sits in L1), the warp
+                     * transposes the 32 rows as a bit matrix, and lane g adds the set bits of column g — the windows of this step
+                     * that carry genome g — to a register. No shared memory, and the cost does not depend on how many distinct
+                     * colour classes the 32 windows have. */
+                    if (active) {
+                        const uint32_t row = cls != BFT_CLS_NONE ? bft_ld_row(class_rows + cls) : 0u;
+                        cnt_reg += (uint32_t)__popc(bft_warp_transpose32(row, lane));
+                    }
+                    continue;
+                }
+                /* merge windows with the same colour class, then bump the per-genome counters warp-wide */
                 if (active) {
                     uint32_t grp = 0;
                     if (cls != BFT_CLS_NONE) grp = __match_any_sync(active, cls);
@@ -1266,7 +1300,7 @@ __global__ void __launch_bounds__(32 * BFT_SEQ_WARPS) k_query_sequences(const bf
         if (n_win > 0) need = (long long)ceil((double)n_win * threshold);
         const bool unreachable = missed > miss_budget;
         for (int w = 0; w < rw; w++) {
-            const uint32_t cnt = counts[w * 32 + lane];
+            const uint32_t cnt = G32 ? cnt_reg : counts[w * 32 + lane];
             const uint32_t bits = __ballot_sync(0xffffffffu, !unreachable && n_win > 0 && cnt > 0 && (long long)cnt >= need);
             if (lane == 0) rows[s * (size_t)rw + w] = bits;
         }
