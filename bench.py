@@ -449,7 +449,8 @@ def kmers_record(run: Run, tag: str, spec: dict, headline: bool):
     nodes_pk, depth_pk, cc_pk = ws["nodes"] / n, ws["search_depth"] / n, ws["cc_probed"] / n
     a_arena = 8 * W + (1 + 4 * RW) + 32.0 * W * bucket_pk
     cap = ncu_capture(tag if not degraded else tag + "_fb")
-    probe = eng.random_gather_probe(4 << 30, 1 << 28) if (headline and not args.no_probe) else None
+    probe = eng.random_gather_probe(4 << 30, 1 << 28) if (headline and not args.no_probe) else getattr(run, "probe", None)
+    run.probe = probe   # the sub-records quote their random-access fraction against the same in-process measurement
     roofline = base_roofline(
         "k_query_kmers_rows" if RW <= 4 else "k_query_kmers_wide", a_arena,
         "8*W in + (1 + 4*RW) out + 32*W * P(walk reaches a bucket)", n, k_ms, cap,
@@ -597,8 +598,11 @@ def sequences_record(run: Run, tag: str, spec: dict, headline: bool):
                              units, ms_step, ncu_capture(tag if not degraded else tag + "_fb"),
                              {"bucket_accesses_per_window": bucket_pw, "filter_rejects_per_window": ws["filter_rejects"] / len(wins),
                               "found_frac_windows": ws["found"] / len(wins),
-                              "note": "one launch per step, so kernel time = step time. This kernel is instruction-issue bound (encode, canonical "
-                                      "pick, class merge, per-genome counters; see the ncu capture), not HBM-bound"})
+                              "random_gather_probe_loads_per_s": getattr(run, "probe", None),
+                              "random_access_frac_upper": (bucket_pw * units / (ms_step / 1e3) / run.probe) if getattr(run, "probe", None) else None,
+                              "note": "one launch per step, so kernel time = step time. Bound by random HBM accesses (one bucket per window "
+                                      "looked up; random_access_frac_upper assumes every window is looked up — the early exit of reads that "
+                                      "cannot reach the threshold skips some) and, second, by instruction issue (see the ncu capture)"})
     e2e = None
     if not args.no_e2e:
         h_chars = E.PinnedBuffer((n * rl,), np.uint8)
@@ -704,6 +708,8 @@ def branching_record(run: Run, tag: str, spec: dict, headline: bool):
                              {"lookups_per_sec": 8 * n / (ms_step / 1e3), "bucket_accesses_per_lookup": bucket_pl,
                               "filter_rejects_per_lookup": ws["filter_rejects"] / len(nb8), "neighbours_present_frac": ws["found"] / len(nb8),
                               "filter_mb": st["filter_bytes"] / 1e6, "walk_stats_match_kernel_counts": bool(stats_consistent),
+                              "random_gather_probe_loads_per_s": getattr(run, "probe", None),
+                              "random_access_frac": (8 * n * bucket_pl / (ms_step / 1e3) / run.probe) if getattr(run, "probe", None) else None,
                               "note": "one launch per step, so kernel time = step time; most of the 8 neighbours of a k-mer are absent and are "
                                       "answered by the L2-resident stored-k-mer filter"})
     e2e = None
