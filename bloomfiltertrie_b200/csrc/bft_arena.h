@@ -25,11 +25,14 @@
  *              Replaces children_type prefix sums (count_children / count_nodes, include/CC.h:471-550).
  *   buckets[]  every CC inline suffix line, as W little-endian 64-bit words holding the suffix as an integer
  *              (nucleotide i at bits 2i; replaces memcmp in binary_search_UC, src/UC.c:81-124), hashed by its own
- *              top bits into fixed-size buckets: a prefix with cnt suffixes owns B = 2^lb consecutive buckets
- *              (B >= cnt/2, lb <= 8) of BFT_BUCKET_KEYS = 4 slots — one 32-byte sector for W = 1, a 64-byte pair
- *              for W = 2, a 128-byte line for W = 4 — and suffix x lives in bucket hash(x) >> (64 - lb). A lookup therefore touches exactly one
- *              aligned bucket: ONE random DRAM access per k-mer. Buckets that would hold more than 4 suffixes keep
- *              3 and an overflow descriptor pointing into ovf[] (rare: the load factor is <= 1/2).
+ *              hash into fixed-size buckets of BFT_BUCKET_KEYS = 4 slots — one 32-byte sector for W = 1, 64 bytes for
+ *              W = 2, a 128-byte line for W = 4: a prefix with cnt suffixes owns B consecutive buckets and suffix x
+ *              lives in bucket (hash(x) * B) >> 64. A lookup therefore touches exactly one aligned bucket: ONE random
+ *              DRAM access per k-mer. For W >= 2, B is a power of two >= cnt/2 and a bucket that would hold more than 4
+ *              suffixes keeps 3 and an overflow descriptor pointing into ovf[] (rare: the load factor is <= 1/2). For
+ *              W = 1 the 32-byte buckets work in PAIRS, because HBM delivers 64 bytes per fetch anyway: B is even,
+ *              about cnt/2.4 (load 0.6), a suffix whose own bucket is full sits in the other half of the same 64-byte
+ *              line, and only a pair that would hold more than 8 falls back to descriptors.
  *              When the colour-class ids fit above the widest suffix (cls_shift != 0) the line's class is stored in
  *              the spare top bits of its most significant word, so a hit needs no second load; otherwise
  *              slotcls[]/ovfcls[] hold it. Bit 63 of the top word marks empty slots / overflow descriptors.
@@ -122,9 +125,17 @@
 #define BFT_KIND_LEAF 4u   /* leaf level (9 nt left): prefix stored, a = colour class */
 #define BFT_KIND_DEEP 5u   /* rootdir_fast only: every k-mer below this prefix in one block of 2^lb dbuckets starting at a */
 #define BFT_KIND_SHIFT 28
-#define BFT_LB_SHIFT 24                /* INLINE entries: log2(#buckets) of the prefix's block */
+#define BFT_LB_SHIFT 24                /* DEEP entries: log2(#buckets) of the block */
 #define BFT_LB_MASK 0xfu
 #define BFT_CNT_MASK ((1u << BFT_LB_SHIFT) - 1u)
+#define BFT_NBK_SHIFT 8                /* INLINE entries: count of suffixes in bits 0-7 (at most 255), number of buckets of */
+#define BFT_NBK_MASK 0xffffu           /* the prefix's block in bits 8-23 */
+#define BFT_INLINE_CNT(e_) ((e_).b & 0xffu)
+#define BFT_INLINE_NBK(e_) (((e_).b >> BFT_NBK_SHIFT) & BFT_NBK_MASK)
+/* One-word keys (k <= 27): a bucket is a 32-byte sector but HBM delivers 64 bytes per fetch, so buckets work in PAIRS — a block
+ * has an even number of them, a suffix that finds its own bucket full goes to the other half of the 64-byte line (fetched by the
+ * same DRAM transaction), and the block can run at a load of 0.6 instead of 0.25-0.5 with a power-of-two bucket count. */
+#define BFT_PAIRED(W_) ((W_) == 1)
 
 #define BFT_CLS_NONE 0xffffffffu
 
@@ -449,21 +460,37 @@ BFT_HD uint32_t bft_search_uc(const bft_view_t* v, uint32_t begin, uint32_t n, c
     return 0xffffffffu;
 }
 
-/* Search one prefix's inline block for `key` (the suffix left after the 9-nt prefix) and return the colour class of
- * the matching line, or BFT_CLS_NONE (binary_search_UC over the block + equality, src/presenceNode.c:1876-1914).
- * The block is 2^lb buckets starting at bucket `base`; a hash of the key names the only bucket that can hold it. */
-BFT_HD uint32_t bft_bucket_of(const uint64_t* key, const int W, const uint32_t lb) {
+/* Searching one prefix's inline block for `key` (the suffix left after the 9-nt prefix) returns the colour class of the matching
+ * line, or BFT_CLS_NONE (binary_search_UC over the block + equality, src/presenceNode.c:1876-1914): a hash of the key names the
+ * bucket that holds it. */
+BFT_HD uint64_t bft_key_hash(const uint64_t* key, const int W) {
     /* multiplicative hash of the whole suffix: the suffixes of one prefix are near-duplicates of each other in a
      * pan-genome (SNP variants share all but one nucleotide), so raw leading bits would pile them into one bucket */
     uint64_t x = key[0];
     for (int w = 1; w < W; w++) x = (x ^ (x >> 31)) * 0xC2B2AE3D27D4EB4FULL + key[w];
     x ^= x >> 29;
-    return lb ? (uint32_t)((x * 0x9E3779B97F4A7C15ULL) >> (64 - lb)) : 0u;
+    return x * 0x9E3779B97F4A7C15ULL;
 }
 
-BFT_HD uint32_t bft_search_block_ex(const bft_view_t* v, uint32_t base, uint32_t lb, const uint64_t* key, const int W, uint32_t* loc,
-                                    const int want_cls) {
-    const size_t bucket = (size_t)base + bft_bucket_of(key, W, lb);
+/* bucket of a key in a block of 2^lb buckets (collapsed subtrees) */
+BFT_HD uint32_t bft_bucket_of(const uint64_t* key, const int W, const uint32_t lb) {
+    return lb ? (uint32_t)(bft_key_hash(key, W) >> (64 - lb)) : 0u;
+}
+
+/* bucket of a key in a block of nbk buckets, any nbk >= 1 (for a power of two this is the top bits of the hash) */
+BFT_HD uint32_t bft_bucket_idx(const uint64_t* key, const int W, const uint32_t nbk) {
+    if (nbk <= 1u) return 0u;
+#ifdef __CUDA_ARCH__
+    return (uint32_t)__umul64hi(bft_key_hash(key, W), (uint64_t)nbk);
+#else
+    return (uint32_t)(((unsigned __int128)bft_key_hash(key, W) * (unsigned __int128)nbk) >> 64);
+#endif
+}
+
+/* the four slots of one bucket against `key`: class of the matching slot (and its location), or BFT_CLS_NONE; *last receives the
+ * top word of the last slot (a key: the bucket is full; all ones: it has room; otherwise an overflow descriptor) */
+BFT_HD uint32_t bft_match_bucket(const bft_view_t* v, size_t bucket, const uint64_t* key, const int W, uint32_t* loc, const int want_cls,
+                                 uint64_t* last) {
     uint64_t s[BFT_BUCKET_KEYS * BFT_MAX_WORDS];
     bft_ld_bucket(v->buckets + bucket * (size_t)(BFT_BUCKET_KEYS * W), s, W);
     const int shift = v->cls_shift;
@@ -481,8 +508,24 @@ BFT_HD uint32_t bft_search_block_ex(const bft_view_t* v, uint32_t base, uint32_t
             if (loc) *loc = (uint32_t)(bucket * BFT_BUCKET_KEYS + j);
         }
     }
-    const uint64_t last = s[(BFT_BUCKET_KEYS - 1) * W + W - 1];
-    if (found == BFT_CLS_NONE && (last & BFT_SLOT_SPECIAL) && last != BFT_SLOT_EMPTY) { /* overflow run */
+    *last = s[(BFT_BUCKET_KEYS - 1) * W + W - 1];
+    return found;
+}
+
+/* Search one prefix's inline block of `nbk` buckets starting at bucket `base`: the bucket the key's hash names; its overflow run
+ * if it carries a descriptor; for one-word keys the other half of its 64-byte line if it is full (slots fill from the front, so
+ * a key in the last slot means no room and no descriptor). */
+BFT_HD uint32_t bft_search_block_ex(const bft_view_t* v, uint32_t base, uint32_t nbk, const uint64_t* key, const int W, uint32_t* loc,
+                                    const int want_cls) {
+    const uint32_t idx = bft_bucket_idx(key, W, nbk);
+    uint64_t last;
+    uint32_t found = bft_match_bucket(v, (size_t)base + idx, key, W, loc, want_cls, &last);
+    if (found != BFT_CLS_NONE) return found;
+    if (last & BFT_SLOT_SPECIAL) {
+        if (last == BFT_SLOT_EMPTY) return BFT_CLS_NONE;
+        /* overflow run */
+        const int shift = v->cls_shift;
+        const uint64_t top_mask = shift ? ((1ULL << shift) - 1ULL) : ~BFT_SLOT_SPECIAL;
         const uint32_t start = (uint32_t)last, cnt = (uint32_t)(last >> 32) & 0x7fffffffu;
         for (uint32_t i = 0; i < cnt; i++) {
             const uint64_t* p = v->ovf + ((size_t)start + i) * W;
@@ -494,12 +537,15 @@ BFT_HD uint32_t bft_search_block_ex(const bft_view_t* v, uint32_t base, uint32_t
                 if (loc) *loc = v->loc_ovf + start + i;
             }
         }
+        return found;
     }
+    if (BFT_PAIRED(W) && nbk > 1u) /* full, no descriptor: the suffix may have moved to the other half of the line */
+        found = bft_match_bucket(v, (size_t)base + (idx ^ 1u), key, W, loc, want_cls, &last);
     return found;
 }
 
-BFT_HD uint32_t bft_search_block(const bft_view_t* v, uint32_t base, uint32_t lb, const uint64_t* key, const int W) {
-    return bft_search_block_ex(v, base, lb, key, W, (uint32_t*)0, 1);
+BFT_HD uint32_t bft_search_block(const bft_view_t* v, uint32_t base, uint32_t nbk, const uint64_t* key, const int W) {
+    return bft_search_block_ex(v, base, nbk, key, W, (uint32_t*)0, 1);
 }
 
 /* Search a collapsed subtree's block (BFT_KIND_DEEP) for `key` (the k-mer without its first 9 nucleotides): buckets of
@@ -637,7 +683,7 @@ BFT_HD uint32_t bft_lookup_loc(const bft_view_t* v, const uint64_t* kmer, const 
     }
     for (;;) {
         const uint32_t kind = e.b >> BFT_KIND_SHIFT;
-        const uint32_t n = e.b & BFT_CNT_MASK;
+        const uint32_t n = kind == BFT_KIND_INLINE ? BFT_INLINE_CNT(e) : (e.b & BFT_CNT_MASK);
         if (kind == BFT_KIND_ABSENT) return BFT_CLS_NONE;
         if (kind == BFT_KIND_DEEP) { /* fast view only (never in statistics mode) */
             bft_shift18(cur, W);
@@ -660,7 +706,7 @@ BFT_HD uint32_t bft_lookup_loc(const bft_view_t* v, const uint64_t* kmer, const 
         sz -= BFT_NB_CHAR_SUF_PREF;
         if (kind == BFT_KIND_INLINE) {
             if (st) { st[1] += bft_ceil_log2p1(n); st[4] += n; st[5] += !rejected && !deep_counted; }
-            const uint32_t cls = bft_search_block_ex(v, e.a, (e.b >> BFT_LB_SHIFT) & BFT_LB_MASK, cur, W, loc, !(flags & BFT_LK_PRESENCE));
+            const uint32_t cls = bft_search_block_ex(v, e.a, BFT_INLINE_NBK(e), cur, W, loc, !(flags & BFT_LK_PRESENCE));
             if (st && cls != BFT_CLS_NONE) st[2]++;
             return cls;
         }

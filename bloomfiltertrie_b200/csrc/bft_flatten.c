@@ -291,24 +291,71 @@ static uint32_t append_uc_lines(ctx_t* c, const uc_body_t* u, int cnt, int key_b
     return start;
 }
 
-/* a prefix's inline suffixes -> 2^lb buckets of BFT_BUCKET_KEYS slots keyed by the top lb bits of the suffix
- * (layout in bft_arena.h). Returns the INLINE entry (first bucket, lb, count). */
+/* one bucket of a block <- the lines idx[0..m): all of them if they fit, else BFT_BUCKET_KEYS - 1 and an overflow descriptor */
+static void fill_bucket(ctx_t* c, uint64_t* bk, uint32_t* bc, size_t t, const uint32_t* idx, int m) {
+    bft_arena_t* a = c->a;
+    const int W = a->W, S = BFT_BUCKET_KEYS;
+    const int in_bucket = m <= S ? m : S - 1;
+    for (int q = 0; q < in_bucket; q++) {
+        for (int w = 0; w < W; w++) bk[(t * S + q) * W + w] = c->tmp[idx[q]].k[w];
+        bc[t * S + q] = c->tmp[idx[q]].cls;
+    }
+    if (m > S) { /* spill the rest; the last slot becomes the overflow descriptor */
+        const int spill = m - (S - 1);
+        if (a->n_ovf + (size_t)spill >= 0xfffffff0u) fail(c, "bft_flatten: overflow area exceeds 2^32 lines");
+        if (a->n_ovf + (size_t)spill > c->cap_ovf) {
+            size_t ncap = c->cap_ovf ? c->cap_ovf : 4096;
+            while (ncap < a->n_ovf + (size_t)spill) ncap += ncap / 2 + 4096;
+            a->ovf = (uint64_t*)xrealloc(c, a->ovf, ncap * (size_t)W * sizeof(uint64_t));
+            a->ovfcls = (uint32_t*)xrealloc(c, a->ovfcls, ncap * sizeof(uint32_t));
+            c->cap_ovf = ncap;
+        }
+        for (int q = 0; q < spill; q++) {
+            for (int w = 0; w < W; w++) a->ovf[(a->n_ovf + (size_t)q) * W + w] = c->tmp[idx[S - 1 + q]].k[w];
+            a->ovfcls[a->n_ovf + (size_t)q] = c->tmp[idx[S - 1 + q]].cls;
+        }
+        for (int w = 0; w < W - 1; w++) bk[(t * S + S - 1) * W + w] = 0;
+        bk[(t * S + S - 1) * W + W - 1] = BFT_SLOT_SPECIAL | ((uint64_t)spill << 32) | (uint64_t)a->n_ovf;
+        a->n_ovf += (size_t)spill;
+    }
+}
+
+static void grow_buckets(ctx_t* c, size_t need) {
+    bft_arena_t* a = c->a;
+    const int W = a->W, S = BFT_BUCKET_KEYS;
+    if (need >= 0xfffffff0u) fail(c, "bft_flatten: more than 2^32 suffix buckets");
+    if (need > c->cap_buckets) {
+        size_t ncap = c->cap_buckets ? c->cap_buckets : 4096;
+        while (ncap < need) ncap += ncap / 2 + 4096;
+        a->buckets = (uint64_t*)xrealloc(c, a->buckets, ncap * (size_t)(S * W) * sizeof(uint64_t));
+        a->slotcls = (uint32_t*)xrealloc(c, a->slotcls, ncap * (size_t)S * sizeof(uint32_t));
+        c->cap_buckets = ncap;
+    }
+}
+
+/* a prefix's inline suffixes -> a block of B buckets of BFT_BUCKET_KEYS slots keyed by a hash of the suffix (layout in
+ * bft_arena.h). Returns the INLINE entry (first bucket, B, count). */
 static bft_entry_t append_inline_block(ctx_t* c, const uc_body_t* u, int first, int cnt, int key_bits, int strip_bit7) {
     bft_arena_t* a = c->a;
     const int W = a->W, S = BFT_BUCKET_KEYS;
     if (cnt > 255) fail(c, "bft_flatten: a prefix with %d inline suffixes (children_type counts are bytes: at most 255)", cnt);
     load_block(c, u, first, cnt, key_bits, strip_bit7);
-    uint32_t lb = 0;
-    while (lb < BFT_MAX_LB && ((size_t)1 << lb) * (S / 2) < (size_t)cnt) lb++;
-    const size_t B = (size_t)1 << lb;
-    if (a->n_buckets + B >= 0xfffffff0u) fail(c, "bft_flatten: more than 2^32 suffix buckets");
-    if (a->n_buckets + B > c->cap_buckets) {
-        size_t ncap = c->cap_buckets ? c->cap_buckets : 4096;
-        while (ncap < a->n_buckets + B) ncap += ncap / 2 + 4096;
-        a->buckets = (uint64_t*)xrealloc(c, a->buckets, ncap * (size_t)(S * W) * sizeof(uint64_t));
-        a->slotcls = (uint32_t*)xrealloc(c, a->slotcls, ncap * (size_t)S * sizeof(uint32_t));
-        c->cap_buckets = ncap;
+    size_t B;
+    if (BFT_PAIRED(W)) { /* load 0.6, an even number of 32-byte buckets so that they pair up in 64-byte lines */
+        B = cnt <= S / 2 ? 1 : ((size_t)cnt * 5 + 11) / 12;
+        if (B > 1 && (B & 1)) B++;
+        if (B > 1 && (a->n_buckets & 1)) { /* blocks of pairs start on a 64-byte line: one unused bucket of padding */
+            grow_buckets(c, a->n_buckets + 1);
+            for (int i = 0; i < S * W; i++) a->buckets[a->n_buckets * (size_t)(S * W) + i] = BFT_SLOT_EMPTY;
+            for (int i = 0; i < S; i++) a->slotcls[a->n_buckets * (size_t)S + i] = BFT_CLS_NONE;
+            a->n_buckets++;
+        }
+    } else {
+        uint32_t lb = 0;
+        while (lb < BFT_MAX_LB && ((size_t)1 << lb) * (S / 2) < (size_t)cnt) lb++;
+        B = (size_t)1 << lb;
     }
+    grow_buckets(c, a->n_buckets + B);
     const uint32_t base = (uint32_t)a->n_buckets;
     uint64_t* bk = a->buckets + (size_t)base * (S * W);
     uint32_t* bc = a->slotcls + (size_t)base * S;
@@ -320,46 +367,42 @@ static bft_entry_t append_inline_block(ctx_t* c, const uc_body_t* u, int first, 
     uint32_t* order = c->bkt + cnt;         /* [cnt] lines grouped by bucket */
     uint32_t* head = c->bkt + 2 * (size_t)cnt; /* [B + 1] */
     for (size_t t = 0; t <= B; t++) head[t] = 0;
-    for (int i = 0; i < cnt; i++) { bkt[i] = bft_bucket_of(c->tmp[i].k, W, lb); head[bkt[i] + 1]++; }
+    for (int i = 0; i < cnt; i++) { bkt[i] = bft_bucket_idx(c->tmp[i].k, W, (uint32_t)B); head[bkt[i] + 1]++; }
     for (size_t t = 0; t < B; t++) head[t + 1] += head[t];
     uint32_t* fill = head + B + 1;          /* [B] running cursor */
     for (size_t t = 0; t < B; t++) fill[t] = head[t];
     for (int i = 0; i < cnt; i++) order[fill[bkt[i]]++] = (uint32_t)i;
     (void)key_bits;
-    for (size_t t = 0; t < B; t++) {
-        const int m = (int)(head[t + 1] - head[t]);
-        if (!m) continue;
-        const uint32_t* idx = order + head[t];
-        const int in_bucket = m <= S ? m : S - 1;
-        for (int q = 0; q < in_bucket; q++) {
-            for (int w = 0; w < W; w++) bk[(t * S + q) * W + w] = c->tmp[idx[q]].k[w];
-            bc[t * S + q] = c->tmp[idx[q]].cls;
+    if (BFT_PAIRED(W) && B > 1) {
+        for (size_t t = 0; t < B; t += 2) {
+            const int m0 = (int)(head[t + 1] - head[t]), m1 = (int)(head[t + 2] - head[t + 1]);
+            const uint32_t* i0 = order + head[t];
+            const uint32_t* i1 = order + head[t + 1];
+            if (m0 + m1 <= 2 * S) {
+                /* the pair holds everything: each half takes up to S of its own lines, the rest sit in the other half's free slots */
+                uint32_t half[2][BFT_BUCKET_KEYS];
+                int n0 = 0, n1 = 0;
+                for (int q = 0; q < m0 && q < S; q++) half[0][n0++] = i0[q];
+                for (int q = 0; q < m1 && q < S; q++) half[1][n1++] = i1[q];
+                for (int q = S; q < m0; q++) half[1][n1++] = i0[q];
+                for (int q = S; q < m1; q++) half[0][n0++] = i1[q];
+                fill_bucket(c, bk, bc, t, half[0], n0);
+                fill_bucket(c, bk, bc, t + 1, half[1], n1);
+            } else { /* too many for the line: each half on its own, with an overflow descriptor where it needs one */
+                if (m0) fill_bucket(c, bk, bc, t, i0, m0);
+                if (m1) fill_bucket(c, bk, bc, t + 1, i1, m1);
+            }
         }
-        if (m > S) { /* spill the rest; the last slot becomes the overflow descriptor */
-            const int spill = m - (S - 1);
-            if (a->n_ovf + (size_t)spill >= 0xfffffff0u) fail(c, "bft_flatten: overflow area exceeds 2^32 lines");
-            if (a->n_ovf + (size_t)spill > c->cap_ovf) {
-                size_t ncap = c->cap_ovf ? c->cap_ovf : 4096;
-                while (ncap < a->n_ovf + (size_t)spill) ncap += ncap / 2 + 4096;
-                a->ovf = (uint64_t*)xrealloc(c, a->ovf, ncap * (size_t)W * sizeof(uint64_t));
-                a->ovfcls = (uint32_t*)xrealloc(c, a->ovfcls, ncap * sizeof(uint32_t));
-                c->cap_ovf = ncap;
-            }
-            for (int q = 0; q < spill; q++) {
-                for (int w = 0; w < W; w++) a->ovf[(a->n_ovf + (size_t)q) * W + w] = c->tmp[idx[S - 1 + q]].k[w];
-                a->ovfcls[a->n_ovf + (size_t)q] = c->tmp[idx[S - 1 + q]].cls;
-            }
-            for (int w = 0; w < W - 1; w++) bk[(t * S + S - 1) * W + w] = 0;
-            bk[(t * S + S - 1) * W + W - 1] = BFT_SLOT_SPECIAL | ((uint64_t)spill << 32) | (uint64_t)a->n_ovf;
-            a->n_ovf += (size_t)spill;
+    } else {
+        for (size_t t = 0; t < B; t++) {
+            const int m = (int)(head[t + 1] - head[t]);
+            if (m) fill_bucket(c, bk, bc, t, order + head[t], m);
         }
     }
     a->n_buckets += B;
     a->n_lines += (size_t)cnt;
     a->n_kmers += (size_t)cnt;
-    bft_entry_t e = bft_mk_entry(BFT_KIND_INLINE, base, (uint32_t)cnt);
-    e.b |= lb << BFT_LB_SHIFT;
-    return e;
+    return bft_mk_entry(BFT_KIND_INLINE, base, (uint32_t)cnt | ((uint32_t)B << BFT_NBK_SHIFT));
 }
 
 static uint32_t parse_node(ctx_t* c, int sz, int* cluster_flag);
@@ -850,7 +893,7 @@ bft_arena_t* bft_arena_from_memory(const uint8_t* buf, size_t len, char* err, si
                     const size_t pj = (size_t)cc->pref_off + stk[sp].j++;
                     const uint32_t kind = a->pref[pj].b >> BFT_KIND_SHIFT;
                     a->pref_out[pj] = run;
-                    if (kind == BFT_KIND_INLINE) run += a->pref[pj].b & BFT_CNT_MASK;
+                    if (kind == BFT_KIND_INLINE) run += BFT_INLINE_CNT(a->pref[pj]);
                     else if (kind == BFT_KIND_LEAF) run += 1;
                     else if (kind == BFT_KIND_NODE) {
                         if (sp + 1 >= 16) fail(c, "bft_flatten: trie deeper than 16 levels");

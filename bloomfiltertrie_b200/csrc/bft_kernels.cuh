@@ -728,7 +728,7 @@ __global__ void __launch_bounds__(32 * BFT_EXTRACT_WARPS) k_extract_prefix_kmers
             continue;
         }
         const int shift_bits = BFT_PREFIX_BITS * (int)(path.depth + 1);
-        const uint32_t n_slots = BFT_BUCKET_KEYS << ((e.b >> BFT_LB_SHIFT) & BFT_LB_MASK);
+        const uint32_t n_slots = BFT_BUCKET_KEYS * BFT_INLINE_NBK(e);
         /* gather: every line of the block -> (byte-swapped key, class, storage location), in any order */
         uint32_t n_got = 0;
         for (uint32_t s0 = 0; s0 < n_slots; s0 += 32) {

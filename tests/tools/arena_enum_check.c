@@ -58,7 +58,7 @@ int main(int argc, char** argv) {
             memcpy(out + o * BFT_MAX_WORDS, base, sizeof base);
             continue;
         }
-        const uint32_t n_slots = BFT_BUCKET_KEYS << ((e.b >> BFT_LB_SHIFT) & BFT_LB_MASK);
+        const uint32_t n_slots = BFT_BUCKET_KEYS * BFT_INLINE_NBK(e);
         uint32_t n = 0;
         for (uint32_t s = 0; s < n_slots; s++) {
             const uint64_t* p = a->buckets + ((size_t)e.a * BFT_BUCKET_KEYS + s) * W;
@@ -78,7 +78,7 @@ int main(int argc, char** argv) {
                 }
             }
         }
-        if (n != (e.b & BFT_CNT_MASK)) { fprintf(stderr, "prefix %zu: %u lines gathered, %u declared\n", j, n, e.b & BFT_CNT_MASK); return 1; }
+        if (n != BFT_INLINE_CNT(e)) { fprintf(stderr, "prefix %zu: %u lines gathered, %u declared\n", j, n, BFT_INLINE_CNT(e)); return 1; }
         for (uint32_t i = 0; i < n; i++)
             for (int w = 0; w < W; w++) lines[i].be[w] = __builtin_bswap64(lines[i].key[w]);
         qsort(lines, n, sizeof(line_t), cmp_line);
