@@ -212,7 +212,7 @@ typedef struct {
      * word 0 = the rootdir entry of the prefix, words 1-3 = 3 x 64 filter bits. */
     const uint64_t* rootkf;
     uint32_t rkf_sectors;
-    uint32_t rkf_pad;
+    uint32_t rows_keep; /* != 0: the class-row table is small enough to be worth an evict-last priority in L2 (device only) */
     /* collapsed subtrees (see above); rootdir_fast == NULL: none (no Node below the root, or no memory for the blocks) */
     const bft_entry_t* rootdir_fast;
     const uint64_t* dbuckets;  /* n_dbuckets * BFT_BUCKET_KEYS * W words */

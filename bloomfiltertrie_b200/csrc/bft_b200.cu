@@ -519,6 +519,7 @@ extern "C" int bft_b200_open(const char* path, int device, bft_b200_ctx** out) {
     if (!rc) {
         c->d_class_rows = (uint32_t*)((char*)c->d_hot + rootdir_bytes);
         c->dview.rootdir = (const bft_entry_t*)c->d_hot;
+        c->dview.rows_keep = row_bytes <= ((size_t)48 << 20); /* evict-last priority only for a table that can stay in L2 */
     }
     if (!rc && cudaMalloc((void**)&c->d_class_counts, (a->n_classes + 1) * sizeof(uint32_t)) != cudaSuccess) rc = set_err(BFT_B200_ERR_NOMEM, "cudaMalloc(class counts) failed");
     if (!rc && cudaMalloc((void**)&d_bad, sizeof(int)) != cudaSuccess) rc = set_err(BFT_B200_ERR_NOMEM, "cudaMalloc failed");

@@ -210,7 +210,9 @@ __global__ void __launch_bounds__(BFT_TPB) k_query_kmers_wide(const bft_view_t v
             const int kk = t / rwv, w = t - kk * rwv;
             const uint32_t c = __shfl_sync(0xffffffffu, cls, kk);
             T r = T();
-            if (c != BFT_CLS_NONE) r = bft_ld_row(class_rows + (size_t)c * rwv + w);
+            /* a row table larger than L2 (1000 colours x 10^6 classes = 127 MB) gets no priority: it would only push the
+             * root directory and the filters out */
+            if (c != BFT_CLS_NONE) r = v.rows_keep ? bft_ld_row(class_rows + (size_t)c * rwv + w) : __ldg(class_rows + (size_t)c * rwv + w);
             if ((size_t)t < live) __stcs(out + t, r);
         }
     }
@@ -341,7 +343,7 @@ __global__ void __launch_bounds__(BFT_TPB) k_query_records(const bft_view_t v, c
             if (present) present[base + threadIdx.x] = hit;
             uint8_t* o = BFT_OUT_BUF(b) + (size_t)threadIdx.x * rb;
             for (int j = 0; j < rb; j += 4) {
-                const uint32_t word = hit ? bft_ld_row(class_rows + (size_t)cls * rw + (j >> 2)) : 0u;
+                const uint32_t word = !hit ? 0u : (v.rows_keep ? bft_ld_row(class_rows + (size_t)cls * rw + (j >> 2)) : __ldg(class_rows + (size_t)cls * rw + (j >> 2)));
                 for (int q = 0; q < 4 && j + q < rb; q++) o[j + q] = (uint8_t)(word >> (8 * q));
             }
         }
