@@ -128,6 +128,24 @@ def test_storage_locations_are_unique_per_stored_kmer(name, tmp_path):
 
 
 @pytest.mark.parametrize("name", NAMES)
+def test_bucket_block_invariants(name, tmp_path):
+    """Occupancy and shape of the hashed suffix blocks: every inline prefix's lines add up to its declared count (slots + overflow
+    runs), slots fill from the front (the look-up reads "last slot holds a key" as "bucket full"), the overflow area holds exactly
+    what the descriptors announce, and for one-word keys the blocks of more than one bucket have an even number of buckets and
+    start on a 64-byte line (buckets pair up inside a DRAM fetch) at a load of at most 0.6 + rounding."""
+    import re
+    exe = str(tmp_path / "arena_stats")
+    _gcc(["-O2", "-std=c11", "-I", CSRC, os.path.join(ROOT, "tests", "tools", "arena_stats.c"), os.path.join(CSRC, "bft_flatten.c"), "-o", exe])
+    out = subprocess.run([exe, os.path.join(refutil.GOLDEN, name + ".bft")], stdout=subprocess.PIPE, check=True).stdout.decode()
+    f = {m.group(1): int(m.group(2)) for m in re.finditer(r"(\w+)=(\d+)", out)}
+    assert f["count_mismatch"] == 0 and f["holes"] == 0 and f["odd_blocks"] == 0 and f["misaligned"] == 0, out
+    assert f["in_ovf"] == f["n_ovf"], out
+    assert f["block_buckets"] <= f["buckets"] <= f["block_buckets"] + f["blocks"], out      # at most one padding bucket per block
+    if f["blocks"]:
+        assert f["load_permille"] <= 1000 and (f["W"] > 1 or f["load_permille"] <= 700), out
+
+
+@pytest.mark.parametrize("name", NAMES)
 def test_arena_enumeration_order_is_the_reference_order(name, tmp_path):
     """The serializer's enumeration tables (depth-first pref_out, uc_rank, memcmp rank inside a prefix's lines) walked on
     the host exactly as the extraction kernels walk them: the k-mers must come out in the reference's
