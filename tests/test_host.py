@@ -128,6 +128,32 @@ def test_storage_locations_are_unique_per_stored_kmer(name, tmp_path):
 
 
 @pytest.mark.parametrize("name", NAMES)
+def test_accelerated_lookup_equals_the_structural_walk_on_the_host(name, tmp_path):
+    """The accelerator tables the engine builds on the device (stored-k-mer filter, fused root directory + filter, collapsed
+    subtrees) rebuilt sequentially on the host with the same hash functions and slot formats; the look-up code that reads them
+    (bft_arena.h, shared with the kernels) must answer like the walk over the structure: every stored k-mer found with its own
+    class, every golden query the same, with and without filters, presence-only, and with the collapsed blocks at a load of 1."""
+    import re
+    exe = str(tmp_path / "arena_accel_check")
+    _gcc(["-O2", "-std=c11", "-I", CSRC, os.path.join(ROOT, "tests", "tools", "arena_accel_check.c"),
+          os.path.join(CSRC, "bft_flatten.c"), os.path.join(CSRC, "bft_io.c"), "-o", exe])
+    z = np.load(os.path.join(refutil.GOLDEN, name + ".npz"))
+    k = int(z["k"])
+    q = str(tmp_path / "q.kc")
+    synth.write_kmers_comp(q, z["queries"], k)
+    for sectors, tight in ((0, 0), (1, 0), (3, 1), (4, 1)):
+        out = subprocess.run([exe, os.path.join(refutil.GOLDEN, name + ".bft"), q, str(sectors), str(tight)], stdout=subprocess.PIPE, check=True).stdout.decode()
+        f = {m.group(1): int(m.group(2)) for m in re.finditer(r"(\w+)=(\d+)", out)}
+        assert f["stored_bad"] == 0 and f["mismatch"] == 0, out
+        assert f["queries"] == len(z["queries"]) and f["present"] == int(z["present"].sum()), out
+        if name == "golden_deep_k63_g12":
+            assert f["deep_kmers"] > 0 and f["deep_prefixes"] > 0, out
+            if tight:
+                assert f["moved_by_probing"] > 0, out     # the linear probing was actually exercised
+        assert f["filter_rejects"] > 0, out                # the filters do reject absent queries
+
+
+@pytest.mark.parametrize("name", NAMES)
 def test_bucket_block_invariants(name, tmp_path):
     """Occupancy and shape of the hashed suffix blocks: every inline prefix's lines add up to its declared count (slots + overflow
     runs), slots fill from the front (the look-up reads "last slot holds a key" as "bucket full"), the overflow area holds exactly
