@@ -153,6 +153,27 @@ def test_accelerated_lookup_equals_the_structural_walk_on_the_host(name, tmp_pat
         assert f["filter_rejects"] > 0, out                # the filters do reject absent queries
 
 
+def test_accelerated_lookup_on_a_bench_size_bft(tmp_path):
+    """The same check on the 4-genome x 5 Mbp BFT of BASELINE config[0] (8.6 M k-mers, paired buckets at load 0.6) when the bench
+    data is present in this checkout: all stored k-mers through the accelerated view, plus 200 000 random queries."""
+    import re
+    import bench_workloads as wl
+    bft = wl.bft_path(wl.C1, 27, 5_000_000)
+    if not os.path.exists(bft):
+        pytest.skip("data/ BFT of config c1 not built in this checkout (tools/build_bench_data.py c1)")
+    exe = str(tmp_path / "arena_accel_check")
+    _gcc(["-O2", "-std=c11", "-I", CSRC, os.path.join(ROOT, "tests", "tools", "arena_accel_check.c"),
+          os.path.join(CSRC, "bft_flatten.c"), os.path.join(CSRC, "bft_io.c"), "-o", exe])
+    rng = np.random.default_rng(7)
+    qw = rng.integers(0, 1 << 54, size=(200_000, 1), dtype=np.uint64)
+    q = str(tmp_path / "q.kc")
+    synth.write_kmers_comp(q, qw, 27)
+    out = subprocess.run([exe, bft, q, "1", "0"], stdout=subprocess.PIPE, check=True).stdout.decode()
+    f = {m.group(1): int(m.group(2)) for m in re.finditer(r"(\w+)=(\d+)", out)}
+    assert f["stored"] > 8_000_000 and f["stored_bad"] == 0 and f["mismatch"] == 0, out
+    assert f["filter_rejects"] > 150_000, out     # random 27-mers are absent and nearly all rejected by the fused filter
+
+
 @pytest.mark.parametrize("name", NAMES)
 def test_bucket_block_invariants(name, tmp_path):
     """Occupancy and shape of the hashed suffix blocks: every inline prefix's lines add up to its declared count (slots + overflow
